@@ -1,0 +1,81 @@
+"""tcgen05 GEMM (C ABI vb200_gemm) against a plain fp32 torch reference on the same 16-bit inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+SHAPES = [
+    (128, 256, 64), (256, 256, 128), (384, 512, 192), (200, 96, 144), (4096, 736, 2944),
+    (4096, 2944, 736), (512, 3072, 768), (130, 40, 72), (1000, 192, 96), (333, 384, 1536),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_kmajor_bias_residual(cuda, M, N, K, dtype):
+    from viscy_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device=cuda, generator=g).to(dtype)
+    b = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).to(dtype)
+    bias = torch.randn(N, device=cuda, generator=g)
+    res = torch.randn(M, N, device=cuda, generator=g).to(dtype)
+    ref = a.float() @ b.float().t() + bias + res.float()
+    out = ops.gemm(a, b, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    tol = 5e-3 if dtype == torch.bfloat16 else 1e-3
+    assert _rel(out, ref) < tol
+    assert torch.allclose(out.float(), ref, atol=tol * 8, rtol=tol * 4)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 2944, 736), (512, 96, 384)])
+def test_gemm_epilogues(cuda, M, N, K):
+    from viscy_b200 import ops, _lib as L
+    g = torch.Generator(device=cuda).manual_seed(5)
+    dtype = torch.bfloat16
+    a = torch.randn(M, K, device=cuda, generator=g).to(dtype)
+    b = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).to(dtype)
+    bias = torch.randn(N, device=cuda, generator=g)
+    u_ref = a.float() @ b.float().t() + bias
+    u, gl = ops.gemm(a, b, bias=bias, epilogue=L.EPI_GELU_DUAL)
+    assert _rel(u, u_ref) < 5e-3
+    assert _rel(gl, torch.nn.functional.gelu(u_ref)) < 5e-3
+    r = ops.gemm(a, b, bias=bias, act=L.ACT_RELU)
+    assert _rel(r, torch.relu(u_ref)) < 5e-3
+    ge = ops.gemm(a, b, bias=bias, act=L.ACT_GELU)
+    assert _rel(ge, torch.nn.functional.gelu(u_ref)) < 5e-3
+    aux = torch.randn(M, N, device=cuda, generator=g).to(dtype)
+    xa = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(xa).sum().backward()
+    dg = ops.gemm(a, b, aux=aux, epilogue=L.EPI_DGELU)
+    assert _rel(dg, (a.float() @ b.float().t()) * xa.grad) < 5e-3
+    f = ops.gemm(a, b, bias=bias, epilogue=L.EPI_F32)
+    assert f.dtype == torch.float32 and _rel(f, u_ref) < 1e-5 * 50
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("P,M,N,splits", [
+    (256, 128, 256, 1), (4096, 736, 2944, 4), (4096, 2944, 736, 8), (1000, 96, 144, 3),
+    (32768, 384, 96, 16), (512, 768, 3072, 1), (130, 40, 72, 2),
+])
+def test_gemm_mnmajor_wgrad(cuda, P, M, N, splits, dtype):
+    from viscy_b200 import ops, _lib as L
+    g = torch.Generator(device=cuda).manual_seed(P + M + N)
+    a = torch.randn(P, M, device=cuda, generator=g).to(dtype)
+    b = torch.randn(P, N, device=cuda, generator=g).to(dtype)
+    ref = a.float().t() @ b.float()
+    out = ops.gemm(a, b, mn_major=True, epilogue=L.EPI_F32, k_splits=splits)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 1e-4
+
+
+def test_gemm_unsupported_raises(cuda):
+    from viscy_b200 import ops
+    a = torch.randn(64, 60, device=cuda).bfloat16()  # ld % 8 != 0
+    b = torch.randn(32, 60, device=cuda).bfloat16()
+    with pytest.raises(NotImplementedError):
+        ops.gemm(a, b)

@@ -1,0 +1,84 @@
+"""ctypes binding of libviscy_b200.so (C ABI declared in include/viscy_b200.h).
+
+The product path never falls back: if the library is missing, `lib()` raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libviscy_b200.so"
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
+BF16, FP16 = 0, 1
+EPI_STORE, EPI_GELU_DUAL, EPI_DGELU, EPI_F32 = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("dtype", C.c_int32), ("mn_major", C.c_int32), ("epilogue", C.c_int32),
+        ("act", C.c_int32), ("k_splits", C.c_int32), ("atomic_out", C.c_int32),
+        ("lda", C.c_int64), ("ldb", C.c_int64),
+        ("ldo", C.c_int64), ("ldo2", C.c_int64), ("ldr", C.c_int64), ("ldaux", C.c_int64),
+        ("split_out_stride", C.c_int64),
+        ("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("aux", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the native library; raise loudly when it is absent (no CPU / library fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} not built: run `python -m viscy_b200.build` "
+                "(the sm_100a kernels are mandatory for CUDA tensors; there is no fallback)"
+            )
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.vb200_last_error.argtypes = [C.c_char_p, C.c_size_t]
+        _lib.vb200_launch_count.restype = C.c_int64
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    lib().vb200_last_error(buf, 512)
+    return buf.value.decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        msg = last_error()
+        if rc == ERR_UNSUPPORTED:
+            raise NotImplementedError(f"{what}: unsupported on the sm_100a path: {msg}")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return BF16
+    if dt == torch.float16:
+        return FP16
+    raise NotImplementedError(f"sm_100a kernels take 16-bit activations, got {dt}")
+
+
+def ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def launch_count() -> int:
+    return int(lib().vb200_launch_count())

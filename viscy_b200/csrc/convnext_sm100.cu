@@ -1,0 +1,582 @@
+// HBM-bound kernels of the ConvNeXt / ConvNeXt-V2 block on channels-last 16-bit activations:
+// depthwise 7x7 (fwd, dgrad, wgrad), LayerNorm over C (fwd, bwd), GELU + Global Response Norm
+// (fwd two-phase, bwd two-phase), column sums (bias gradients).
+// Reference semantics: timm ConvNeXtBlock / LayerNorm2d / GlobalResponseNormMlp as composed by
+// VM/unet/unext2.py:40-49 and VM/components/blocks.py:54-74.
+#include "common.cuh"
+
+namespace vb {
+
+// ------------------------------------------------------------------------------ depthwise 7x7
+// x [B,H,W,C] 16-bit, wt [49][C] fp32 (tap-major so that channel loads coalesce), bias [C] or null,
+// add [B,H,W,C] 16-bit or null (residual gradient folded into the dgrad call).
+// One thread = 2 adjacent channels x TW output pixels of one row; sliding 7-wide window in registers.
+constexpr int DW_TW = 8;
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+dwconv7_kernel(const uint32_t* __restrict__ x, const float* __restrict__ wt,
+               const float* __restrict__ bias, const uint32_t* __restrict__ add,
+               uint32_t* __restrict__ y, int B, int H, int W, int C2) {
+  const int cp = blockIdx.y * 128 + threadIdx.x;  // channel pair
+  if (cp >= C2) return;
+  const int wtiles = (W + DW_TW - 1) / DW_TW;
+  int t = blockIdx.x;
+  const int w0 = (t % wtiles) * DW_TW;
+  t /= wtiles;
+  const int h = t % H;
+  const int n = t / H;
+  const int C = C2 * 2;
+  float2 acc[DW_TW];
+  float2 b2 = make_float2(0.f, 0.f);
+  if (bias != nullptr) b2 = *reinterpret_cast<const float2*>(bias + 2 * cp);
+#pragma unroll
+  for (int j = 0; j < DW_TW; ++j) acc[j] = b2;
+  const long long img = (long long)n * H * W;
+#pragma unroll 1
+  for (int kh = 0; kh < 7; ++kh) {
+    const int ih = h + kh - 3;
+    if (ih < 0 || ih >= H) continue;
+    float2 in[DW_TW + 6];
+#pragma unroll
+    for (int j = 0; j < DW_TW + 6; ++j) {
+      const int iw = w0 + j - 3;
+      in[j] = make_float2(0.f, 0.f);
+      if (iw >= 0 && iw < W) in[j] = H16<BF16>::unpack(__ldg(x + (img + (long long)ih * W + iw) * C2 + cp));
+    }
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) {
+      const float2 wv = __ldg(reinterpret_cast<const float2*>(wt + (kh * 7 + kw) * C + 2 * cp));
+#pragma unroll
+      for (int j = 0; j < DW_TW; ++j) {
+        acc[j].x = fmaf(in[j + kw].x, wv.x, acc[j].x);
+        acc[j].y = fmaf(in[j + kw].y, wv.y, acc[j].y);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DW_TW; ++j) {
+    const int ow = w0 + j;
+    if (ow < W) {
+      const long long o = (img + (long long)h * W + ow) * C2 + cp;
+      float2 v = acc[j];
+      if (add != nullptr) {
+        const float2 a = H16<BF16>::unpack(__ldg(add + o));
+        v.x += a.x;
+        v.y += a.y;
+      }
+      y[o] = H16<BF16>::pack(v.x, v.y);
+    }
+  }
+}
+
+// wgrad: dwt[tap][c] += sum_{pixels} dy[p][c] * x[p + tap offset][c];  db[c] += sum dy[p][c].
+// One block = 128 channel pairs x a strip of rows of one image; per-thread 49x2 accumulators.
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+dwconv7_wgrad_kernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ dy,
+                     float* __restrict__ dwt, float* __restrict__ db, int B, int H, int W, int C2,
+                     int rows_per_block) {
+  const int cp = blockIdx.y * 128 + threadIdx.x;
+  if (cp >= C2) return;
+  const int strips = (H + rows_per_block - 1) / rows_per_block;
+  const int n = blockIdx.x / strips;
+  const int h0 = (blockIdx.x % strips) * rows_per_block;
+  const int h1 = min(H, h0 + rows_per_block);
+  const int C = 2 * C2;
+  const long long img = (long long)n * H * W;
+  float2 bsum = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int kh = 0; kh < 7; ++kh) {
+    float2 acc[7];
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) acc[kw] = make_float2(0.f, 0.f);
+    for (int h = h0; h < h1; ++h) {
+      const int ih = h + kh - 3;
+      if (ih < 0 || ih >= H) continue;
+      // slide along the row: keep a 7-wide window of x in registers
+      float2 win[7];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int iw = j - 3;
+        win[j + 1] = make_float2(0.f, 0.f);
+        if (iw >= 0 && iw < W) win[j + 1] = H16<BF16>::unpack(__ldg(x + (img + (long long)ih * W + iw) * C2 + cp));
+      }
+      for (int w = 0; w < W; ++w) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+        const int iw = w + 3;
+        win[6] = make_float2(0.f, 0.f);
+        if (iw < W) win[6] = H16<BF16>::unpack(__ldg(x + (img + (long long)ih * W + iw) * C2 + cp));
+        const float2 g = H16<BF16>::unpack(__ldg(dy + (img + (long long)h * W + w) * C2 + cp));
+        if (kh == 3) {  // count every dy exactly once for the bias gradient (ih == h always valid)
+          bsum.x += g.x;
+          bsum.y += g.y;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) {
+          acc[kw].x = fmaf(g.x, win[kw].x, acc[kw].x);
+          acc[kw].y = fmaf(g.y, win[kw].y, acc[kw].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) {
+      atomicAdd(dwt + (kh * 7 + kw) * C + 2 * cp, acc[kw].x);
+      atomicAdd(dwt + (kh * 7 + kw) * C + 2 * cp + 1, acc[kw].y);
+    }
+  }
+  if (db != nullptr) {
+    atomicAdd(db + 2 * cp, bsum.x);
+    atomicAdd(db + 2 * cp + 1, bsum.y);
+  }
+}
+
+// ------------------------------------------------------------------------------ LayerNorm over C
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per row; x, y [M, C] 16-bit (ld = C); stats fp32 [M]
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const uint32_t* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, uint32_t* __restrict__ y,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int C2,
+                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const uint32_t* xr = x + row * C2;
+  float s = 0.f;
+  for (int i = lane; i < C2; i += 32) {
+    const float2 v = H16<BF16>::unpack(__ldg(xr + i));
+    s += v.x + v.y;
+  }
+  const float mean = warp_sum(s) / (2.0f * C2);
+  float q = 0.f;
+  for (int i = lane; i < C2; i += 32) {
+    const float2 v = H16<BF16>::unpack(__ldg(xr + i));
+    const float a = v.x - mean, b = v.y - mean;
+    q += a * a + b * b;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (2.0f * C2) + eps);
+  for (int i = lane; i < C2; i += 32) {
+    const float2 v = H16<BF16>::unpack(__ldg(xr + i));
+    const float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + i);
+    const float2 b = __ldg(reinterpret_cast<const float2*>(beta) + i);
+    y[row * C2 + i] = H16<BF16>::pack((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y);
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;  dgamma += dy * xhat; dbeta += dy
+// Each warp walks rows with a grid stride and keeps its dgamma/dbeta partials in registers
+// (NP channel pairs per lane), reduced through shared memory and one atomicAdd per block and channel.
+template <bool BF16, int NP>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const uint32_t* __restrict__ dy, const uint32_t* __restrict__ x,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, uint32_t* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C2) {
+  extern __shared__ float red[];  // [2][C]
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int C = 2 * C2;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float2 gacc[NP], bacc[NP], gm[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    gacc[k] = make_float2(0.f, 0.f);
+    bacc[k] = make_float2(0.f, 0.f);
+    const int i = lane + 32 * k;
+    gm[k] = i < C2 ? __ldg(reinterpret_cast<const float2*>(gamma) + i) : make_float2(0.f, 0.f);
+  }
+  for (long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5); row < M;
+       row += (long long)gridDim.x * warps) {
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float2 g[NP], xh[NP];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int i = lane + 32 * k;
+      g[k] = make_float2(0.f, 0.f);
+      xh[k] = make_float2(0.f, 0.f);
+      if (i < C2) {
+        const float2 d = H16<BF16>::unpack(__ldg(dy + row * C2 + i));
+        const float2 v = H16<BF16>::unpack(__ldg(x + row * C2 + i));
+        xh[k] = make_float2((v.x - mu) * rs, (v.y - mu) * rs);
+        gacc[k].x += d.x * xh[k].x;
+        gacc[k].y += d.y * xh[k].y;
+        bacc[k].x += d.x;
+        bacc[k].y += d.y;
+        g[k] = make_float2(d.x * gm[k].x, d.y * gm[k].y);
+        s1 += g[k].x + g[k].y;
+        s2 += g[k].x * xh[k].x + g[k].y * xh[k].y;
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int i = lane + 32 * k;
+      if (i < C2)
+        dx[row * C2 + i] = H16<BF16>::pack(rs * (g[k].x - s1 - xh[k].x * s2), rs * (g[k].y - s1 - xh[k].y * s2));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int i = lane + 32 * k;
+    if (i < C2) {
+      atomicAdd(&red[2 * i], gacc[k].x);
+      atomicAdd(&red[2 * i + 1], gacc[k].y);
+      atomicAdd(&red[C + 2 * i], bacc[k].x);
+      atomicAdd(&red[C + 2 * i + 1], bacc[k].y);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[C + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------ GELU + GRN
+// h [B, R, C] 16-bit (R = pixels per sample).  Column kernels: thread = channel pair, block walks a
+// chunk of rows of one sample, one atomicAdd per (block, channel) at the end.
+// mode 0: sumsq[n,c] += gelu(h)^2
+// mode 1: S1[n,c] += dy * gelu(h);  sdy[c] += dy
+template <bool BF16, int MODE>
+__global__ void __launch_bounds__(128)
+grn_reduce_kernel(const uint32_t* __restrict__ h, const uint32_t* __restrict__ dy,
+                  float* __restrict__ acc0, float* __restrict__ acc1, int R, int C2,
+                  int rows_per_block) {
+  const int cp = blockIdx.x * 128 + threadIdx.x;
+  if (cp >= C2) return;
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  const long long base = (long long)n * R;
+  float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const float2 u = H16<BF16>::unpack(__ldg(h + (base + r) * C2 + cp));
+    const float gx = gelu_f(u.x), gy = gelu_f(u.y);
+    if (MODE == 0) {
+      a.x = fmaf(gx, gx, a.x);
+      a.y = fmaf(gy, gy, a.y);
+    } else {
+      const float2 d = H16<BF16>::unpack(__ldg(dy + (base + r) * C2 + cp));
+      a.x = fmaf(d.x, gx, a.x);
+      a.y = fmaf(d.y, gy, a.y);
+      b.x += d.x;
+      b.y += d.y;
+    }
+  }
+  const int C = 2 * C2;
+  atomicAdd(acc0 + (long long)n * C + 2 * cp, a.x);
+  atomicAdd(acc0 + (long long)n * C + 2 * cp + 1, a.y);
+  if (MODE == 1) {
+    atomicAdd(acc1 + 2 * cp, b.x);
+    atomicAdd(acc1 + 2 * cp + 1, b.y);
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) t += scratch[i];
+  return t;
+}
+
+// forward coefficients: s[n,c] = 1 + w[c] * Gx[n,c] / (mean_c Gx[n,:] + eps),  Gx = sqrt(sumsq)
+__global__ void grn_coef_fwd_kernel(const float* __restrict__ sumsq, const float* __restrict__ w,
+                                    float* __restrict__ s, int C, float eps) {
+  __shared__ float scratch[32];
+  const int n = blockIdx.x;
+  float part = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += sqrtf(sumsq[(long long)n * C + c]);
+  const float m = block_sum(part, scratch) / C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    s[(long long)n * C + c] = 1.0f + w[c] * sqrtf(sumsq[(long long)n * C + c]) / (m + eps);
+}
+
+// backward coefficients from S1[n,c] = sum_r dy * g:
+//   dNx = w * S1;  dw[c] += Nx * S1;  dGx = dNx/(m+eps) - (1/C) * sum_c'(dNx * Gx) / (m+eps)^2
+//   t[n,c] = dGx / Gx   (so that dg = dy * s + g * t)
+__global__ void grn_coef_bwd_kernel(const float* __restrict__ sumsq, const float* __restrict__ S1,
+                                    const float* __restrict__ w, float* __restrict__ t,
+                                    float* __restrict__ dw, int C, float eps) {
+  __shared__ float scratch[32];
+  const int n = blockIdx.x;
+  float pm = 0.f, pd = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float gx = sqrtf(sumsq[(long long)n * C + c]);
+    pm += gx;
+    pd += w[c] * S1[(long long)n * C + c] * gx;
+  }
+  const float m = block_sum(pm, scratch) / C;
+  const float dot = block_sum(pd, scratch);
+  const float inv = 1.0f / (m + eps);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float gx = sqrtf(sumsq[(long long)n * C + c]);
+    const float s1 = S1[(long long)n * C + c];
+    const float dgx = w[c] * s1 * inv - dot * inv * inv / C;
+    t[(long long)n * C + c] = gx > 0.f ? dgx / gx : 0.f;
+    atomicAdd(dw + c, gx * inv * s1);
+  }
+}
+
+// y = gelu(h) * s[n,c] + b[c]
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+grn_apply_fwd_kernel(const uint4* __restrict__ h, const float* __restrict__ s,
+                     const float* __restrict__ b, uint4* __restrict__ y, int R, int C8,
+                     long long total8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = (int)(i % C8);
+  const long long row = i / C8;
+  const int n = (int)(row / R);
+  const uint4 q = __ldg(h + i);
+  const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+  uint32_t o[4];
+  const float* sp = s + ((long long)n * C8 + c8) * 8;
+  const float* bp = b + c8 * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 u = H16<BF16>::unpack(in[k]);
+    o[k] = H16<BF16>::pack(fmaf(gelu_f(u.x), __ldg(sp + 2 * k), __ldg(bp + 2 * k)),
+                           fmaf(gelu_f(u.y), __ldg(sp + 2 * k + 1), __ldg(bp + 2 * k + 1)));
+  }
+  y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// dh = (dy * s[n,c] + gelu(h) * t[n,c]) * gelu'(h);  dbias[c] += sum_rows dh  (fc1 bias gradient)
+// thread = channel pair, block = chunk of rows of one sample (same decomposition as grn_reduce).
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+grn_apply_bwd_kernel(const uint32_t* __restrict__ h, const uint32_t* __restrict__ dy,
+                     const float* __restrict__ s, const float* __restrict__ t,
+                     uint32_t* __restrict__ dh, float* __restrict__ dbias, int R, int C2,
+                     int rows_per_block) {
+  const int cp = blockIdx.x * 128 + threadIdx.x;
+  if (cp >= C2) return;
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  const long long base = (long long)n * R;
+  const int C = 2 * C2;
+  const float2 sv = *reinterpret_cast<const float2*>(s + (long long)n * C + 2 * cp);
+  float2 tv = make_float2(0.f, 0.f);
+  if (t != nullptr) tv = *reinterpret_cast<const float2*>(t + (long long)n * C + 2 * cp);
+  float2 bs = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const long long o = (base + r) * C2 + cp;
+    const float2 u = H16<BF16>::unpack(__ldg(h + o));
+    const float2 d = H16<BF16>::unpack(__ldg(dy + o));
+    const float ox = (d.x * sv.x + gelu_f(u.x) * tv.x) * dgelu_f(u.x);
+    const float oy = (d.y * sv.y + gelu_f(u.y) * tv.y) * dgelu_f(u.y);
+    const uint32_t packed = H16<BF16>::pack(ox, oy);
+    dh[o] = packed;
+    const float2 rq = H16<BF16>::unpack(packed);  // sum what the wgrad GEMM will actually see
+    bs.x += rq.x;
+    bs.y += rq.y;
+  }
+  if (dbias != nullptr) {
+    atomicAdd(dbias + 2 * cp, bs.x);
+    atomicAdd(dbias + 2 * cp + 1, bs.y);
+  }
+}
+
+// out[c] += sum_rows x[r][c]
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+colsum_kernel(const uint32_t* __restrict__ x, float* __restrict__ out, long long M, int C2,
+              int rows_per_block) {
+  const int cp = blockIdx.x * 128 + threadIdx.x;
+  if (cp >= C2) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float2 a = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (long long r = r0; r < r1; ++r) {
+    const float2 v = H16<BF16>::unpack(__ldg(x + r * C2 + cp));
+    a.x += v.x;
+    a.y += v.y;
+  }
+  atomicAdd(out + 2 * cp, a.x);
+  atomicAdd(out + 2 * cp + 1, a.y);
+}
+
+static int rows_per_block_for(long long rows, int col_blocks, int samples) {
+  // aim for ~8 blocks per SM in total, at least 16 rows per block
+  const long long target_blocks = 148LL * 8;
+  long long per = (rows * col_blocks * samples + target_blocks - 1) / target_blocks;
+  if (per < 16) per = 16;
+  if (per > rows) per = rows;
+  return (int)per;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+#define DISPATCH_DT(dtype, ...)                                              \
+  do {                                                                       \
+    if ((dtype) == VB200_BF16) { constexpr bool BF = true; __VA_ARGS__; }    \
+    else if ((dtype) == VB200_FP16) { constexpr bool BF = false; __VA_ARGS__; } \
+    else return vb::fail(VB200_ERR_UNSUPPORTED, "dtype %d", (int)(dtype));   \
+  } while (0)
+
+extern "C" int vb200_dwconv7(const void* x, const float* wt, const float* bias, const void* add,
+                             void* y, int B, int H, int W, int C, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(x && wt && y, "null pointer");
+  VB_SUPPORTED(C % 2 == 0, "C (%d) must be even", C);
+  const int C2 = C / 2;
+  dim3 grid((unsigned)(((W + DW_TW - 1) / DW_TW) * H * B), (unsigned)((C2 + 127) / 128));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, dwconv7_kernel<BF><<<grid, 128, 0, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
+                                                             (uint32_t*)y, B, H, W, C2));
+  return check_launch("vb200_dwconv7");
+}
+
+extern "C" int vb200_dwconv7_wgrad(const void* x, const void* dy, float* dwt, float* db, int B, int H,
+                                   int W, int C, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(x && dy && dwt, "null pointer");
+  VB_SUPPORTED(C % 2 == 0, "C (%d) must be even", C);
+  const int C2 = C / 2;
+  const int colb = (C2 + 127) / 128;
+  int rpb = (int)(((long long)H * B * colb + 148 * 4 - 1) / (148 * 4));
+  if (rpb < 1) rpb = 1;
+  if (rpb > H) rpb = H;
+  const int strips = (H + rpb - 1) / rpb;
+  dim3 grid((unsigned)(B * strips), (unsigned)colb);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, dwconv7_wgrad_kernel<BF><<<grid, 128, 0, st>>>((const uint32_t*)x, (const uint32_t*)dy, dwt,
+                                                                   db, B, H, W, C2, rpb));
+  return check_launch("vb200_dwconv7_wgrad");
+}
+
+extern "C" int vb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
+                                   float* mean, float* rstd, int64_t M, int C, float eps, int dtype,
+                                   vb200_stream_t stream) {
+  VB_REQUIRE(x && gamma && beta && y && mean && rstd, "null pointer");
+  VB_SUPPORTED(C % 2 == 0, "C (%d) must be even", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((M + 7) / 8);
+  DISPATCH_DT(dtype, layernorm_fwd_kernel<BF><<<grid, 256, 0, st>>>((const uint32_t*)x, gamma, beta, (uint32_t*)y,
+                                                                   mean, rstd, M, C / 2, eps));
+  return check_launch("vb200_layernorm_fwd");
+}
+
+template <bool BF, int NP>
+static void ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd,
+                          const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t M, int C,
+                          cudaStream_t st) {
+  long long blocks = (M + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  layernorm_bwd_kernel<BF, NP><<<(unsigned)blocks, 256, 2 * C * sizeof(float), st>>>(
+      (const uint32_t*)dy, (const uint32_t*)x, mean, rstd, gamma, (uint32_t*)dx, dgamma, dbeta, M, C / 2);
+}
+
+extern "C" int vb200_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                                   const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t M,
+                                   int C, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "null pointer");
+  VB_SUPPORTED(C % 2 == 0 && C <= 3072, "C (%d) must be even and <= 3072", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np = (C / 2 + 31) / 32;
+#define LN_BWD(NP) DISPATCH_DT(dtype, (ln_bwd_launch<BF, NP>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, C, st)))
+  if (np <= 3) LN_BWD(3);
+  else if (np <= 6) LN_BWD(6);
+  else if (np <= 12) LN_BWD(12);
+  else if (np <= 24) LN_BWD(24);
+  else LN_BWD(48);
+#undef LN_BWD
+  return check_launch("vb200_layernorm_bwd");
+}
+
+extern "C" int vb200_grn_sumsq(const void* h, float* sumsq, int B, int R, int C, int dtype,
+                               vb200_stream_t stream) {
+  VB_REQUIRE(h && sumsq, "null pointer");
+  VB_SUPPORTED(C % 2 == 0, "C even");
+  const int C2 = C / 2, colb = (C2 + 127) / 128;
+  const int rpb = rows_per_block_for(R, colb, B);
+  dim3 grid(colb, (R + rpb - 1) / rpb, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, grn_reduce_kernel<BF, 0><<<grid, 128, 0, st>>>((const uint32_t*)h, nullptr, sumsq, nullptr, R,
+                                                                   C2, rpb));
+  return check_launch("vb200_grn_sumsq");
+}
+
+extern "C" int vb200_grn_coef_fwd(const float* sumsq, const float* w, float* s, int B, int C, float eps,
+                                  vb200_stream_t stream) {
+  VB_REQUIRE(sumsq && w && s, "null pointer");
+  grn_coef_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(sumsq, w, s, C, eps);
+  return check_launch("vb200_grn_coef_fwd");
+}
+
+extern "C" int vb200_grn_apply_fwd(const void* h, const float* s, const float* b, void* y, int B, int R,
+                                   int C, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(h && s && b && y, "null pointer");
+  VB_SUPPORTED(C % 8 == 0, "C (%d) %% 8", C);
+  const long long total8 = (long long)B * R * C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, grn_apply_fwd_kernel<BF><<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+                         (const uint4*)h, s, b, (uint4*)y, R, C / 8, total8));
+  return check_launch("vb200_grn_apply_fwd");
+}
+
+extern "C" int vb200_grn_bwd_reduce(const void* h, const void* dy, float* S1, float* sdy, int B, int R,
+                                    int C, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(h && dy && S1 && sdy, "null pointer");
+  VB_SUPPORTED(C % 2 == 0, "C even");
+  const int C2 = C / 2, colb = (C2 + 127) / 128;
+  const int rpb = rows_per_block_for(R, colb, B);
+  dim3 grid(colb, (R + rpb - 1) / rpb, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, grn_reduce_kernel<BF, 1><<<grid, 128, 0, st>>>((const uint32_t*)h, (const uint32_t*)dy, S1, sdy,
+                                                                   R, C2, rpb));
+  return check_launch("vb200_grn_bwd_reduce");
+}
+
+extern "C" int vb200_grn_coef_bwd(const float* sumsq, const float* S1, const float* w, float* t, float* dw,
+                                  int B, int C, float eps, vb200_stream_t stream) {
+  VB_REQUIRE(sumsq && S1 && w && t && dw, "null pointer");
+  grn_coef_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(sumsq, S1, w, t, dw, C, eps);
+  return check_launch("vb200_grn_coef_bwd");
+}
+
+extern "C" int vb200_grn_apply_bwd(const void* h, const void* dy, const float* s, const float* t, void* dh,
+                                   float* dbias, int B, int R, int C, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(h && dy && s && dh, "null pointer");
+  VB_SUPPORTED(C % 2 == 0, "C even");
+  const int C2 = C / 2, colb = (C2 + 127) / 128;
+  const int rpb = rows_per_block_for(R, colb, B);
+  dim3 grid(colb, (R + rpb - 1) / rpb, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, grn_apply_bwd_kernel<BF><<<grid, 128, 0, st>>>((const uint32_t*)h, (const uint32_t*)dy, s, t,
+                                                                   (uint32_t*)dh, dbias, R, C2, rpb));
+  return check_launch("vb200_grn_apply_bwd");
+}
+
+extern "C" int vb200_colsum(const void* x, float* out, int64_t M, int C, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(x && out, "null pointer");
+  VB_SUPPORTED(C % 2 == 0, "C even");
+  const int C2 = C / 2, colb = (C2 + 127) / 128;
+  const int rpb = rows_per_block_for(M, colb, 1);
+  dim3 grid(colb, (unsigned)((M + rpb - 1) / rpb));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, colsum_kernel<BF><<<grid, 128, 0, st>>>((const uint32_t*)x, out, M, C2, rpb));
+  return check_launch("vb200_colsum");
+}

@@ -1,0 +1,455 @@
+// tcgen05 GEMM for sm_100a: persistent, warp-specialised (TMA producer / single-thread MMA issuer /
+// 8 epilogue warps), 128 x BN x 64 tiles, 4-stage (BN=256) mbarrier ring in shared memory, two
+// accumulator buffers in TMEM so that the drain of tile i overlaps the MMAs of tile i+1.
+//
+// Two operand forms (include/viscy_b200.h : vb200_gemm_desc):
+//   mn_major = 0 : D[M,N] = A[M,K] . B[N,K]^T   (forward 1x1-conv / Linear, and dgrad)
+//   mn_major = 1 : D[M,N] = sum_k At[k,M] * Bt[k,N]  (wgrad; k runs over pixels, K-split with red.add)
+// Replaces the cuBLAS / cuDNN calls behind nn.Linear / 1x1 nn.Conv2d / kernel==stride convs of the
+// reference hot path (VM/components/blocks.py:60-74, VM/components/stems.py:26-50).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vb {
+
+thread_local char g_err[512] = {0};
+std::atomic<long long> g_launches{0};
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, k_splits, kb_total, kb_per_split;
+  int bf16;
+  int act;
+  int atomic_out;
+  long long ldo, ldo2, ldr, ldaux;
+  long long split_out_stride;
+  void* out;
+  void* out2;
+  const float* bias;
+  const void* residual;
+  const void* aux;
+};
+
+template <bool BF16>
+__device__ __forceinline__ void load8(const void* p, float* v) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  float2 a = H16<BF16>::unpack(q.x), b = H16<BF16>::unpack(q.y), c = H16<BF16>::unpack(q.z),
+         d = H16<BF16>::unpack(q.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <bool BF16>
+__device__ __forceinline__ void store8(void* p, const float* v) {
+  uint4 q;
+  q.x = H16<BF16>::pack(v[0], v[1]);
+  q.y = H16<BF16>::pack(v[2], v[3]);
+  q.z = H16<BF16>::pack(v[4], v[5]);
+  q.w = H16<BF16>::pack(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+// One group of 8 consecutive output columns of one row.
+template <int EPI, bool BF16>
+__device__ __forceinline__ void epilogue8(const GemmParams& p, const uint32_t* r, long long row,
+                                          int col, int split) {
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr && split == 0) {
+    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if constexpr (EPI == VB200_EPI_STORE) {
+    if (p.act == VB200_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+    } else if (p.act == VB200_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
+    }
+    if (p.residual != nullptr) {
+      float q[8];
+      load8<BF16>(reinterpret_cast<const uint16_t*>(p.residual) + row * p.ldr + col, q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += q[j];
+    }
+    store8<BF16>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col, v);
+  } else if constexpr (EPI == VB200_EPI_GELU_DUAL) {
+    store8<BF16>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
+    store8<BF16>(reinterpret_cast<uint16_t*>(p.out2) + row * p.ldo2 + col, v);
+  } else if constexpr (EPI == VB200_EPI_DGELU) {
+    float u[8];
+    load8<BF16>(reinterpret_cast<const uint16_t*>(p.aux) + row * p.ldaux + col, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= dgelu_f(u[j]);
+    store8<BF16>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col, v);
+  } else {  // VB200_EPI_F32
+    float* o = reinterpret_cast<float*>(p.out) + (long long)split * p.split_out_stride +
+               row * p.ldo + col;
+    if (p.atomic_out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+template <int BN, bool MN_MAJOR, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int units = tiles * p.k_splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int split = unit / tiles;
+        const int t = unit - split * tiles;
+        const int m0 = (t / p.tiles_n) * BM;
+        const int n0 = (t % p.tiles_n) * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if constexpr (!MN_MAJOR) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (64 * BK * 2), &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (64 * BK * 2), &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = make_idesc(BM, BN, p.bf16 != 0, MN_MAJOR, MN_MAJOR);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int split = unit / tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t da, db;
+            if constexpr (!MN_MAJOR) {
+              // K-major SW128: 8-row groups 1024 B apart; step 16 elements (32 B) inside the row
+              da = make_smem_desc(sa + k * 32, 0, 1024);
+              db = make_smem_desc(sb + k * 32, 0, 1024);
+            } else {
+              // MN-major SW128: 64-wide MN atoms (one TMA box each) 64*BK*2 B apart (LBO),
+              // 8-row k groups 1024 B apart (SBO); step 16 k rows = 2048 B
+              da = make_smem_desc(sa + k * 2048, 64 * BK * 2, 1024);
+              db = make_smem_desc(sb + k * 2048, 64 * BK * 2, 1024);
+            }
+            tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int e = warp - 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    const int half = e >> 2;       // which half of the BN columns
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int split = unit / tiles;
+      const int t = unit - split * tiles;
+      const int m0 = (t / p.tiles_n) * BM;
+      const int n0 = (t % p.tiles_n) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_addr =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int cc = half * (BN / 2) + c * 32;
+        const int col0 = n0 + cc;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_addr + cc, r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.N) {
+              if (p.bf16)
+                epilogue8<EPI, true>(p, r + g * 8, row, col, split);
+              else
+                epilogue8<EPI, false>(p, r + g * 8, row, col, split);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) ==
+            cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// 2-D row-major 16-bit tensor [rows, cols] with leading dimension ld (elements); box = {box_c, box_r}
+int make_tmap_2d(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld,
+                 int box_c, int box_r, bool bf16) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0)
+    return fail(VB200_ERR_UNSUPPORTED, "TMA operand needs 16-byte aligned base and ld %% 8 == 0 (ld=%lld)", ld);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_r)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return VB200_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool MN_MAJOR, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                  cudaStream_t st) {
+  static bool configured = false;  // per instantiation
+  auto kern = gemm_kernel<BN, MN_MAJOR, EPI>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  return check_launch("vb200_gemm");
+}
+
+template <int BN, bool MN_MAJOR>
+static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                      int grid, cudaStream_t st) {
+  if constexpr (MN_MAJOR) {
+    if (epi == VB200_EPI_F32) return launch<BN, true, VB200_EPI_F32>(ta, tb, p, grid, st);
+    return fail(VB200_ERR_UNSUPPORTED, "mn_major GEMM supports EPI_F32 only");
+  } else {
+    switch (epi) {
+      case VB200_EPI_STORE: return launch<BN, false, VB200_EPI_STORE>(ta, tb, p, grid, st);
+      case VB200_EPI_GELU_DUAL: return launch<BN, false, VB200_EPI_GELU_DUAL>(ta, tb, p, grid, st);
+      case VB200_EPI_DGELU: return launch<BN, false, VB200_EPI_DGELU>(ta, tb, p, grid, st);
+      case VB200_EPI_F32: return launch<BN, false, VB200_EPI_F32>(ta, tb, p, grid, st);
+    }
+    return fail(VB200_ERR_INVALID, "unknown epilogue %d", epi);
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
+  VB_REQUIRE(d != nullptr, "null descriptor");
+  VB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "bad GEMM shape %d x %d x %d", d->M, d->N, d->K);
+  VB_REQUIRE(d->A && d->B && d->out, "null operand pointer");
+  VB_SUPPORTED(d->dtype == VB200_BF16 || d->dtype == VB200_FP16, "dtype %d", d->dtype);
+  VB_SUPPORTED(d->N % 8 == 0, "N (%d) must be a multiple of 8", d->N);
+  VB_SUPPORTED(d->ldo % 8 == 0, "ldo (%lld) must be a multiple of 8", (long long)d->ldo);
+  const bool bf16 = d->dtype == VB200_BF16;
+  const int epi = d->epilogue;
+  if (epi == VB200_EPI_GELU_DUAL)
+    VB_REQUIRE(d->out2 != nullptr && d->ldo2 % 8 == 0, "GELU_DUAL needs out2 with ldo2 %% 8 == 0");
+  if (epi == VB200_EPI_DGELU)
+    VB_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "DGELU needs aux with ldaux %% 8 == 0");
+  if (d->residual) VB_REQUIRE(d->ldr % 8 == 0, "ldr %% 8");
+  int splits = d->k_splits > 0 ? d->k_splits : 1;
+  VB_REQUIRE(splits == 1 || epi == VB200_EPI_F32, "k_splits > 1 needs EPI_F32");
+  VB_REQUIRE(splits == 1 || d->atomic_out || d->split_out_stride > 0,
+             "k_splits > 1 needs atomic_out or per-split slabs");
+
+  // tile width: widest tile that still gives every SM work, else narrower
+  const int sms = sm_count();
+  const int tiles_m = (d->M + BM - 1) / BM;
+  int bn = 256;
+  if (d->N <= 64) bn = 64;
+  else if (d->N <= 128) bn = 128;
+  else {
+    auto units = [&](int b) { return (long long)tiles_m * ((d->N + b - 1) / b) * splits; };
+    if (units(256) < sms) bn = (units(128) < sms && d->N > 64) ? 64 : 128;
+    // avoid > 1/3 of a 256-wide last tile being padding when the problem is tiny
+  }
+  const int tiles_n = (d->N + bn - 1) / bn;
+  const int kb_total = (d->K + BK - 1) / BK;
+  if (splits > kb_total) splits = kb_total;
+  int kb_per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + kb_per - 1) / kb_per;  // no empty split
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!d->mn_major) {
+    if ((rc = make_tmap_2d(&ta, d->A, d->M, d->K, d->lda, BK, BM, bf16))) return rc;
+    if ((rc = make_tmap_2d(&tb, d->B, d->N, d->K, d->ldb, BK, bn, bf16))) return rc;
+  } else {
+    if ((rc = make_tmap_2d(&ta, d->A, d->K, d->M, d->lda, 64, BK, bf16))) return rc;
+    if ((rc = make_tmap_2d(&tb, d->B, d->K, d->N, d->ldb, 64, BK, bf16))) return rc;
+  }
+  GemmParams p;
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.k_splits = splits;
+  p.kb_total = kb_total; p.kb_per_split = kb_per;
+  p.bf16 = bf16 ? 1 : 0;
+  p.act = d->act;
+  p.atomic_out = d->atomic_out;
+  p.ldo = d->ldo; p.ldo2 = d->ldo2; p.ldr = d->ldr; p.ldaux = d->ldaux;
+  p.split_out_stride = d->atomic_out ? 0 : d->split_out_stride;
+  p.out = d->out; p.out2 = d->out2; p.bias = d->bias; p.residual = d->residual; p.aux = d->aux;
+  const long long units = (long long)tiles_m * tiles_n * splits;
+  const int grid = (int)(units < sms ? units : sms);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!d->mn_major) {
+    if (bn == 256) return launch_epi<256, false>(epi, ta, tb, p, grid, st);
+    if (bn == 128) return launch_epi<128, false>(epi, ta, tb, p, grid, st);
+    return launch_epi<64, false>(epi, ta, tb, p, grid, st);
+  } else {
+    if (bn == 256) return launch_epi<256, true>(epi, ta, tb, p, grid, st);
+    if (bn == 128) return launch_epi<128, true>(epi, ta, tb, p, grid, st);
+    return launch_epi<64, true>(epi, ta, tb, p, grid, st);
+  }
+}
+
+extern "C" int vb200_last_error(char* buf, size_t n) {
+  if (buf == nullptr || n == 0) return VB200_ERR_INVALID;
+  snprintf(buf, n, "%s", g_err);
+  return VB200_OK;
+}
+extern "C" int vb200_abi_version(void) { return 1; }
+extern "C" int64_t vb200_launch_count(void) { return g_launches.load(); }

@@ -64,6 +64,84 @@ typedef struct vb200_gemm_desc {
 
 int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);
 
+/* ---- ConvNeXt / ConvNeXt-V2 block pieces (timm ConvNeXtBlock as composed by VM/unet/unext2.py:40-49,
+ * VM/components/blocks.py:54-74, VM/contrastive/encoder.py:93-99).  All activations channels-last 16-bit. ---- */
+
+/* depthwise 7x7, pad 3: y = dwconv(x; wt) (+ bias) (+ add).  wt is tap-major fp32 [49][C].
+ * forward: wt = conv_dw.weight^T, bias = conv_dw.bias.  dgrad: wt = flipped taps, add = residual gradient. */
+int vb200_dwconv7(const void* x, const float* wt, const float* bias, const void* add, void* y,
+                  int B, int H, int W, int C, int dtype, vb200_stream_t stream);
+/* dwt[49][C] += sum_pixels dy * shifted x;  db[C] += sum dy  (outputs pre-zeroed by the caller) */
+int vb200_dwconv7_wgrad(const void* x, const void* dy, float* dwt, float* db, int B, int H, int W, int C,
+                        int dtype, vb200_stream_t stream);
+
+/* LayerNorm over the channel dim of [M, C] rows (timm LayerNorm / LayerNorm2d, eps 1e-6) */
+int vb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                        float* rstd, int64_t M, int C, float eps, int dtype, vb200_stream_t stream);
+/* dgamma, dbeta are accumulated into (pre-zeroed by the caller) */
+int vb200_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                        const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t M, int C,
+                        int dtype, vb200_stream_t stream);
+
+/* GELU + GlobalResponseNorm (timm GlobalResponseNormMlp) on h [B, R, C]:
+ *   sumsq[n,c] += sum_r gelu(h)^2 ; s[n,c] = 1 + w[c] * Gx / (mean_c Gx + eps), Gx = sqrt(sumsq) ;
+ *   y = gelu(h) * s[n,c] + b[c]   (== x + addcmul(bias, weight, x * Nx)) */
+int vb200_grn_sumsq(const void* h, float* sumsq, int B, int R, int C, int dtype, vb200_stream_t stream);
+int vb200_grn_coef_fwd(const float* sumsq, const float* w, float* s, int B, int C, float eps, vb200_stream_t stream);
+int vb200_grn_apply_fwd(const void* h, const float* s, const float* b, void* y, int B, int R, int C, int dtype,
+                        vb200_stream_t stream);
+/* backward: S1[n,c] += sum_r dy*gelu(h), sdy[c] += sum dy (= d grn.bias);  t from S1 (and d grn.weight += ...);
+ *   dh = (dy * s + gelu(h) * t) * gelu'(h), dbias[c] += sum_r dh (fc1 bias gradient; may be NULL).
+ *   With t == NULL and s == ones the apply kernel is a plain GELU backward. */
+int vb200_grn_bwd_reduce(const void* h, const void* dy, float* S1, float* sdy, int B, int R, int C, int dtype,
+                         vb200_stream_t stream);
+int vb200_grn_coef_bwd(const float* sumsq, const float* S1, const float* w, float* t, float* dw, int B, int C,
+                       float eps, vb200_stream_t stream);
+int vb200_grn_apply_bwd(const void* h, const void* dy, const float* s, const float* t, void* dh, float* dbias,
+                        int B, int R, int C, int dtype, vb200_stream_t stream);
+
+/* out[c] += sum_rows x[r][c]  (bias gradients; out pre-zeroed) */
+int vb200_colsum(const void* x, float* out, int64_t M, int C, int dtype, vb200_stream_t stream);
+
+/* ---- layout kernels ---- */
+/* monai SubpixelUpsample(pre_conv=None, scale 2) + torch.cat([up, skip], 1) (VM/components/blocks.py:137-172):
+ * out[n,2h+i,2w+j,c'] = prev[n,h,w,c'*4+i*2+j] (c' < Cp/4) else skip[n,2h+i,2w+j,c'-Cp/4] */
+int vb200_pixshuf_cat_fwd(const void* prev, const void* skip, void* out, int B, int h, int w, int Cp, int Cs,
+                          vb200_stream_t stream);
+int vb200_pixshuf_cat_bwd(const void* dout, void* dprev, void* dskip, int B, int h, int w, int Cp, int Cs,
+                          vb200_stream_t stream);
+/* rows for the k2s2 downsample conv (timm ConvNeXtStage.downsample[1]): dst[(n,oh,ow),(kh,kw,c)] = src[n,2oh+kh,2ow+kw,c];
+ * inverse != 0 scatters rows back (dgrad) */
+int vb200_patchify2(const void* src, void* dst, int B, int H, int W, int C, int inverse, vb200_stream_t stream);
+/* rows for UNeXt2Stem / StemDepthtoChannels (VM/components/stems.py:26-50,117-134): NCDHW input (x_dtype 0 bf16,
+ * 1 fp16, 2 fp32) -> A[(n,oh,ow), ((c*D+z)*kH+kh)*kW+kw], row pitch Kpad */
+int vb200_stem_patchify(const void* x, int x_dtype, void* A, int B, int Cin, int D, int H, int W, int kH, int kW,
+                        int Kpad, int dtype, vb200_stream_t stream);
+/* generic NDHWC (C % 8 == 0) im2col / col2im, geom = {N,D,H,W,C, kd,kh,kw, sd,sh,sw, pd,ph,pw, OD,OH,OW};
+ * K order is (kd,kh,kw,c).  Lowers nn.Conv3d / ConvTranspose3d of VM/components/heads.py:607-628,
+ * VM/unet/blocks.py:88-113, VM/unet/unet3d_base.py:90-138, VM/components/conv_block_3d.py:261-274 onto vb200_gemm. */
+int vb200_im2col3d(const void* u, void* col, const int32_t* geom, vb200_stream_t stream);
+int vb200_col2im3d(const void* dcol, void* du, const int32_t* geom, int dtype, vb200_stream_t stream);
+/* fp32 [R,Cc] -> 16-bit (weight packing); transpose != 0 writes [Cc,R] */
+int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype, vb200_stream_t stream);
+
+/* ---- PixelToVoxelHead (VM/components/heads.py:594-641) ---- */
+/* forward (backward == 0): dec [B,h,w,4*Cm] -> u [B,Dz,2h,2w,Cu] = unfold(pool(pixelshuffle2(dec)));
+ * backward (!= 0): src = du, dst = ddec */
+int vb200_head_shuffle_pool(const void* src, void* dst, int B, int h, int w, int Cm, int Dz, int Cu, int pool,
+                            int backward, int dtype, vb200_stream_t stream);
+/* InstanceNorm3d statistics of z [B,R,C]: mean, rstd [B,C] (sum, sumsq are scratch [B,C]) */
+int vb200_instnorm_stats(const void* z, float* sum, float* sumsq, float* mean, float* rstd, int B, int64_t R, int C,
+                         float eps, int dtype, vb200_stream_t stream);
+/* out (B,Co,Dz,2H,2W) NCDHW 16-bit = PixelShuffle2(Conv3d_k1(PReLU(InstanceNorm(z)))) */
+int vb200_head_tail_fwd(const void* z, const float* mean, const float* rstd, const float* alpha, int alpha_n,
+                        const float* W1, const float* b1, void* out, int B, int Dz, int H, int W, int Cmid, int Co4,
+                        int dtype, vb200_stream_t stream);
+int vb200_head_tail_bwd(int phase, const void* z, const float* mean, const float* rstd, const float* alpha,
+                        int alpha_n, const float* W1, const void* dout, float* sdp, float* sdpx, float* dW1,
+                        float* db1, float* dalpha, void* dz, float* dbz, int B, int Dz, int H, int W, int Cmid,
+                        int Co4, int dtype, vb200_stream_t stream);
+
 /* copies the last error message of the calling thread into buf (NUL terminated) */
 int vb200_last_error(char* buf, size_t n);
 /* library / kernel ABI version, bumped on any struct change */

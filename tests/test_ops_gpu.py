@@ -1,0 +1,242 @@
+"""Each HBM-bound sm_100a kernel against a plain PyTorch fp32 reference of the same op (same 16-bit inputs)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.bfloat16, torch.float16]
+
+
+def tol(dtype):
+    return 6e-3 if dtype == torch.bfloat16 else 1e-3
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def rnd(shape, dev, seed, dtype=None, scale=1.0):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    t = torch.randn(shape, device=dev, generator=g) * scale
+    return t.to(dtype) if dtype is not None else t
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 96), (1, 8, 8, 768), (2, 13, 21, 40), (1, 64, 64, 736)])
+def test_dwconv7_fwd_bwd(cuda, B, H, W, C, dtype):
+    from viscy_b200 import ops
+    x = rnd((B, H, W, C), cuda, 1, dtype)
+    w = rnd((C, 1, 7, 7), cuda, 2, scale=0.1)
+    b = rnd((C,), cuda, 3)
+    dy = rnd((B, H, W, C), cuda, 4, dtype)
+    res = rnd((B, H, W, C), cuda, 5, dtype)
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wf = w.clone().requires_grad_(True)
+    bf = b.clone().requires_grad_(True)
+    ref = F.conv2d(xf, wf, bf, padding=3, groups=C)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    wt = w.reshape(C, 49).t().contiguous()
+    y = ops.dwconv7(x, wt, b)
+    assert rel(y, ref.permute(0, 2, 3, 1)) < tol(dtype)
+    wt_flip = w.flip(2, 3).reshape(C, 49).t().contiguous()
+    dx = ops.dwconv7(dy, wt_flip, None, add=res)
+    assert rel(dx, xf.grad.permute(0, 2, 3, 1) + res.float()) < tol(dtype)
+    dwt, db = ops.dwconv7_wgrad(x, dy)
+    assert rel(dwt.t().reshape(C, 1, 7, 7), wf.grad) < 1e-4
+    assert rel(db, bf.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,C", [(64, 96), (1000, 192), (77, 768), (4096, 736), (33, 144), (16, 1536)])
+def test_layernorm_fwd_bwd(cuda, M, C, dtype):
+    from viscy_b200 import ops
+    x = rnd((M, C), cuda, 1, dtype)
+    g = rnd((C,), cuda, 2) * 0.5 + 1.0
+    b = rnd((C,), cuda, 3)
+    dy = rnd((M, C), cuda, 4, dtype)
+    xf = x.float().requires_grad_(True)
+    gf, bf = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xf, (C,), gf, bf, 1e-6)
+    ref.backward(dy.float())
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6)
+    assert rel(y, ref) < tol(dtype)
+    dx, dg, db = ops.layernorm_bwd(dy, x, mean, rstd, g)
+    assert rel(dx, xf.grad) < tol(dtype)
+    assert rel(dg, gf.grad) < 1e-4 and rel(db, bf.grad) < 1e-4
+
+
+def grn_ref(h, w, b, eps=1e-6):
+    x = F.gelu(h)
+    gx = x.norm(p=2, dim=1, keepdim=True)
+    nx = gx / (gx.mean(dim=-1, keepdim=True) + eps)
+    return x + torch.addcmul(b.view(1, 1, -1), w.view(1, 1, -1), x * nx)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,R,C", [(2, 64, 384), (3, 100, 160), (2, 4096, 2944), (8, 64, 3072)])
+def test_gelu_grn_fwd_bwd(cuda, B, R, C, dtype):
+    from viscy_b200 import ops
+    h = rnd((B, R, C), cuda, 1, dtype)
+    w = rnd((C,), cuda, 2) * 0.5
+    b = rnd((C,), cuda, 3) * 0.5
+    dy = rnd((B, R, C), cuda, 4, dtype)
+    hf = h.float().requires_grad_(True)
+    wf, bf = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = grn_ref(hf, wf, bf)
+    ref.backward(dy.float())
+    y, sumsq, s = ops.gelu_grn_fwd(h, w, b)
+    assert rel(y, ref) < tol(dtype)
+    dh, dw, dbg, dbias = ops.gelu_grn_bwd(h, dy, sumsq, s, w)
+    assert rel(dh, hf.grad) < tol(dtype)
+    assert rel(dw, wf.grad) < 2e-4 and rel(dbg, bf.grad) < 2e-4
+    assert rel(dbias, hf.grad.sum((0, 1))) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_colsum(cuda, dtype):
+    from viscy_b200 import ops
+    x = rnd((5000, 736), cuda, 1, dtype)
+    assert rel(ops.colsum(x), x.float().sum(0)) < 1e-4
+    x = rnd((100000, 32), cuda, 2, dtype)
+    assert rel(ops.colsum(x), x.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,h,w,Cp,Cs", [(2, 8, 8, 768, 384), (1, 5, 7, 64, 24), (2, 4, 4, 32, 0)])
+def test_pixshuf_cat(cuda, B, h, w, Cp, Cs, dtype):
+    from viscy_b200 import ops
+    prev = rnd((B, h, w, Cp), cuda, 1, dtype)
+    skip = rnd((B, 2 * h, 2 * w, Cs), cuda, 2, dtype) if Cs else None
+    ref = F.pixel_shuffle(prev.permute(0, 3, 1, 2), 2)
+    if Cs:
+        ref = torch.cat([ref, skip.permute(0, 3, 1, 2)], 1)
+    out = ops.pixshuf_cat_fwd(prev, skip)
+    assert torch.equal(out, ref.permute(0, 2, 3, 1).contiguous())
+    dprev, dskip = ops.pixshuf_cat_bwd(out, Cp, Cs)
+    assert torch.equal(dprev, prev)
+    if Cs:
+        assert torch.equal(dskip, skip)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_patchify2(cuda, dtype):
+    from viscy_b200 import ops
+    x = rnd((2, 8, 12, 24), cuda, 1, dtype)
+    p = ops.patchify2(x)
+    ref = x.view(2, 4, 2, 6, 2, 24).permute(0, 1, 3, 2, 4, 5).reshape(2, 4, 6, 96)
+    assert torch.equal(p, ref)
+    assert torch.equal(ops.patchify2(p, inverse=True, shape=x.shape), x)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("xdt", [torch.float32, None])
+def test_stem_patchify(cuda, dtype, xdt):
+    from viscy_b200 import ops
+    x = rnd((2, 2, 6, 16, 24), cuda, 1, xdt or dtype)
+    A = ops.stem_patchify(x, 4, 4, dtype)
+    ref = x.view(2, 2, 6, 4, 4, 6, 4).permute(0, 3, 5, 1, 2, 4, 6).reshape(2 * 4 * 6, 2 * 6 * 16).to(dtype)
+    assert torch.equal(A, ref)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape,k,s,p", [
+    ((1, 5, 8, 8, 8), (3, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ((2, 6, 6, 10, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    ((1, 8, 8, 8, 8), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    ((1, 4, 9, 9, 8), (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+])
+def test_im2col_col2im(cuda, shape, k, s, p, dtype):
+    from viscy_b200 import ops
+    N, D, H, W, C = shape
+    u = rnd(shape, cuda, 1, dtype)
+    geom = ops.conv3d_geom(shape, k, s, p)
+    col = ops.im2col3d(u, geom)
+    # reference via a conv with identity-like weights: compare conv results instead of the raw layout
+    wgt = rnd((16, C, *k), cuda, 2, dtype)
+    ref = F.conv3d(u.float().permute(0, 4, 1, 2, 3), wgt.float(), stride=s, padding=p)
+    wk = wgt.permute(0, 2, 3, 4, 1).reshape(16, -1)  # (kd,kh,kw,c)
+    out = (col.float() @ wk.float().t()).view(N, geom[14], geom[15], geom[16], 16).permute(0, 4, 1, 2, 3)
+    assert rel(out, ref) < 1e-5
+    # col2im = adjoint: <col2im(dcol), u'> == <dcol, im2col(u')>
+    dcol = rnd(tuple(col.shape), cuda, 3, dtype)
+    du = ops.col2im3d(dcol, geom)
+    uf = u.float().requires_grad_(True)
+    cols_ref = F.unfold  # noqa: F841  (3-D unfold unavailable; use autograd through conv instead)
+    dz = (dcol.float() @ wk.float()).sum() * 0  # placeholder to keep shapes clear
+    out2 = F.conv3d(uf.permute(0, 4, 1, 2, 3), wgt.float(), stride=s, padding=p)
+    dout = rnd(tuple(out2.shape), cuda, 4)
+    out2.backward(dout)
+    dcol2 = (dout.permute(0, 2, 3, 4, 1).reshape(-1, 16) @ wk.float()).to(dtype)
+    du2 = ops.col2im3d(dcol2.contiguous(), geom)
+    assert rel(du2, uf.grad) < tol(dtype)
+    assert du.shape == u.shape
+
+
+def head_ref(dec_nchw, Dz, pool, conv_w, conv_b, alpha, w1, b1):
+    """PixelToVoxelHead math (VM/components/heads.py:632-641 with monai pieces restated)."""
+    x = F.pixel_shuffle(dec_nchw, 2)
+    if pool:
+        x = F.avg_pool2d(F.pad(x, (1, 0, 1, 0)), 2, stride=1)
+    b, c, h, w = x.shape
+    x = x.reshape(b, c // Dz, Dz, h, w)
+    x = F.conv3d(x, conv_w, conv_b, padding=(0, 1, 1))
+    x = F.instance_norm(x, eps=1e-5)
+    x = F.prelu(x, alpha)
+    x = F.conv3d(x, w1, b1)
+    x = x.transpose(1, 2)
+    x = F.pixel_shuffle(x, 2)
+    return x.transpose(1, 2)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("pool", [True, False])
+def test_head_shuffle_pool(cuda, dtype, pool):
+    from viscy_b200 import ops
+    B, h, w, Dz, Cc = 2, 6, 10, 7, 8
+    Cm = Cc * Dz
+    dec = rnd((B, h, w, 4 * Cm), cuda, 1, dtype)
+    df = dec.float().permute(0, 3, 1, 2).requires_grad_(True)
+    x = F.pixel_shuffle(df, 2)
+    if pool:
+        x = F.avg_pool2d(F.pad(x, (1, 0, 1, 0)), 2, stride=1)
+    ref = x.reshape(B, Cc, Dz, 2 * h, 2 * w)
+    u = ops.head_shuffle_pool_fwd(dec, Dz, pool, 8)
+    assert rel(u.permute(0, 4, 1, 2, 3), ref) < tol(dtype)
+    du = rnd(tuple(u.shape), cuda, 2, dtype)
+    ref.backward(du.float().permute(0, 4, 1, 2, 3))
+    ddec = ops.head_shuffle_pool_bwd(du, Cm, pool)
+    assert rel(ddec, df.grad.permute(0, 2, 3, 1)) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_head_tail(cuda, dtype):
+    from viscy_b200 import ops
+    B, Dz, H, W, Cmid, Co = 2, 5, 12, 16, 32, 2
+    z = rnd((B, Dz * H * W, Cmid), cuda, 1, dtype)
+    alpha = torch.tensor([0.25], device=cuda)
+    w1 = rnd((Co * 4, Cmid), cuda, 2) * 0.2
+    b1 = rnd((Co * 4,), cuda, 3)
+    zf = z.float().view(B, Dz, H, W, Cmid).permute(0, 4, 1, 2, 3).requires_grad_(True)
+    af, wf, bf = alpha.clone().requires_grad_(True), w1.clone().requires_grad_(True), b1.clone().requires_grad_(True)
+    x = F.prelu(F.instance_norm(zf, eps=1e-5), af)
+    x = F.conv3d(x, wf.view(Co * 4, Cmid, 1, 1, 1), bf)
+    ref = F.pixel_shuffle(x.transpose(1, 2), 2).transpose(1, 2)
+    mean, rstd = ops.instnorm_stats(z)
+    out = ops.head_tail_fwd(z, mean, rstd, alpha, w1, b1, Dz, H, W)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < tol(dtype)
+    dout = rnd(tuple(ref.shape), cuda, 4, dtype)
+    ref.backward(dout.float())
+    dz, dW1, db1, dalpha, dbz = ops.head_tail_bwd(z, mean, rstd, alpha, w1, dout, Dz, H, W)
+    assert rel(dz.view(B, Dz, H, W, Cmid).permute(0, 4, 1, 2, 3), zf.grad) < tol(dtype) * 2
+    assert rel(dW1, wf.grad) < 2e-3 and rel(db1, bf.grad) < 2e-3 and rel(dalpha, af.grad) < 2e-3
+    assert rel(dbz, dz.float().sum((0, 1))) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_cast_pack(cuda, dtype):
+    from viscy_b200 import ops
+    w = rnd((96, 40, 1, 1), cuda, 1)
+    assert torch.equal(ops.cast_pack(w, dtype), w.view(96, 40).to(dtype))
+    assert torch.equal(ops.cast_pack(w, dtype, transpose=True), w.view(96, 40).t().contiguous().to(dtype))

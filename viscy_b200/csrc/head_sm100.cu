@@ -1,0 +1,473 @@
+// PixelToVoxelHead (VM/components/heads.py:594-641) on channels-last 16-bit activations:
+//   pixelshuffle(2) [+ ConstantPad2d((1,0,1,0)) + AvgPool2d(2, stride 1)] + (c//d, d) un-fold  -> u [B,Dz,2h,2w,Cu]
+//   (Conv3d k3 pad (0,1,1) runs through the im2col + tcgen05 GEMM path)
+//   InstanceNorm3d(affine=False, eps 1e-5) + PReLU + Conv3d(k=1) + transpose + PixelShuffle(2) + transpose -> NCDHW
+// and the matching backward kernels.
+#include "common.cuh"
+
+namespace vb {
+
+// S[n, cm, 2h+i, 2w+j] = dec[n,h,w, cm*4 + i*2 + j];  P = pool ? avg2x2(pad_left_top(S)) : S
+// u[n, dz, Y, X, c] = P[n, c*Dz + dz, Y, X]  (c < Cc; zero for Cc <= c < Cu)
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+head_shuffle_pool_fwd_kernel(const uint16_t* __restrict__ dec, uint16_t* __restrict__ u, int h, int w,
+                             int Cm, int Dz, int Cc, int Cu, int pool) {
+  extern __shared__ uint16_t sm[];  // [32][Cm]
+  const int X0 = blockIdx.x * 32, Y = blockIdx.y;
+  const long long n = blockIdx.z;
+  const int Cd = Cm * 4;
+  const int Hs = 2 * h, Ws = 2 * w;
+  for (int idx = threadIdx.x; idx < 32 * Cm; idx += blockDim.x) {
+    const int xl = idx / Cm, cm = idx % Cm;
+    const int X = X0 + xl;
+    float acc = 0.f;
+    if (X < Ws) {
+      if (pool) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int yy = Y - a, xx = X - b;
+            if (yy >= 0 && xx >= 0) {
+              const uint16_t raw = __ldg(dec + ((n * h + (yy >> 1)) * w + (xx >> 1)) * Cd + cm * 4 + (yy & 1) * 2 + (xx & 1));
+              acc += H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&raw));
+            }
+          }
+        acc *= 0.25f;
+      } else {
+        const uint16_t raw = __ldg(dec + ((n * h + (Y >> 1)) * w + (X >> 1)) * Cd + cm * 4 + (Y & 1) * 2 + (X & 1));
+        acc = H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&raw));
+      }
+    }
+    typename H16<BF16>::T hv = H16<BF16>::from_f(acc);
+    sm[idx] = *reinterpret_cast<uint16_t*>(&hv);
+  }
+  __syncthreads();
+  const int per_dz = 32 * Cu;
+  for (int idx = threadIdx.x; idx < Dz * per_dz; idx += blockDim.x) {
+    const int dz = idx / per_dz;
+    const int rem = idx % per_dz;
+    const int xl = rem / Cu, c = rem % Cu;
+    const int X = X0 + xl;
+    if (X < Ws) {
+      const uint16_t v = c < Cc ? sm[xl * Cm + c * Dz + dz] : (uint16_t)0;
+      u[(((n * Dz + dz) * Hs + Y) * Ws + X) * (long long)Cu + c] = v;
+    }
+  }
+}
+
+// ddec[n,h,w, cm*4+i*2+j] = dS[n,cm,2h+i,2w+j];  dS[Y,X] = pool ? 0.25*(dP[Y,X]+dP[Y,X+1]+dP[Y+1,X]+dP[Y+1,X+1]) : dP
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+head_shuffle_pool_bwd_kernel(const uint16_t* __restrict__ du, uint16_t* __restrict__ ddec, int h, int w,
+                             int Cm, int Dz, int Cc, int Cu, int pool) {
+  extern __shared__ uint16_t sm[];  // [3][33][Cm]  (rows 2h..2h+2, columns 2w0..2w0+32)
+  const int w0 = blockIdx.x * 16, hh = blockIdx.y;
+  const long long n = blockIdx.z;
+  const int Hs = 2 * h, Ws = 2 * w;
+  const int Cd = Cm * 4;
+  // load: iterate (r, dz, xl, c) with c fastest (c < Cu contiguous in u)
+  const int per_r = Dz * 33 * Cu;
+  for (int idx = threadIdx.x; idx < 3 * per_r; idx += blockDim.x) {
+    const int r = idx / per_r;
+    int rem = idx % per_r;
+    const int dz = rem / (33 * Cu);
+    rem %= 33 * Cu;
+    const int xl = rem / Cu, c = rem % Cu;
+    if (c >= Cc) continue;
+    const int Y = 2 * hh + r, X = 2 * w0 + xl;
+    uint16_t v = 0;
+    if (Y < Hs && X < Ws) v = __ldg(du + (((n * Dz + dz) * Hs + Y) * Ws + X) * (long long)Cu + c);
+    sm[(r * 33 + xl) * Cm + c * Dz + dz] = v;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 16 * Cd; idx += blockDim.x) {
+    const int wl = idx / Cd, cd = idx % Cd;
+    const int ww = w0 + wl;
+    if (ww >= w) continue;
+    const int cm = cd >> 2, i = (cd >> 1) & 1, j = cd & 1;
+    const int r = i, xl = 2 * wl + j;
+    auto at = [&](int rr, int xx) {
+      const uint16_t raw = sm[(rr * 33 + xx) * Cm + cm];
+      return H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&raw));
+    };
+    float v;
+    if (pool)
+      v = 0.25f * (at(r, xl) + at(r, xl + 1) + at(r + 1, xl) + at(r + 1, xl + 1));
+    else
+      v = at(r, xl);
+    typename H16<BF16>::T hv = H16<BF16>::from_f(v);
+    ddec[((n * h + hh) * w + ww) * (long long)Cd + cd] = *reinterpret_cast<uint16_t*>(&hv);
+  }
+}
+
+// per-sample, per-channel sum and sum of squares of z [B, R, C] (C % 8 == 0, C <= 256)
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+instnorm_stats_kernel(const uint4* __restrict__ z, float* __restrict__ sum, float* __restrict__ sumsq,
+                      int R, int C8, int rows_per_block) {
+  __shared__ float red[2 * 256];
+  const int n = blockIdx.y;
+  const int v = threadIdx.x % C8, rl = threadIdx.x / C8, rstep = blockDim.x / C8;
+  const int C = C8 * 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < rstep) {
+    for (int r = r0 + rl; r < r1; r += rstep) {
+      const uint4 t = __ldg(z + ((long long)n * R + r) * C8 + v);
+      const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = H16<BF16>::unpack(w4[k]);
+        s[2 * k] += f.x;
+        s[2 * k + 1] += f.y;
+        q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+        q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&red[v * 8 + k], s[k]);
+      atomicAdd(&red[C + v * 8 + k], q[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(sum + (long long)n * C + i, red[i]);
+    atomicAdd(sumsq + (long long)n * C + i, red[C + i]);
+  }
+}
+
+__global__ void instnorm_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                         float* __restrict__ mean, float* __restrict__ rstd, int total,
+                                         float inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = sum[i] * inv_count;
+  const float var = fmaxf(sumsq[i] * inv_count - m * m, 0.f);
+  mean[i] = m;
+  rstd[i] = rsqrtf(var + eps);
+}
+
+constexpr int HT_MAXO = 16;  // max (out_channels * 4)
+
+// out[n, o>>2, dz, 2y + ((o>>1)&1), 2x + (o&1)] = b1[o] + sum_c W1[o][c] * prelu((z - mean) * rstd)
+// one thread per row (n, dz, y, x); z [B, R, Cmid], R = Dz*H*W
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+head_tail_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ alpha, int alpha_n,
+                     const float* __restrict__ W1, const float* __restrict__ b1,
+                     uint16_t* __restrict__ out, int Dz, int H, int W, int Cmid, int Co4) {
+  extern __shared__ float smf[];  // W1 [Co4][Cmid], b1[Co4], mean[Cmid], rstd[Cmid], alpha[Cmid]
+  float* sW = smf;
+  float* sb = sW + Co4 * Cmid;
+  float* sm_ = sb + Co4;
+  float* sr = sm_ + Cmid;
+  float* sa = sr + Cmid;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < Co4 * Cmid; i += blockDim.x) sW[i] = W1[i];
+  for (int i = threadIdx.x; i < Co4; i += blockDim.x) sb[i] = b1[i];
+  for (int i = threadIdx.x; i < Cmid; i += blockDim.x) {
+    sm_[i] = mean[(long long)n * Cmid + i];
+    sr[i] = rstd[(long long)n * Cmid + i];
+    sa[i] = alpha[alpha_n == 1 ? 0 : i];
+  }
+  __syncthreads();
+  const long long R = (long long)Dz * H * W;
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= R) return;
+  const int x = (int)(row % W);
+  const int y = (int)((row / W) % H);
+  const int dz = (int)(row / ((long long)W * H));
+  float acc[HT_MAXO];
+#pragma unroll
+  for (int o = 0; o < HT_MAXO; ++o) acc[o] = o < Co4 ? sb[o] : 0.f;
+  const int C8 = Cmid / 8;
+  for (int v = 0; v < C8; ++v) {
+    const uint4 t = __ldg(z + ((long long)n * R + row) * C8 + v);
+    const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = H16<BF16>::unpack(w4[k]);
+      a[2 * k] = f.x;
+      a[2 * k + 1] = f.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = v * 8 + k;
+      const float p = (a[k] - sm_[c]) * sr[c];
+      a[k] = p > 0.f ? p : p * sa[c];
+    }
+#pragma unroll
+    for (int o = 0; o < HT_MAXO; ++o)
+      if (o < Co4) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[o] = fmaf(sW[o * Cmid + v * 8 + k], a[k], acc[o]);
+      }
+  }
+  const int Co = Co4 / 4;
+#pragma unroll
+  for (int o = 0; o < HT_MAXO; o += 2)
+    if (o < Co4) {
+      const int co = o >> 2, i = (o >> 1) & 1;
+      const long long oi = ((((long long)n * Co + co) * Dz + dz) * (2 * H) + 2 * y + i) * (2LL * W) + 2 * x;
+      *reinterpret_cast<uint32_t*>(out + oi) = H16<BF16>::pack(acc[o], acc[o + 1]);
+    }
+}
+
+// Backward, phase 1 (MODE 0): reductions  sdp[n,c] = sum dpre, sdpx[n,c] = sum dpre*xhat, dW1, db1, dalpha
+// Backward, phase 2 (MODE 1): dz = rstd * (dpre - sdp/R - xhat * sdpx/R), dbz[c] += sum dz
+// thread = (row, 8-channel chunk)
+template <bool BF16, int MODE>
+__global__ void __launch_bounds__(256)
+head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ alpha, int alpha_n,
+                     const float* __restrict__ W1, const uint16_t* __restrict__ dout,
+                     float* __restrict__ sdp, float* __restrict__ sdpx, float* __restrict__ dW1,
+                     float* __restrict__ db1, float* __restrict__ dalpha, uint4* __restrict__ dz,
+                     float* __restrict__ dbz, int Dz, int H, int W, int Cmid, int Co4,
+                     int rows_per_block) {
+  extern __shared__ float smf[];
+  float* sW = smf;                   // [Co4][Cmid]
+  float* sm_ = sW + Co4 * Cmid;      // mean
+  float* sr = sm_ + Cmid;            // rstd
+  float* sa = sr + Cmid;             // alpha
+  float* red = sa + Cmid;            // MODE 0: sdp[Cmid], sdpx[Cmid], dW1[Co4*Cmid], db1[Co4], dalpha[Cmid]; MODE 1: dbz[Cmid]
+  float* s1 = red + Cmid;            // MODE 1: (sdp/R), (sdpx/R) staged after the dbz slot
+  const int n = blockIdx.y;
+  const int C8 = Cmid / 8;
+  const long long R = (long long)Dz * H * W;
+  const int nred = MODE == 0 ? (2 * Cmid + Co4 * Cmid + Co4 + Cmid) : (3 * Cmid);
+  for (int i = threadIdx.x; i < Co4 * Cmid; i += blockDim.x) sW[i] = W1[i];
+  for (int i = threadIdx.x; i < nred; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cmid; i += blockDim.x) {
+    sm_[i] = mean[(long long)n * Cmid + i];
+    sr[i] = rstd[(long long)n * Cmid + i];
+    sa[i] = alpha[alpha_n == 1 ? 0 : i];
+    if (MODE == 1) {
+      s1[i] = sdp[(long long)n * Cmid + i] / (float)R;
+      s1[Cmid + i] = sdpx[(long long)n * Cmid + i] / (float)R;
+    }
+  }
+  __syncthreads();
+  const int v = threadIdx.x % C8, rl = threadIdx.x / C8, rstep = blockDim.x / C8;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  const int Co = Co4 / 4;
+  float a_sdp[8], a_sdpx[8], a_dal[8], a_db[HT_MAXO];
+  float a_dW[HT_MAXO][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a_sdp[k] = a_sdpx[k] = a_dal[k] = 0.f;
+#pragma unroll
+  for (int o = 0; o < HT_MAXO; ++o) {
+    a_db[o] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a_dW[o][k] = 0.f;
+  }
+  if (rl < rstep) {
+    for (long long row = r0 + rl; row < r1; row += rstep) {
+      const int x = (int)(row % W);
+      const int y = (int)((row / W) % H);
+      const int dzi = (int)(row / ((long long)W * H));
+      float dt[HT_MAXO];
+#pragma unroll
+      for (int o = 0; o < HT_MAXO; o += 2) {
+        dt[o] = dt[o + 1] = 0.f;
+        if (o < Co4) {
+          const int co = o >> 2, i = (o >> 1) & 1;
+          const long long oi = ((((long long)n * Co + co) * Dz + dzi) * (2 * H) + 2 * y + i) * (2LL * W) + 2 * x;
+          const float2 f = H16<BF16>::unpack(__ldg(reinterpret_cast<const uint32_t*>(dout + oi)));
+          dt[o] = f.x;
+          dt[o + 1] = f.y;
+        }
+      }
+      const uint4 t = __ldg(z + ((long long)n * R + row) * C8 + v);
+      const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+      float xh[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = H16<BF16>::unpack(w4[k]);
+        xh[2 * k] = f.x;
+        xh[2 * k + 1] = f.y;
+      }
+      float dpre[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = v * 8 + k;
+        xh[k] = (xh[k] - sm_[c]) * sr[c];
+        float da = 0.f;
+#pragma unroll
+        for (int o = 0; o < HT_MAXO; ++o)
+          if (o < Co4) da = fmaf(sW[o * Cmid + c], dt[o], da);
+        const bool pos = xh[k] > 0.f;
+        dpre[k] = pos ? da : da * sa[c];
+        if (MODE == 0) {
+          const float act = pos ? xh[k] : xh[k] * sa[c];
+          a_sdp[k] += dpre[k];
+          a_sdpx[k] = fmaf(dpre[k], xh[k], a_sdpx[k]);
+          if (!pos) a_dal[k] = fmaf(da, xh[k], a_dal[k]);
+#pragma unroll
+          for (int o = 0; o < HT_MAXO; ++o)
+            if (o < Co4) a_dW[o][k] = fmaf(dt[o], act, a_dW[o][k]);
+        }
+      }
+      if (MODE == 0) {
+        if (v == 0) {
+#pragma unroll
+          for (int o = 0; o < HT_MAXO; ++o)
+            if (o < Co4) a_db[o] += dt[o];
+        }
+      } else {
+        float o8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = v * 8 + k;
+          o8[k] = sr[c] * (dpre[k] - s1[c] - xh[k] * s1[Cmid + c]);
+        }
+        const uint4 q = make_uint4(H16<BF16>::pack(o8[0], o8[1]), H16<BF16>::pack(o8[2], o8[3]),
+                                   H16<BF16>::pack(o8[4], o8[5]), H16<BF16>::pack(o8[6], o8[7]));
+        dz[((long long)n * R + row) * C8 + v] = q;
+        const uint32_t w4o[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = H16<BF16>::unpack(w4o[k]);
+          a_sdp[2 * k] += f.x;  // reused as the dbz accumulator
+          a_sdp[2 * k + 1] += f.y;
+        }
+      }
+    }
+    // block reduction through shared-memory atomics
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = v * 8 + k;
+      atomicAdd(&red[c], a_sdp[k]);
+      if (MODE == 0) {
+        atomicAdd(&red[Cmid + c], a_sdpx[k]);
+        atomicAdd(&red[2 * Cmid + Co4 * Cmid + Co4 + c], a_dal[k]);
+#pragma unroll
+        for (int o = 0; o < HT_MAXO; ++o)
+          if (o < Co4) atomicAdd(&red[2 * Cmid + o * Cmid + c], a_dW[o][k]);
+      }
+    }
+    if (MODE == 0 && v == 0) {
+#pragma unroll
+      for (int o = 0; o < HT_MAXO; ++o)
+        if (o < Co4) atomicAdd(&red[2 * Cmid + Co4 * Cmid + o], a_db[o]);
+    }
+  }
+  __syncthreads();
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < Cmid; i += blockDim.x) {
+      atomicAdd(sdp + (long long)n * Cmid + i, red[i]);
+      atomicAdd(sdpx + (long long)n * Cmid + i, red[Cmid + i]);
+      atomicAdd(dalpha + (alpha_n == 1 ? 0 : i), red[2 * Cmid + Co4 * Cmid + Co4 + i]);
+    }
+    for (int i = threadIdx.x; i < Co4 * Cmid; i += blockDim.x) atomicAdd(dW1 + i, red[2 * Cmid + i]);
+    for (int i = threadIdx.x; i < Co4; i += blockDim.x) atomicAdd(db1 + i, red[2 * Cmid + Co4 * Cmid + i]);
+  } else {
+    for (int i = threadIdx.x; i < Cmid; i += blockDim.x) atomicAdd(dbz + i, red[i]);
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vb200_head_shuffle_pool(const void* src, void* dst, int B, int h, int w, int Cm, int Dz,
+                                       int Cu, int pool, int backward, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(src && dst, "null pointer");
+  VB_REQUIRE(Cm % Dz == 0, "mid channels %d not divisible by depth %d", Cm, Dz);
+  const int Cc = Cm / Dz;
+  VB_REQUIRE(Cu >= Cc && Cu % 8 == 0, "Cu (%d) must be a multiple of 8 >= %d", Cu, Cc);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!backward) {
+    dim3 grid((2 * w + 31) / 32, 2 * h, B);
+    const size_t smem = (size_t)32 * Cm * 2;
+    VB_SUPPORTED(smem <= 48 * 1024, "head: Cm (%d) too large", Cm);
+    if (dtype == VB200_BF16)
+      head_shuffle_pool_fwd_kernel<true><<<grid, 256, smem, st>>>((const uint16_t*)src, (uint16_t*)dst, h, w, Cm, Dz, Cc, Cu, pool);
+    else
+      head_shuffle_pool_fwd_kernel<false><<<grid, 256, smem, st>>>((const uint16_t*)src, (uint16_t*)dst, h, w, Cm, Dz, Cc, Cu, pool);
+  } else {
+    dim3 grid((w + 15) / 16, h, B);
+    const size_t smem = (size_t)3 * 33 * Cm * 2;
+    VB_SUPPORTED(smem <= 48 * 1024, "head: Cm (%d) too large", Cm);
+    if (dtype == VB200_BF16)
+      head_shuffle_pool_bwd_kernel<true><<<grid, 256, smem, st>>>((const uint16_t*)src, (uint16_t*)dst, h, w, Cm, Dz, Cc, Cu, pool);
+    else
+      head_shuffle_pool_bwd_kernel<false><<<grid, 256, smem, st>>>((const uint16_t*)src, (uint16_t*)dst, h, w, Cm, Dz, Cc, Cu, pool);
+  }
+  return check_launch("vb200_head_shuffle_pool");
+}
+
+extern "C" int vb200_instnorm_stats(const void* z, float* sum, float* sumsq, float* mean, float* rstd, int B,
+                                    int64_t R, int C, float eps, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(z && sum && sumsq && mean && rstd, "null pointer");
+  VB_SUPPORTED(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "instnorm C (%d) must be 8*2^k <= 256", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sum, 0, sizeof(float) * B * C, st);
+  cudaMemsetAsync(sumsq, 0, sizeof(float) * B * C, st);
+  long long rpb = (R * B + 148 * 8 - 1) / (148 * 8);
+  if (rpb < 64) rpb = 64;
+  if (rpb > R) rpb = R;
+  dim3 grid((unsigned)((R + rpb - 1) / rpb), B);
+  if (dtype == VB200_BF16)
+    instnorm_stats_kernel<true><<<grid, 256, 0, st>>>((const uint4*)z, sum, sumsq, (int)R, C / 8, (int)rpb);
+  else
+    instnorm_stats_kernel<false><<<grid, 256, 0, st>>>((const uint4*)z, sum, sumsq, (int)R, C / 8, (int)rpb);
+  if (int rc = check_launch("vb200_instnorm_stats")) return rc;
+  instnorm_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(sum, sumsq, mean, rstd, B * C, 1.0f / (float)R, eps);
+  return check_launch("vb200_instnorm_finalize");
+}
+
+extern "C" int vb200_head_tail_fwd(const void* z, const float* mean, const float* rstd, const float* alpha,
+                                   int alpha_n, const float* W1, const float* b1, void* out, int B, int Dz,
+                                   int H, int W, int Cmid, int Co4, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(z && mean && rstd && alpha && W1 && b1 && out, "null pointer");
+  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= HT_MAXO, "head tail: Cmid %d / Co4 %d", Cmid, Co4);
+  VB_REQUIRE(alpha_n == 1 || alpha_n == Cmid, "PReLU parameter count %d", alpha_n);
+  const long long R = (long long)Dz * H * W;
+  dim3 grid((unsigned)((R + 127) / 128), B);
+  const size_t smem = sizeof(float) * (Co4 * Cmid + Co4 + 3 * Cmid);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_BF16)
+    head_tail_fwd_kernel<true><<<grid, 128, smem, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, b1, (uint16_t*)out, Dz, H, W, Cmid, Co4);
+  else
+    head_tail_fwd_kernel<false><<<grid, 128, smem, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, b1, (uint16_t*)out, Dz, H, W, Cmid, Co4);
+  return check_launch("vb200_head_tail_fwd");
+}
+
+/* phase 0: reductions into sdp, sdpx [B,Cmid], dW1 [Co4,Cmid], db1 [Co4], dalpha [alpha_n] (all pre-zeroed)
+ * phase 1: dz [B,R,Cmid] and dbz [Cmid] (pre-zeroed) */
+extern "C" int vb200_head_tail_bwd(int phase, const void* z, const float* mean, const float* rstd,
+                                   const float* alpha, int alpha_n, const float* W1, const void* dout,
+                                   float* sdp, float* sdpx, float* dW1, float* db1, float* dalpha, void* dz,
+                                   float* dbz, int B, int Dz, int H, int W, int Cmid, int Co4, int dtype,
+                                   vb200_stream_t stream) {
+  VB_REQUIRE(z && mean && rstd && alpha && W1 && dout && sdp && sdpx, "null pointer");
+  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= HT_MAXO && 256 % (Cmid / 8) == 0, "head tail: Cmid %d / Co4 %d", Cmid, Co4);
+  const long long R = (long long)Dz * H * W;
+  long long rpb = (R * B + 148 * 4 - 1) / (148 * 4);
+  if (rpb < 256) rpb = 256;
+  if (rpb > R) rpb = R;
+  dim3 grid((unsigned)((R + rpb - 1) / rpb), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem0 = sizeof(float) * (Co4 * Cmid + 3 * Cmid + 2 * Cmid + Co4 * Cmid + Co4 + Cmid);
+  const size_t smem1 = sizeof(float) * (Co4 * Cmid + 3 * Cmid + 3 * Cmid);
+#define HT(BF, MODE, SM) head_tail_bwd_kernel<BF, MODE><<<grid, 256, SM, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, (const uint16_t*)dout, sdp, sdpx, dW1, db1, dalpha, (uint4*)dz, dbz, Dz, H, W, Cmid, Co4, (int)rpb)
+  if (phase == 0) {
+    VB_REQUIRE(dW1 && db1 && dalpha, "null pointer");
+    if (dtype == VB200_BF16) HT(true, 0, smem0); else HT(false, 0, smem0);
+  } else {
+    VB_REQUIRE(dz && dbz, "null pointer");
+    if (dtype == VB200_BF16) HT(true, 1, smem1); else HT(false, 1, smem1);
+  }
+#undef HT
+  return check_launch("vb200_head_tail_bwd");
+}

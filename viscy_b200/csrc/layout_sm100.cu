@@ -1,0 +1,306 @@
+// Data-movement kernels on channels-last 16-bit activations: pixel-shuffle + skip concat (fwd/bwd),
+// 2x2 patchify for the k2s2 downsample convs (fwd/bwd), stem patchify (NCDHW -> GEMM rows),
+// generic 3-D im2col / col2im for 3x3x3-style convolutions (v1 lowering of the 3-D convs).
+// Reference semantics: monai SubpixelUpsample(pre_conv=None) + torch.cat (VM/components/blocks.py:137-172),
+// timm ConvNeXtStage.downsample Conv2d(k=2,s=2), UNeXt2Stem / StemDepthtoChannels (VM/components/stems.py:26-50,117-134).
+#include "common.cuh"
+
+namespace vb {
+
+// out[n, 2h+i, 2w+j, c'] = prev[n,h,w, c'*4 + i*2 + j]  (c' < Cq = Cp/4)   else skip[n,2h+i,2w+j,c'-Cq]
+__global__ void __launch_bounds__(256)
+pixshuf_cat_fwd_kernel(const uint16_t* __restrict__ prev, const uint16_t* __restrict__ skip,
+                       uint16_t* __restrict__ out, int h, int w, int Cp, int Cs, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Cq = Cp / 4, Co = Cq + Cs;
+  const int c = (int)(idx % Co);
+  long long pix = idx / Co;  // (n, Y, X) of the 2h x 2w grid
+  const int X = (int)(pix % (2 * w));
+  const long long t = pix / (2 * w);
+  const int Y = (int)(t % (2 * h));
+  const long long n = t / (2 * h);
+  uint16_t v;
+  if (c < Cq)
+    v = prev[((n * h + (Y >> 1)) * w + (X >> 1)) * Cp + c * 4 + (Y & 1) * 2 + (X & 1)];
+  else
+    v = skip[pix * Cs + (c - Cq)];
+  out[idx] = v;
+}
+
+__global__ void __launch_bounds__(256)
+pixshuf_cat_bwd_kernel(const uint16_t* __restrict__ dout, uint16_t* __restrict__ dprev,
+                       uint16_t* __restrict__ dskip, int h, int w, int Cp, int Cs, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Cq = Cp / 4, Co = Cq + Cs;
+  const int c = (int)(idx % Co);
+  long long pix = idx / Co;
+  const int X = (int)(pix % (2 * w));
+  const long long t = pix / (2 * w);
+  const int Y = (int)(t % (2 * h));
+  const long long n = t / (2 * h);
+  const uint16_t v = dout[idx];
+  if (c < Cq)
+    dprev[((n * h + (Y >> 1)) * w + (X >> 1)) * Cp + c * 4 + (Y & 1) * 2 + (X & 1)] = v;
+  else
+    dskip[pix * Cs + (c - Cq)] = v;
+}
+
+// out[(n,oh,ow), (kh,kw,c)] = x[n, 2oh+kh, 2ow+kw, c]; 8 channels (16 B) per thread. inverse=1 scatters back.
+__global__ void __launch_bounds__(256)
+patchify2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int C8,
+                 long long total, int inverse) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  // idx enumerates the patchified tensor [(n,oh,ow)][kh][kw][c8]
+  const int c8 = (int)(idx % C8);
+  long long t = idx / C8;
+  const int kw = (int)(t & 1);
+  t >>= 1;
+  const int kh = (int)(t & 1);
+  t >>= 1;
+  const int ow = (int)(t % (W / 2));
+  t /= (W / 2);
+  const int oh = (int)(t % (H / 2));
+  const long long n = t / (H / 2);
+  const long long xi = ((n * H + 2 * oh + kh) * W + 2 * ow + kw) * C8 + c8;
+  if (!inverse)
+    dst[idx] = src[xi];
+  else
+    dst[xi] = src[idx];
+}
+
+// Stem rows: A[(n,oh,ow), k] with k = ((c*D + z)*kH + kh)*kW + kw  <- x[n,c,z, oh*kH+kh, ow*kW+kw]
+// (the whole Z extent goes into K; the block-diagonal weight built on the host side reproduces
+//  Conv3d(kernel == stride) followed by the reference's (B,C,D,H,W)->(B,C*D,H,W) reshape.)
+template <typename TIN, bool BF16>
+__global__ void __launch_bounds__(256)
+stem_patchify_kernel(const TIN* __restrict__ x, uint16_t* __restrict__ A, int Cin, int D, int H, int W,
+                     int kH, int kW, int Kpad, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  // idx enumerates (n, c, z, ih, ow) ; each thread moves kW contiguous input values
+  const int OW = W / kW, OH = H / kH;
+  const int ow = (int)(idx % OW);
+  long long t = idx / OW;
+  const int ih = (int)(t % H);
+  t /= H;
+  const int z = (int)(t % D);
+  t /= D;
+  const int c = (int)(t % Cin);
+  const long long n = t / Cin;
+  const int oh = ih / kH, kh = ih % kH;
+  const TIN* src = x + (((n * Cin + c) * D + z) * H + ih) * (long long)W + (long long)ow * kW;
+  uint16_t* dst = A + ((n * OH + oh) * OW + ow) * (long long)Kpad + ((c * D + z) * kH + kh) * kW;
+  for (int j = 0; j < kW; ++j) {
+    const float v = static_cast<float>(src[j]);
+    typename H16<BF16>::T hv = H16<BF16>::from_f(v);
+    dst[j] = *reinterpret_cast<uint16_t*>(&hv);
+  }
+}
+
+// col[(n,oz,oy,ox), (kd,kh,kw,c)] = u[n, oz*sd+kd-pd, oy*sh+kh-ph, ox*sw+kw-pw, c]  (0 outside); 8 ch / thread
+struct Conv3dGeom {
+  int N, D, H, W, C;        // input NDHWC
+  int OD, OH, OW;           // output extent
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+};
+
+__global__ void __launch_bounds__(256)
+im2col3d_kernel(const uint4* __restrict__ u, uint4* __restrict__ col, Conv3dGeom g, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C8 = g.C / 8;
+  const int c8 = (int)(idx % C8);
+  long long t = idx / C8;
+  const int taps = g.kd * g.kh * g.kw;
+  const int tap = (int)(t % taps);
+  long long row = t / taps;
+  const int kw = tap % g.kw, kh = (tap / g.kw) % g.kh, kd = tap / (g.kw * g.kh);
+  const int ox = (int)(row % g.OW);
+  long long r = row / g.OW;
+  const int oy = (int)(r % g.OH);
+  r /= g.OH;
+  const int oz = (int)(r % g.OD);
+  const long long n = r / g.OD;
+  const int iz = oz * g.sd + kd - g.pd, iy = oy * g.sh + kh - g.ph, ix = ox * g.sw + kw - g.pw;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (iz >= 0 && iz < g.D && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+    v = __ldg(u + (((n * g.D + iz) * g.H + iy) * (long long)g.W + ix) * C8 + c8);
+  col[idx] = v;
+}
+
+// du[n,z,y,x,c] = sum over taps of dcol[(n,oz,oy,ox),(tap,c)] with oz*sd + kd - pd == z etc. (gather, no atomics)
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+col2im3d_kernel(const uint4* __restrict__ dcol, uint4* __restrict__ du, Conv3dGeom g, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C8 = g.C / 8;
+  const int c8 = (int)(idx % C8);
+  long long t = idx / C8;
+  const int x = (int)(t % g.W);
+  t /= g.W;
+  const int y = (int)(t % g.H);
+  t /= g.H;
+  const int z = (int)(t % g.D);
+  const long long n = t / g.D;
+  const int taps = g.kd * g.kh * g.kw;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int kd = 0; kd < g.kd; ++kd) {
+    const int zz = z + g.pd - kd;
+    if (zz < 0 || zz % g.sd != 0) continue;
+    const int oz = zz / g.sd;
+    if (oz >= g.OD) continue;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int yy = y + g.ph - kh;
+      if (yy < 0 || yy % g.sh != 0) continue;
+      const int oy = yy / g.sh;
+      if (oy >= g.OH) continue;
+      for (int kw = 0; kw < g.kw; ++kw) {
+        const int xx = x + g.pw - kw;
+        if (xx < 0 || xx % g.sw != 0) continue;
+        const int ox = xx / g.sw;
+        if (ox >= g.OW) continue;
+        const long long row = ((n * g.OD + oz) * g.OH + oy) * (long long)g.OW + ox;
+        const int tap = (kd * g.kh + kh) * g.kw + kw;
+        const uint4 q = __ldg(dcol + (row * taps + tap) * C8 + c8);
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = H16<BF16>::unpack(w4[k]);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
+        }
+      }
+    }
+  }
+  du[idx] = make_uint4(H16<BF16>::pack(acc[0], acc[1]), H16<BF16>::pack(acc[2], acc[3]),
+                       H16<BF16>::pack(acc[4], acc[5]), H16<BF16>::pack(acc[6], acc[7]));
+}
+
+// fp32 -> 16-bit cast (weight packing), optional transpose of a [R, Cc] matrix to [Cc, R]
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+cast_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long R, long long Cc,
+            int transpose) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * Cc) return;
+  long long s = idx;
+  if (transpose) {
+    const long long c = idx / R, r = idx % R;  // dst is [Cc, R]
+    s = r * Cc + c;
+  }
+  typename H16<BF16>::T hv = H16<BF16>::from_f(src[s]);
+  dst[idx] = *reinterpret_cast<uint16_t*>(&hv);
+}
+
+static inline unsigned blocks_for(long long total, int bs = 256) { return (unsigned)((total + bs - 1) / bs); }
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vb200_pixshuf_cat_fwd(const void* prev, const void* skip, void* out, int B, int h, int w,
+                                     int Cp, int Cs, vb200_stream_t stream) {
+  VB_REQUIRE(prev && out && (skip || Cs == 0), "null pointer");
+  VB_REQUIRE(Cp % 4 == 0, "pixel shuffle needs Cp %% 4 == 0 (Cp=%d)", Cp);
+  const long long total = (long long)B * 4 * h * w * (Cp / 4 + Cs);
+  pixshuf_cat_fwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)prev, (const uint16_t*)skip, (uint16_t*)out, h, w, Cp, Cs, total);
+  return check_launch("vb200_pixshuf_cat_fwd");
+}
+
+extern "C" int vb200_pixshuf_cat_bwd(const void* dout, void* dprev, void* dskip, int B, int h, int w, int Cp,
+                                     int Cs, vb200_stream_t stream) {
+  VB_REQUIRE(dout && dprev && (dskip || Cs == 0), "null pointer");
+  VB_REQUIRE(Cp % 4 == 0, "pixel shuffle needs Cp %% 4 == 0 (Cp=%d)", Cp);
+  const long long total = (long long)B * 4 * h * w * (Cp / 4 + Cs);
+  pixshuf_cat_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)dout, (uint16_t*)dprev, (uint16_t*)dskip, h, w, Cp, Cs, total);
+  return check_launch("vb200_pixshuf_cat_bwd");
+}
+
+extern "C" int vb200_patchify2(const void* src, void* dst, int B, int H, int W, int C, int inverse,
+                               vb200_stream_t stream) {
+  VB_REQUIRE(src && dst, "null pointer");
+  VB_SUPPORTED(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "patchify2 needs C %% 8 == 0 and even H, W");
+  const long long total = (long long)B * H * W * (C / 8);
+  patchify2_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, H, W,
+                                                                        C / 8, total, inverse);
+  return check_launch("vb200_patchify2");
+}
+
+extern "C" int vb200_stem_patchify(const void* x, int x_dtype /*0 bf16, 1 fp16, 2 fp32*/, void* A, int B,
+                                   int Cin, int D, int H, int W, int kH, int kW, int Kpad, int dtype,
+                                   vb200_stream_t stream) {
+  VB_REQUIRE(x && A, "null pointer");
+  VB_REQUIRE(H % kH == 0 && W % kW == 0 && Kpad >= Cin * D * kH * kW, "bad stem geometry");
+  const long long total = (long long)B * Cin * D * H * (W / kW);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = blocks_for(total);
+#define STEM(TIN, BF) stem_patchify_kernel<TIN, BF><<<grid, 256, 0, st>>>((const TIN*)x, (uint16_t*)A, Cin, D, H, W, kH, kW, Kpad, total)
+  if (dtype == VB200_BF16) {
+    if (x_dtype == 2) STEM(float, true);
+    else if (x_dtype == 0) STEM(__nv_bfloat16, true);
+    else return fail(VB200_ERR_UNSUPPORTED, "stem input dtype %d for bf16 path", x_dtype);
+  } else if (dtype == VB200_FP16) {
+    if (x_dtype == 2) STEM(float, false);
+    else if (x_dtype == 1) STEM(__half, false);
+    else return fail(VB200_ERR_UNSUPPORTED, "stem input dtype %d for fp16 path", x_dtype);
+  } else {
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  }
+#undef STEM
+  return check_launch("vb200_stem_patchify");
+}
+
+static int geom_from(const int32_t* g, Conv3dGeom* o) {
+  o->N = g[0]; o->D = g[1]; o->H = g[2]; o->W = g[3]; o->C = g[4];
+  o->kd = g[5]; o->kh = g[6]; o->kw = g[7];
+  o->sd = g[8]; o->sh = g[9]; o->sw = g[10];
+  o->pd = g[11]; o->ph = g[12]; o->pw = g[13];
+  o->OD = g[14]; o->OH = g[15]; o->OW = g[16];
+  if (o->C % 8 != 0) return fail(VB200_ERR_UNSUPPORTED, "conv3d lowering needs C %% 8 == 0 (C=%d)", o->C);
+  return VB200_OK;
+}
+
+/* geom = {N,D,H,W,C, kd,kh,kw, sd,sh,sw, pd,ph,pw, OD,OH,OW} */
+extern "C" int vb200_im2col3d(const void* u, void* col, const int32_t* geom, vb200_stream_t stream) {
+  VB_REQUIRE(u && col && geom, "null pointer");
+  Conv3dGeom g;
+  if (int rc = geom_from(geom, &g)) return rc;
+  const long long total = (long long)g.N * g.OD * g.OH * g.OW * g.kd * g.kh * g.kw * (g.C / 8);
+  im2col3d_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)u, (uint4*)col, g, total);
+  return check_launch("vb200_im2col3d");
+}
+
+extern "C" int vb200_col2im3d(const void* dcol, void* du, const int32_t* geom, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(dcol && du && geom, "null pointer");
+  Conv3dGeom g;
+  if (int rc = geom_from(geom, &g)) return rc;
+  const long long total = (long long)g.N * g.D * g.H * g.W * (g.C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_BF16)
+    col2im3d_kernel<true><<<blocks_for(total), 256, 0, st>>>((const uint4*)dcol, (uint4*)du, g, total);
+  else if (dtype == VB200_FP16)
+    col2im3d_kernel<false><<<blocks_for(total), 256, 0, st>>>((const uint4*)dcol, (uint4*)du, g, total);
+  else
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return check_launch("vb200_col2im3d");
+}
+
+extern "C" int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype,
+                               vb200_stream_t stream) {
+  VB_REQUIRE(src && dst, "null pointer");
+  const long long total = R * Cc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_BF16)
+    cast_kernel<true><<<blocks_for(total), 256, 0, st>>>(src, (uint16_t*)dst, R, Cc, transpose);
+  else if (dtype == VB200_FP16)
+    cast_kernel<false><<<blocks_for(total), 256, 0, st>>>(src, (uint16_t*)dst, R, Cc, transpose);
+  else
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return check_launch("vb200_cast_pack");
+}

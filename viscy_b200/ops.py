@@ -85,3 +85,257 @@ def gemm(
     if epilogue == L.EPI_GELU_DUAL:
         return out, out2
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+def _p(t):
+    return L.ptr(t)
+
+
+def _call(name: str, *args) -> None:
+    L.check(getattr(L.lib(), name)(*args, L.stream_ptr()), name)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous fp32")
+    return t
+
+
+def _act(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous (channels-last rows)")
+    L.dtype_code(t.dtype)
+    return t
+
+
+def cast_pack(w: torch.Tensor, dtype: torch.dtype, transpose: bool = False) -> torch.Tensor:
+    """fp32 [R, C] parameter -> 16-bit operand copy ([C, R] when transpose)."""
+    w2 = _f32(w.detach().reshape(w.shape[0], -1), "w")
+    R, Cc = w2.shape
+    out = torch.empty((Cc, R) if transpose else (R, Cc), device=w.device, dtype=dtype)
+    _call("vb200_cast_pack", _p(w2), _p(out), C.c_int64(R), C.c_int64(Cc), int(transpose), L.dtype_code(dtype))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# ConvNeXt block pieces
+def dwconv7(x, wt, bias=None, add=None):
+    """x [B,H,W,C] 16-bit, wt fp32 [49,C] tap-major."""
+    _act(x, "x")
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    _call("vb200_dwconv7", _p(x), _p(_f32(wt, "wt")), _p(bias), _p(add), _p(y), B, H, W, Cc, L.dtype_code(x.dtype))
+    return y
+
+
+def dwconv7_wgrad(x, dy, want_bias=True):
+    B, H, W, Cc = x.shape
+    dwt = torch.zeros((49, Cc), device=x.device, dtype=torch.float32)
+    db = torch.zeros((Cc,), device=x.device, dtype=torch.float32) if want_bias else None
+    _call("vb200_dwconv7_wgrad", _p(_act(x, "x")), _p(_act(dy, "dy")), _p(dwt), _p(db), B, H, W, Cc, L.dtype_code(x.dtype))
+    return dwt, db
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    """x [..., C] 16-bit rows -> (y, mean, rstd)."""
+    _act(x, "x")
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    y = torch.empty_like(x)
+    mean = torch.empty((M,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((M,), device=x.device, dtype=torch.float32)
+    _call("vb200_layernorm_fwd", _p(x), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(y), _p(mean), _p(rstd),
+          C.c_int64(M), Cc, C.c_float(eps), L.dtype_code(x.dtype))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma):
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
+    dbeta = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
+    _call("vb200_layernorm_bwd", _p(_act(dy, "dy")), _p(_act(x, "x")), _p(mean), _p(rstd), _p(_f32(gamma, "gamma")),
+          _p(dx), _p(dgamma), _p(dbeta), C.c_int64(M), Cc, L.dtype_code(x.dtype))
+    return dx, dgamma, dbeta
+
+
+def gelu_grn_fwd(h, w, b, eps=1e-6):
+    """h [B, R, C] 16-bit -> (y, sumsq [B,C], s [B,C])."""
+    _act(h, "h")
+    B, R, Cc = h.shape
+    dt = L.dtype_code(h.dtype)
+    sumsq = torch.zeros((B, Cc), device=h.device, dtype=torch.float32)
+    _call("vb200_grn_sumsq", _p(h), _p(sumsq), B, R, Cc, dt)
+    s = torch.empty_like(sumsq)
+    _call("vb200_grn_coef_fwd", _p(sumsq), _p(_f32(w, "grn.weight")), _p(s), B, Cc, C.c_float(eps))
+    y = torch.empty_like(h)
+    _call("vb200_grn_apply_fwd", _p(h), _p(s), _p(_f32(b, "grn.bias")), _p(y), B, R, Cc, dt)
+    return y, sumsq, s
+
+
+def gelu_grn_bwd(h, dy, sumsq, s, w, eps=1e-6, want_dbias=True):
+    """-> (dh, d grn.weight, d grn.bias, d fc1.bias)"""
+    B, R, Cc = h.shape
+    dt = L.dtype_code(h.dtype)
+    dev = h.device
+    S1 = torch.zeros((B, Cc), device=dev, dtype=torch.float32)
+    sdy = torch.zeros((Cc,), device=dev, dtype=torch.float32)
+    _call("vb200_grn_bwd_reduce", _p(_act(h, "h")), _p(_act(dy, "dy")), _p(S1), _p(sdy), B, R, Cc, dt)
+    t = torch.empty_like(S1)
+    dw = torch.zeros((Cc,), device=dev, dtype=torch.float32)
+    _call("vb200_grn_coef_bwd", _p(sumsq), _p(S1), _p(_f32(w, "grn.weight")), _p(t), _p(dw), B, Cc, C.c_float(eps))
+    dh = torch.empty_like(h)
+    dbias = torch.zeros((Cc,), device=dev, dtype=torch.float32) if want_dbias else None
+    _call("vb200_grn_apply_bwd", _p(h), _p(dy), _p(s), _p(t), _p(dh), _p(dbias), B, R, Cc, dt)
+    return dh, dw, sdy, dbias
+
+
+def colsum(x):
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    out = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
+    _call("vb200_colsum", _p(_act(x, "x")), _p(out), C.c_int64(M), Cc, L.dtype_code(x.dtype))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# layout
+def pixshuf_cat_fwd(prev, skip):
+    _act(prev, "prev")
+    B, h, w, Cp = prev.shape
+    Cs = 0 if skip is None else skip.shape[-1]
+    if skip is not None:
+        _act(skip, "skip")
+        if skip.shape[:3] != (B, 2 * h, 2 * w):
+            raise ValueError(f"skip {tuple(skip.shape)} does not match upsampled {(B, 2 * h, 2 * w)}")
+    out = torch.empty((B, 2 * h, 2 * w, Cp // 4 + Cs), device=prev.device, dtype=prev.dtype)
+    _call("vb200_pixshuf_cat_fwd", _p(prev), _p(skip), _p(out), B, h, w, Cp, Cs)
+    return out
+
+
+def pixshuf_cat_bwd(dout, Cp, Cs):
+    _act(dout, "dout")
+    B, H2, W2, _ = dout.shape
+    h, w = H2 // 2, W2 // 2
+    dprev = torch.empty((B, h, w, Cp), device=dout.device, dtype=dout.dtype)
+    dskip = torch.empty((B, H2, W2, Cs), device=dout.device, dtype=dout.dtype) if Cs else None
+    _call("vb200_pixshuf_cat_bwd", _p(dout), _p(dprev), _p(dskip), B, h, w, Cp, Cs)
+    return dprev, dskip
+
+
+def patchify2(x, inverse=False, shape=None):
+    """forward: [B,H,W,C] -> [B,H/2,W/2,4C];  inverse: rows back to [B,H,W,C] (shape = (B,H,W,C))."""
+    _act(x, "x")
+    if not inverse:
+        B, H, W, Cc = x.shape
+        out = torch.empty((B, H // 2, W // 2, 4 * Cc), device=x.device, dtype=x.dtype)
+    else:
+        B, H, W, Cc = shape
+        out = torch.empty((B, H, W, Cc), device=x.device, dtype=x.dtype)
+    _call("vb200_patchify2", _p(x), _p(out), B, H, W, Cc, int(inverse))
+    return out
+
+
+_XDT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+
+
+def stem_patchify(x, kH, kW, dtype):
+    """x (B,Cin,D,H,W) NCDHW fp32/16-bit -> rows [B*H/kH*W/kW, Cin*D*kH*kW] in `dtype`."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    B, Cin, D, H, W = x.shape
+    K = Cin * D * kH * kW
+    if K % 8:
+        raise NotImplementedError(f"stem K={K} must be a multiple of 8")
+    A = torch.empty((B * (H // kH) * (W // kW), K), device=x.device, dtype=dtype)
+    _call("vb200_stem_patchify", _p(x), _XDT[x.dtype], _p(A), B, Cin, D, H, W, kH, kW, K, L.dtype_code(dtype))
+    return A
+
+
+def conv3d_geom(shape, kernel, stride, padding):
+    N, D, H, W, Cc = shape
+    kd, kh, kw = kernel
+    sd, sh, sw = stride
+    pd, ph, pw = padding
+    OD = (D + 2 * pd - kd) // sd + 1
+    OH = (H + 2 * ph - kh) // sh + 1
+    OW = (W + 2 * pw - kw) // sw + 1
+    return [N, D, H, W, Cc, kd, kh, kw, sd, sh, sw, pd, ph, pw, OD, OH, OW]
+
+
+def im2col3d(u, geom):
+    _act(u, "u")
+    g = (C.c_int32 * 17)(*geom)
+    N, OD, OH, OW = geom[0], geom[14], geom[15], geom[16]
+    K = geom[5] * geom[6] * geom[7] * geom[4]
+    col = torch.empty((N * OD * OH * OW, K), device=u.device, dtype=u.dtype)
+    _call("vb200_im2col3d", _p(u), _p(col), g)
+    return col
+
+
+def col2im3d(dcol, geom):
+    _act(dcol, "dcol")
+    g = (C.c_int32 * 17)(*geom)
+    du = torch.empty(tuple(geom[0:5]), device=dcol.device, dtype=dcol.dtype)
+    _call("vb200_col2im3d", _p(dcol), _p(du), g, L.dtype_code(dcol.dtype))
+    return du
+
+
+# ----------------------------------------------------------------------------------------------
+# PixelToVoxelHead pieces
+def head_shuffle_pool_fwd(dec, Dz, pool, Cu):
+    _act(dec, "dec")
+    B, h, w, Cd = dec.shape
+    Cm = Cd // 4
+    u = torch.empty((B, Dz, 2 * h, 2 * w, Cu), device=dec.device, dtype=dec.dtype)
+    _call("vb200_head_shuffle_pool", _p(dec), _p(u), B, h, w, Cm, Dz, Cu, int(pool), 0, L.dtype_code(dec.dtype))
+    return u
+
+
+def head_shuffle_pool_bwd(du, Cm, pool):
+    _act(du, "du")
+    B, Dz, H2, W2, Cu = du.shape
+    h, w = H2 // 2, W2 // 2
+    ddec = torch.empty((B, h, w, 4 * Cm), device=du.device, dtype=du.dtype)
+    _call("vb200_head_shuffle_pool", _p(du), _p(ddec), B, h, w, Cm, Dz, Cu, int(pool), 1, L.dtype_code(du.dtype))
+    return ddec
+
+
+def instnorm_stats(z, eps=1e-5):
+    """z [B, R, C] -> mean, rstd [B, C]"""
+    _act(z, "z")
+    B, R, Cc = z.shape
+    scratch = torch.empty((4, B, Cc), device=z.device, dtype=torch.float32)
+    _call("vb200_instnorm_stats", _p(z), _p(scratch[0]), _p(scratch[1]), _p(scratch[2]), _p(scratch[3]), B,
+          C.c_int64(R), Cc, C.c_float(eps), L.dtype_code(z.dtype))
+    return scratch[2], scratch[3]
+
+
+def head_tail_fwd(z, mean, rstd, alpha, W1, b1, Dz, H, W):
+    B, R, Cmid = z.shape
+    Co4 = W1.shape[0]
+    out = torch.empty((B, Co4 // 4, Dz, 2 * H, 2 * W), device=z.device, dtype=z.dtype)
+    _call("vb200_head_tail_fwd", _p(_act(z, "z")), _p(mean), _p(rstd), _p(_f32(alpha, "alpha")), alpha.numel(),
+          _p(_f32(W1, "W1")), _p(_f32(b1, "b1")), _p(out), B, Dz, H, W, Cmid, Co4, L.dtype_code(z.dtype))
+    return out
+
+
+def head_tail_bwd(z, mean, rstd, alpha, W1, dout, Dz, H, W):
+    """-> dz, dW1, db1, dalpha, dbz (bias gradient of the conv that produced z)"""
+    B, R, Cmid = z.shape
+    Co4 = W1.shape[0]
+    dev = z.device
+    f = dict(device=dev, dtype=torch.float32)
+    sdp, sdpx = torch.zeros((B, Cmid), **f), torch.zeros((B, Cmid), **f)
+    dW1, db1 = torch.zeros((Co4, Cmid), **f), torch.zeros((Co4,), **f)
+    dalpha, dbz = torch.zeros((alpha.numel(),), **f), torch.zeros((Cmid,), **f)
+    dz = torch.empty_like(z)
+    dt = L.dtype_code(z.dtype)
+    dout = _act(dout, "dout")
+    for phase in (0, 1):
+        _call("vb200_head_tail_bwd", phase, _p(z), _p(mean), _p(rstd), _p(alpha), alpha.numel(), _p(W1), _p(dout),
+              _p(sdp), _p(sdpx), _p(dW1), _p(db1), _p(dalpha), _p(dz), _p(dbz), B, Dz, H, W, Cmid, Co4, dt)
+    return dz, dW1, db1, dalpha, dbz

@@ -158,12 +158,10 @@ def test_im2col_col2im(cuda, shape, k, s, p, dtype):
     wk = wgt.permute(0, 2, 3, 4, 1).reshape(16, -1)  # (kd,kh,kw,c)
     out = (col.float() @ wk.float().t()).view(N, geom[14], geom[15], geom[16], 16).permute(0, 4, 1, 2, 3)
     assert rel(out, ref) < 1e-5
-    # col2im = adjoint: <col2im(dcol), u'> == <dcol, im2col(u')>
+    # col2im against autograd through the equivalent conv
     dcol = rnd(tuple(col.shape), cuda, 3, dtype)
     du = ops.col2im3d(dcol, geom)
     uf = u.float().requires_grad_(True)
-    cols_ref = F.unfold  # noqa: F841  (3-D unfold unavailable; use autograd through conv instead)
-    dz = (dcol.float() @ wk.float()).sum() * 0  # placeholder to keep shapes clear
     out2 = F.conv3d(uf.permute(0, 4, 1, 2, 3), wgt.float(), stride=s, padding=p)
     dout = rnd(tuple(out2.shape), cuda, 4)
     out2.backward(dout)

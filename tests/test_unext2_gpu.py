@@ -1,0 +1,90 @@
+"""UNeXt2 through the sm_100a kernels vs the fp32 CPU oracle (oracle/models.py) on the same seeded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(in_channels=1, out_channels=2, in_stack_depth=14, backbone="convnextv2_tiny",
+           stem_kernel_size=(7, 4, 4), head_pool=True)
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _pair(cuda, cfg, seed=0):
+    from oracle import models as OM
+    from viscy_b200 import UNeXt2
+    torch.manual_seed(seed)
+    o = OM.UNeXt2(**cfg)
+    # GRN weights are zero-initialised: give them (and biases) values so every path carries signal
+    with torch.no_grad():
+        for n, p in o.named_parameters():
+            if "grn" in n or n.endswith("bias"):
+                p.normal_(0, 0.2)
+    m = UNeXt2(**cfg)
+    m.load_state_dict(o.state_dict())
+    return o, m.to(cuda)
+
+
+@pytest.mark.parametrize("dtype,ftol,gtol", [(torch.float16, 4e-3, 3e-2), (torch.bfloat16, 3e-2, 1.5e-1)])
+def test_unext2_fwd_bwd_parity(cuda, dtype, ftol, gtol):
+    o, m = _pair(cuda, CFG)
+    torch.manual_seed(1)
+    x = torch.randn(2, 1, 14, 64, 64)
+    tgt = torch.randn(2, 2, 14, 64, 64)
+    ref = o(x)
+    torch.nn.functional.mse_loss(ref, tgt).backward()
+    with torch.autocast("cuda", dtype=dtype):
+        out = m(x.to(cuda))
+        loss = torch.nn.functional.mse_loss(out.float(), tgt.to(cuda))
+    loss.backward()
+    assert out.shape == ref.shape and out.dtype == dtype
+    e = rel(out.float().cpu(), ref)
+    print(f"\n[{dtype}] forward rel-L2 {e:.3e}")
+    assert e < ftol
+    og = dict(o.named_parameters())
+    worst = []
+    for n, p in m.named_parameters():
+        assert p.grad is not None, n
+        assert p.grad.shape == p.shape
+        worst.append((rel(p.grad.cpu(), og[n].grad), n))
+    worst.sort(reverse=True)
+    print("worst grads:", [(f"{w:.2e}", n) for w, n in worst[:6]])
+    import statistics
+    print("median grad rel-L2", statistics.median(w for w, _ in worst))
+    assert worst[0][0] < gtol
+
+
+def test_unext2_eval_no_grad_and_state_dict(cuda):
+    o, m = _pair(cuda, CFG)
+    assert list(o.state_dict()) == list(m.state_dict())
+    m.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        y = m(torch.randn(1, 1, 14, 64, 64, device=cuda))
+    assert y.shape == (1, 2, 14, 64, 64) and torch.isfinite(y).all()
+
+
+def test_unext2_requires_16bit(cuda):
+    _, m = _pair(cuda, CFG)
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(1, 1, 14, 64, 64, device=cuda))
+
+
+def test_unext2_full_config_step(cuda):
+    """BASELINE config 2 shape: one fwd+bwd at B=8, 21x256x256 bf16 must run and stay finite."""
+    from viscy_b200 import UNeXt2
+    torch.manual_seed(0)
+    m = UNeXt2(in_channels=1, out_channels=2, in_stack_depth=21, backbone="convnextv2_tiny",
+               stem_kernel_size=(7, 4, 4), head_pool=True).to(cuda)
+    x = torch.randn(8, 1, 21, 256, 256, device=cuda)
+    tgt = torch.randn(8, 2, 21, 256, 256, device=cuda)
+    for _ in range(2):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(x)
+            loss = torch.nn.functional.mse_loss(out.float(), tgt)
+        loss.backward()
+    torch.cuda.synchronize()
+    assert out.shape == (8, 2, 21, 256, 256)
+    assert torch.isfinite(loss)
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())

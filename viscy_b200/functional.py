@@ -1,0 +1,334 @@
+"""Autograd wiring of the sm_100a kernels: one `torch.autograd.Function` per fused block of the hot path.
+
+All activations between these functions are channels-last 16-bit tensors ([B,H,W,C] / rows [M,C]);
+parameters stay fp32 in the reference's (PyTorch-native) layout and are re-packed to 16-bit GEMM
+operands on use.  Gradients of parameters come back fp32 in the parameter's own shape.
+"""
+
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib as L
+from . import ops
+
+LN_EPS = 1e-6  # timm LayerNorm / LayerNorm2d
+
+
+# --------------------------------------------------------------------------------------------------
+def _wgrad_splits(n_out: int, k_in: int, pixels: int) -> int:
+    """K-split for the MN-major wgrad GEMM so that ~2 waves of tiles exist."""
+    tiles = -(-n_out // 128) * -(-k_in // 256)
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    kb = max(1, pixels // 64)
+    return max(1, min(want, kb // 4 if kb >= 4 else 1, 64))
+
+
+def linear_fwd(a2d, w, bias, *, residual=None, act=L.ACT_NONE, epilogue=L.EPI_STORE):
+    """a2d [M,K] 16-bit, w fp32 [N,K,...] -> [M,N] 16-bit."""
+    wp = ops.cast_pack(w, a2d.dtype)
+    return ops.gemm(a2d, wp, bias=bias, residual=residual, act=act, epilogue=epilogue)
+
+
+def linear_bwd(dout2d, a2d, w, *, need_da=True, need_db=True):
+    """-> (da [M,K] 16-bit or None, dW fp32 shaped like w, db fp32 [N] or None)"""
+    N = w.shape[0]
+    K = w.numel() // N
+    M = dout2d.shape[0]
+    dw = ops.gemm(dout2d, a2d, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(N, K, M))
+    db = ops.colsum(dout2d) if need_db else None
+    da = None
+    if need_da:
+        wt = ops.cast_pack(w, dout2d.dtype, transpose=True)  # [K, N]
+        da = ops.gemm(dout2d, wt)
+    return da, dw.view(w.shape), db
+
+
+def _dw_taps(w):
+    """conv_dw.weight [C,1,7,7] fp32 -> (tap-major [49,C], flipped tap-major [49,C])"""
+    C = w.shape[0]
+    w2 = w.detach().reshape(C, 49)
+    return w2.t().contiguous(), w2.flip(1).t().contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+class ConvNeXtBlockFn(Function):
+    """timm ConvNeXtBlock (V2: GRN, no layer scale / V1: layer-scale gamma, no GRN), NHWC in / NHWC out.
+
+    forward:  d = dwconv7(x)+b ; l = LN(d) ; h = l W1^T + b1 ; y = GRN(GELU(h)) | GELU(h) ;
+              out = (y W2^T + b2) [* gamma] + x
+    """
+
+    @staticmethod
+    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b, grn_w, grn_b, gamma):
+        B, H, W, C = x.shape
+        M = B * H * W
+        wt, _ = _dw_taps(dw_w)
+        d = ops.dwconv7(x, wt, dw_b)
+        l, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS)
+        l2 = l.view(M, C)
+        C4 = fc1_w.shape[0]
+        use_grn = grn_w is not None
+        if use_grn:
+            h = linear_fwd(l2, fc1_w, fc1_b)
+            y, sumsq, s = ops.gelu_grn_fwd(h.view(B, H * W, C4), grn_w, grn_b)
+            y2 = y.view(M, C4)
+        else:
+            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_DUAL)
+            sumsq = s = None
+        if gamma is not None:
+            w2_eff = fc2_w.detach().reshape(C, C4) * gamma.detach()[:, None]
+            b2_eff = fc2_b.detach() * gamma.detach()
+        else:
+            w2_eff, b2_eff = fc2_w.detach().reshape(C, C4), fc2_b.detach()
+        out = ops.gemm(y2, ops.cast_pack(w2_eff, x.dtype), bias=b2_eff.contiguous(), residual=x.view(M, C))
+        ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma)
+        ctx.use_grn = use_grn
+        return out.view(B, H, W, C)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma = ctx.saved_tensors
+        B, H, W, C = x.shape
+        M = B * H * W
+        C4 = fc1_w.shape[0]
+        dout = dout.contiguous()
+        do2 = dout.view(M, C)
+        if gamma is not None:
+            w2_eff = fc2_w.reshape(C, C4) * gamma[:, None]
+        else:
+            w2_eff = fc2_w.reshape(C, C4)
+        dy, dw2_eff, db2_eff = linear_bwd(do2, y2, w2_eff)
+        if gamma is not None:
+            # out = gamma * (y W2^T + b2): chain rule through the folded layer scale
+            dgamma = (dw2_eff * fc2_w.reshape(C, C4)).sum(1) + db2_eff * fc2_b
+            dw2 = (dw2_eff * gamma[:, None]).view(fc2_w.shape)
+            db2 = db2_eff * gamma
+        else:
+            dgamma, dw2, db2 = None, dw2_eff.view(fc2_w.shape), db2_eff
+        if ctx.use_grn:
+            dh, dgw, dgb, db1 = ops.gelu_grn_bwd(h.view(B, H * W, C4), dy.view(B, H * W, C4), sumsq, s, grn_w)
+        else:
+            ones = torch.ones((B, C4), device=x.device, dtype=torch.float32)
+            dh = torch.empty_like(h)
+            db1 = torch.zeros((C4,), device=x.device, dtype=torch.float32)
+            ops._call("vb200_grn_apply_bwd", ops._p(h), ops._p(dy), ops._p(ones), ops._p(None), ops._p(dh), ops._p(db1),
+                      B, H * W, C4, L.dtype_code(h.dtype))
+            dgw = dgb = None
+        dl, dw1, _ = linear_bwd(dh.view(M, C4), l.view(M, C), fc1_w, need_db=False)
+        dd, dlnw, dlnb = ops.layernorm_bwd(dl.view(B, H, W, C), d, mean, rstd, ln_w)
+        _, wt_flip = _dw_taps(dw_w)
+        dx = ops.dwconv7(dd, wt_flip, None, add=dout)
+        dwt, ddb = ops.dwconv7_wgrad(x, dd)
+        ddw = dwt.t().reshape(dw_w.shape)
+        return dx, ddw, ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma
+
+
+def convnext_block(x, blk) -> torch.Tensor:
+    """blk: module with conv_dw, norm, mlp.fc1, mlp.fc2, optional mlp.grn, optional gamma."""
+    grn = getattr(blk.mlp, "grn", None)
+    return ConvNeXtBlockFn.apply(
+        x, blk.conv_dw.weight, blk.conv_dw.bias, blk.norm.weight, blk.norm.bias,
+        blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias,
+        None if grn is None else grn.weight, None if grn is None else grn.bias, getattr(blk, "gamma", None),
+    )
+
+
+# --------------------------------------------------------------------------------------------------
+class LayerNormFn(Function):
+    """LayerNorm over the channel dim of channels-last rows (timm LayerNorm2d on NCHW == this on NHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, eps)
+        ctx.save_for_backward(x, mean, rstd, w)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, mean, rstd, w = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, w)
+        return dx, dw, db, None
+
+
+def layernorm(x, w, b, eps=LN_EPS):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+class LNConvFn(Function):
+    """LayerNorm2d + Conv2d(k=1) or Conv2d(k=2,s=2): timm ConvNeXtStage.downsample (encoder k2s2, decoder k1)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w, b):
+        B, H, W, C = x.shape
+        k = w.shape[-1]
+        l, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, LN_EPS)
+        if k == 2:
+            a = ops.patchify2(l)
+            wk = w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()  # (kh,kw,c)
+            Ho, Wo = H // 2, W // 2
+        elif k == 1:
+            a, wk, Ho, Wo = l, w.detach().reshape(w.shape[0], -1), H, W
+        else:
+            raise NotImplementedError(f"downsample kernel {k}")
+        a2 = a.view(B * Ho * Wo, -1)
+        out = ops.gemm(a2, ops.cast_pack(wk, x.dtype), bias=b)
+        ctx.save_for_backward(x, mean, rstd, ln_w, a2, w)
+        ctx.k = k
+        return out.view(B, Ho, Wo, w.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, mean, rstd, ln_w, a2, w = ctx.saved_tensors
+        B, H, W, C = x.shape
+        k = ctx.k
+        Co = w.shape[0]
+        do2 = dout.contiguous().view(-1, Co)
+        wk = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous() if k == 2 else w.reshape(Co, -1)
+        da, dwk, db = linear_bwd(do2, a2, wk)
+        if k == 2:
+            dl = ops.patchify2(da.view(B, H // 2, W // 2, 4 * C), inverse=True, shape=(B, H, W, C))
+            dw = dwk.view(Co, 2, 2, C).permute(0, 3, 1, 2)
+        else:
+            dl = da.view(B, H, W, C)
+            dw = dwk.view(w.shape)
+        dx, dlnw, dlnb = ops.layernorm_bwd(dl, x, mean, rstd, ln_w)
+        return dx, dlnw, dlnb, dw, db
+
+
+def ln_conv(x, ln, conv):
+    return LNConvFn.apply(x, ln.weight, ln.bias, conv.weight, conv.bias)
+
+
+# --------------------------------------------------------------------------------------------------
+class PixShufCatFn(Function):
+    """monai SubpixelUpsample(scale 2, pre_conv=None) + torch.cat([up, skip], 1) on NHWC tensors."""
+
+    @staticmethod
+    def forward(ctx, prev, skip):
+        ctx.Cp = prev.shape[-1]
+        ctx.Cs = 0 if skip is None else skip.shape[-1]
+        return ops.pixshuf_cat_fwd(prev, skip)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        dprev, dskip = ops.pixshuf_cat_bwd(dout.contiguous(), ctx.Cp, ctx.Cs)
+        return dprev, dskip
+
+
+def pixshuf_cat(prev, skip):
+    return PixShufCatFn.apply(prev, skip)
+
+
+# --------------------------------------------------------------------------------------------------
+def _stem_full_weight(w, b, D, sD):
+    """Conv3d(kernel (kD,kH,kW), stride (sD,kH,kW)) + (B,C,D',H,W)->(B,C*D',H,W) as one [C*D', Cin*D*kH*kW] matrix."""
+    Co, Cin, kD, kH, kW = w.shape
+    Dd = (D - kD) // sD + 1
+    full = w.new_zeros((Co, Dd, Cin, D, kH, kW))
+    for dd in range(Dd):
+        full[:, dd, :, dd * sD: dd * sD + kD] = w
+    bias = None if b is None else b.repeat_interleave(Dd)
+    return full.view(Co * Dd, -1), bias, Dd
+
+
+class StemFn(Function):
+    """UNeXt2Stem / StemDepthtoChannels (VM/components/stems.py:33-50,117-134): NCDHW in, NHWC (C*D') out."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, dtype):
+        Bn, Cin, D, H, W = x.shape
+        Co, _, kD, kH, kW = w.shape
+        sD, sH, sW = stride
+        if (sH, sW) != (kH, kW):
+            raise NotImplementedError("sm_100a stem needs in-plane stride == kernel (patchify)")
+        if H % kH or W % kW:
+            raise NotImplementedError("sm_100a stem needs H, W divisible by the stem kernel")
+        A = ops.stem_patchify(x, kH, kW, dtype)
+        wfull, bfull, Dd = _stem_full_weight(w.detach(), b.detach(), D, sD)
+        out = ops.gemm(A, ops.cast_pack(wfull, dtype), bias=bfull.contiguous())
+        ctx.save_for_backward(A, w)
+        ctx.geom = (D, sD, Dd)
+        return out.view(Bn, H // kH, W // kW, Co * Dd)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        A, w = ctx.saved_tensors
+        D, sD, Dd = ctx.geom
+        Co, Cin, kD, kH, kW = w.shape
+        do2 = dout.contiguous().view(-1, Co * Dd)
+        dfull = ops.gemm(do2, A, mn_major=True, epilogue=L.EPI_F32,
+                         k_splits=_wgrad_splits(Co * Dd, A.shape[1], A.shape[0]))
+        dfull = dfull.view(Co, Dd, Cin, D, kH, kW)
+        dw = torch.zeros_like(w)
+        for dd in range(Dd):
+            dw += dfull[:, dd, :, dd * sD: dd * sD + kD]
+        db = ops.colsum(do2).view(Co, Dd).sum(1)
+        return None, dw, db, None, None
+
+
+def stem(x, conv, dtype):
+    if x.requires_grad:
+        raise NotImplementedError("sm_100a stem does not produce an input gradient")
+    return StemFn.apply(x, conv.weight, conv.bias, tuple(conv.stride), dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+class HeadFn(Function):
+    """PixelToVoxelHead (VM/components/heads.py:632-641): NHWC decoder features -> (B, Cout, D, 4h, 4w) NCDHW."""
+
+    @staticmethod
+    def forward(ctx, dec, conv_w, conv_b, alpha, w1, b1, out_depth, pool):
+        B, h, w, Cd = dec.shape
+        Dz = out_depth + 2
+        Cm = Cd // 4
+        Cc = Cm // Dz
+        Cmid = conv_w.shape[0]
+        Cu = -(-Cc // 8) * 8
+        u = ops.head_shuffle_pool_fwd(dec, Dz, pool, Cu)
+        geom = ops.conv3d_geom(tuple(u.shape), (3, 3, 3), (1, 1, 1), (0, 1, 1))
+        col = ops.im2col3d(u, geom)
+        wc = conv_w.detach().permute(0, 2, 3, 4, 1)  # [Cmid, 3,3,3, Cc]
+        if Cu != Cc:
+            wc = torch.nn.functional.pad(wc, (0, Cu - Cc))
+        wc = wc.reshape(Cmid, -1).contiguous()
+        z = ops.gemm(col, ops.cast_pack(wc, dec.dtype), bias=conv_b)
+        H2, W2 = 2 * h, 2 * w
+        R = out_depth * H2 * W2
+        z3 = z.view(B, R, Cmid)
+        mean, rstd = ops.instnorm_stats(z3, 1e-5)
+        w1m = w1.detach().reshape(w1.shape[0], Cmid).contiguous()
+        out = ops.head_tail_fwd(z3, mean, rstd, alpha.detach(), w1m, b1.detach(), out_depth, H2, W2)
+        ctx.save_for_backward(col, z3, mean, rstd, alpha, w1, conv_w)
+        ctx.meta = (geom, Cm, Cc, Cu, pool, out_depth, H2, W2)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        col, z3, mean, rstd, alpha, w1, conv_w = ctx.saved_tensors
+        geom, Cm, Cc, Cu, pool, out_depth, H2, W2 = ctx.meta
+        B, R, Cmid = z3.shape
+        w1m = w1.reshape(w1.shape[0], Cmid).contiguous()
+        dz, dW1, db1, dalpha, dbz = ops.head_tail_bwd(z3, mean, rstd, alpha, w1m, dout.contiguous(), out_depth, H2, W2)
+        dz2 = dz.view(B * R, Cmid)
+        wc = conv_w.permute(0, 2, 3, 4, 1)
+        if Cu != Cc:
+            wc = torch.nn.functional.pad(wc, (0, Cu - Cc))
+        wc = wc.reshape(Cmid, -1).contiguous()
+        dcol, dwc, _ = linear_bwd(dz2, col, wc, need_db=False)
+        du = ops.col2im3d(dcol, geom)
+        ddec = ops.head_shuffle_pool_bwd(du, Cm, pool)
+        dconv_w = dwc.view(Cmid, 3, 3, 3, Cu)[..., :Cc].permute(0, 4, 1, 2, 3)
+        return ddec, dconv_w, dbz, dalpha.view(alpha.shape), dW1.view(w1.shape), db1, None, None
+
+
+def pixel_to_voxel_head(dec, conv0, prelu, conv1, out_depth, pool):
+    return HeadFn.apply(dec, conv0.weight, conv0.bias, prelu.weight, conv1.weight, conv1.bias, out_depth, pool)

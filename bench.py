@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Headline benchmark: UNeXt2 256x256x21 bf16 training samples/s (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (DDP over NCCL when N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference math on the host cores (CPU arm)
+
+One "step" = forward + MSE loss + backward + AdamW update of UNeXt2(1->2 ch, convnextv2_tiny, stem (7,4,4),
+head_pool) on a synthetic batch of 8 volumes (1,21,256,256) per GPU under bf16 autocast.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CFG = dict(in_channels=1, out_channels=2, in_stack_depth=21, backbone="convnextv2_tiny",
+           stem_kernel_size=(7, 4, 4), decoder_mode="pixelshuffle", head_pool=True, head_expansion_ratio=4)
+BATCH = 8
+SHAPE_IN = (1, 21, 256, 256)
+SHAPE_OUT = (2, 21, 256, 256)
+TRAIN_TFLOP_PER_SAMPLE = 0.2753  # 2.203 TFLOP / step of 8 (3 x forward MACs x 2)
+METRIC = "UNeXt2 256x256x21 bf16 train samples/sec"
+WORKLOAD = "UNeXt2 1->2ch convnextv2_tiny stem(7,4,4) head_pool, 21x256x256, batch 8/GPU, bf16 autocast, MSE+AdamW"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_steps(steps: int, warmup: int, batch: int = 1):
+    """The reference math (oracle port; the reference's own composition code over restated timm/monai blocks, or
+    the unmodified reference modules when /root/reference is present) on the host cores, fp32, fwd+MSE+bwd+AdamW."""
+    from oracle import models as OM
+    from oracle import reference_loader as RL
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    if RL.available():
+        model = RL.load().UNeXt2(**CFG)
+        kind_note = "reference composition code from /root/reference over restated timm/monai"
+    else:
+        model = OM.UNeXt2(**{k: v for k, v in CFG.items() if k != "decoder_mode"})
+        kind_note = "oracle/models.py restatement"
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    x = torch.randn(batch, *SHAPE_IN)
+    y = torch.randn(batch, *SHAPE_OUT)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(x), y)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return batch / t, t, cores, kind_note
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    v, t, cores, note = cpu_steps(steps, warm, batch=1)
+    sample = f"{steps} timed + {warm} warm-up steps of batch 1 (1/8 of the per-GPU batch), fp32, {note}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    from viscy_b200 import UNeXt2, _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ddp = world > 1
+    if ddp:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly when the native library is missing
+
+    torch.manual_seed(1234)
+    model = UNeXt2(**CFG).to(dev)
+    net = model
+    if ddp:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        static_graph=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn((BATCH, *SHAPE_IN), device=dev, generator=g)
+    y = torch.randn((BATCH, *SHAPE_OUT), device=dev, generator=g)
+
+    def step(xd, yd):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(xd)
+            loss = torch.nn.functional.mse_loss(out.float(), yd)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if ddp:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if ddp:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step(x, y)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(lambda: step(x, y), args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host (pinned) inputs copied in, loss read back, every step
+    xh = x.cpu().pin_memory()
+    yh = y.cpu().pin_memory()
+    xd, yd = torch.empty_like(x), torch.empty_like(y)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        yd.copy_(yh, non_blocking=True)
+        return step(xd, yd).item()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- roofline of the dominant kernel: the decoder-stage-2 fc1/fc2 tcgen05 GEMMs (M=32768, 736 <-> 2944),
+    #      timed with CUDA events around each launch on the launching stream during extra steps
+    prof = {}
+    orig = ops.gemm
+
+    def gemm_timed(a, b, **kw):
+        if kw.get("mn_major"):
+            return orig(a, b, **kw)
+        key = (a.shape[0], b.shape[0], a.shape[1])
+        if key not in ((BATCH * 4096, 2944, 736), (BATCH * 4096, 736, 2944)):
+            return orig(a, b, **kw)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(a, b, **kw)
+        e.record()
+        prof.setdefault(key, []).append((s, e))
+        return r
+
+    ops.gemm = gemm_timed
+    for _ in range(2):
+        step(x, y)
+    torch.cuda.synchronize()
+    ops.gemm = orig
+    durs = [s.elapsed_time(e) for evs in prof.values() for s, e in evs]
+    hbm, tf_burst, tf_sus, src = peaks()
+    roof = None
+    if durs:
+        avg_ms = sum(durs) / len(durs)
+        flops = 2.0 * BATCH * 4096 * 2944 * 736
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
+                "traffic": None, "kernel": "gemm_kernel<256,K-major> dec-stage-2 fc1/fc2/dgrad (M=32768, 736<->2944)",
+                "launches_timed": len(durs), "avg_ms": avg_ms, "peak_source": f"bf16_tflops_sustained ({src})"}
+
+    if rank == 0:
+        value = world * BATCH * args.steps / (ms * 1e-3)
+        e2e_v = world * BATCH * args.steps / (ms_e2e * 1e-3)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, t, cores, note = cpu_steps(2, 1, batch=1)
+            cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"2 timed + 1 warm-up steps of batch 1 at 21x256x256 fp32 ({note})"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"dp{world}",
+                       "l2": "activations per step (>4 GB) exceed the 126 MB L2; no explicit flush",
+                       "step_tflop_fraction_of_sustained_peak": value / world * TRAIN_TFLOP_PER_SAMPLE / tf_sus},
+            "clocks": clocks,
+            "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": (xh.numel() + yh.numel()) * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if ddp:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,7 +48,11 @@ def test_unext2_fwd_bwd_parity(cuda, dtype, ftol, gtol):
     for n, p in m.named_parameters():
         assert p.grad is not None, n
         assert p.grad.shape == p.shape
-        worst.append((rel(p.grad.cpu(), og[n].grad), n))
+        gref = og[n].grad
+        if n == "head.conv.0.conv.bias":  # bias in front of InstanceNorm: analytically zero gradient
+            assert p.grad.float().norm().item() < 1e-2 and gref.norm().item() < 1e-2, n
+            continue
+        worst.append((rel(p.grad.cpu(), gref), n))
     worst.sort(reverse=True)
     print("worst grads:", [(f"{w:.2e}", n) for w, n in worst[:6]])
     import statistics

@@ -33,7 +33,10 @@ enum {
   VB200_EPI_STORE = 0,     /* out = act(acc + bias[col]) (+ residual[row,col]) -> 16-bit          */
   VB200_EPI_GELU_DUAL = 1, /* u = acc + bias; out = u; out2 = gelu(u); optional sum(g^2) partials */
   VB200_EPI_DGELU = 2,     /* out = (acc + bias) * gelu'(u), u = aux[row,col]  (dgrad through GELU)      */
-  VB200_EPI_F32 = 3        /* out(fp32) = acc (+ bias[col]); optional atomic accumulate / K-split slabs */
+  VB200_EPI_F32 = 3,       /* out(fp32) = acc (+ bias[col]); optional atomic accumulate / K-split slabs */
+  VB200_EPI_DGELU_GRN = 4, /* out = (acc*s[n,col] + g*t[n,col]) * gp: g = aux, gp = aux2 (= gelu'(u) from EPI_GELU_GP),
+                              n = row / rows_per_sample; s, t optional (NULL: 1 and 0) */
+  VB200_EPI_GELU_GP = 5    /* u = acc + bias; out = gelu'(u); out2 = gelu(u) */
 };
 enum { VB200_ACT_NONE = 0, VB200_ACT_RELU = 1, VB200_ACT_GELU = 2 };
 
@@ -50,8 +53,11 @@ typedef struct vb200_gemm_desc {
   int32_t act;           /* VB200_ACT_* (EPI_STORE only) */
   int32_t k_splits;      /* >=1; mn_major wgrad form: split the K (pixel) range */
   int32_t atomic_out;    /* EPI_F32: 1 = red.add into out, 0 = plain store */
+  int32_t b_batch_rows;  /* > 0 (K-major only, multiple of 128): B is [nb][N][K], rows [i*b_batch_rows, ..) of D use B[i]
+                            (per-sample GRN-scaled fc2 weights) */
+  int32_t rows_per_sample; /* EPI_DGELU_GRN: rows per sample */
   int64_t lda, ldb;      /* leading dimensions in elements */
-  int64_t ldo, ldo2, ldr, ldaux; /* leading dims (elements) of out, out2, residual, aux */
+  int64_t ldo, ldo2, ldr, ldaux, ldaux2; /* leading dims (elements) of out, out2, residual, aux, aux2 */
   int64_t split_out_stride;      /* EPI_F32: elements between per-split output slabs (0 = same slab) */
   const void* A;
   const void* B;
@@ -59,7 +65,10 @@ typedef struct vb200_gemm_desc {
   void* out2;
   const float* bias;     /* [N] or NULL */
   const void* residual;  /* 16-bit [M,ldr] or NULL */
-  const void* aux;       /* EPI_DGELU: u (pre-activation), 16-bit [M,ldaux] */
+  const void* aux;       /* EPI_DGELU: u (pre-activation), 16-bit [M,ldaux]; EPI_DGELU_GRN: g = gelu(u) */
+  const void* aux2;      /* EPI_DGELU_GRN: gp = gelu'(u), 16-bit [M,ldaux2] */
+  const float* tvec;     /* EPI_DGELU_GRN: t [nsamples, N] fp32 or NULL */
+  const float* svec;     /* EPI_DGELU_GRN: s [nsamples, N] fp32 or NULL */
 } vb200_gemm_desc;
 
 int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);
@@ -100,6 +109,19 @@ int vb200_grn_coef_bwd(const float* sumsq, const float* S1, const float* w, floa
 int vb200_grn_apply_bwd(const void* h, const void* dy, const float* s, const float* t, void* dh, float* dbias,
                         int B, int R, int C, int dtype, vb200_stream_t stream);
 
+/* ---- fused GRN path (pixels-per-sample % 128 == 0): the GRN scale is folded into per-sample fc2 weights so the
+ * hidden tensor y = GRN(g) is never materialised, and the GRN + GELU backward rides in the fc2-dgrad epilogue ---- */
+/* mode 0: out[n,c] += sum_r x[n,r,c]; mode 1: sum of squares.  x [B,R,C] 16-bit, C % 8 == 0, out pre-zeroed */
+int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode, int dtype, vb200_stream_t stream);
+/* out[n][j][k] = W2[j][k] * s[n][k] (16-bit) */
+int vb200_grn_pack_w2(const float* W2, const float* s, void* out, int nb, int C, int C4, int dtype,
+                      vb200_stream_t stream);
+/* out[j] = b2[j] + sum_k W2[j][k] * bgrn[k] */
+int vb200_grn_bias_eff(const float* W2, const float* bgrn, const float* b2, float* out, int C, int C4, vb200_stream_t stream);
+/* from per-sample wgrad partials P[n][j][k]: dW2 (overwritten), S1 [nb,C4] and dbgrn [C4] (accumulated, pre-zeroed) */
+int vb200_grn_wgrad_finish(const float* P, const float* W2, const float* s, const float* bgrn, const float* db2,
+                           float* dW2, float* S1, float* dbgrn, int nb, int C, int C4, vb200_stream_t stream);
+
 /* out[c] += sum_rows x[r][c]  (bias gradients; out pre-zeroed) */
 int vb200_colsum(const void* x, float* out, int64_t M, int C, int dtype, vb200_stream_t stream);
 
@@ -122,6 +144,8 @@ int vb200_stem_patchify(const void* x, int x_dtype, void* A, int B, int Cin, int
  * VM/unet/blocks.py:88-113, VM/unet/unet3d_base.py:90-138, VM/components/conv_block_3d.py:261-274 onto vb200_gemm. */
 int vb200_im2col3d(const void* u, void* col, const int32_t* geom, vb200_stream_t stream);
 int vb200_col2im3d(const void* dcol, void* du, const int32_t* geom, int dtype, vb200_stream_t stream);
+/* conv_dw.weight [C,1,7,7] -> tap-major wt [49][C] and flipped wtf [49][C] (fp32) */
+int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t stream);
 /* fp32 [R,Cc] -> 16-bit (weight packing); transpose != 0 writes [Cc,R] */
 int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype, vb200_stream_t stream);
 

@@ -238,3 +238,61 @@ def test_cast_pack(cuda, dtype):
     w = rnd((96, 40, 1, 1), cuda, 1)
     assert torch.equal(ops.cast_pack(w, dtype), w.view(96, 40).to(dtype))
     assert torch.equal(ops.cast_pack(w, dtype, transpose=True), w.view(96, 40).t().contiguous().to(dtype))
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_colreduce(cuda, dtype):
+    from viscy_b200 import ops
+    x = rnd((3, 1000, 736), cuda, 1, dtype)
+    assert rel(ops.colreduce(x, 0), x.float().sum(1)) < 1e-4
+    assert rel(ops.colreduce(x, 1), (x.float() ** 2).sum(1)) < 1e-4
+    x = rnd((1, 32768, 96), cuda, 2, dtype)
+    assert rel(ops.colreduce(x, 0), x.float().sum(1)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_fused_grn_pieces(cuda, dtype):
+    """per-sample scaled fc2 weights, effective bias, wgrad finishing kernel, fused backward epilogue."""
+    from viscy_b200 import ops, _lib as L
+    nb, R, C, C4 = 3, 256, 96, 384
+    M = nb * R
+    w2 = rnd((C, C4), cuda, 1) * 0.1
+    s = rnd((nb, C4), cuda, 2) * 0.3 + 1.0
+    bg = rnd((C4,), cuda, 3) * 0.2
+    b2 = rnd((C,), cuda, 4)
+    w2s = ops.grn_pack_w2(w2, s, dtype)
+    assert rel(w2s.view(nb, C, C4), w2[None] * s[:, None, :]) < tol(dtype)
+    assert rel(ops.grn_bias_eff(w2, bg, b2), b2 + w2 @ bg) < 1e-5
+    # batched-B GEMM: out[n] = g[n] @ (W2*s[n])^T + b + residual
+    g = rnd((M, C4), cuda, 5, dtype)
+    res = rnd((M, C), cuda, 6, dtype)
+    out = ops.gemm(g, w2s, bias=b2, residual=res, b_batch_rows=R)
+    ref = torch.einsum("nrk,njk->nrj", g.float().view(nb, R, C4), w2s.float().view(nb, C, C4)).reshape(M, C) + b2 + res.float()
+    assert rel(out, ref) < tol(dtype)
+    # per-sample wgrad slabs + finish
+    dout = rnd((M, C), cuda, 7, dtype)
+    P = ops.gemm(dout, g, mn_major=True, epilogue=L.EPI_F32, k_splits=nb, split_slabs=True)
+    Pref = torch.einsum("nrj,nrk->njk", dout.float().view(nb, R, C), g.float().view(nb, R, C4))
+    assert rel(P, Pref) < 1e-4
+    db2 = dout.float().sum(0)
+    dW2, S1, dbg = ops.grn_wgrad_finish(P, w2, s, bg, db2)
+    assert rel(dW2, (Pref * s[:, None, :]).sum(0) + db2[:, None] * bg[None, :]) < 1e-4
+    assert rel(S1, (Pref * w2[None]).sum(1)) < 1e-4
+    assert rel(dbg, w2.t() @ db2) < 1e-4
+    # fused backward epilogue: dh = (dout @ W2 * s + g*t) * gp
+    t = rnd((nb, C4), cuda, 8) * 0.1
+    gp = rnd((M, C4), cuda, 9, dtype)
+    w2t = ops.cast_pack(w2, dtype, transpose=True)
+    dh = ops.gemm(dout, w2t, epilogue=L.EPI_DGELU_GRN, aux=g, aux2=gp, tvec=t, svec=s, rows_per_sample=R)
+    dy = dout.float() @ w2t.float().t()
+    ref = (dy.view(nb, R, C4) * s[:, None] + g.float().view(nb, R, C4) * t[:, None]) * gp.float().view(nb, R, C4)
+    assert rel(dh, ref.view(M, C4)) < tol(dtype)
+    # forward dual epilogue: gelu' and gelu
+    a = rnd((M, C), cuda, 10, dtype)
+    w1 = (rnd((C4, C), cuda, 11) / C ** 0.5).to(dtype)
+    b1 = rnd((C4,), cuda, 12)
+    gpo, go = ops.gemm(a, w1, bias=b1, epilogue=L.EPI_GELU_GP)
+    u = (a.float() @ w1.float().t() + b1).requires_grad_(True)
+    gr = F.gelu(u)
+    gr.sum().backward()
+    assert rel(go, gr) < tol(dtype) and rel(gpo, u.grad) < tol(dtype)

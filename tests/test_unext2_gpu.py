@@ -27,7 +27,7 @@ def _pair(cuda, cfg, seed=0):
     return o, m.to(cuda)
 
 
-@pytest.mark.parametrize("dtype,ftol,gtol", [(torch.float16, 4e-3, 3e-2), (torch.bfloat16, 3e-2, 1.5e-1)])
+@pytest.mark.parametrize("dtype,ftol,gtol", [(torch.float16, 2e-3, 6e-2), (torch.bfloat16, 2e-2, 2.5e-1)])
 def test_unext2_fwd_bwd_parity(cuda, dtype, ftol, gtol):
     o, m = _pair(cuda, CFG)
     torch.manual_seed(1)

@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libviscy_b200.so"
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 BF16, FP16 = 0, 1
-EPI_STORE, EPI_GELU_DUAL, EPI_DGELU, EPI_F32 = 0, 1, 2, 3
+EPI_STORE, EPI_GELU_DUAL, EPI_DGELU, EPI_F32, EPI_DGELU_GRN, EPI_GELU_GP = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 
@@ -24,11 +24,13 @@ class GemmDesc(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("dtype", C.c_int32), ("mn_major", C.c_int32), ("epilogue", C.c_int32),
         ("act", C.c_int32), ("k_splits", C.c_int32), ("atomic_out", C.c_int32),
+        ("b_batch_rows", C.c_int32), ("rows_per_sample", C.c_int32),
         ("lda", C.c_int64), ("ldb", C.c_int64),
-        ("ldo", C.c_int64), ("ldo2", C.c_int64), ("ldr", C.c_int64), ("ldaux", C.c_int64),
+        ("ldo", C.c_int64), ("ldo2", C.c_int64), ("ldr", C.c_int64), ("ldaux", C.c_int64), ("ldaux2", C.c_int64),
         ("split_out_stride", C.c_int64),
         ("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p),
-        ("bias", C.c_void_p), ("residual", C.c_void_p), ("aux", C.c_void_p),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("aux", C.c_void_p), ("aux2", C.c_void_p),
+        ("tvec", C.c_void_p), ("svec", C.c_void_p),
     ]
 
 

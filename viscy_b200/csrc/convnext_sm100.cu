@@ -10,67 +10,104 @@ namespace vb {
 // ------------------------------------------------------------------------------ depthwise 7x7
 // x [B,H,W,C] 16-bit, wt [49][C] fp32 (tap-major so that channel loads coalesce), bias [C] or null,
 // add [B,H,W,C] 16-bit or null (residual gradient folded into the dgrad call).
-// One thread = 2 adjacent channels x TW output pixels of one row; sliding 7-wide window in registers.
+// One thread = 2 adjacent channels x (DW_TH x DW_TW) output pixels, accumulators as float2 (channel pair) so every
+// multiply-add is one packed FFMA2 (sm_100 fma.rn.f32x2).  The thread walks the DW_TH+6 input rows once, fully
+// unrolled (static tap indices, loads of the next row overlap the FMAs of the current one); each input row
+// (DW_TW+6 values) feeds up to DW_TH output rows.  The 49 taps of the block's 128 channel pairs sit in shared
+// memory (conflict-free 8-byte reads).  All offsets are 32-bit (host checks numel < 2^31).
 constexpr int DW_TW = 8;
+constexpr int DW_TH = 4;
+constexpr int DW_SMEM = 49 * 128 * 8;
+
+template <bool BF16>
+__device__ __forceinline__ float2 ldpair(const uint32_t* p, int off, bool ok) {
+  uint32_t raw = 0;
+  if (ok) raw = __ldg(p + off);
+  return H16<BF16>::unpack(raw);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(128)
 dwconv7_kernel(const uint32_t* __restrict__ x, const float* __restrict__ wt,
                const float* __restrict__ bias, const uint32_t* __restrict__ add,
                uint32_t* __restrict__ y, int B, int H, int W, int C2) {
-  const int cp = blockIdx.y * 128 + threadIdx.x;  // channel pair
+  extern __shared__ float2 sw[];  // [49][128]
+  const int cp0 = blockIdx.y * 128;
+  const int cp = cp0 + threadIdx.x;
+  const int C = C2 * 2;
+  for (int i = threadIdx.x; i < 49 * 128; i += 128) {
+    const int tap = i >> 7, c = cp0 + (i & 127);
+    sw[i] = c < C2 ? __ldg(reinterpret_cast<const float2*>(wt + tap * C) + c) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
   if (cp >= C2) return;
-  const int wtiles = (W + DW_TW - 1) / DW_TW;
+  const int wtiles = (W + DW_TW - 1) / DW_TW, htiles = (H + DW_TH - 1) / DW_TH;
   int t = blockIdx.x;
   const int w0 = (t % wtiles) * DW_TW;
   t /= wtiles;
-  const int h = t % H;
-  const int n = t / H;
-  const int C = C2 * 2;
-  float2 acc[DW_TW];
+  const int h0 = (t % htiles) * DW_TH;
+  const int n = t / htiles;
+  const int pix0 = n * H * W;  // pixel index of the image origin
+  const uint32_t* xb = x + cp;
+  int coff[DW_TW + 6];
+  bool cok[DW_TW + 6];
+#pragma unroll
+  for (int j = 0; j < DW_TW + 6; ++j) {
+    const int iw = w0 + j - 3;
+    cok[j] = iw >= 0 && iw < W;
+    coff[j] = (pix0 + iw) * C2;
+  }
+  float2 acc[DW_TH][DW_TW];
   float2 b2 = make_float2(0.f, 0.f);
   if (bias != nullptr) b2 = *reinterpret_cast<const float2*>(bias + 2 * cp);
 #pragma unroll
-  for (int j = 0; j < DW_TW; ++j) acc[j] = b2;
-  const long long img = (long long)n * H * W;
-#pragma unroll 1
-  for (int kh = 0; kh < 7; ++kh) {
-    const int ih = h + kh - 3;
-    if (ih < 0 || ih >= H) continue;
+  for (int r = 0; r < DW_TH; ++r)
+#pragma unroll
+    for (int j = 0; j < DW_TW; ++j) acc[r][j] = b2;
+  const float2* swl = sw + threadIdx.x;
+#pragma unroll
+  for (int ir = 0; ir < DW_TH + 6; ++ir) {
+    const int ih = h0 + ir - 3;
+    const bool rok = ih >= 0 && ih < H;
+    const int roff = ih * W * C2;
     float2 in[DW_TW + 6];
 #pragma unroll
-    for (int j = 0; j < DW_TW + 6; ++j) {
-      const int iw = w0 + j - 3;
-      in[j] = make_float2(0.f, 0.f);
-      if (iw >= 0 && iw < W) in[j] = H16<BF16>::unpack(__ldg(x + (img + (long long)ih * W + iw) * C2 + cp));
-    }
+    for (int j = 0; j < DW_TW + 6; ++j) in[j] = ldpair<BF16>(xb, roff + coff[j], rok && cok[j]);
 #pragma unroll
-    for (int kw = 0; kw < 7; ++kw) {
-      const float2 wv = __ldg(reinterpret_cast<const float2*>(wt + (kh * 7 + kw) * C + 2 * cp));
+    for (int r = 0; r < DW_TH; ++r) {
+      const int kh = ir - r;  // static after unrolling
+      if (kh >= 0 && kh < 7) {
 #pragma unroll
-      for (int j = 0; j < DW_TW; ++j) {
-        acc[j].x = fmaf(in[j + kw].x, wv.x, acc[j].x);
-        acc[j].y = fmaf(in[j + kw].y, wv.y, acc[j].y);
+        for (int kw = 0; kw < 7; ++kw) {
+          const float2 wv = swl[(kh * 7 + kw) * 128];
+#pragma unroll
+          for (int j = 0; j < DW_TW; ++j) acc[r][j] = __ffma2_rn(in[j + kw], wv, acc[r][j]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < DW_TW; ++j) {
-    const int ow = w0 + j;
-    if (ow < W) {
-      const long long o = (img + (long long)h * W + ow) * C2 + cp;
-      float2 v = acc[j];
-      if (add != nullptr) {
-        const float2 a = H16<BF16>::unpack(__ldg(add + o));
-        v.x += a.x;
-        v.y += a.y;
+  for (int r = 0; r < DW_TH; ++r) {
+    const int oh = h0 + r;
+    if (oh < H) {
+#pragma unroll
+      for (int j = 0; j < DW_TW; ++j) {
+        const int ow = w0 + j;
+        if (ow < W) {
+          const int o = ((pix0 + oh * W) + ow) * C2 + cp;
+          float2 v = acc[r][j];
+          if (add != nullptr) v = __fadd2_rn(v, H16<BF16>::unpack(__ldg(add + o)));
+          y[o] = H16<BF16>::pack(v.x, v.y);
+        }
       }
-      y[o] = H16<BF16>::pack(v.x, v.y);
     }
   }
 }
 
 // wgrad: dwt[tap][c] += sum_{pixels} dy[p][c] * x[p + tap offset][c];  db[c] += sum dy[p][c].
-// One block = 128 channel pairs x a strip of rows of one image; per-thread 49x2 accumulators.
+// One thread = 2 channels with all 49 float2 accumulators in registers; it walks a strip of rows of one image
+// two output rows x 8 pixels at a time: the 8 x-rows h-3..h+4 (14 values each) feed both output rows
+// (98 x 8 packed FFMA2 per 16 + 112 loads).
 template <bool BF16>
 __global__ void __launch_bounds__(128)
 dwconv7_wgrad_kernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ dy,
@@ -83,48 +120,60 @@ dwconv7_wgrad_kernel(const uint32_t* __restrict__ x, const uint32_t* __restrict_
   const int h0 = (blockIdx.x % strips) * rows_per_block;
   const int h1 = min(H, h0 + rows_per_block);
   const int C = 2 * C2;
-  const long long img = (long long)n * H * W;
+  const int pix0 = n * H * W;
+  const uint32_t* xb = x + cp;
+  const uint32_t* gb = dy + cp;
+  float2 acc[7][7];
+#pragma unroll
+  for (int a = 0; a < 7; ++a)
+#pragma unroll
+    for (int b = 0; b < 7; ++b) acc[a][b] = make_float2(0.f, 0.f);
   float2 bsum = make_float2(0.f, 0.f);
-#pragma unroll 1
-  for (int kh = 0; kh < 7; ++kh) {
-    float2 acc[7];
+  for (int h = h0; h < h1; h += 2) {
+    const bool row1 = h + 1 < h1;
+    for (int w0 = 0; w0 < W; w0 += 8) {
+      float2 g0[8], g1[8];
 #pragma unroll
-    for (int kw = 0; kw < 7; ++kw) acc[kw] = make_float2(0.f, 0.f);
-    for (int h = h0; h < h1; ++h) {
-      const int ih = h + kh - 3;
-      if (ih < 0 || ih >= H) continue;
-      // slide along the row: keep a 7-wide window of x in registers
-      float2 win[7];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int iw = j - 3;
-        win[j + 1] = make_float2(0.f, 0.f);
-        if (iw >= 0 && iw < W) win[j + 1] = H16<BF16>::unpack(__ldg(x + (img + (long long)ih * W + iw) * C2 + cp));
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = w0 + j < W;
+        const int off = (pix0 + h * W + w0 + j) * C2;
+        g0[j] = ldpair<BF16>(gb, off, ok);
+        g1[j] = ldpair<BF16>(gb, off + W * C2, ok && row1);
+        bsum = __fadd2_rn(bsum, __fadd2_rn(g0[j], g1[j]));
       }
-      for (int w = 0; w < W; ++w) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-        const int iw = w + 3;
-        win[6] = make_float2(0.f, 0.f);
-        if (iw < W) win[6] = H16<BF16>::unpack(__ldg(x + (img + (long long)ih * W + iw) * C2 + cp));
-        const float2 g = H16<BF16>::unpack(__ldg(dy + (img + (long long)h * W + w) * C2 + cp));
-        if (kh == 3) {  // count every dy exactly once for the bias gradient (ih == h always valid)
-          bsum.x += g.x;
-          bsum.y += g.y;
+      for (int xr = 0; xr < 8; ++xr) {
+        const int ih = h - 3 + xr;
+        const bool rok = ih >= 0 && ih < H;
+        const int roff = (pix0 + ih * W + w0 - 3) * C2;
+        float2 in[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) {
+          const int iw = w0 + j - 3;
+          in[j] = ldpair<BF16>(xb, roff + j * C2, rok && iw >= 0 && iw < W);
         }
+        if (xr < 7) {
 #pragma unroll
-        for (int kw = 0; kw < 7; ++kw) {
-          acc[kw].x = fmaf(g.x, win[kw].x, acc[kw].x);
-          acc[kw].y = fmaf(g.y, win[kw].y, acc[kw].y);
+          for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[xr][kw] = __ffma2_rn(g0[j], in[j + kw], acc[xr][kw]);
+        }
+        if (xr >= 1) {
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[xr - 1][kw] = __ffma2_rn(g1[j], in[j + kw], acc[xr - 1][kw]);
         }
       }
-    }
-#pragma unroll
-    for (int kw = 0; kw < 7; ++kw) {
-      atomicAdd(dwt + (kh * 7 + kw) * C + 2 * cp, acc[kw].x);
-      atomicAdd(dwt + (kh * 7 + kw) * C + 2 * cp + 1, acc[kw].y);
     }
   }
+#pragma unroll
+  for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) {
+      atomicAdd(dwt + (kh * 7 + kw) * C + 2 * cp, acc[kh][kw].x);
+      atomicAdd(dwt + (kh * 7 + kw) * C + 2 * cp + 1, acc[kh][kw].y);
+    }
   if (db != nullptr) {
     atomicAdd(db + 2 * cp, bsum.x);
     atomicAdd(db + 2 * cp + 1, bsum.y);
@@ -418,6 +467,122 @@ colsum_kernel(const uint32_t* __restrict__ x, float* __restrict__ out, long long
   atomicAdd(out + 2 * cp + 1, a.y);
 }
 
+// ---- 16-byte vectorised column reductions: block = 128 column-threads (8 channels each) x 4 row lanes;
+// the row lanes are combined through shared memory, then one atomicAdd per (block, channel).
+// MODE 0: out[n,c] += sum x ; MODE 1: out[n,c] += sum x^2
+template <bool BF16, int MODE>
+__global__ void __launch_bounds__(512)
+colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, int R, int C8, int rows_per_block) {
+  __shared__ float red[4][128 * 8];
+  const int c8 = blockIdx.x * 128 + threadIdx.x;
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c8 < C8) {
+    const uint4* xp = x + ((long long)n * R) * C8 + c8;
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < r1; r += 4) {
+      const uint4 q = __ldg(xp + (long long)r * C8);
+      const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = H16<BF16>::unpack(w4[k]);
+        if (MODE == 0) {
+          a[2 * k] += f.x;
+          a[2 * k + 1] += f.y;
+        } else {
+          a[2 * k] = fmaf(f.x, f.x, a[2 * k]);
+          a[2 * k + 1] = fmaf(f.y, f.y, a[2 * k + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.y][k * 128 + threadIdx.x] = a[k];
+  __syncthreads();
+  // 1024 sums per block; 512 threads take two each
+  for (int i = threadIdx.y * 128 + threadIdx.x; i < 1024; i += 512) {
+    const int k = i >> 7, cl = i & 127;
+    const int cc = blockIdx.x * 128 + cl;
+    if (cc < C8) atomicAdd(out + ((long long)n * C8 + cc) * 8 + k, red[0][i] + red[1][i] + red[2][i] + red[3][i]);
+  }
+}
+
+// per-sample GRN-scaled fc2 weights: out[n][j][k] = W2[j][k] * s[n][k]; thread = 8 consecutive k of one row j, all n
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+grn_pack_w2_kernel(const float* __restrict__ W2, const float* __restrict__ s, uint4* __restrict__ out,
+                   int nb, int C, int C48) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * C48) return;
+  const int k8 = idx % C48;
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(W2) + 2 * idx);
+  const float4 w1 = __ldg(reinterpret_cast<const float4*>(W2) + 2 * idx + 1);
+  for (int n = 0; n < nb; ++n) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(s) + ((long long)n * C48 + k8) * 2);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(s) + ((long long)n * C48 + k8) * 2 + 1);
+    out[(long long)n * C * C48 + idx] =
+        make_uint4(H16<BF16>::pack(w0.x * s0.x, w0.y * s0.y), H16<BF16>::pack(w0.z * s0.z, w0.w * s0.w),
+                   H16<BF16>::pack(w1.x * s1.x, w1.y * s1.y), H16<BF16>::pack(w1.z * s1.z, w1.w * s1.w));
+  }
+}
+
+// b2eff[j] = b2[j] + sum_k W2[j][k] * bgrn[k]   (one warp per output row)
+__global__ void __launch_bounds__(256)
+grn_bias_eff_kernel(const float* __restrict__ W2, const float* __restrict__ bgrn, const float* __restrict__ b2,
+                    float* __restrict__ out, int C, int C4) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= C) return;
+  const int lane = threadIdx.x & 31;
+  float a = 0.f;
+  for (int k = lane; k < C4; k += 32) a = fmaf(W2[(long long)j * C4 + k], bgrn[k], a);
+  a = warp_sum(a);
+  if (lane == 0) out[j] = b2[j] + a;
+}
+
+// From the per-sample wgrad partials P[n][j][k] = sum_{rows of n} dout[r][j] * g[r][k]:
+//   dW2[j][k]  = sum_n s[n][k] * P[n][j][k] + bgrn[k] * db2[j]
+//   S1[n][k]  += sum_j W2[j][k] * P[n][j][k]         (= sum_r dy * g with dy = dout W2)
+//   dbgrn[k]  += sum_j W2[j][k] * db2[j]             (= sum_r dy)
+// thread = column k, block = chunk of rows j; NB <= 16 samples per launch.
+template <int NB>
+__global__ void __launch_bounds__(128)
+grn_wgrad_finish_kernel(const float* __restrict__ P, const float* __restrict__ W2, const float* __restrict__ s,
+                        const float* __restrict__ bgrn, const float* __restrict__ db2, float* __restrict__ dW2,
+                        float* __restrict__ S1, float* __restrict__ dbgrn, int nb, int C, int C4, int jchunk) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  if (k >= C4) return;
+  const int j0 = blockIdx.y * jchunk, j1 = min(C, j0 + jchunk);
+  float sv[NB], s1[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    sv[n] = n < nb ? s[(long long)n * C4 + k] : 0.f;
+    s1[n] = 0.f;
+  }
+  const float bg = bgrn[k];
+  float dbg = 0.f;
+  const long long per = (long long)C * C4;
+  for (int j = j0; j < j1; ++j) {
+    const float w = W2[(long long)j * C4 + k];
+    const float d = db2[j];
+    float acc = bg * d;
+    dbg = fmaf(w, d, dbg);
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+      if (n < nb) {
+        const float pv = P[n * per + (long long)j * C4 + k];
+        acc = fmaf(sv[n], pv, acc);
+        s1[n] = fmaf(w, pv, s1[n]);
+      }
+    dW2[(long long)j * C4 + k] = acc;
+  }
+#pragma unroll
+  for (int n = 0; n < NB; ++n)
+    if (n < nb) atomicAdd(S1 + (long long)n * C4 + k, s1[n]);
+  atomicAdd(dbgrn + k, dbg);
+}
+
 static int rows_per_block_for(long long rows, int col_blocks, int samples) {
   // aim for ~8 blocks per SM in total, at least 16 rows per block
   const long long target_blocks = 148LL * 8;
@@ -441,23 +606,30 @@ using namespace vb;
 extern "C" int vb200_dwconv7(const void* x, const float* wt, const float* bias, const void* add,
                              void* y, int B, int H, int W, int C, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(x && wt && y, "null pointer");
-  VB_SUPPORTED(C % 2 == 0, "C (%d) must be even", C);
+  VB_SUPPORTED(C % 2 == 0 && (long long)B * H * W * C < (1LL << 31), "C (%d) must be even, tensor < 2^31 elements", C);
   const int C2 = C / 2;
-  dim3 grid((unsigned)(((W + DW_TW - 1) / DW_TW) * H * B), (unsigned)((C2 + 127) / 128));
+  dim3 grid((unsigned)(((W + DW_TW - 1) / DW_TW) * ((H + DW_TH - 1) / DW_TH) * B), (unsigned)((C2 + 127) / 128));
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_DT(dtype, dwconv7_kernel<BF><<<grid, 128, 0, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
-                                                             (uint32_t*)y, B, H, W, C2));
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dwconv7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+    cudaFuncSetAttribute(dwconv7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+    configured = true;
+  }
+  DISPATCH_DT(dtype, dwconv7_kernel<BF><<<grid, 128, DW_SMEM, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
+                                                                   (uint32_t*)y, B, H, W, C2));
   return check_launch("vb200_dwconv7");
 }
 
 extern "C" int vb200_dwconv7_wgrad(const void* x, const void* dy, float* dwt, float* db, int B, int H,
                                    int W, int C, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(x && dy && dwt, "null pointer");
-  VB_SUPPORTED(C % 2 == 0, "C (%d) must be even", C);
+  VB_SUPPORTED(C % 2 == 0 && (long long)B * H * W * C < (1LL << 31), "C (%d) must be even, tensor < 2^31 elements", C);
   const int C2 = C / 2;
   const int colb = (C2 + 127) / 128;
   int rpb = (int)(((long long)H * B * colb + 148 * 4 - 1) / (148 * 4));
-  if (rpb < 1) rpb = 1;
+  rpb = (rpb + 1) & ~1;  // the kernel walks two rows at a time
+  if (rpb < 2) rpb = 2;
   if (rpb > H) rpb = H;
   const int strips = (H + rpb - 1) / rpb;
   dim3 grid((unsigned)(B * strips), (unsigned)colb);
@@ -579,4 +751,58 @@ extern "C" int vb200_colsum(const void* x, float* out, int64_t M, int C, int dty
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_DT(dtype, colsum_kernel<BF><<<grid, 128, 0, st>>>((const uint32_t*)x, out, M, C2, rpb));
   return check_launch("vb200_colsum");
+}
+
+/* MODE 0: out[n,c] += sum_r x[n,r,c];  MODE 1: out[n,c] += sum_r x[n,r,c]^2   (x [B,R,C], C % 8 == 0, out pre-zeroed) */
+extern "C" int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode, int dtype,
+                               vb200_stream_t stream) {
+  VB_REQUIRE(x && out, "null pointer");
+  VB_SUPPORTED(C % 8 == 0 && R < (1LL << 31), "C (%d) %% 8", C);
+  const int C8 = C / 8, colb = (C8 + 127) / 128;
+  // ~2 blocks of 512 threads per SM, at least 32 rows per block
+  long long rpb = (R * colb * B + 148 * 2 - 1) / (148 * 2);
+  if (rpb < 32) rpb = 32;
+  if (rpb > R) rpb = R;
+  dim3 grid(colb, (unsigned)((R + rpb - 1) / rpb), B), block(128, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0)
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 0><<<grid, block, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb));
+  else
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 1><<<grid, block, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb));
+  return check_launch("vb200_colreduce");
+}
+
+extern "C" int vb200_grn_pack_w2(const float* W2, const float* s, void* out, int nb, int C, int C4, int dtype,
+                                 vb200_stream_t stream) {
+  VB_REQUIRE(W2 && s && out, "null pointer");
+  VB_SUPPORTED(C4 % 8 == 0, "C4 (%d) %% 8", C4);
+  const long long total = (long long)C * (C4 / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, grn_pack_w2_kernel<BF><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W2, s, (uint4*)out, nb, C,
+                                                                                           C4 / 8));
+  return check_launch("vb200_grn_pack_w2");
+}
+
+extern "C" int vb200_grn_bias_eff(const float* W2, const float* bgrn, const float* b2, float* out, int C, int C4,
+                                  vb200_stream_t stream) {
+  VB_REQUIRE(W2 && bgrn && b2 && out, "null pointer");
+  grn_bias_eff_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(W2, bgrn, b2, out, C, C4);
+  return check_launch("vb200_grn_bias_eff");
+}
+
+extern "C" int vb200_grn_wgrad_finish(const float* P, const float* W2, const float* s, const float* bgrn,
+                                      const float* db2, float* dW2, float* S1, float* dbgrn, int nb, int C, int C4,
+                                      vb200_stream_t stream) {
+  VB_REQUIRE(P && W2 && s && bgrn && db2 && dW2 && S1 && dbgrn, "null pointer");
+  VB_SUPPORTED(nb <= 16, "at most 16 samples per call (nb=%d)", nb);
+  const int colb = (C4 + 127) / 128;
+  int jchunk = (C * colb + 148 * 4 - 1) / (148 * 4);
+  if (jchunk < 8) jchunk = 8;
+  dim3 grid(colb, (C + jchunk - 1) / jchunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nb <= 8)
+    grn_wgrad_finish_kernel<8><<<grid, 128, 0, st>>>(P, W2, s, bgrn, db2, dW2, S1, dbgrn, nb, C, C4, jchunk);
+  else
+    grn_wgrad_finish_kernel<16><<<grid, 128, 0, st>>>(P, W2, s, bgrn, db2, dW2, S1, dbgrn, nb, C, C4, jchunk);
+  return check_launch("vb200_grn_wgrad_finish");
 }

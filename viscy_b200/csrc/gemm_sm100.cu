@@ -31,7 +31,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int COLV_BYTES = 2 * 3 * BN * 4;  // [2 tiles in flight][bias, s, t][BN] fp32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES;
 };
 
 struct GemmParams {
@@ -40,13 +41,18 @@ struct GemmParams {
   int bf16;
   int act;
   int atomic_out;
-  long long ldo, ldo2, ldr, ldaux;
+  int b_batch_rows;     // > 0: B is [nb][N][K]; tile rows [m0, m0+128) use batch m0 / b_batch_rows
+  int rows_per_sample;  // EPI_DGELU_GRN: n = row / rows_per_sample
+  long long ldo, ldo2, ldr, ldaux, ldaux2;
   long long split_out_stride;
   void* out;
   void* out2;
   const float* bias;
   const void* residual;
   const void* aux;
+  const void* aux2;
+  const float* tvec;
+  const float* svec;
 };
 
 template <bool BF16>
@@ -66,19 +72,63 @@ __device__ __forceinline__ void store8(void* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = q;
 }
 
-// One group of 8 consecutive output columns of one row.
-template <int EPI, bool BF16>
-__device__ __forceinline__ void epilogue8(const GemmParams& p, const uint32_t* r, long long row,
-                                          int col, int split) {
+__device__ __forceinline__ void unpack8(bool bf16, const uint4& q, float* v) {
+  const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = bf16 ? H16<true>::unpack(w4[k]) : H16<false>::unpack(w4[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(bool bf16, const float* v) {
+  uint4 q;
+  if (bf16) {
+    q.x = H16<true>::pack(v[0], v[1]); q.y = H16<true>::pack(v[2], v[3]);
+    q.z = H16<true>::pack(v[4], v[5]); q.w = H16<true>::pack(v[6], v[7]);
+  } else {
+    q.x = H16<false>::pack(v[0], v[1]); q.y = H16<false>::pack(v[2], v[3]);
+    q.z = H16<false>::pack(v[4], v[5]); q.w = H16<false>::pack(v[6], v[7]);
+  }
+  return q;
+}
+
+// Auxiliary 16-bit operands of one 32-column chunk of one row, fetched ahead of the accumulator drain.
+struct AuxRegs {
+  uint4 a[4];  // residual (EPI_STORE) | u (EPI_DGELU) | g (EPI_DGELU_GRN)
+  uint4 b[4];  // gp (EPI_DGELU_GRN)
+};
+
+template <int EPI>
+__device__ __forceinline__ void load_aux(const GemmParams& p, long long row, int col0, bool row_ok, AuxRegs& x) {
+  const uint16_t* pa = nullptr;
+  long long lda = 0;
+  if constexpr (EPI == VB200_EPI_STORE) { pa = reinterpret_cast<const uint16_t*>(p.residual); lda = p.ldr; }
+  if constexpr (EPI == VB200_EPI_DGELU) { pa = reinterpret_cast<const uint16_t*>(p.aux); lda = p.ldaux; }
+  if constexpr (EPI == VB200_EPI_DGELU_GRN) {
+    if (p.tvec != nullptr) { pa = reinterpret_cast<const uint16_t*>(p.aux); lda = p.ldaux; }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    const bool ok = row_ok && col < p.N;
+    x.a[g] = make_uint4(0, 0, 0, 0);
+    if (pa != nullptr && ok) x.a[g] = __ldg(reinterpret_cast<const uint4*>(pa + row * lda + col));
+    if constexpr (EPI == VB200_EPI_DGELU_GRN) {
+      x.b[g] = make_uint4(0, 0, 0, 0);
+      if (ok) x.b[g] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux2) + row * p.ldaux2 + col));
+    }
+  }
+}
+
+// One group of 8 consecutive output columns of one row.  cv = staged [bias | s | t] for the tile (fp32, smem).
+template <int EPI, int BN>
+__device__ __forceinline__ void epilogue8(const GemmParams& p, const uint32_t* r, long long row, int col, int cl,
+                                          int split, const float* cv, const uint4& xa, const uint4& xb) {
+  const bool bf16 = p.bf16 != 0;
   float v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.bias != nullptr && split == 0) {
-    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + cv[cl + j];
   if constexpr (EPI == VB200_EPI_STORE) {
     if (p.act == VB200_ACT_RELU) {
 #pragma unroll
@@ -89,25 +139,48 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, const uint32_t* r
     }
     if (p.residual != nullptr) {
       float q[8];
-      load8<BF16>(reinterpret_cast<const uint16_t*>(p.residual) + row * p.ldr + col, q);
+      unpack8(bf16, xa, q);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += q[j];
     }
-    store8<BF16>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col, v);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
   } else if constexpr (EPI == VB200_EPI_GELU_DUAL) {
-    store8<BF16>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col, v);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
-    store8<BF16>(reinterpret_cast<uint16_t*>(p.out2) + row * p.ldo2 + col, v);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + row * p.ldo2 + col) = pack8(bf16, v);
+  } else if constexpr (EPI == VB200_EPI_GELU_GP) {
+    // out = gelu'(u), out2 = gelu(u): the backward never needs u itself
+    float gp[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float2 cdf, pdf;
+      const float2 u = make_float2(v[j], v[j + 1]);
+      gelu_parts2(u, cdf, pdf);
+      const float2 d = __ffma2_rn(u, pdf, cdf);
+      const float2 gl = __fmul2_rn(u, cdf);
+      gp[j] = d.x; gp[j + 1] = d.y;
+      v[j] = gl.x; v[j + 1] = gl.y;
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, gp);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + row * p.ldo2 + col) = pack8(bf16, v);
   } else if constexpr (EPI == VB200_EPI_DGELU) {
     float u[8];
-    load8<BF16>(reinterpret_cast<const uint16_t*>(p.aux) + row * p.ldaux + col, u);
+    unpack8(bf16, xa, u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= dgelu_f(u[j]);
-    store8<BF16>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col, v);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
+  } else if constexpr (EPI == VB200_EPI_DGELU_GRN) {
+    // dh = (acc * s[n,col] + g * t[n,col]) * gp:  g = aux, gp = aux2 = gelu'(u) saved by the forward epilogue
+    // (GRN + GELU backward fused into the fc2 dgrad; s / t staged as 1 / 0 when absent)
+    float g[8], gp[8];
+    unpack8(bf16, xa, g);
+    unpack8(bf16, xb, gp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(g[j], cv[2 * BN + cl + j], v[j] * cv[BN + cl + j]) * gp[j];
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
   } else {  // VB200_EPI_F32
-    float* o = reinterpret_cast<float*>(p.out) + (long long)split * p.split_out_stride +
-               row * p.ldo + col;
+    float* o = reinterpret_cast<float*>(p.out) + (long long)split * p.split_out_stride + row * p.ldo + col;
     if (p.atomic_out) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
@@ -179,7 +252,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           if constexpr (!MN_MAJOR) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+            const int brow = p.b_batch_rows > 0 ? (m0 / p.b_batch_rows) * p.N + n0 : n0;
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, brow);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
@@ -240,6 +314,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int e = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int half = e >> 2;       // which half of the BN columns
+    const int et = threadIdx.x - 64;
+    float* colv = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    constexpr int NCH = BN / 64;   // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -247,29 +324,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int t = unit - split * tiles;
       const int m0 = (t / p.tiles_n) * BM;
       const int n0 = (t % p.tiles_n) * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      // stage this tile's per-column vectors (bias and, for the fused GRN backward, s and t of the tile's sample)
+      float* cv = colv + acc * 3 * BN;
+      if (et < BN) {
+        const int col = n0 + et;
+        const bool ok = col < p.N;
+        cv[et] = (p.bias != nullptr && split == 0 && ok) ? __ldg(p.bias + col) : 0.0f;
+        if constexpr (EPI == VB200_EPI_DGELU_GRN) {
+          const long long ns = p.rows_per_sample > 0 ? m0 / p.rows_per_sample : 0;
+          cv[BN + et] = (p.svec != nullptr && ok) ? __ldg(p.svec + ns * p.N + col) : 1.0f;
+          cv[2 * BN + et] = (p.tvec != nullptr && ok) ? __ldg(p.tvec + ns * p.N + col) : 0.0f;
+        }
+      }
       const long long row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      AuxRegs aux[2];
+      load_aux<EPI>(p, row, n0 + half * (BN / 2), row_ok, aux[0]);
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // cv visible to all epilogue warps
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const uint32_t t_addr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         const int cc = half * (BN / 2) + c * 32;
         const int col0 = n0 + cc;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_addr + cc, r);
-        tmem_ld_wait();
-        if (row_ok) {
+        if (col0 < p.N) {  // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(t_addr + cc, r);
+          if (c + 1 < NCH) load_aux<EPI>(p, row, col0 + 32, row_ok, aux[(c + 1) & 1]);
+          tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              if (p.bf16)
-                epilogue8<EPI, true>(p, r + g * 8, row, col, split);
-              else
-                epilogue8<EPI, false>(p, r + g * 8, row, col, split);
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col < p.N)
+                epilogue8<EPI, BN>(p, r + g * 8, row, col, cc + g * 8, split, cv, aux[c & 1].a[g], aux[c & 1].b[g]);
             }
           }
         }
@@ -367,6 +457,8 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
       case VB200_EPI_STORE: return launch<BN, false, VB200_EPI_STORE>(ta, tb, p, grid, st);
       case VB200_EPI_GELU_DUAL: return launch<BN, false, VB200_EPI_GELU_DUAL>(ta, tb, p, grid, st);
       case VB200_EPI_DGELU: return launch<BN, false, VB200_EPI_DGELU>(ta, tb, p, grid, st);
+      case VB200_EPI_DGELU_GRN: return launch<BN, false, VB200_EPI_DGELU_GRN>(ta, tb, p, grid, st);
+      case VB200_EPI_GELU_GP: return launch<BN, false, VB200_EPI_GELU_GP>(ta, tb, p, grid, st);
       case VB200_EPI_F32: return launch<BN, false, VB200_EPI_F32>(ta, tb, p, grid, st);
     }
     return fail(VB200_ERR_INVALID, "unknown epilogue %d", epi);
@@ -386,11 +478,21 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
   VB_SUPPORTED(d->ldo % 8 == 0, "ldo (%lld) must be a multiple of 8", (long long)d->ldo);
   const bool bf16 = d->dtype == VB200_BF16;
   const int epi = d->epilogue;
-  if (epi == VB200_EPI_GELU_DUAL)
+  if (epi == VB200_EPI_GELU_DUAL || epi == VB200_EPI_GELU_GP)
     VB_REQUIRE(d->out2 != nullptr && d->ldo2 % 8 == 0, "GELU_DUAL needs out2 with ldo2 %% 8 == 0");
   if (epi == VB200_EPI_DGELU)
     VB_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "DGELU needs aux with ldaux %% 8 == 0");
   if (d->residual) VB_REQUIRE(d->ldr % 8 == 0, "ldr %% 8");
+  if (epi == VB200_EPI_DGELU_GRN && (d->svec || d->tvec))
+    VB_REQUIRE(d->rows_per_sample % BM == 0, "rows_per_sample (%d) must be a multiple of %d", d->rows_per_sample, BM);
+  if (epi == VB200_EPI_DGELU_GRN)
+    VB_REQUIRE(d->aux2 && d->ldaux2 % 8 == 0 && (!d->tvec || (d->aux && d->ldaux % 8 == 0)) &&
+                   ((!d->tvec && !d->svec) || d->rows_per_sample > 0),
+               "DGELU_GRN needs aux2 (gp); tvec needs aux (g); svec / tvec need rows_per_sample");
+  const int nb = d->b_batch_rows > 0 ? (d->M + d->b_batch_rows - 1) / d->b_batch_rows : 1;
+  if (d->b_batch_rows > 0)
+    VB_REQUIRE(!d->mn_major && d->b_batch_rows % BM == 0, "b_batch_rows (%d) must be a multiple of %d (K-major only)",
+               d->b_batch_rows, BM);
   int splits = d->k_splits > 0 ? d->k_splits : 1;
   VB_REQUIRE(splits == 1 || epi == VB200_EPI_F32, "k_splits > 1 needs EPI_F32");
   VB_REQUIRE(splits == 1 || d->atomic_out || d->split_out_stride > 0,
@@ -417,7 +519,7 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
   int rc;
   if (!d->mn_major) {
     if ((rc = make_tmap_2d(&ta, d->A, d->M, d->K, d->lda, BK, BM, bf16))) return rc;
-    if ((rc = make_tmap_2d(&tb, d->B, d->N, d->K, d->ldb, BK, bn, bf16))) return rc;
+    if ((rc = make_tmap_2d(&tb, d->B, (long long)d->N * nb, d->K, d->ldb, BK, bn, bf16))) return rc;
   } else {
     if ((rc = make_tmap_2d(&ta, d->A, d->K, d->M, d->lda, 64, BK, bf16))) return rc;
     if ((rc = make_tmap_2d(&tb, d->B, d->K, d->N, d->ldb, 64, BK, bf16))) return rc;
@@ -429,7 +531,9 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
   p.bf16 = bf16 ? 1 : 0;
   p.act = d->act;
   p.atomic_out = d->atomic_out;
-  p.ldo = d->ldo; p.ldo2 = d->ldo2; p.ldr = d->ldr; p.ldaux = d->ldaux;
+  p.ldo = d->ldo; p.ldo2 = d->ldo2; p.ldr = d->ldr; p.ldaux = d->ldaux; p.ldaux2 = d->ldaux2;
+  p.b_batch_rows = d->b_batch_rows; p.rows_per_sample = d->rows_per_sample;
+  p.aux2 = d->aux2; p.tvec = d->tvec; p.svec = d->svec;
   p.split_out_stride = d->atomic_out ? 0 : d->split_out_stride;
   p.out = d->out; p.out2 = d->out2; p.bias = d->bias; p.residual = d->residual; p.aux = d->aux;
   const long long units = (long long)tiles_m * tiles_n * splits;

@@ -152,11 +152,10 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ sum, const fl
   rstd[i] = rsqrtf(var + eps);
 }
 
-constexpr int HT_MAXO = 16;  // max (out_channels * 4)
 
 // out[n, o>>2, dz, 2y + ((o>>1)&1), 2x + (o&1)] = b1[o] + sum_c W1[o][c] * prelu((z - mean) * rstd)
 // one thread per row (n, dz, y, x); z [B, R, Cmid], R = Dz*H*W
-template <bool BF16>
+template <bool BF16, int HT_MAXO>
 __global__ void __launch_bounds__(128)
 head_tail_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ alpha, int alpha_n,
@@ -177,18 +176,20 @@ head_tail_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
     sa[i] = alpha[alpha_n == 1 ? 0 : i];
   }
   __syncthreads();
-  const long long R = (long long)Dz * H * W;
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = Dz * H * W;  // host guarantees per-sample extents < 2^31
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= R) return;
-  const int x = (int)(row % W);
-  const int y = (int)((row / W) % H);
-  const int dz = (int)(row / ((long long)W * H));
+  const int x = row % W;
+  const int y = (row / W) % H;
+  const int dz = row / (W * H);
+  z += (long long)n * R * (Cmid / 8);
+  out += (long long)n * (Co4 / 4) * Dz * 4 * H * W;
   float acc[HT_MAXO];
 #pragma unroll
   for (int o = 0; o < HT_MAXO; ++o) acc[o] = o < Co4 ? sb[o] : 0.f;
   const int C8 = Cmid / 8;
   for (int v = 0; v < C8; ++v) {
-    const uint4 t = __ldg(z + ((long long)n * R + row) * C8 + v);
+    const uint4 t = __ldg(z + row * C8 + v);
     const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
     float a[8];
 #pragma unroll
@@ -215,7 +216,7 @@ head_tail_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
   for (int o = 0; o < HT_MAXO; o += 2)
     if (o < Co4) {
       const int co = o >> 2, i = (o >> 1) & 1;
-      const long long oi = ((((long long)n * Co + co) * Dz + dz) * (2 * H) + 2 * y + i) * (2LL * W) + 2 * x;
+      const int oi = ((co * Dz + dz) * (2 * H) + 2 * y + i) * (2 * W) + 2 * x;
       *reinterpret_cast<uint32_t*>(out + oi) = H16<BF16>::pack(acc[o], acc[o + 1]);
     }
 }
@@ -223,7 +224,7 @@ head_tail_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
 // Backward, phase 1 (MODE 0): reductions  sdp[n,c] = sum dpre, sdpx[n,c] = sum dpre*xhat, dW1, db1, dalpha
 // Backward, phase 2 (MODE 1): dz = rstd * (dpre - sdp/R - xhat * sdpx/R), dbz[c] += sum dz
 // thread = (row, 8-channel chunk)
-template <bool BF16, int MODE>
+template <bool BF16, int MODE, int HT_MAXO>
 __global__ void __launch_bounds__(256)
 head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ alpha, int alpha_n,
@@ -241,7 +242,7 @@ head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
   float* s1 = red + Cmid;            // MODE 1: (sdp/R), (sdpx/R) staged after the dbz slot
   const int n = blockIdx.y;
   const int C8 = Cmid / 8;
-  const long long R = (long long)Dz * H * W;
+  const int R = Dz * H * W;
   const int nred = MODE == 0 ? (2 * Cmid + Co4 * Cmid + Co4 + Cmid) : (3 * Cmid);
   for (int i = threadIdx.x; i < Co4 * Cmid; i += blockDim.x) sW[i] = W1[i];
   for (int i = threadIdx.x; i < nred; i += blockDim.x) red[i] = 0.f;
@@ -257,11 +258,25 @@ head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
   }
   __syncthreads();
   const int v = threadIdx.x % C8, rl = threadIdx.x / C8, rstep = blockDim.x / C8;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(R, r0 + rows_per_block);
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
   const int Co = Co4 / 4;
+  z += (long long)n * R * C8;
+  if (MODE == 1) dz += (long long)n * R * C8;
+  dout += (long long)n * Co * Dz * 4 * H * W;
+  const int HW = H * W;
   float a_sdp[8], a_sdpx[8], a_dal[8], a_db[HT_MAXO];
   float a_dW[HT_MAXO][8];
+  float wr[HT_MAXO][8], mu8[8], rs8[8], al8[8];  // this thread's slice of W1 / mean / rstd / alpha in registers
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = (threadIdx.x % C8) * 8 + k;
+    mu8[k] = sm_[c];
+    rs8[k] = sr[c];
+    al8[k] = sa[c];
+#pragma unroll
+    for (int o = 0; o < HT_MAXO; ++o) wr[o][k] = o < Co4 ? sW[o * Cmid + c] : 0.f;
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) a_sdp[k] = a_sdpx[k] = a_dal[k] = 0.f;
 #pragma unroll
@@ -271,23 +286,24 @@ head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
     for (int k = 0; k < 8; ++k) a_dW[o][k] = 0.f;
   }
   if (rl < rstep) {
-    for (long long row = r0 + rl; row < r1; row += rstep) {
-      const int x = (int)(row % W);
-      const int y = (int)((row / W) % H);
-      const int dzi = (int)(row / ((long long)W * H));
+    for (int row = r0 + rl; row < r1; row += rstep) {
+      const int dzi = row / HW;
+      const int rem = row - dzi * HW;
+      const int y = rem / W;
+      const int x = rem - y * W;
       float dt[HT_MAXO];
 #pragma unroll
       for (int o = 0; o < HT_MAXO; o += 2) {
         dt[o] = dt[o + 1] = 0.f;
         if (o < Co4) {
           const int co = o >> 2, i = (o >> 1) & 1;
-          const long long oi = ((((long long)n * Co + co) * Dz + dzi) * (2 * H) + 2 * y + i) * (2LL * W) + 2 * x;
+          const int oi = ((co * Dz + dzi) * (2 * H) + 2 * y + i) * (2 * W) + 2 * x;
           const float2 f = H16<BF16>::unpack(__ldg(reinterpret_cast<const uint32_t*>(dout + oi)));
           dt[o] = f.x;
           dt[o + 1] = f.y;
         }
       }
-      const uint4 t = __ldg(z + ((long long)n * R + row) * C8 + v);
+      const uint4 t = __ldg(z + row * C8 + v);
       const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
       float xh[8];
 #pragma unroll
@@ -299,22 +315,19 @@ head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
       float dpre[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int c = v * 8 + k;
-        xh[k] = (xh[k] - sm_[c]) * sr[c];
+        xh[k] = (xh[k] - mu8[k]) * rs8[k];
         float da = 0.f;
 #pragma unroll
-        for (int o = 0; o < HT_MAXO; ++o)
-          if (o < Co4) da = fmaf(sW[o * Cmid + c], dt[o], da);
+        for (int o = 0; o < HT_MAXO; ++o) da = fmaf(wr[o][k], dt[o], da);
         const bool pos = xh[k] > 0.f;
-        dpre[k] = pos ? da : da * sa[c];
+        dpre[k] = pos ? da : da * al8[k];
         if (MODE == 0) {
-          const float act = pos ? xh[k] : xh[k] * sa[c];
+          const float act = pos ? xh[k] : xh[k] * al8[k];
           a_sdp[k] += dpre[k];
           a_sdpx[k] = fmaf(dpre[k], xh[k], a_sdpx[k]);
           if (!pos) a_dal[k] = fmaf(da, xh[k], a_dal[k]);
 #pragma unroll
-          for (int o = 0; o < HT_MAXO; ++o)
-            if (o < Co4) a_dW[o][k] = fmaf(dt[o], act, a_dW[o][k]);
+          for (int o = 0; o < HT_MAXO; ++o) a_dW[o][k] = fmaf(dt[o], act, a_dW[o][k]);
         }
       }
       if (MODE == 0) {
@@ -328,11 +341,11 @@ head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int c = v * 8 + k;
-          o8[k] = sr[c] * (dpre[k] - s1[c] - xh[k] * s1[Cmid + c]);
+          o8[k] = rs8[k] * (dpre[k] - s1[c] - xh[k] * s1[Cmid + c]);
         }
         const uint4 q = make_uint4(H16<BF16>::pack(o8[0], o8[1]), H16<BF16>::pack(o8[2], o8[3]),
                                    H16<BF16>::pack(o8[4], o8[5]), H16<BF16>::pack(o8[6], o8[7]));
-        dz[((long long)n * R + row) * C8 + v] = q;
+        dz[row * C8 + v] = q;
         const uint32_t w4o[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -430,16 +443,18 @@ extern "C" int vb200_head_tail_fwd(const void* z, const float* mean, const float
                                    int alpha_n, const float* W1, const float* b1, void* out, int B, int Dz,
                                    int H, int W, int Cmid, int Co4, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(z && mean && rstd && alpha && W1 && b1 && out, "null pointer");
-  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= HT_MAXO, "head tail: Cmid %d / Co4 %d", Cmid, Co4);
+  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= 16, "head tail: Cmid %d / Co4 %d", Cmid, Co4);
   VB_REQUIRE(alpha_n == 1 || alpha_n == Cmid, "PReLU parameter count %d", alpha_n);
   const long long R = (long long)Dz * H * W;
+  VB_SUPPORTED(R * Cmid < (1LL << 31) && R * Co4 < (1LL << 31), "head: per-sample extent too large");
   dim3 grid((unsigned)((R + 127) / 128), B);
   const size_t smem = sizeof(float) * (Co4 * Cmid + Co4 + 3 * Cmid);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == VB200_BF16)
-    head_tail_fwd_kernel<true><<<grid, 128, smem, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, b1, (uint16_t*)out, Dz, H, W, Cmid, Co4);
-  else
-    head_tail_fwd_kernel<false><<<grid, 128, smem, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, b1, (uint16_t*)out, Dz, H, W, Cmid, Co4);
+#define HTF(BF, MO) head_tail_fwd_kernel<BF, MO><<<grid, 128, smem, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, b1, (uint16_t*)out, Dz, H, W, Cmid, Co4)
+  if (dtype == VB200_BF16) { if (Co4 <= 4) HTF(true, 4); else if (Co4 <= 8) HTF(true, 8); else HTF(true, 16); }
+  else if (dtype == VB200_FP16) { if (Co4 <= 4) HTF(false, 4); else if (Co4 <= 8) HTF(false, 8); else HTF(false, 16); }
+  else return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+#undef HTF
   return check_launch("vb200_head_tail_fwd");
 }
 
@@ -451,16 +466,18 @@ extern "C" int vb200_head_tail_bwd(int phase, const void* z, const float* mean, 
                                    float* dbz, int B, int Dz, int H, int W, int Cmid, int Co4, int dtype,
                                    vb200_stream_t stream) {
   VB_REQUIRE(z && mean && rstd && alpha && W1 && dout && sdp && sdpx, "null pointer");
-  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= HT_MAXO && 256 % (Cmid / 8) == 0, "head tail: Cmid %d / Co4 %d", Cmid, Co4);
+  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= 16 && 256 % (Cmid / 8) == 0, "head tail: Cmid %d / Co4 %d", Cmid, Co4);
   const long long R = (long long)Dz * H * W;
-  long long rpb = (R * B + 148 * 4 - 1) / (148 * 4);
+  VB_SUPPORTED(R * Cmid < (1LL << 31) && R * Co4 < (1LL << 31), "head: per-sample extent too large");
+  long long rpb = (R * B + 148 * 16 - 1) / (148 * 16);
   if (rpb < 256) rpb = 256;
   if (rpb > R) rpb = R;
   dim3 grid((unsigned)((R + rpb - 1) / rpb), B);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem0 = sizeof(float) * (Co4 * Cmid + 3 * Cmid + 2 * Cmid + Co4 * Cmid + Co4 + Cmid);
   const size_t smem1 = sizeof(float) * (Co4 * Cmid + 3 * Cmid + 3 * Cmid);
-#define HT(BF, MODE, SM) head_tail_bwd_kernel<BF, MODE><<<grid, 256, SM, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, (const uint16_t*)dout, sdp, sdpx, dW1, db1, dalpha, (uint4*)dz, dbz, Dz, H, W, Cmid, Co4, (int)rpb)
+#define HT2(BF, MODE, SM, MO) head_tail_bwd_kernel<BF, MODE, MO><<<grid, 256, SM, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, (const uint16_t*)dout, sdp, sdpx, dW1, db1, dalpha, (uint4*)dz, dbz, Dz, H, W, Cmid, Co4, (int)rpb)
+#define HT(BF, MODE, SM) do { if (Co4 <= 4) HT2(BF, MODE, SM, 4); else if (Co4 <= 8) HT2(BF, MODE, SM, 8); else HT2(BF, MODE, SM, 16); } while (0)
   if (phase == 0) {
     VB_REQUIRE(dW1 && db1 && dalpha, "null pointer");
     if (dtype == VB200_BF16) HT(true, 0, smem0); else HT(false, 0, smem0);
@@ -469,5 +486,6 @@ extern "C" int vb200_head_tail_bwd(int phase, const void* z, const float* mean, 
     if (dtype == VB200_BF16) HT(true, 1, smem1); else HT(false, 1, smem1);
   }
 #undef HT
+#undef HT2
   return check_launch("vb200_head_tail_bwd");
 }

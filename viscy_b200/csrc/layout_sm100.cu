@@ -196,6 +196,17 @@ cast_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long
   dst[idx] = *reinterpret_cast<uint16_t*>(&hv);
 }
 
+// conv_dw.weight [C][49] fp32 -> tap-major [49][C] and its spatially flipped copy (dgrad taps), one launch
+__global__ void __launch_bounds__(256)
+dw_pack_kernel(const float* __restrict__ w, float* __restrict__ wt, float* __restrict__ wtf, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 49 * C) return;
+  const int tap = idx / C, c = idx % C;
+  const float v = w[c * 49 + tap];
+  wt[idx] = v;
+  wtf[(48 - tap) * C + c] = v;
+}
+
 static inline unsigned blocks_for(long long total, int bs = 256) { return (unsigned)((total + bs - 1) / bs); }
 
 }  // namespace vb
@@ -303,4 +314,10 @@ extern "C" int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t C
   else
     return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
   return check_launch("vb200_cast_pack");
+}
+
+extern "C" int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t stream) {
+  VB_REQUIRE(w && wt && wtf, "null pointer");
+  dw_pack_kernel<<<blocks_for(49LL * C), 256, 0, (cudaStream_t)stream>>>(w, wt, wtf, C);
+  return check_launch("vb200_dw_pack");
 }

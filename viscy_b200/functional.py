@@ -38,7 +38,7 @@ def linear_bwd(dout2d, a2d, w, *, need_da=True, need_db=True):
     K = w.numel() // N
     M = dout2d.shape[0]
     dw = ops.gemm(dout2d, a2d, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(N, K, M))
-    db = ops.colsum(dout2d) if need_db else None
+    db = ops.colreduce(dout2d.view(1, M, N), 0).view(N) if (need_db and N % 8 == 0) else (ops.colsum(dout2d) if need_db else None)
     da = None
     if need_da:
         wt = ops.cast_pack(w, dout2d.dtype, transpose=True)  # [K, N]
@@ -48,9 +48,7 @@ def linear_bwd(dout2d, a2d, w, *, need_da=True, need_db=True):
 
 def _dw_taps(w):
     """conv_dw.weight [C,1,7,7] fp32 -> (tap-major [49,C], flipped tap-major [49,C])"""
-    C = w.shape[0]
-    w2 = w.detach().reshape(C, 49)
-    return w2.t().contiguous(), w2.flip(1).t().contiguous()
+    return ops.dw_pack(w)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -65,18 +63,34 @@ class ConvNeXtBlockFn(Function):
     def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b, grn_w, grn_b, gamma):
         B, H, W, C = x.shape
         M = B * H * W
-        wt, _ = _dw_taps(dw_w)
+        wt, wt_flip = _dw_taps(dw_w)
+        ctx.wt_flip = wt_flip
         d = ops.dwconv7(x, wt, dw_b)
         l, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS)
         l2 = l.view(M, C)
         C4 = fc1_w.shape[0]
         use_grn = grn_w is not None
+        R = H * W
+        fused = use_grn and R % 128 == 0 and B <= 16
+        if fused:
+            # gp = gelu'(u) and g = gelu(u) from the fc1 epilogue; GRN scale folded into per-sample fc2 weights
+            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP)
+            sumsq = ops.colreduce(y2.view(B, R, C4), 1)
+            s = torch.empty_like(sumsq)
+            ops._call("vb200_grn_coef_fwd", ops._p(sumsq), ops._p(grn_w), ops._p(s), B, C4, ops.C.c_float(1e-6))
+            w2 = fc2_w.detach().reshape(C, C4)
+            w2s = ops.grn_pack_w2(w2, s, x.dtype)
+            b2e = ops.grn_bias_eff(w2, grn_b.detach(), fc2_b.detach())
+            out = ops.gemm(y2, w2s, bias=b2e, residual=x.view(M, C), b_batch_rows=R)
+            ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, grn_b)
+            ctx.use_grn, ctx.fused = True, True
+            return out.view(B, H, W, C)
         if use_grn:
             h = linear_fwd(l2, fc1_w, fc1_b)
             y, sumsq, s = ops.gelu_grn_fwd(h.view(B, H * W, C4), grn_w, grn_b)
             y2 = y.view(M, C4)
         else:
-            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_DUAL)
+            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP)  # h := gelu'(u)
             sumsq = s = None
         if gamma is not None:
             w2_eff = fc2_w.detach().reshape(C, C4) * gamma.detach()[:, None]
@@ -84,6 +98,7 @@ class ConvNeXtBlockFn(Function):
         else:
             w2_eff, b2_eff = fc2_w.detach().reshape(C, C4), fc2_b.detach()
         out = ops.gemm(y2, ops.cast_pack(w2_eff, x.dtype), bias=b2_eff.contiguous(), residual=x.view(M, C))
+        ctx.fused = False
         ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma)
         ctx.use_grn = use_grn
         return out.view(B, H, W, C)
@@ -97,32 +112,52 @@ class ConvNeXtBlockFn(Function):
         C4 = fc1_w.shape[0]
         dout = dout.contiguous()
         do2 = dout.view(M, C)
-        if gamma is not None:
-            w2_eff = fc2_w.reshape(C, C4) * gamma[:, None]
+        ar = ops.Arena(x.device, [C, (B + 2) * C4, C4, 2 * C, 50 * C])
+        if ctx.fused:
+            grn_b = gamma  # the 16th saved tensor is grn.bias on the fused path (V2 blocks carry no layer scale)
+            gamma = None
+            R = H * W
+            w2 = fc2_w.reshape(C, C4)
+            db2 = ops.colreduce(do2.view(1, M, C), 0, ar).view(C)
+            # per-sample wgrad partials P[n] = dout_n^T g_n  (g = y2 here)
+            P = ops.gemm(do2, y2, mn_major=True, epilogue=L.EPI_F32, k_splits=B, split_slabs=True)
+            dw2, S1, dgb = ops.grn_wgrad_finish(P, w2, s, grn_b, db2, ar)
+            t = torch.empty_like(S1)
+            dgw = ar.take(C4)
+            ops._call("vb200_grn_coef_bwd", ops._p(sumsq), ops._p(S1), ops._p(grn_w), ops._p(t), ops._p(dgw), B, C4,
+                      ops.C.c_float(1e-6))
+            w2t = ops.cast_pack(w2, x.dtype, transpose=True)  # [C4, C]
+            dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux=y2, aux2=h, tvec=t, svec=s, rows_per_sample=R)
+            db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
+            dw2 = dw2.view(fc2_w.shape)
+            dgamma = None
         else:
-            w2_eff = fc2_w.reshape(C, C4)
-        dy, dw2_eff, db2_eff = linear_bwd(do2, y2, w2_eff)
-        if gamma is not None:
-            # out = gamma * (y W2^T + b2): chain rule through the folded layer scale
-            dgamma = (dw2_eff * fc2_w.reshape(C, C4)).sum(1) + db2_eff * fc2_b
-            dw2 = (dw2_eff * gamma[:, None]).view(fc2_w.shape)
-            db2 = db2_eff * gamma
-        else:
-            dgamma, dw2, db2 = None, dw2_eff.view(fc2_w.shape), db2_eff
-        if ctx.use_grn:
-            dh, dgw, dgb, db1 = ops.gelu_grn_bwd(h.view(B, H * W, C4), dy.view(B, H * W, C4), sumsq, s, grn_w)
-        else:
-            ones = torch.ones((B, C4), device=x.device, dtype=torch.float32)
-            dh = torch.empty_like(h)
-            db1 = torch.zeros((C4,), device=x.device, dtype=torch.float32)
-            ops._call("vb200_grn_apply_bwd", ops._p(h), ops._p(dy), ops._p(ones), ops._p(None), ops._p(dh), ops._p(db1),
-                      B, H * W, C4, L.dtype_code(h.dtype))
-            dgw = dgb = None
+            if gamma is not None:
+                w2_eff = fc2_w.reshape(C, C4) * gamma[:, None]
+            else:
+                w2_eff = fc2_w.reshape(C, C4)
+            if ctx.use_grn:
+                dy, dw2_eff, db2_eff = linear_bwd(do2, y2, w2_eff)
+                dw2, db2, dgamma = dw2_eff.view(fc2_w.shape), db2_eff, None
+                dh, dgw, dgb, db1 = ops.gelu_grn_bwd(h.view(B, H * W, C4), dy.view(B, H * W, C4), sumsq, s, grn_w)
+            else:
+                # ConvNeXt-V1: GELU backward rides in the fc2-dgrad epilogue (h holds gelu'(u))
+                _, dw2_eff, db2_eff = linear_bwd(do2, y2, w2_eff, need_da=False)
+                w2t = ops.cast_pack(w2_eff, x.dtype, transpose=True)
+                dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux2=h)
+                db1 = ops.colreduce(dh.view(1, M, C4), 0).view(C4)
+                dgw = dgb = None
+                if gamma is not None:
+                    # out = gamma * (y W2^T + b2): chain rule through the folded layer scale
+                    dgamma = (dw2_eff * fc2_w.reshape(C, C4)).sum(1) + db2_eff * fc2_b
+                    dw2 = (dw2_eff * gamma[:, None]).view(fc2_w.shape)
+                    db2 = db2_eff * gamma
+                else:
+                    dgamma, dw2, db2 = None, dw2_eff.view(fc2_w.shape), db2_eff
         dl, dw1, _ = linear_bwd(dh.view(M, C4), l.view(M, C), fc1_w, need_db=False)
-        dd, dlnw, dlnb = ops.layernorm_bwd(dl.view(B, H, W, C), d, mean, rstd, ln_w)
-        _, wt_flip = _dw_taps(dw_w)
-        dx = ops.dwconv7(dd, wt_flip, None, add=dout)
-        dwt, ddb = ops.dwconv7_wgrad(x, dd)
+        dd, dlnw, dlnb = ops.layernorm_bwd(dl.view(B, H, W, C), d, mean, rstd, ln_w, ar)
+        dx = ops.dwconv7(dd, ctx.wt_flip, None, add=dout)
+        dwt, ddb = ops.dwconv7_wgrad(x, dd, arena=ar)
         ddw = dwt.t().reshape(dw_w.shape)
         return dx, ddw, ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma
 

@@ -33,6 +33,12 @@ def gemm(
     out: torch.Tensor | None = None,
     out2: torch.Tensor | None = None,
     accumulate: bool = False,
+    b_batch_rows: int = 0,
+    aux2: torch.Tensor | None = None,
+    tvec: torch.Tensor | None = None,
+    svec: torch.Tensor | None = None,
+    rows_per_sample: int = 0,
+    split_slabs: bool = False,
 ) -> torch.Tensor | tuple[torch.Tensor, torch.Tensor]:
     """tcgen05 GEMM.  K-major form: a [M,K], b [N,K] -> [M,N].  MN-major (wgrad) form: a [P,M], b [P,N]."""
     lda = _rowmajor2d(a, "a")
@@ -45,6 +51,8 @@ def gemm(
     else:
         M, K = a.shape
         N, K2 = b.shape
+        if b_batch_rows:
+            N = N // (-(-M // b_batch_rows))
     if K != K2:
         raise ValueError(f"reduction dims differ: {K} vs {K2}")
     d = L.GemmDesc()
@@ -54,6 +62,19 @@ def gemm(
     d.epilogue = epilogue
     d.act = act
     d.k_splits = max(1, k_splits)
+    d.b_batch_rows = b_batch_rows
+    d.rows_per_sample = rows_per_sample
+    if epilogue == L.EPI_F32 and split_slabs:
+        # one fp32 slab per K-split (no atomics): out [k_splits, M, N]
+        if out is None:
+            out = torch.empty((d.k_splits, M, N), device=a.device, dtype=torch.float32)
+        d.atomic_out = 0
+        d.split_out_stride = M * N
+        d.lda, d.ldb = lda, ldb
+        d.ldo = N
+        d.A, d.B, d.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
+        L.check(L.lib().vb200_gemm(C.byref(d), L.stream_ptr()), "vb200_gemm")
+        return out
     if epilogue == L.EPI_F32:
         if out is None:
             out = (torch.zeros if (k_splits > 1 or accumulate) else torch.empty)(
@@ -66,7 +87,7 @@ def gemm(
     d.lda, d.ldb = lda, ldb
     d.ldo = _rowmajor2d(out, "out")
     d.A, d.B, d.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
-    if epilogue == L.EPI_GELU_DUAL:
+    if epilogue in (L.EPI_GELU_DUAL, L.EPI_GELU_GP):
         if out2 is None:
             out2 = torch.empty((M, N), device=a.device, dtype=a.dtype)
         d.out2 = out2.data_ptr()
@@ -81,8 +102,19 @@ def gemm(
     if aux is not None:
         d.aux = aux.data_ptr()
         d.ldaux = _rowmajor2d(aux, "aux")
+    if aux2 is not None:
+        d.aux2 = aux2.data_ptr()
+        d.ldaux2 = _rowmajor2d(aux2, "aux2")
+    if tvec is not None:
+        if tvec.dtype != torch.float32 or not tvec.is_contiguous():
+            raise ValueError("tvec must be contiguous fp32")
+        d.tvec = tvec.data_ptr()
+    if svec is not None:
+        if svec.dtype != torch.float32 or not svec.is_contiguous():
+            raise ValueError("svec must be contiguous fp32")
+        d.svec = svec.data_ptr()
     L.check(L.lib().vb200_gemm(C.byref(d), L.stream_ptr()), "vb200_gemm")
-    if epilogue == L.EPI_GELU_DUAL:
+    if epilogue in (L.EPI_GELU_DUAL, L.EPI_GELU_GP):
         return out, out2
     return out
 
@@ -119,6 +151,30 @@ def cast_pack(w: torch.Tensor, dtype: torch.dtype, transpose: bool = False) -> t
     return out
 
 
+class Arena:
+    """One zero-filled fp32 allocation handed out in slices (accumulators that kernels add into)."""
+
+    def __init__(self, device, sizes):
+        self.buf = torch.zeros((int(sum(sizes)),), device=device, dtype=torch.float32)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n
+        return v
+
+
+def dw_pack(w):
+    """conv_dw.weight [C,1,7,7] fp32 -> (tap-major [49,C], flipped tap-major [49,C])."""
+    Cc = w.shape[0]
+    out = torch.empty((2, 49, Cc), device=w.device, dtype=torch.float32)
+    _call("vb200_dw_pack", _p(_f32(w.detach(), "conv_dw.weight")), _p(out[0]), _p(out[1]), Cc)
+    return out[0], out[1]
+
+
 # ----------------------------------------------------------------------------------------------
 # ConvNeXt block pieces
 def dwconv7(x, wt, bias=None, add=None):
@@ -130,10 +186,13 @@ def dwconv7(x, wt, bias=None, add=None):
     return y
 
 
-def dwconv7_wgrad(x, dy, want_bias=True):
+def dwconv7_wgrad(x, dy, want_bias=True, arena=None):
     B, H, W, Cc = x.shape
-    dwt = torch.zeros((49, Cc), device=x.device, dtype=torch.float32)
-    db = torch.zeros((Cc,), device=x.device, dtype=torch.float32) if want_bias else None
+    if arena is not None:
+        dwt, db = arena.take(49, Cc), (arena.take(Cc) if want_bias else None)
+    else:
+        dwt = torch.zeros((49, Cc), device=x.device, dtype=torch.float32)
+        db = torch.zeros((Cc,), device=x.device, dtype=torch.float32) if want_bias else None
     _call("vb200_dwconv7_wgrad", _p(_act(x, "x")), _p(_act(dy, "dy")), _p(dwt), _p(db), B, H, W, Cc, L.dtype_code(x.dtype))
     return dwt, db
 
@@ -151,12 +210,15 @@ def layernorm_fwd(x, gamma, beta, eps):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma):
+def layernorm_bwd(dy, x, mean, rstd, gamma, arena=None):
     Cc = x.shape[-1]
     M = x.numel() // Cc
     dx = torch.empty_like(x)
-    dgamma = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
-    dbeta = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
+    if arena is not None:
+        dgamma, dbeta = arena.take(Cc), arena.take(Cc)
+    else:
+        dgamma = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
+        dbeta = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
     _call("vb200_layernorm_bwd", _p(_act(dy, "dy")), _p(_act(x, "x")), _p(mean), _p(rstd), _p(_f32(gamma, "gamma")),
           _p(dx), _p(dgamma), _p(dbeta), C.c_int64(M), Cc, L.dtype_code(x.dtype))
     return dx, dgamma, dbeta
@@ -339,3 +401,40 @@ def head_tail_bwd(z, mean, rstd, alpha, W1, dout, Dz, H, W):
         _call("vb200_head_tail_bwd", phase, _p(z), _p(mean), _p(rstd), _p(alpha), alpha.numel(), _p(W1), _p(dout),
               _p(sdp), _p(sdpx), _p(dW1), _p(db1), _p(dalpha), _p(dz), _p(dbz), B, Dz, H, W, Cmid, Co4, dt)
     return dz, dW1, db1, dalpha, dbz
+
+
+# ----------------------------------------------------------------------------------------------
+# fused GRN path helpers
+def colreduce(x, mode, arena=None):
+    """x [B,R,C] 16-bit -> fp32 [B,C]: mode 0 column sums, mode 1 column sums of squares."""
+    _act(x, "x")
+    B, R, Cc = x.shape
+    out = arena.take(B, Cc) if arena is not None else torch.zeros((B, Cc), device=x.device, dtype=torch.float32)
+    _call("vb200_colreduce", _p(x), _p(out), B, C.c_int64(R), Cc, mode, L.dtype_code(x.dtype))
+    return out
+
+
+def grn_pack_w2(w2, s, dtype):
+    """w2 fp32 [C,C4], s fp32 [nb,C4] -> 16-bit [nb*C, C4]: per-sample GRN-scaled fc2 weights."""
+    Cc, C4 = w2.shape
+    nb = s.shape[0]
+    out = torch.empty((nb * Cc, C4), device=w2.device, dtype=dtype)
+    _call("vb200_grn_pack_w2", _p(_f32(w2, "w2")), _p(_f32(s, "s")), _p(out), nb, Cc, C4, L.dtype_code(dtype))
+    return out
+
+
+def grn_bias_eff(w2, bgrn, b2):
+    Cc, C4 = w2.shape
+    out = torch.empty((Cc,), device=w2.device, dtype=torch.float32)
+    _call("vb200_grn_bias_eff", _p(_f32(w2, "w2")), _p(_f32(bgrn, "bgrn")), _p(_f32(b2, "b2")), _p(out), Cc, C4)
+    return out
+
+
+def grn_wgrad_finish(P, w2, s, bgrn, db2, arena=None):
+    """P fp32 [nb,C,C4] -> (dW2 [C,C4], S1 [nb,C4], dbgrn [C4])"""
+    nb, Cc, C4 = P.shape
+    dW2 = torch.empty((Cc, C4), device=P.device, dtype=torch.float32)
+    acc = arena.take(nb + 1, C4) if arena is not None else torch.zeros((nb + 1, C4), device=P.device, dtype=torch.float32)
+    _call("vb200_grn_wgrad_finish", _p(P), _p(_f32(w2, "w2")), _p(_f32(s, "s")), _p(_f32(bgrn, "bgrn")), _p(_f32(db2, "db2")),
+          _p(dW2), _p(acc[:nb]), _p(acc[nb]), nb, Cc, C4)
+    return dW2, acc[:nb], acc[nb]

@@ -32,7 +32,9 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int COLV_BYTES = 2 * 3 * BN * 4;  // [2 tiles in flight][bias, s, t][BN] fp32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES;
+  static constexpr int STG_BYTES = NUM_EPI_WARPS * 2048;  // per-warp 32 rows x 64 B store-staging tile
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES + STG_BYTES;
 };
 
 struct GemmParams {
@@ -121,14 +123,44 @@ __device__ __forceinline__ void load_aux(const GemmParams& p, long long row, int
   }
 }
 
-// One group of 8 consecutive output columns of one row.  cv = staged [bias | s | t] for the tile (fp32, smem).
-template <int EPI, int BN>
-__device__ __forceinline__ void epilogue8(const GemmParams& p, const uint32_t* r, long long row, int col, int cl,
-                                          int split, const float* cv, const uint4& xa, const uint4& xb) {
-  const bool bf16 = p.bf16 != 0;
-  float v[8];
+// Store one 32-row x 64-byte tile (this warp's rows, 16 B per lane and group) through a swizzled shared-memory
+// staging tile so that global stores are row-contiguous: 4 lanes cover one row's 64 B, one instruction covers 8 rows.
+// `vals` = this lane's row: 4 x uint4.  ATOMIC: red.add.v4.f32 instead of a store (fp32 data).
+template <bool ATOMIC>
+__device__ __forceinline__ void stage_store(uint8_t* stg, int lane, const uint4* vals, void* gbase, long long ld_bytes,
+                                            long long row0, int rows_valid, long long col_byte0, int cols16_valid) {
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + cv[cl + j];
+  for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ sw) << 4)) = vals[g];
+  __syncwarp();
+  const int ch = lane & 3;
+  if (ch < cols16_valid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 2) + 8 * i;
+      if (rr < rows_valid) {
+        const uint4 q = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+        uint8_t* dst = reinterpret_cast<uint8_t*>(gbase) + (row0 + rr) * ld_bytes + col_byte0 + ch * 16;
+        if constexpr (ATOMIC) {
+          atomicAdd(reinterpret_cast<float4*>(dst), make_float4(__uint_as_float(q.x), __uint_as_float(q.y),
+                                                                 __uint_as_float(q.z), __uint_as_float(q.w)));
+        } else {
+          *reinterpret_cast<uint4*>(dst) = q;
+        }
+      }
+    }
+  }
+}
+
+// Epilogue math for 8 consecutive columns of one row.  cv = staged [bias | s | t] of the tile (fp32, smem).
+// v: accumulators in, primary result out; w: secondary result (dual-output epilogues).
+template <int EPI, int BN>
+__device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, float* w, int cl, const float* cv,
+                                               const uint4& xa, const uint4& xb) {
+  const bool bf16 = p.bf16 != 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] += cv[cl + j];
   if constexpr (EPI == VB200_EPI_STORE) {
     if (p.act == VB200_ACT_RELU) {
 #pragma unroll
@@ -143,15 +175,11 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, const uint32_t* r
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += q[j];
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
   } else if constexpr (EPI == VB200_EPI_GELU_DUAL) {
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + row * p.ldo2 + col) = pack8(bf16, v);
+    for (int j = 0; j < 8; ++j) w[j] = gelu_f(v[j]);
   } else if constexpr (EPI == VB200_EPI_GELU_GP) {
-    // out = gelu'(u), out2 = gelu(u): the backward never needs u itself
-    float gp[8];
+    // v = gelu'(u), w = gelu(u): the backward never needs u itself
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       float2 cdf, pdf;
@@ -159,35 +187,21 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, const uint32_t* r
       gelu_parts2(u, cdf, pdf);
       const float2 d = __ffma2_rn(u, pdf, cdf);
       const float2 gl = __fmul2_rn(u, cdf);
-      gp[j] = d.x; gp[j + 1] = d.y;
-      v[j] = gl.x; v[j + 1] = gl.y;
+      v[j] = d.x; v[j + 1] = d.y;
+      w[j] = gl.x; w[j + 1] = gl.y;
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, gp);
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + row * p.ldo2 + col) = pack8(bf16, v);
   } else if constexpr (EPI == VB200_EPI_DGELU) {
     float u[8];
     unpack8(bf16, xa, u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= dgelu_f(u[j]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
   } else if constexpr (EPI == VB200_EPI_DGELU_GRN) {
     // dh = (acc * s[n,col] + g * t[n,col]) * gp:  g = aux, gp = aux2 = gelu'(u) saved by the forward epilogue
-    // (GRN + GELU backward fused into the fc2 dgrad; s / t staged as 1 / 0 when absent)
     float g[8], gp[8];
     unpack8(bf16, xa, g);
     unpack8(bf16, xb, gp);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaf(g[j], cv[2 * BN + cl + j], v[j] * cv[BN + cl + j]) * gp[j];
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + col) = pack8(bf16, v);
-  } else {  // VB200_EPI_F32
-    float* o = reinterpret_cast<float*>(p.out) + (long long)split * p.split_out_stride + row * p.ldo + col;
-    if (p.atomic_out) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
-    } else {
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    }
   }
 }
 
@@ -316,6 +330,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = e >> 2;       // which half of the BN columns
     const int et = threadIdx.x - 64;
     float* colv = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES + 256 + C::COLV_BYTES + e * 2048;
     constexpr int NCH = BN / 64;   // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -354,12 +369,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld32(t_addr + cc, r);
           if (c + 1 < NCH) load_aux<EPI>(p, row, col0 + 32, row_ok, aux[(c + 1) & 1]);
           tmem_ld_wait();
-          if (row_ok) {
+          // this warp's 32 rows x 32 columns: math per row, then row-contiguous stores through the staging tile
+          const long long row0 = m0 + quarter * 32;
+          const int rows_valid = (int)min(32LL, (long long)p.M - row0);
+          const int cols8_valid = min(4, (p.N - col0) >> 3);
+          if (rows_valid > 0) {
+            uint4 o1[4], o2[4];
+            float f32buf[32];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col < p.N)
-                epilogue8<EPI, BN>(p, r + g * 8, row, col, cc + g * 8, split, cv, aux[c & 1].a[g], aux[c & 1].b[g]);
+              float v[8], w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              epilogue_math8<EPI, BN>(p, v, w, cc + g * 8, cv, aux[c & 1].a[g], aux[c & 1].b[g]);
+              if constexpr (EPI == VB200_EPI_F32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f32buf[g * 8 + j] = v[j];
+              } else {
+                o1[g] = pack8(p.bf16 != 0, v);
+                if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP) o2[g] = pack8(p.bf16 != 0, w);
+              }
+            }
+            if constexpr (EPI == VB200_EPI_F32) {
+              float* ob = reinterpret_cast<float*>(p.out) + (long long)split * p.split_out_stride;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {  // 16 fp32 columns (64 B per row) at a time
+                uint4 q[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  q[g] = make_uint4(__float_as_uint(f32buf[hh * 16 + g * 4]), __float_as_uint(f32buf[hh * 16 + g * 4 + 1]),
+                                    __float_as_uint(f32buf[hh * 16 + g * 4 + 2]), __float_as_uint(f32buf[hh * 16 + g * 4 + 3]));
+                const int c4v = min(4, (p.N - (col0 + hh * 16)) >> 2);
+                if (p.atomic_out)
+                  stage_store<true>(stg, lane, q, ob, p.ldo * 4, row0, rows_valid, (long long)(col0 + hh * 16) * 4, c4v);
+                else
+                  stage_store<false>(stg, lane, q, ob, p.ldo * 4, row0, rows_valid, (long long)(col0 + hh * 16) * 4, c4v);
+              }
+            } else {
+              stage_store<false>(stg, lane, o1, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
+              if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP)
+                stage_store<false>(stg, lane, o2, p.out2, p.ldo2 * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
             }
           }
         }

@@ -9,3 +9,25 @@ architecture registries.
 from .unext2 import UNeXt2  # noqa: F401
 
 __all__ = ["UNeXt2"]
+
+
+def patch_viscy() -> list[str]:
+    """Swap the reference's architecture registry entries for the B200-native classes.
+
+    Touches only modules that are importable; returns the list of patched registries."""
+    import importlib
+
+    patched = []
+    for mod_name, attr in (("cytoland.engine", "_UNET_ARCHITECTURE"), ("dynacell.engine", "_ARCHITECTURE")):
+        try:
+            mod = importlib.import_module(mod_name)
+        except Exception:
+            continue
+        reg = getattr(mod, attr, None)
+        if isinstance(reg, dict) and "UNeXt2" in reg:
+            reg["UNeXt2"] = UNeXt2
+            patched.append(f"{mod_name}.{attr}")
+    return patched
+
+
+__all__.append("patch_viscy")

@@ -142,15 +142,21 @@ def run_gpu(args):
     ddp = world > 1
     if ddp:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required for NCCL inside CUDA graphs
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly when the native library is missing
 
     torch.manual_seed(1234)
     model = UNeXt2(**CFG).to(dev)
     net = model
-    if ddp:
+    exchange = None
+    if ddp and args.ddp == "torch":
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         static_graph=True)
+    elif ddp:
+        from viscy_b200.parallel import FlatGradAllReduce
+        exchange = FlatGradAllReduce(model.parameters())
+        exchange.broadcast_parameters(0)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=not args.no_graph)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn((BATCH, *SHAPE_IN), device=dev, generator=g)
@@ -162,6 +168,8 @@ def run_gpu(args):
             out = net(xd)
             loss = torch.nn.functional.mse_loss(out.float(), yd)
         loss.backward()
+        if exchange is not None:
+            exchange()  # NCCL all-reduce (mean) of the flat fp32 gradient buffer
         opt.step()
         return loss
 
@@ -185,7 +193,7 @@ def run_gpu(args):
 
     eager_step = step
     graphed = None
-    if not args.no_graph:
+    if not args.no_graph and not (ddp and args.ddp == "torch"):
         from viscy_b200.graphs import GraphedStep
         try:
             graphed = GraphedStep(eager_step, (x, y), warmup=11 if ddp else 3)
@@ -284,6 +292,9 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"dp{world}",
                        "cuda_graph": graphed is not None,
+                       "grad_exchange": ("none" if not ddp else
+                                         "torch DDP (bucketed NCCL all-reduce)" if args.ddp == "torch" else
+                                         "flat fp32 NCCL all-reduce recorded in the step graph"),
                        "l2": "activations per step (>4 GB) exceed the 126 MB L2; no explicit flush",
                        "step_tflop_fraction_of_sustained_peak": value / world * TRAIN_TFLOP_PER_SAMPLE / tf_sus},
             "clocks": clocks,
@@ -293,9 +304,17 @@ def run_gpu(args):
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if ddp:
-        dist.destroy_process_group()
+        # NCCL communicators captured in CUDA graphs can block a clean teardown: drop the graph, meet at a barrier,
+        # then leave without running destructors (exit code 0 for the launcher).
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -305,6 +324,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
+                    help="N>1 gradient exchange: flat all-reduce inside the CUDA graph (default) or stock torch DDP (eager)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup

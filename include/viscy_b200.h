@@ -116,6 +116,9 @@ int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode
 /* out[n][j][k] = W2[j][k] * s[n][k] (16-bit) */
 int vb200_grn_pack_w2(const float* W2, const float* s, void* out, int nb, int C, int C4, int dtype,
                       vb200_stream_t stream);
+/* per-sample scaled weights (as vb200_grn_pack_w2) and the effective bias (as vb200_grn_bias_eff) in one launch */
+int vb200_grn_prepare(const float* s, const float* gb, const float* W2, const float* b2, void* w2s, float* b2e, int nb,
+                      int C, int C4, int dtype, vb200_stream_t stream);
 /* out[j] = b2[j] + sum_k W2[j][k] * bgrn[k] */
 int vb200_grn_bias_eff(const float* W2, const float* bgrn, const float* b2, float* out, int C, int C4, vb200_stream_t stream);
 /* from per-sample wgrad partials P[n][j][k]: dW2 (overwritten), S1 [nb,C4] and dbgrn [C4] (accumulated, pre-zeroed) */

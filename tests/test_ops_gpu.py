@@ -263,6 +263,15 @@ def test_fused_grn_pieces(cuda, dtype):
     w2s = ops.grn_pack_w2(w2, s, dtype)
     assert rel(w2s.view(nb, C, C4), w2[None] * s[:, None, :]) < tol(dtype)
     assert rel(ops.grn_bias_eff(w2, bg, b2), b2 + w2 @ bg) < 1e-5
+    # one-launch preparation == the three separate kernels
+    sumsq = rnd((nb, C4), cuda, 20).abs() + 0.1
+    gw = rnd((C4,), cuda, 21) * 0.5
+    s_ref = torch.empty_like(sumsq)
+    ops._call("vb200_grn_coef_fwd", ops._p(sumsq), ops._p(gw), ops._p(s_ref), nb, C4, ops.C.c_float(1e-6))
+    s2, w2s2, b2e2 = ops.grn_prepare(sumsq, gw, bg, w2, b2, dtype)
+    assert rel(s2, s_ref) < 1e-6
+    assert rel(w2s2.view(nb, C, C4), w2[None] * s_ref[:, None, :]) < tol(dtype)
+    assert rel(b2e2, b2 + w2 @ bg) < 1e-5
     # batched-B GEMM: out[n] = g[n] @ (W2*s[n])^T + b + residual
     g = rnd((M, C4), cuda, 5, dtype)
     res = rnd((M, C), cuda, 6, dtype)

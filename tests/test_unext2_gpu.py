@@ -117,7 +117,7 @@ def test_unext2_against_reference_golden(cuda, name):
     bad = []
     for n, p in m.named_parameters():
         ref = g["grad_norms"][n]
-        if ref < 1e-6:
+        if ref < 1e-6 or n == "head.conv.0.conv.bias":  # bias before InstanceNorm: analytically zero gradient
             continue
         if abs(p.grad.float().norm().item() - ref) > 5e-2 * ref:
             bad.append((n, p.grad.float().norm().item(), ref))

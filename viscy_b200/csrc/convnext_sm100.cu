@@ -15,8 +15,6 @@ namespace vb {
 // unrolled (static tap indices, loads of the next row overlap the FMAs of the current one); each input row
 // (DW_TW+6 values) feeds up to DW_TH output rows.  The 49 taps of the block's 128 channel pairs sit in shared
 // memory (conflict-free 8-byte reads).  All offsets are 32-bit (host checks numel < 2^31).
-constexpr int DW_TW = 8;
-constexpr int DW_TH = 4;
 constexpr int DW_SMEM = 49 * 128 * 8;
 
 template <bool BF16>
@@ -26,7 +24,7 @@ __device__ __forceinline__ float2 ldpair(const uint32_t* p, int off, bool ok) {
   return H16<BF16>::unpack(raw);
 }
 
-template <bool BF16>
+template <bool BF16, int DW_TH, int DW_TW>
 __global__ void __launch_bounds__(128)
 dwconv7_kernel(const uint32_t* __restrict__ x, const float* __restrict__ wt,
                const float* __restrict__ bias, const uint32_t* __restrict__ add,
@@ -528,6 +526,39 @@ grn_pack_w2_kernel(const float* __restrict__ W2, const float* __restrict__ s, ui
   }
 }
 
+// Per-sample scaled fc2 weights out[n][j][k] = W2[j][k] * s[n][k] (16-bit) and b2eff[j] = b2[j] + sum_k W2[j][k]*bgrn[k]
+// in one launch: one block per GRN_JB rows of W2, thread = 8 consecutive k.
+constexpr int GRN_JB = 2;
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+grn_prepare_kernel(const float* __restrict__ s, const float* __restrict__ gb, const float* __restrict__ W2,
+                   const float* __restrict__ b2, uint4* __restrict__ w2s, float* __restrict__ b2e, int nb, int C,
+                   int C4) {
+  __shared__ float scratch[32];
+  const int C48 = C4 / 8;
+  for (int jj = 0; jj < GRN_JB; ++jj) {
+    const int j = blockIdx.x * GRN_JB + jj;
+    if (j >= C) break;
+    float bacc = 0.f;
+    for (int k8 = threadIdx.x; k8 < C48; k8 += blockDim.x) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W2 + (long long)j * C4) + 2 * k8);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W2 + (long long)j * C4) + 2 * k8 + 1);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gb) + 2 * k8);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gb) + 2 * k8 + 1);
+      bacc += w0.x * g0.x + w0.y * g0.y + w0.z * g0.z + w0.w * g0.w + w1.x * g1.x + w1.y * g1.y + w1.z * g1.z + w1.w * g1.w;
+      for (int n = 0; n < nb; ++n) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (long long)n * C4) + 2 * k8);
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (long long)n * C4) + 2 * k8 + 1);
+        w2s[((long long)n * C + j) * C48 + k8] =
+            make_uint4(H16<BF16>::pack(w0.x * s0.x, w0.y * s0.y), H16<BF16>::pack(w0.z * s0.z, w0.w * s0.w),
+                       H16<BF16>::pack(w1.x * s1.x, w1.y * s1.y), H16<BF16>::pack(w1.z * s1.z, w1.w * s1.w));
+      }
+    }
+    const float tot = block_sum(bacc, scratch);
+    if (threadIdx.x == 0) b2e[j] = b2[j] + tot;
+  }
+}
+
 // b2eff[j] = b2[j] + sum_k W2[j][k] * bgrn[k]   (one warp per output row)
 __global__ void __launch_bounds__(256)
 grn_bias_eff_kernel(const float* __restrict__ W2, const float* __restrict__ bgrn, const float* __restrict__ b2,
@@ -603,21 +634,32 @@ using namespace vb;
     else return vb::fail(VB200_ERR_UNSUPPORTED, "dtype %d", (int)(dtype));   \
   } while (0)
 
+template <bool BF, int TH, int TW>
+static void dwconv7_launch(const void* x, const float* wt, const float* bias, const void* add, void* y, int B, int H,
+                           int W, int C2, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dwconv7_kernel<BF, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+    configured = true;
+  }
+  dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B), (unsigned)((C2 + 127) / 128));
+  dwconv7_kernel<BF, TH, TW><<<grid, 128, DW_SMEM, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
+                                                        (uint32_t*)y, B, H, W, C2);
+}
+
 extern "C" int vb200_dwconv7(const void* x, const float* wt, const float* bias, const void* add,
                              void* y, int B, int H, int W, int C, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(x && wt && y, "null pointer");
   VB_SUPPORTED(C % 2 == 0 && (long long)B * H * W * C < (1LL << 31), "C (%d) must be even, tensor < 2^31 elements", C);
   const int C2 = C / 2;
-  dim3 grid((unsigned)(((W + DW_TW - 1) / DW_TW) * ((H + DW_TH - 1) / DW_TH) * B), (unsigned)((C2 + 127) / 128));
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(dwconv7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
-    cudaFuncSetAttribute(dwconv7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
-    configured = true;
+  // small feature maps: 2x4-pixel tiles so that enough blocks exist to fill the SMs
+  const long long big_blocks = (long long)((W + 7) / 8) * ((H + 3) / 4) * B * ((C2 + 127) / 128);
+  if (big_blocks >= 2 * 148) {
+    DISPATCH_DT(dtype, (dwconv7_launch<BF, 4, 8>(x, wt, bias, add, y, B, H, W, C2, st)));
+  } else {
+    DISPATCH_DT(dtype, (dwconv7_launch<BF, 2, 4>(x, wt, bias, add, y, B, H, W, C2, st)));
   }
-  DISPATCH_DT(dtype, dwconv7_kernel<BF><<<grid, 128, DW_SMEM, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
-                                                                   (uint32_t*)y, B, H, W, C2));
   return check_launch("vb200_dwconv7");
 }
 
@@ -805,4 +847,14 @@ extern "C" int vb200_grn_wgrad_finish(const float* P, const float* W2, const flo
   else
     grn_wgrad_finish_kernel<16><<<grid, 128, 0, st>>>(P, W2, s, bgrn, db2, dW2, S1, dbgrn, nb, C, C4, jchunk);
   return check_launch("vb200_grn_wgrad_finish");
+}
+
+extern "C" int vb200_grn_prepare(const float* s, const float* gb, const float* W2, const float* b2, void* w2s,
+                                 float* b2e, int nb, int C, int C4, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(s && gb && W2 && b2 && w2s && b2e, "null pointer");
+  VB_SUPPORTED(C4 % 8 == 0, "grn_prepare: C4 (%d) %% 8", C4);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((C + GRN_JB - 1) / GRN_JB);
+  DISPATCH_DT(dtype, grn_prepare_kernel<BF><<<grid, 256, 0, st>>>(s, gb, W2, b2, (uint4*)w2s, b2e, nb, C, C4));
+  return check_launch("vb200_grn_prepare");
 }

@@ -16,6 +16,20 @@ from . import ops
 
 LN_EPS = 1e-6  # timm LayerNorm / LayerNorm2d
 
+# Backward runs the weight-gradient kernels (wgrad GEMMs, bias column sums, depthwise wgrad) on a side stream so
+# that on small feature maps they overlap the latency-bound dgrad chain; every block joins the side stream before
+# it returns.  Inside a CUDA graph this becomes a fork/join of parallel branches.
+_SIDE: dict[int, torch.cuda.Stream] = {}
+OVERLAP_WGRAD = True
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE.get(idx)
+    if st is None:
+        st = _SIDE[idx] = torch.cuda.Stream(device=device)
+    return st
+
 
 # --------------------------------------------------------------------------------------------------
 def _wgrad_splits(n_out: int, k_in: int, pixels: int) -> int:
@@ -76,11 +90,8 @@ class ConvNeXtBlockFn(Function):
             # gp = gelu'(u) and g = gelu(u) from the fc1 epilogue; GRN scale folded into per-sample fc2 weights
             h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP)
             sumsq = ops.colreduce(y2.view(B, R, C4), 1)
-            s = torch.empty_like(sumsq)
-            ops._call("vb200_grn_coef_fwd", ops._p(sumsq), ops._p(grn_w), ops._p(s), B, C4, ops.C.c_float(1e-6))
             w2 = fc2_w.detach().reshape(C, C4)
-            w2s = ops.grn_pack_w2(w2, s, x.dtype)
-            b2e = ops.grn_bias_eff(w2, grn_b.detach(), fc2_b.detach())
+            s, w2s, b2e = ops.grn_prepare(sumsq, grn_w.detach(), grn_b.detach(), w2, fc2_b.detach(), x.dtype)
             out = ops.gemm(y2, w2s, bias=b2e, residual=x.view(M, C), b_batch_rows=R)
             ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, grn_b)
             ctx.use_grn, ctx.fused = True, True
@@ -128,7 +139,6 @@ class ConvNeXtBlockFn(Function):
                       ops.C.c_float(1e-6))
             w2t = ops.cast_pack(w2, x.dtype, transpose=True)  # [C4, C]
             dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux=y2, aux2=h, tvec=t, svec=s, rows_per_sample=R)
-            db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
             dw2 = dw2.view(fc2_w.shape)
             dgamma = None
         else:
@@ -154,10 +164,25 @@ class ConvNeXtBlockFn(Function):
                     db2 = db2_eff * gamma
                 else:
                     dgamma, dw2, db2 = None, dw2_eff.view(fc2_w.shape), db2_eff
-        dl, dw1, _ = linear_bwd(dh.view(M, C4), l.view(M, C), fc1_w, need_db=False)
+        dh2 = dh.view(M, C4)
+        main = torch.cuda.current_stream()
+        side = _side_stream(x.device) if OVERLAP_WGRAD else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if ctx.fused:
+                db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
+            dw1 = ops.gemm(dh2, l.view(M, C), mn_major=True, epilogue=L.EPI_F32,
+                           k_splits=_wgrad_splits(C4, C, M)).view(fc1_w.shape)
+        dl = ops.gemm(dh2, ops.cast_pack(fc1_w, x.dtype, transpose=True))
         dd, dlnw, dlnb = ops.layernorm_bwd(dl.view(B, H, W, C), d, mean, rstd, ln_w, ar)
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dwt, ddb = ops.dwconv7_wgrad(x, dd, arena=ar)
         dx = ops.dwconv7(dd, ctx.wt_flip, None, add=dout)
-        dwt, ddb = ops.dwconv7_wgrad(x, dd, arena=ar)
+        if side is not main:
+            main.wait_stream(side)
         ddw = dwt.t().reshape(dw_w.shape)
         return dx, ddw, ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma
 
@@ -211,7 +236,14 @@ class LNConvFn(Function):
         else:
             raise NotImplementedError(f"downsample kernel {k}")
         a2 = a.view(B * Ho * Wo, -1)
-        out = ops.gemm(a2, ops.cast_pack(wk, x.dtype), bias=b)
+        Kc = a2.shape[1]
+        if Kc % 8:  # TMA rows need a 16-byte pitch: zero-pad K (only odd channel counts, e.g. convnextv2_atto decoders)
+            K8 = -(-Kc // 8) * 8
+            a_p = a2.new_zeros((a2.shape[0], K8))
+            a_p[:, :Kc] = a2
+            a2 = a_p
+            wk = torch.nn.functional.pad(wk, (0, K8 - Kc))
+        out = ops.gemm(a2, ops.cast_pack(wk.contiguous(), x.dtype), bias=b)
         ctx.save_for_backward(x, mean, rstd, ln_w, a2, w)
         ctx.k = k
         return out.view(B, Ho, Wo, w.shape[0])
@@ -225,13 +257,18 @@ class LNConvFn(Function):
         Co = w.shape[0]
         do2 = dout.contiguous().view(-1, Co)
         wk = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous() if k == 2 else w.reshape(Co, -1)
+        Kc, K8 = wk.shape[1], a2.shape[1]
+        if K8 != Kc:
+            wk = torch.nn.functional.pad(wk, (0, K8 - Kc)).contiguous()
         da, dwk, db = linear_bwd(do2, a2, wk)
+        if K8 != Kc:
+            da, dwk = da[:, :Kc].contiguous(), dwk[:, :Kc]
         if k == 2:
             dl = ops.patchify2(da.view(B, H // 2, W // 2, 4 * C), inverse=True, shape=(B, H, W, C))
-            dw = dwk.view(Co, 2, 2, C).permute(0, 3, 1, 2)
+            dw = dwk.reshape(Co, 2, 2, C).permute(0, 3, 1, 2)
         else:
             dl = da.view(B, H, W, C)
-            dw = dwk.view(w.shape)
+            dw = dwk.reshape(w.shape)
         dx, dlnw, dlnb = ops.layernorm_bwd(dl, x, mean, rstd, ln_w)
         return dx, dlnw, dlnb, dw, db
 

@@ -423,6 +423,19 @@ def grn_pack_w2(w2, s, dtype):
     return out
 
 
+def grn_prepare(sumsq, gw, gb, w2, b2, dtype, eps=1e-6):
+    """-> (s [nb,C4] fp32, w2s [nb*C, C4] 16-bit, b2eff [C] fp32): GRN coefficients, then weights + bias in one launch."""
+    nb, C4 = sumsq.shape
+    Cc = w2.shape[0]
+    s = torch.empty_like(sumsq)
+    _call("vb200_grn_coef_fwd", _p(sumsq), _p(_f32(gw, "grn.weight")), _p(s), nb, C4, C.c_float(eps))
+    w2s = torch.empty((nb * Cc, C4), device=w2.device, dtype=dtype)
+    b2e = torch.empty((Cc,), device=w2.device, dtype=torch.float32)
+    _call("vb200_grn_prepare", _p(s), _p(_f32(gb, "grn.bias")), _p(_f32(w2, "w2")), _p(_f32(b2, "b2")), _p(w2s), _p(b2e),
+          nb, Cc, C4, L.dtype_code(dtype))
+    return s, w2s, b2e
+
+
 def grn_bias_eff(w2, bgrn, b2):
     Cc, C4 = w2.shape
     out = torch.empty((Cc,), device=w2.device, dtype=torch.float32)

@@ -152,6 +152,19 @@ int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t s
 /* fp32 [R,Cc] -> 16-bit (weight packing); transpose != 0 writes [Cc,R] */
 int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype, vb200_stream_t stream);
 
+/* ---- implicit-GEMM Conv3d k=3, stride 1, small channel counts (tcgen05, im2col folded into 5-D TMA boxes) ----
+ * Replaces nn.Conv3d(k=3) of monai Convolution in PixelToVoxelHead (VM/components/heads.py:607-628) and its cuDNN
+ * dgrad / wgrad.  geom = {N, D, H, W, pd, ph, pw}; u [N,D,H,W,cin] 16-bit channels-last (cin in 8|16|32);
+ * out [N,OD,OH,OW,co_store], OD = D + 2*pd - 2 etc.
+ * wpack: 16-bit [KCH][cout_pad][8], K order (kd, kh, channel chunk, kw), KCH = 27*cin/8 padded to even with a zero
+ * chunk; cout_pad in {16,32} is the MMA N; co_store <= cout_pad channels are written per voxel.
+ * The data gradient is the same call with flipped / transposed weights and padding 2 - p. */
+int vb200_conv3d_k3(const void* u, const void* wpack, const float* bias, void* out, const int32_t* geom, int cin,
+                    int cout_pad, int co_store, int dtype, vb200_stream_t stream);
+/* dw[cout][9 (kd,kh)][3 (kw)][8 (ci)] fp32 (pre-zeroed, accumulated with atomics); cin == 8; dz [N,OD,OH,OW,cout] */
+int vb200_conv3d_k3_wgrad(const void* u, const void* dz, float* dw, const int32_t* geom, int cin, int cout, int dtype,
+                          vb200_stream_t stream);
+
 /* ---- PixelToVoxelHead (VM/components/heads.py:594-641) ---- */
 /* forward (backward == 0): dec [B,h,w,4*Cm] -> u [B,Dz,2h,2w,Cu] = unfold(pool(pixelshuffle2(dec)));
  * backward (!= 0): src = du, dst = ddec */

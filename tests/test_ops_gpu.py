@@ -305,3 +305,34 @@ def test_fused_grn_pieces(cuda, dtype):
     gr = F.gelu(u)
     gr.sum().backward()
     assert rel(go, gr) < tol(dtype) and rel(gpo, u.grad) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape,pad,Co", [
+    ((1, 5, 8, 128, 8), (0, 1, 1), 32),
+    ((2, 4, 6, 40, 8), (1, 1, 1), 32),
+    ((1, 3, 5, 200, 8), (0, 1, 1), 16),
+])
+def test_conv3d_k3_implicit_gemm(cuda, shape, pad, Co, dtype):
+    """tcgen05 implicit-GEMM conv3d (fwd, dgrad via flipped weights, wgrad) vs torch conv3d autograd."""
+    from viscy_b200 import ops
+    N, D, H, W, Ci = shape
+    u = rnd(shape, cuda, 1, dtype)
+    w = rnd((Co, Ci, 3, 3, 3), cuda, 2) * 0.1
+    b = rnd((Co,), cuda, 3)
+    uf = u.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wf = w.to(dtype).float().requires_grad_(True)
+    ref = F.conv3d(uf, wf, b, padding=pad)
+    wp = ops.conv3d_pack_weights(w, dtype, 8, Co)
+    z = ops.conv3d_k3(u, wp, b, pad, Co, Co)
+    assert z.shape == (N, *ref.shape[2:], Co)
+    assert rel(z.permute(0, 4, 1, 2, 3), ref) < tol(dtype)
+    dz = rnd(tuple(z.shape), cuda, 4, dtype)
+    ref.backward(dz.float().permute(0, 4, 1, 2, 3))
+    # data gradient: same kernel, flipped/transposed weights, padding 2 - p, cin = Co
+    wpt = ops.conv3d_pack_weights(w, dtype, Co, 16, transpose_flip=True)
+    du = ops.conv3d_k3(dz, wpt, None, tuple(2 - p for p in pad), 16, 8)
+    assert du.shape == u.shape
+    assert rel(du.permute(0, 4, 1, 2, 3), uf.grad) < tol(dtype)
+    dw = ops.conv3d_k3_wgrad(u, dz, pad)
+    assert rel(dw, wf.grad) < 1e-3

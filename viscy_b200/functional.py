@@ -365,13 +365,20 @@ class HeadFn(Function):
         Cmid = conv_w.shape[0]
         Cu = -(-Cc // 8) * 8
         u = ops.head_shuffle_pool_fwd(dec, Dz, pool, Cu)
-        geom = ops.conv3d_geom(tuple(u.shape), (3, 3, 3), (1, 1, 1), (0, 1, 1))
-        col = ops.im2col3d(u, geom)
-        wc = conv_w.detach().permute(0, 2, 3, 4, 1)  # [Cmid, 3,3,3, Cc]
-        if Cu != Cc:
-            wc = torch.nn.functional.pad(wc, (0, Cu - Cc))
-        wc = wc.reshape(Cmid, -1).contiguous()
-        z = ops.gemm(col, ops.cast_pack(wc, dec.dtype), bias=conv_b)
+        implicit = Cu == 8 and Cmid in (16, 32)
+        if implicit:
+            # tcgen05 implicit GEMM: im2col folded into shifted 5-D TMA boxes (csrc/conv3d_sm100.cu)
+            wp = ops.conv3d_pack_weights(conv_w, dec.dtype, 8, Cmid)
+            z = ops.conv3d_k3(u, wp, conv_b, (0, 1, 1), Cmid, Cmid).view(-1, Cmid)
+            col, geom = u, None
+        else:
+            geom = ops.conv3d_geom(tuple(u.shape), (3, 3, 3), (1, 1, 1), (0, 1, 1))
+            col = ops.im2col3d(u, geom)
+            wc = conv_w.detach().permute(0, 2, 3, 4, 1)  # [Cmid, 3,3,3, Cc]
+            if Cu != Cc:
+                wc = torch.nn.functional.pad(wc, (0, Cu - Cc))
+            wc = wc.reshape(Cmid, -1).contiguous()
+            z = ops.gemm(col, ops.cast_pack(wc, dec.dtype), bias=conv_b)
         H2, W2 = 2 * h, 2 * w
         R = out_depth * H2 * W2
         z3 = z.view(B, R, Cmid)
@@ -379,26 +386,40 @@ class HeadFn(Function):
         w1m = w1.detach().reshape(w1.shape[0], Cmid).contiguous()
         out = ops.head_tail_fwd(z3, mean, rstd, alpha.detach(), w1m, b1.detach(), out_depth, H2, W2)
         ctx.save_for_backward(col, z3, mean, rstd, alpha, w1, conv_w)
-        ctx.meta = (geom, Cm, Cc, Cu, pool, out_depth, H2, W2)
+        ctx.meta = (geom, Cm, Cc, Cu, pool, out_depth, H2, W2, implicit)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         col, z3, mean, rstd, alpha, w1, conv_w = ctx.saved_tensors
-        geom, Cm, Cc, Cu, pool, out_depth, H2, W2 = ctx.meta
+        geom, Cm, Cc, Cu, pool, out_depth, H2, W2, implicit = ctx.meta
         B, R, Cmid = z3.shape
         w1m = w1.reshape(w1.shape[0], Cmid).contiguous()
         dz, dW1, db1, dalpha, dbz = ops.head_tail_bwd(z3, mean, rstd, alpha, w1m, dout.contiguous(), out_depth, H2, W2)
-        dz2 = dz.view(B * R, Cmid)
-        wc = conv_w.permute(0, 2, 3, 4, 1)
-        if Cu != Cc:
-            wc = torch.nn.functional.pad(wc, (0, Cu - Cc))
-        wc = wc.reshape(Cmid, -1).contiguous()
-        dcol, dwc, _ = linear_bwd(dz2, col, wc, need_db=False)
-        du = ops.col2im3d(dcol, geom)
+        if implicit:
+            u = col
+            dz5 = dz.view(B, out_depth, H2, W2, Cmid)
+            main = torch.cuda.current_stream()
+            side = _side_stream(dz.device) if OVERLAP_WGRAD else main
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dconv_w = ops.conv3d_k3_wgrad(u, dz5, (0, 1, 1))[:, :Cc]
+            wpt = ops.conv3d_pack_weights(conv_w, dz.dtype, Cmid, 16, transpose_flip=True)
+            du = ops.conv3d_k3(dz5, wpt, None, (2, 1, 1), 16, 8)
+            if side is not main:
+                main.wait_stream(side)
+        else:
+            dz2 = dz.view(B * R, Cmid)
+            wc = conv_w.permute(0, 2, 3, 4, 1)
+            if Cu != Cc:
+                wc = torch.nn.functional.pad(wc, (0, Cu - Cc))
+            wc = wc.reshape(Cmid, -1).contiguous()
+            dcol, dwc, _ = linear_bwd(dz2, col, wc, need_db=False)
+            du = ops.col2im3d(dcol, geom)
+            dconv_w = dwc.view(Cmid, 3, 3, 3, Cu)[..., :Cc].permute(0, 4, 1, 2, 3)
         ddec = ops.head_shuffle_pool_bwd(du, Cm, pool)
-        dconv_w = dwc.view(Cmid, 3, 3, 3, Cu)[..., :Cc].permute(0, 4, 1, 2, 3)
         return ddec, dconv_w, dbz, dalpha.view(alpha.shape), dW1.view(w1.shape), db1, None, None
 
 

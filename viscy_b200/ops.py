@@ -451,3 +451,46 @@ def grn_wgrad_finish(P, w2, s, bgrn, db2, arena=None):
     _call("vb200_grn_wgrad_finish", _p(P), _p(_f32(w2, "w2")), _p(_f32(s, "s")), _p(_f32(bgrn, "bgrn")), _p(_f32(db2, "db2")),
           _p(dW2), _p(acc[:nb]), _p(acc[nb]), nb, Cc, C4)
     return dW2, acc[:nb], acc[nb]
+
+
+# ----------------------------------------------------------------------------------------------
+# implicit-GEMM conv3d (k=3, stride 1, small channel counts)
+def conv3d_pack_weights(w, dtype, cin_pad, cout_pad, transpose_flip=False):
+    """w fp32 [Co, Ci, 3,3,3] -> 16-bit [KCH][cout_pad][8] in K order (kd, kh, channel chunk, kw).
+
+    transpose_flip=True builds the data-gradient weights W'[ci, co, kd, kh, kw] = W[co, ci, 2-kd, 2-kh, 2-kw]."""
+    w = w.detach()
+    if transpose_flip:
+        w = w.flip(2, 3, 4).transpose(0, 1)
+    Co, Ci = w.shape[:2]
+    wp = w.new_zeros((cout_pad, cin_pad, 3, 3, 3))
+    wp[:Co, :Ci] = w
+    cch = cin_pad // 8
+    # [co, chunk, j, kd, kh, kw] -> [kd, kh, chunk, kw, co, j]
+    wp = wp.view(cout_pad, cch, 8, 3, 3, 3).permute(3, 4, 1, 5, 0, 2).reshape(27 * cch, cout_pad, 8)
+    if (27 * cch) % 2:
+        wp = torch.cat([wp, wp.new_zeros((1, cout_pad, 8))], 0)
+    return wp.contiguous().to(dtype)
+
+
+def conv3d_k3(u, wpack, bias, padding, cout_pad, co_store):
+    """u [N,D,H,W,cin] 16-bit channels-last -> [N,OD,OH,OW,co_store]"""
+    _act(u, "u")
+    N, D, H, W, cin = u.shape
+    pd, ph, pw = padding
+    out = torch.empty((N, D + 2 * pd - 2, H + 2 * ph - 2, W + 2 * pw - 2, co_store), device=u.device, dtype=u.dtype)
+    g = (C.c_int32 * 7)(N, D, H, W, pd, ph, pw)
+    _call("vb200_conv3d_k3", _p(u), _p(wpack), _p(bias), _p(out), g, cin, cout_pad, co_store, L.dtype_code(u.dtype))
+    return out
+
+
+def conv3d_k3_wgrad(u, dz, padding):
+    """-> dW fp32 [Co, 8 (ci), 3,3,3] for cin == 8"""
+    N, D, H, W, cin = u.shape
+    Co = dz.shape[-1]
+    pd, ph, pw = padding
+    dw = torch.zeros((Co, 9, 3, 8), device=u.device, dtype=torch.float32)
+    g = (C.c_int32 * 7)(N, D, H, W, pd, ph, pw)
+    _call("vb200_conv3d_k3_wgrad", _p(_act(u, "u")), _p(_act(dz, "dz")), _p(dw), g, cin, Co, L.dtype_code(u.dtype))
+    # [co, (kd,kh), kw, ci] -> [co, ci, kd, kh, kw]
+    return dw.view(Co, 3, 3, 3, 8).permute(0, 4, 1, 2, 3)

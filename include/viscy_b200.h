@@ -177,10 +177,12 @@ int vb200_instnorm_stats(const void* z, float* sum, float* sumsq, float* mean, f
 int vb200_head_tail_fwd(const void* z, const float* mean, const float* rstd, const float* alpha, int alpha_n,
                         const float* W1, const float* b1, void* out, int B, int Dz, int H, int W, int Cmid, int Co4,
                         int dtype, vb200_stream_t stream);
+/* phase 0: reductions sdp, sdpx [B,Cmid], db1 [Co4], dalpha (pre-zeroed) + materialised act [B,R,Cmid] and
+ * dt [B,R,ldt] (ldt = Co4 rounded up to 8) for the dW1 = dt^T act GEMM;  phase 1: dz [B,R,Cmid], dbz [Cmid] */
 int vb200_head_tail_bwd(int phase, const void* z, const float* mean, const float* rstd, const float* alpha,
-                        int alpha_n, const float* W1, const void* dout, float* sdp, float* sdpx, float* dW1,
-                        float* db1, float* dalpha, void* dz, float* dbz, int B, int Dz, int H, int W, int Cmid,
-                        int Co4, int dtype, vb200_stream_t stream);
+                        int alpha_n, const float* W1, const void* dout, float* sdp, float* sdpx, float* db1,
+                        float* dalpha, void* act_out, void* dt_out, void* dz, float* dbz, int B, int Dz, int H, int W,
+                        int Cmid, int Co4, int dtype, vb200_stream_t stream);
 
 /* copies the last error message of the calling thread into buf (NUL terminated) */
 int vb200_last_error(char* buf, size_t n);

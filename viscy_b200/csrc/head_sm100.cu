@@ -221,157 +221,166 @@ head_tail_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
     }
 }
 
-// Backward, phase 1 (MODE 0): reductions  sdp[n,c] = sum dpre, sdpx[n,c] = sum dpre*xhat, dW1, db1, dalpha
-// Backward, phase 2 (MODE 1): dz = rstd * (dpre - sdp/R - xhat * sdpx/R), dbz[c] += sum dz
-// thread = (row, 8-channel chunk)
-template <bool BF16, int MODE, int HT_MAXO>
+// Backward of the fused tail.  thread = (voxel row, 8-channel chunk v); W1 sits in shared memory as [c][MAXO].
+// MODE 0: reductions sdp[n,c] = sum dpre, sdpx[n,c] = sum dpre*xhat, db1[o] = sum dt, dalpha = sum da*xhat*(xhat<=0);
+//         also materialises act = prelu(xhat) [M,Cmid] and dt (the un-shuffled output gradient) [M,ldt] so that
+//         dW1 = dt^T act runs on the tensor cores (MN-major tcgen05 GEMM).
+// MODE 1: dz = rstd * (dpre - sdp/R - xhat * sdpx/R), dbz[c] += sum dz
+template <bool BF16, int MODE, int MAXO>
 __global__ void __launch_bounds__(256)
-head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, const float* __restrict__ alpha, int alpha_n,
-                     const float* __restrict__ W1, const uint16_t* __restrict__ dout,
-                     float* __restrict__ sdp, float* __restrict__ sdpx, float* __restrict__ dW1,
-                     float* __restrict__ db1, float* __restrict__ dalpha, uint4* __restrict__ dz,
-                     float* __restrict__ dbz, int Dz, int H, int W, int Cmid, int Co4,
-                     int rows_per_block) {
+head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ alpha, int alpha_n, const float* __restrict__ W1,
+                     const uint16_t* __restrict__ dout, float* __restrict__ sdp, float* __restrict__ sdpx,
+                     float* __restrict__ db1, float* __restrict__ dalpha, uint4* __restrict__ act_out,
+                     uint16_t* __restrict__ dt_out, uint4* __restrict__ dz, float* __restrict__ dbz, int Dz, int H,
+                     int W, int Cmid, int Co4, int ldt, int rows_per_block) {
   extern __shared__ float smf[];
-  float* sW = smf;                   // [Co4][Cmid]
-  float* sm_ = sW + Co4 * Cmid;      // mean
-  float* sr = sm_ + Cmid;            // rstd
-  float* sa = sr + Cmid;             // alpha
-  float* red = sa + Cmid;            // MODE 0: sdp[Cmid], sdpx[Cmid], dW1[Co4*Cmid], db1[Co4], dalpha[Cmid]; MODE 1: dbz[Cmid]
-  float* s1 = red + Cmid;            // MODE 1: (sdp/R), (sdpx/R) staged after the dbz slot
+  float* sW = smf;                 // [Cmid][MAXO]
+  float* red = sW + Cmid * MAXO;   // MODE 0: sdp[Cmid] sdpx[Cmid] dalpha[Cmid] db1[MAXO];  MODE 1: dbz[Cmid]
   const int n = blockIdx.y;
   const int C8 = Cmid / 8;
   const int R = Dz * H * W;
-  const int nred = MODE == 0 ? (2 * Cmid + Co4 * Cmid + Co4 + Cmid) : (3 * Cmid);
-  for (int i = threadIdx.x; i < Co4 * Cmid; i += blockDim.x) sW[i] = W1[i];
-  for (int i = threadIdx.x; i < nred; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  for (int i = threadIdx.x; i < Cmid; i += blockDim.x) {
-    sm_[i] = mean[(long long)n * Cmid + i];
-    sr[i] = rstd[(long long)n * Cmid + i];
-    sa[i] = alpha[alpha_n == 1 ? 0 : i];
-    if (MODE == 1) {
-      s1[i] = sdp[(long long)n * Cmid + i] / (float)R;
-      s1[Cmid + i] = sdpx[(long long)n * Cmid + i] / (float)R;
-    }
+  const int nred = MODE == 0 ? 3 * Cmid + MAXO : Cmid;
+  for (int i = threadIdx.x; i < Cmid * MAXO; i += blockDim.x) {
+    const int c = i / MAXO, o = i % MAXO;
+    sW[i] = o < Co4 ? W1[o * Cmid + c] : 0.f;
   }
+  for (int i = threadIdx.x; i < nred; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int v = threadIdx.x % C8, rl = threadIdx.x / C8, rstep = blockDim.x / C8;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
   const int Co = Co4 / 4;
   z += (long long)n * R * C8;
-  if (MODE == 1) dz += (long long)n * R * C8;
   dout += (long long)n * Co * Dz * 4 * H * W;
+  if (MODE == 0) {
+    act_out += (long long)n * R * C8;
+    dt_out += (long long)n * R * ldt;
+  } else {
+    dz += (long long)n * R * C8;
+  }
   const int HW = H * W;
-  float a_sdp[8], a_sdpx[8], a_dal[8], a_db[HT_MAXO];
-  float a_dW[HT_MAXO][8];
-  float wr[HT_MAXO][8], mu8[8], rs8[8], al8[8];  // this thread's slice of W1 / mean / rstd / alpha in registers
+  float mu8[8], rs8[8], al8[8], m1[8], m2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int c = (threadIdx.x % C8) * 8 + k;
-    mu8[k] = sm_[c];
-    rs8[k] = sr[c];
-    al8[k] = sa[c];
-#pragma unroll
-    for (int o = 0; o < HT_MAXO; ++o) wr[o][k] = o < Co4 ? sW[o * Cmid + c] : 0.f;
+    const int c = v * 8 + k;
+    mu8[k] = mean[(long long)n * Cmid + c];
+    rs8[k] = rstd[(long long)n * Cmid + c];
+    al8[k] = alpha[alpha_n == 1 ? 0 : c];
+    m1[k] = MODE == 1 ? sdp[(long long)n * Cmid + c] / (float)R : 0.f;
+    m2[k] = MODE == 1 ? sdpx[(long long)n * Cmid + c] / (float)R : 0.f;
   }
+  const float4* sw4 = reinterpret_cast<const float4*>(sW + v * 8 * MAXO);
+  float acc0[8], acc1[8], acc2[8], accb[MAXO];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a_sdp[k] = a_sdpx[k] = a_dal[k] = 0.f;
+  for (int k = 0; k < 8; ++k) acc0[k] = acc1[k] = acc2[k] = 0.f;
 #pragma unroll
-  for (int o = 0; o < HT_MAXO; ++o) {
-    a_db[o] = 0.f;
+  for (int o = 0; o < MAXO; ++o) accb[o] = 0.f;
+
+  for (int row = r0 + rl; row < r1; row += rstep) {
+    const int dzi = row / HW;
+    const int rem = row - dzi * HW;
+    const int y = rem / W;
+    const int x = rem - y * W;
+    const uint4 t = __ldg(z + row * C8 + v);
+    float dt[MAXO];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a_dW[o][k] = 0.f;
-  }
-  if (rl < rstep) {
-    for (int row = r0 + rl; row < r1; row += rstep) {
-      const int dzi = row / HW;
-      const int rem = row - dzi * HW;
-      const int y = rem / W;
-      const int x = rem - y * W;
-      float dt[HT_MAXO];
-#pragma unroll
-      for (int o = 0; o < HT_MAXO; o += 2) {
-        dt[o] = dt[o + 1] = 0.f;
-        if (o < Co4) {
-          const int co = o >> 2, i = (o >> 1) & 1;
-          const int oi = ((co * Dz + dzi) * (2 * H) + 2 * y + i) * (2 * W) + 2 * x;
-          const float2 f = H16<BF16>::unpack(__ldg(reinterpret_cast<const uint32_t*>(dout + oi)));
-          dt[o] = f.x;
-          dt[o + 1] = f.y;
-        }
-      }
-      const uint4 t = __ldg(z + row * C8 + v);
-      const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
-      float xh[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = H16<BF16>::unpack(w4[k]);
-        xh[2 * k] = f.x;
-        xh[2 * k + 1] = f.y;
-      }
-      float dpre[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        xh[k] = (xh[k] - mu8[k]) * rs8[k];
-        float da = 0.f;
-#pragma unroll
-        for (int o = 0; o < HT_MAXO; ++o) da = fmaf(wr[o][k], dt[o], da);
-        const bool pos = xh[k] > 0.f;
-        dpre[k] = pos ? da : da * al8[k];
-        if (MODE == 0) {
-          const float act = pos ? xh[k] : xh[k] * al8[k];
-          a_sdp[k] += dpre[k];
-          a_sdpx[k] = fmaf(dpre[k], xh[k], a_sdpx[k]);
-          if (!pos) a_dal[k] = fmaf(da, xh[k], a_dal[k]);
-#pragma unroll
-          for (int o = 0; o < HT_MAXO; ++o) a_dW[o][k] = fmaf(dt[o], act, a_dW[o][k]);
-        }
-      }
-      if (MODE == 0) {
-        if (v == 0) {
-#pragma unroll
-          for (int o = 0; o < HT_MAXO; ++o)
-            if (o < Co4) a_db[o] += dt[o];
-        }
-      } else {
-        float o8[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int c = v * 8 + k;
-          o8[k] = rs8[k] * (dpre[k] - s1[c] - xh[k] * s1[Cmid + c]);
-        }
-        const uint4 q = make_uint4(H16<BF16>::pack(o8[0], o8[1]), H16<BF16>::pack(o8[2], o8[3]),
-                                   H16<BF16>::pack(o8[4], o8[5]), H16<BF16>::pack(o8[6], o8[7]));
-        dz[row * C8 + v] = q;
-        const uint32_t w4o[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = H16<BF16>::unpack(w4o[k]);
-          a_sdp[2 * k] += f.x;  // reused as the dbz accumulator
-          a_sdp[2 * k + 1] += f.y;
-        }
+    for (int o = 0; o < MAXO; o += 2) {
+      dt[o] = dt[o + 1] = 0.f;
+      if (o < Co4) {
+        const int co = o >> 2, i = (o >> 1) & 1;
+        const int oi = ((co * Dz + dzi) * (2 * H) + 2 * y + i) * (2 * W) + 2 * x;
+        const float2 f = H16<BF16>::unpack(__ldg(reinterpret_cast<const uint32_t*>(dout + oi)));
+        dt[o] = f.x;
+        dt[o + 1] = f.y;
       }
     }
-    // block reduction through shared-memory atomics
+    const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+    float xh[8], o8[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = H16<BF16>::unpack(w4[k]);
+      xh[2 * k] = (f.x - mu8[2 * k]) * rs8[2 * k];
+      xh[2 * k + 1] = (f.y - mu8[2 * k + 1]) * rs8[2 * k + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float da = 0.f;
+#pragma unroll
+      for (int o4 = 0; o4 < MAXO / 4; ++o4) {
+        const float4 wv = sw4[k * (MAXO / 4) + o4];
+        da = fmaf(wv.x, dt[o4 * 4], da);
+        da = fmaf(wv.y, dt[o4 * 4 + 1], da);
+        da = fmaf(wv.z, dt[o4 * 4 + 2], da);
+        da = fmaf(wv.w, dt[o4 * 4 + 3], da);
+      }
+      const bool pos = xh[k] > 0.f;
+      const float dpre = pos ? da : da * al8[k];
+      if (MODE == 0) {
+        o8[k] = pos ? xh[k] : xh[k] * al8[k];  // act
+        acc0[k] += dpre;
+        acc1[k] = fmaf(dpre, xh[k], acc1[k]);
+        acc2[k] += pos ? 0.f : da * xh[k];
+      } else {
+        o8[k] = rs8[k] * (dpre - m1[k] - xh[k] * m2[k]);
+      }
+    }
+    const uint4 q = make_uint4(H16<BF16>::pack(o8[0], o8[1]), H16<BF16>::pack(o8[2], o8[3]),
+                               H16<BF16>::pack(o8[4], o8[5]), H16<BF16>::pack(o8[6], o8[7]));
+    if (MODE == 0) {
+      act_out[row * C8 + v] = q;
+      if (v == 0) {
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o) accb[o] += dt[o];
+#pragma unroll
+        for (int o8i = 0; o8i < MAXO / 8; ++o8i) {
+          if (o8i * 8 < ldt)
+            *reinterpret_cast<uint4*>(dt_out + (long long)row * ldt + o8i * 8) =
+                make_uint4(H16<BF16>::pack(dt[o8i * 8], dt[o8i * 8 + 1]), H16<BF16>::pack(dt[o8i * 8 + 2], dt[o8i * 8 + 3]),
+                           H16<BF16>::pack(dt[o8i * 8 + 4], dt[o8i * 8 + 5]), H16<BF16>::pack(dt[o8i * 8 + 6], dt[o8i * 8 + 7]));
+        }
+      }
+    } else {
+      dz[row * C8 + v] = q;
+      const uint32_t w4o[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = H16<BF16>::unpack(w4o[k]);
+        acc0[2 * k] += f.x;
+        acc0[2 * k + 1] += f.y;
+      }
+    }
+  }
+  // combine the lanes that share a channel chunk (lane % C8), then one shared atomic per warp and value
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    for (int off = 16; off >= C8; off >>= 1) {
+      acc0[k] += __shfl_xor_sync(0xffffffffu, acc0[k], off);
+      if (MODE == 0) {
+        acc1[k] += __shfl_xor_sync(0xffffffffu, acc1[k], off);
+        acc2[k] += __shfl_xor_sync(0xffffffffu, acc2[k], off);
+      }
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o)
+      for (int off = 16; off >= C8; off >>= 1) accb[o] += __shfl_xor_sync(0xffffffffu, accb[o], off);
+  }
+  if (lane < C8) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = v * 8 + k;
-      atomicAdd(&red[c], a_sdp[k]);
+      atomicAdd(&red[c], acc0[k]);
       if (MODE == 0) {
-        atomicAdd(&red[Cmid + c], a_sdpx[k]);
-        atomicAdd(&red[2 * Cmid + Co4 * Cmid + Co4 + c], a_dal[k]);
-#pragma unroll
-        for (int o = 0; o < HT_MAXO; ++o)
-          if (o < Co4) atomicAdd(&red[2 * Cmid + o * Cmid + c], a_dW[o][k]);
+        atomicAdd(&red[Cmid + c], acc1[k]);
+        atomicAdd(&red[2 * Cmid + c], acc2[k]);
       }
     }
     if (MODE == 0 && v == 0) {
 #pragma unroll
-      for (int o = 0; o < HT_MAXO; ++o)
-        if (o < Co4) atomicAdd(&red[2 * Cmid + Co4 * Cmid + o], a_db[o]);
+      for (int o = 0; o < MAXO; ++o) atomicAdd(&red[3 * Cmid + o], accb[o]);
     }
   }
   __syncthreads();
@@ -379,10 +388,9 @@ head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
     for (int i = threadIdx.x; i < Cmid; i += blockDim.x) {
       atomicAdd(sdp + (long long)n * Cmid + i, red[i]);
       atomicAdd(sdpx + (long long)n * Cmid + i, red[Cmid + i]);
-      atomicAdd(dalpha + (alpha_n == 1 ? 0 : i), red[2 * Cmid + Co4 * Cmid + Co4 + i]);
+      atomicAdd(dalpha + (alpha_n == 1 ? 0 : i), red[2 * Cmid + i]);
     }
-    for (int i = threadIdx.x; i < Co4 * Cmid; i += blockDim.x) atomicAdd(dW1 + i, red[2 * Cmid + i]);
-    for (int i = threadIdx.x; i < Co4; i += blockDim.x) atomicAdd(db1 + i, red[2 * Cmid + Co4 * Cmid + i]);
+    for (int i = threadIdx.x; i < Co4; i += blockDim.x) atomicAdd(db1 + i, red[3 * Cmid + i]);
   } else {
     for (int i = threadIdx.x; i < Cmid; i += blockDim.x) atomicAdd(dbz + i, red[i]);
   }
@@ -458,32 +466,39 @@ extern "C" int vb200_head_tail_fwd(const void* z, const float* mean, const float
   return check_launch("vb200_head_tail_fwd");
 }
 
-/* phase 0: reductions into sdp, sdpx [B,Cmid], dW1 [Co4,Cmid], db1 [Co4], dalpha [alpha_n] (all pre-zeroed)
+/* phase 0: reductions into sdp, sdpx [B,Cmid], db1 [Co4], dalpha [alpha_n] (all pre-zeroed) and the materialised
+ *          act [B,R,Cmid] / dt [B,R,ldt] operands of the dW1 GEMM (ldt = Co4 rounded up to 8, zero padded)
  * phase 1: dz [B,R,Cmid] and dbz [Cmid] (pre-zeroed) */
 extern "C" int vb200_head_tail_bwd(int phase, const void* z, const float* mean, const float* rstd,
                                    const float* alpha, int alpha_n, const float* W1, const void* dout,
-                                   float* sdp, float* sdpx, float* dW1, float* db1, float* dalpha, void* dz,
-                                   float* dbz, int B, int Dz, int H, int W, int Cmid, int Co4, int dtype,
+                                   float* sdp, float* sdpx, float* db1, float* dalpha, void* act_out, void* dt_out,
+                                   void* dz, float* dbz, int B, int Dz, int H, int W, int Cmid, int Co4, int dtype,
                                    vb200_stream_t stream) {
   VB_REQUIRE(z && mean && rstd && alpha && W1 && dout && sdp && sdpx, "null pointer");
-  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= 16 && 256 % (Cmid / 8) == 0, "head tail: Cmid %d / Co4 %d", Cmid, Co4);
+  VB_SUPPORTED(Cmid % 8 == 0 && Co4 % 4 == 0 && Co4 <= 16 && 32 % (Cmid / 8) == 0 && Cmid <= 256,
+               "head tail: Cmid %d / Co4 %d", Cmid, Co4);
   const long long R = (long long)Dz * H * W;
-  VB_SUPPORTED(R * Cmid < (1LL << 31) && R * Co4 < (1LL << 31), "head: per-sample extent too large");
+  VB_SUPPORTED(R * Cmid < (1LL << 31) && R * 16 < (1LL << 31), "head: per-sample extent too large");
   long long rpb = (R * B + 148 * 16 - 1) / (148 * 16);
   if (rpb < 256) rpb = 256;
   if (rpb > R) rpb = R;
   dim3 grid((unsigned)((R + rpb - 1) / rpb), B);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem0 = sizeof(float) * (Co4 * Cmid + 3 * Cmid + 2 * Cmid + Co4 * Cmid + Co4 + Cmid);
-  const size_t smem1 = sizeof(float) * (Co4 * Cmid + 3 * Cmid + 3 * Cmid);
-#define HT2(BF, MODE, SM, MO) head_tail_bwd_kernel<BF, MODE, MO><<<grid, 256, SM, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1, (const uint16_t*)dout, sdp, sdpx, dW1, db1, dalpha, (uint4*)dz, dbz, Dz, H, W, Cmid, Co4, (int)rpb)
-#define HT(BF, MODE, SM) do { if (Co4 <= 4) HT2(BF, MODE, SM, 4); else if (Co4 <= 8) HT2(BF, MODE, SM, 8); else HT2(BF, MODE, SM, 16); } while (0)
+  const int maxo = Co4 <= 8 ? 8 : 16;
+  const int ldt = (Co4 + 7) / 8 * 8;
+  const size_t smem = sizeof(float) * (Cmid * maxo + 3 * Cmid + maxo);
+#define HT2(BF, MODE, MO)                                                                                             \
+  head_tail_bwd_kernel<BF, MODE, MO><<<grid, 256, smem, st>>>((const uint4*)z, mean, rstd, alpha, alpha_n, W1,        \
+                                                             (const uint16_t*)dout, sdp, sdpx, db1, dalpha,          \
+                                                             (uint4*)act_out, (uint16_t*)dt_out, (uint4*)dz, dbz, Dz, \
+                                                             H, W, Cmid, Co4, ldt, (int)rpb)
+#define HT(BF, MODE) do { if (maxo == 8) HT2(BF, MODE, 8); else HT2(BF, MODE, 16); } while (0)
   if (phase == 0) {
-    VB_REQUIRE(dW1 && db1 && dalpha, "null pointer");
-    if (dtype == VB200_BF16) HT(true, 0, smem0); else HT(false, 0, smem0);
+    VB_REQUIRE(db1 && dalpha && act_out && dt_out, "null pointer");
+    if (dtype == VB200_BF16) HT(true, 0); else if (dtype == VB200_FP16) HT(false, 0); else return fail(VB200_ERR_UNSUPPORTED, "dtype");
   } else {
     VB_REQUIRE(dz && dbz, "null pointer");
-    if (dtype == VB200_BF16) HT(true, 1, smem1); else HT(false, 1, smem1);
+    if (dtype == VB200_BF16) HT(true, 1); else if (dtype == VB200_FP16) HT(false, 1); else return fail(VB200_ERR_UNSUPPORTED, "dtype");
   }
 #undef HT
 #undef HT2

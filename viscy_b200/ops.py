@@ -389,17 +389,23 @@ def head_tail_bwd(z, mean, rstd, alpha, W1, dout, Dz, H, W):
     """-> dz, dW1, db1, dalpha, dbz (bias gradient of the conv that produced z)"""
     B, R, Cmid = z.shape
     Co4 = W1.shape[0]
+    ldt = -(-Co4 // 8) * 8
     dev = z.device
-    f = dict(device=dev, dtype=torch.float32)
-    sdp, sdpx = torch.zeros((B, Cmid), **f), torch.zeros((B, Cmid), **f)
-    dW1, db1 = torch.zeros((Co4, Cmid), **f), torch.zeros((Co4,), **f)
-    dalpha, dbz = torch.zeros((alpha.numel(),), **f), torch.zeros((Cmid,), **f)
+    ar = Arena(dev, [2 * B * Cmid, Co4, alpha.numel(), Cmid])
+    sdp, sdpx = ar.take(B, Cmid), ar.take(B, Cmid)
+    db1, dalpha, dbz = ar.take(Co4), ar.take(alpha.numel()), ar.take(Cmid)
+    act = torch.empty_like(z)
+    dt_rows = torch.empty((B, R, ldt), device=dev, dtype=z.dtype)
     dz = torch.empty_like(z)
     dt = L.dtype_code(z.dtype)
     dout = _act(dout, "dout")
     for phase in (0, 1):
         _call("vb200_head_tail_bwd", phase, _p(z), _p(mean), _p(rstd), _p(alpha), alpha.numel(), _p(W1), _p(dout),
-              _p(sdp), _p(sdpx), _p(dW1), _p(db1), _p(dalpha), _p(dz), _p(dbz), B, Dz, H, W, Cmid, Co4, dt)
+              _p(sdp), _p(sdpx), _p(db1), _p(dalpha), _p(act), _p(dt_rows), _p(dz), _p(dbz), B, Dz, H, W, Cmid, Co4, dt)
+        if phase == 0:
+            # dW1[o, c] = sum_rows dt[row, o] * act[row, c] on the tensor cores (MN-major wgrad GEMM, K-split)
+            dW1 = gemm(dt_rows.view(B * R, ldt), act.view(B * R, Cmid), mn_major=True, epilogue=L.EPI_F32,
+                       k_splits=min(148, max(1, (B * R) // 4096)))[:Co4]
     return dz, dW1, db1, dalpha, dbz
 
 

@@ -272,7 +272,9 @@ def run_gpu(args):
         flops = 2.0 * M * C * C4
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
-                "traffic": None,
+                # dram__bytes_read+write per launch, mean of the four launches, from the committed `ncu --set full`
+                # capture of this same command (profiles/r1_gemm_dec2_ncu_summary.txt)
+                "traffic": 384.0e6,
                 "kernel": "gemm_kernel<256,K-major,*>: decoder-stage-2 GEMMs M=32768, 736<->2944 (142 GFLOP per launch)",
                 "per_launch_ms": per, "avg_ms": avg_ms, "launches_timed": reps * len(per),
                 "peak_source": f"bf16_tflops_sustained ({src})"}

@@ -30,7 +30,7 @@ enum { VB200_BF16 = 0, VB200_FP16 = 1 };
 
 /* GEMM epilogues (fused into the tcgen05 kernel's TMEM->register drain) */
 enum {
-  VB200_EPI_STORE = 0,     /* out = act(acc + bias[col]) (+ residual[row,col]) -> 16-bit          */
+  VB200_EPI_STORE = 0,     /* out = act((acc + bias[col]) * s[col]) (+ residual[row,col]) -> 16-bit; s = svec or 1 */
   VB200_EPI_GELU_DUAL = 1, /* u = acc + bias; out = u; out2 = gelu(u); optional sum(g^2) partials */
   VB200_EPI_DGELU = 2,     /* out = (acc + bias) * gelu'(u), u = aux[row,col]  (dgrad through GELU)      */
   VB200_EPI_F32 = 3,       /* out(fp32) = acc (+ bias[col]); optional atomic accumulate / K-split slabs */
@@ -68,7 +68,7 @@ typedef struct vb200_gemm_desc {
   const void* aux;       /* EPI_DGELU: u (pre-activation), 16-bit [M,ldaux]; EPI_DGELU_GRN: g = gelu(u) */
   const void* aux2;      /* EPI_DGELU_GRN: gp = gelu'(u), 16-bit [M,ldaux2] */
   const float* tvec;     /* EPI_DGELU_GRN: t [nsamples, N] fp32 or NULL */
-  const float* svec;     /* EPI_DGELU_GRN: s [nsamples, N] fp32 or NULL */
+  const float* svec;     /* EPI_DGELU_GRN: s [nsamples, N] fp32 or NULL; EPI_STORE: per-column scale [N] or NULL */
 } vb200_gemm_desc;
 
 int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);
@@ -151,6 +151,18 @@ int vb200_col2im3d(const void* dcol, void* du, const int32_t* geom, int dtype, v
 int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t stream);
 /* fp32 [R,Cc] -> 16-bit (weight packing); transpose != 0 writes [Cc,R] */
 int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype, vb200_stream_t stream);
+
+/* ---- ContrastiveEncoder pooled head + projection MLP (VM/contrastive/encoder.py:114-124,138-154) ---- */
+/* nn.BatchNorm1d over rows of x [B,C] 16-bit (+ optional fused ReLU); training: batch statistics, var_unbiased (for the
+ * running-var update) written when non-NULL; eval: run_mean / run_var are used */
+int vb200_bn_rows_fwd(const void* x, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
+                      void* y, float* mean, float* rstd, float* var_unbiased, int B, int C, float eps, int training,
+                      int relu, int dtype, vb200_stream_t stream);
+int vb200_bn_rows_bwd(const void* dy, const void* x, const void* y, const float* gamma, const float* mean,
+                      const float* rstd, void* dx, float* dgamma, float* dbeta, int B, int C, int training, int relu,
+                      int dtype, vb200_stream_t stream);
+/* out[b,r,c] = src[b,c] * scale: gradient of timm's global average pool (SelectAdaptivePool2d('avg')) */
+int vb200_bcast_rows(const void* src, void* out, int B, int R, int C, float scale, int dtype, vb200_stream_t stream);
 
 /* ---- implicit-GEMM Conv3d k=3, stride 1, small channel counts (tcgen05, im2col folded into 5-D TMA boxes) ----
  * Replaces nn.Conv3d(k=3) of monai Convolution in PixelToVoxelHead (VM/components/heads.py:607-628) and its cuDNN

@@ -6,9 +6,10 @@ Drop-in modules with the reference's constructor / forward / state_dict surface:
 architecture registries.
 """
 
+from .contrastive import ContrastiveEncoder  # noqa: F401
 from .unext2 import UNeXt2  # noqa: F401
 
-__all__ = ["UNeXt2"]
+__all__ = ["UNeXt2", "ContrastiveEncoder"]
 
 
 def patch_viscy() -> list[str]:

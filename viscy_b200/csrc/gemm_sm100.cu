@@ -162,6 +162,10 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] += cv[cl + j];
   if constexpr (EPI == VB200_EPI_STORE) {
+    if (p.svec != nullptr) {  // per-column fp32 scale (ConvNeXt-V1 layer scale gamma): (acc + bias) * s
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= cv[BN + cl + j];
+    }
     if (p.act == VB200_ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -345,7 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int col = n0 + et;
         const bool ok = col < p.N;
         cv[et] = (p.bias != nullptr && split == 0 && ok) ? __ldg(p.bias + col) : 0.0f;
-        if constexpr (EPI == VB200_EPI_DGELU_GRN) {
+        if constexpr (EPI == VB200_EPI_DGELU_GRN || EPI == VB200_EPI_STORE) {
           const long long ns = p.rows_per_sample > 0 ? m0 / p.rows_per_sample : 0;
           cv[BN + et] = (p.svec != nullptr && ok) ? __ldg(p.svec + ns * p.N + col) : 1.0f;
           cv[2 * BN + et] = (p.tvec != nullptr && ok) ? __ldg(p.tvec + ns * p.N + col) : 0.0f;

@@ -321,3 +321,147 @@ extern "C" int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200
   dw_pack_kernel<<<blocks_for(49LL * C), 256, 0, (cudaStream_t)stream>>>(w, wt, wtf, C);
   return check_launch("vb200_dw_pack");
 }
+
+// ------------------------------------------------------------------------------ small-row helpers (projection head)
+namespace vb {
+
+// BatchNorm1d over rows of x [B, C] (16-bit): one thread per column.
+// training: batch statistics (biased variance for normalisation), mean / rstd / unbiased var written out;
+// eval: use the provided running mean / var.  Optional fused ReLU.
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+bn_rows_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ run_mean, const float* __restrict__ run_var, uint16_t* __restrict__ y,
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ var_unbiased,
+                   int B, int C, float eps, int training, int relu) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  using T = typename H16<BF16>::T;
+  const T* xp = reinterpret_cast<const T*>(x);
+  float m, var;
+  if (training) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += H16<BF16>::to_f(xp[(long long)b * C + c]);
+    m = s / B;
+    float q = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float d = H16<BF16>::to_f(xp[(long long)b * C + c]) - m;
+      q = fmaf(d, d, q);
+    }
+    var = q / B;
+    if (var_unbiased != nullptr) var_unbiased[c] = B > 1 ? q / (B - 1) : q;
+  } else {
+    m = run_mean[c];
+    var = run_var[c];
+  }
+  const float rs = rsqrtf(var + eps);
+  mean_out[c] = m;
+  rstd_out[c] = rs;
+  const float g = gamma[c], bt = beta[c];
+  T* yp = reinterpret_cast<T*>(y);
+  for (int b = 0; b < B; ++b) {
+    float v = (H16<BF16>::to_f(xp[(long long)b * C + c]) - m) * rs * g + bt;
+    if (relu) v = fmaxf(v, 0.f);
+    yp[(long long)b * C + c] = H16<BF16>::from_f(v);
+  }
+}
+
+// backward of the above (y is the forward output, used for the ReLU mask)
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+bn_rows_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                   const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                   uint16_t* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C,
+                   int training, int relu) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  using T = typename H16<BF16>::T;
+  const T* dyp = reinterpret_cast<const T*>(dy);
+  const T* xp = reinterpret_cast<const T*>(x);
+  const T* yp = reinterpret_cast<const T*>(y);
+  const float m = mean[c], rs = rstd[c], g = gamma[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float d = H16<BF16>::to_f(dyp[(long long)b * C + c]);
+    if (relu && !(H16<BF16>::to_f(yp[(long long)b * C + c]) > 0.f)) d = 0.f;
+    const float xh = (H16<BF16>::to_f(xp[(long long)b * C + c]) - m) * rs;
+    s1 += d;
+    s2 = fmaf(d, xh, s2);
+  }
+  dgamma[c] = s2;
+  dbeta[c] = s1;
+  T* dxp = reinterpret_cast<T*>(dx);
+  for (int b = 0; b < B; ++b) {
+    float d = H16<BF16>::to_f(dyp[(long long)b * C + c]);
+    if (relu && !(H16<BF16>::to_f(yp[(long long)b * C + c]) > 0.f)) d = 0.f;
+    const float xh = (H16<BF16>::to_f(xp[(long long)b * C + c]) - m) * rs;
+    const float v = training ? g * rs * (d - s1 / B - xh * s2 / B) : g * rs * d;
+    dxp[(long long)b * C + c] = H16<BF16>::from_f(v);
+  }
+}
+
+// out[b, r, c] = src[b, c] * scale   (gradient of the global average pool), 8 channels per thread
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+bcast_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ out, int R, int C8, float scale, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  const long long b = idx / ((long long)R * C8);
+  const uint4 q = __ldg(src + b * C8 + c8);
+  const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = H16<BF16>::unpack(w4[k]);
+    o[k] = H16<BF16>::pack(f.x * scale, f.y * scale);
+  }
+  out[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+}  // namespace vb
+
+extern "C" int vb200_bn_rows_fwd(const void* x, const float* gamma, const float* beta, const float* run_mean,
+                                 const float* run_var, void* y, float* mean, float* rstd, float* var_unbiased, int B,
+                                 int C, float eps, int training, int relu, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(x && gamma && beta && y && mean && rstd && (training || (run_mean && run_var)), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((C + 127) / 128);
+  if (dtype == VB200_BF16)
+    bn_rows_fwd_kernel<true><<<grid, 128, 0, st>>>((const uint16_t*)x, gamma, beta, run_mean, run_var, (uint16_t*)y, mean, rstd, var_unbiased, B, C, eps, training, relu);
+  else if (dtype == VB200_FP16)
+    bn_rows_fwd_kernel<false><<<grid, 128, 0, st>>>((const uint16_t*)x, gamma, beta, run_mean, run_var, (uint16_t*)y, mean, rstd, var_unbiased, B, C, eps, training, relu);
+  else
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return check_launch("vb200_bn_rows_fwd");
+}
+
+extern "C" int vb200_bn_rows_bwd(const void* dy, const void* x, const void* y, const float* gamma, const float* mean,
+                                 const float* rstd, void* dx, float* dgamma, float* dbeta, int B, int C, int training,
+                                 int relu, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(dy && x && y && gamma && mean && rstd && dx && dgamma && dbeta, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((C + 127) / 128);
+  if (dtype == VB200_BF16)
+    bn_rows_bwd_kernel<true><<<grid, 128, 0, st>>>((const uint16_t*)dy, (const uint16_t*)x, (const uint16_t*)y, gamma, mean, rstd, (uint16_t*)dx, dgamma, dbeta, B, C, training, relu);
+  else if (dtype == VB200_FP16)
+    bn_rows_bwd_kernel<false><<<grid, 128, 0, st>>>((const uint16_t*)dy, (const uint16_t*)x, (const uint16_t*)y, gamma, mean, rstd, (uint16_t*)dx, dgamma, dbeta, B, C, training, relu);
+  else
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return check_launch("vb200_bn_rows_bwd");
+}
+
+extern "C" int vb200_bcast_rows(const void* src, void* out, int B, int R, int C, float scale, int dtype,
+                                vb200_stream_t stream) {
+  VB_REQUIRE(src && out, "null pointer");
+  VB_SUPPORTED(C % 8 == 0, "C (%d) %% 8", C);
+  const long long total = (long long)B * R * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_BF16)
+    bcast_rows_kernel<true><<<blocks_for(total), 256, 0, st>>>((const uint4*)src, (uint4*)out, R, C / 8, scale, total);
+  else if (dtype == VB200_FP16)
+    bcast_rows_kernel<false><<<blocks_for(total), 256, 0, st>>>((const uint4*)src, (uint4*)out, R, C / 8, scale, total);
+  else
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return check_launch("vb200_bcast_rows");
+}

@@ -103,12 +103,9 @@ class ConvNeXtBlockFn(Function):
         else:
             h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP)  # h := gelu'(u)
             sumsq = s = None
-        if gamma is not None:
-            w2_eff = fc2_w.detach().reshape(C, C4) * gamma.detach()[:, None]
-            b2_eff = fc2_b.detach() * gamma.detach()
-        else:
-            w2_eff, b2_eff = fc2_w.detach().reshape(C, C4), fc2_b.detach()
-        out = ops.gemm(y2, ops.cast_pack(w2_eff, x.dtype), bias=b2_eff.contiguous(), residual=x.view(M, C))
+        # ConvNeXt-V1 layer scale: out = gamma * (y W2^T + b2) + x, gamma applied in fp32 in the epilogue
+        out = ops.gemm(y2, ops.cast_pack(fc2_w.detach().reshape(C, C4), x.dtype), bias=fc2_b.detach(),
+                       svec=None if gamma is None else gamma.detach(), residual=x.view(M, C))
         ctx.fused = False
         ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma)
         ctx.use_grn = use_grn
@@ -142,28 +139,28 @@ class ConvNeXtBlockFn(Function):
             dw2 = dw2.view(fc2_w.shape)
             dgamma = None
         else:
-            if gamma is not None:
-                w2_eff = fc2_w.reshape(C, C4) * gamma[:, None]
-            else:
-                w2_eff = fc2_w.reshape(C, C4)
+            w2 = fc2_w.reshape(C, C4)
             if ctx.use_grn:
-                dy, dw2_eff, db2_eff = linear_bwd(do2, y2, w2_eff)
-                dw2, db2, dgamma = dw2_eff.view(fc2_w.shape), db2_eff, None
+                dy, dw2, db2 = linear_bwd(do2, y2, w2)
+                dw2, dgamma = dw2.view(fc2_w.shape), None
                 dh, dgw, dgb, db1 = ops.gelu_grn_bwd(h.view(B, H * W, C4), dy.view(B, H * W, C4), sumsq, s, grn_w)
             else:
                 # ConvNeXt-V1: GELU backward rides in the fc2-dgrad epilogue (h holds gelu'(u))
-                _, dw2_eff, db2_eff = linear_bwd(do2, y2, w2_eff, need_da=False)
-                w2t = ops.cast_pack(w2_eff, x.dtype, transpose=True)
-                dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux2=h)
-                db1 = ops.colreduce(dh.view(1, M, C4), 0).view(C4)
-                dgw = dgb = None
+                _, G, db_raw = linear_bwd(do2, y2, w2, need_da=False)  # G = dout^T y (without the layer scale)
                 if gamma is not None:
-                    # out = gamma * (y W2^T + b2): chain rule through the folded layer scale
-                    dgamma = (dw2_eff * fc2_w.reshape(C, C4)).sum(1) + db2_eff * fc2_b
-                    dw2 = (dw2_eff * gamma[:, None]).view(fc2_w.shape)
-                    db2 = db2_eff * gamma
+                    # out = gamma * (y W2^T + b2): weights carry gamma / max|gamma| (16-bit safe), the epilogue the rest
+                    gmax = gamma.abs().max().clamp_min(1e-30)
+                    w2n = w2 * (gamma / gmax)[:, None]
+                    sv = gmax.expand(C4).contiguous()
+                    dgamma = (G * w2).sum(1) + db_raw * fc2_b
+                    dw2, db2 = (G * gamma[:, None]).view(fc2_w.shape), db_raw * gamma
                 else:
-                    dgamma, dw2, db2 = None, dw2_eff.view(fc2_w.shape), db2_eff
+                    w2n, sv, dgamma, dw2, db2 = w2, None, None, G.view(fc2_w.shape), db_raw
+                w2t = ops.cast_pack(w2n, x.dtype, transpose=True)
+                dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux2=h, svec=sv,
+                              rows_per_sample=128 * (-(-M // 128)) if sv is not None else 0)
+                db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
+                dgw = dgb = None
         dh2 = dh.view(M, C4)
         main = torch.cuda.current_stream()
         side = _side_stream(x.device) if OVERLAP_WGRAD else main
@@ -425,3 +422,83 @@ class HeadFn(Function):
 
 def pixel_to_voxel_head(dec, conv0, prelu, conv1, out_depth, pool):
     return HeadFn.apply(dec, conv0.weight, conv0.bias, prelu.weight, conv1.weight, conv1.bias, out_depth, pool)
+
+
+# --------------------------------------------------------------------------------------------------
+class AvgPoolLNFn(Function):
+    """timm NormMlpClassifierHead up to `flatten`: global average pool over (H, W) then LayerNorm2d over C.
+    NHWC [B,H,W,C] -> [B,C]."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps):
+        B, H, W, C = x.shape
+        pooled = (ops.colreduce(x.view(B, H * W, C), 0) * (1.0 / (H * W))).to(x.dtype)
+        y, mean, rstd = ops.layernorm_fwd(pooled, ln_w, ln_b, eps)
+        ctx.save_for_backward(pooled, mean, rstd, ln_w)
+        ctx.hw = (H, W)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        pooled, mean, rstd, ln_w = ctx.saved_tensors
+        H, W = ctx.hw
+        dp, dw, db = ops.layernorm_bwd(dy.contiguous().to(pooled.dtype), pooled, mean, rstd, ln_w)
+        dx = ops.bcast_rows(dp, H * W, 1.0 / (H * W))
+        return dx.view(pooled.shape[0], H, W, pooled.shape[1]), dw, db, None
+
+
+def avgpool_ln(x, ln):
+    return AvgPoolLNFn.apply(x, ln.weight, ln.bias, ln.eps)
+
+
+class LinearFn(Function):
+    """nn.Linear on 16-bit rows through the tcgen05 GEMM."""
+
+    @staticmethod
+    def forward(ctx, a, w, b):
+        ctx.save_for_backward(a, w)
+        return linear_fwd(a, w, b)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        a, w = ctx.saved_tensors
+        da, dw, db = linear_bwd(dout.contiguous(), a, w)
+        return da, dw, db
+
+
+class BatchNormRowsFn(Function):
+    """nn.BatchNorm1d (+ optional ReLU) over [B, C] rows; running statistics are updated by the caller."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run_mean, run_var, eps, training, relu):
+        y, mean, rstd, var_unb = ops.bn_rows_fwd(x, weight, bias, run_mean, run_var, eps, training, relu)
+        ctx.save_for_backward(x, y, weight, mean, rstd)
+        ctx.flags = (training, relu)
+        ctx.mark_non_differentiable(mean)
+        if var_unb is None:
+            var_unb = mean
+        ctx.mark_non_differentiable(var_unb)
+        return y, mean, var_unb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _dm, _dv):
+        x, y, weight, mean, rstd = ctx.saved_tensors
+        training, relu = ctx.flags
+        dx, dg, db = ops.bn_rows_bwd(dy.contiguous(), x, y, weight, mean, rstd, training, relu)
+        return dx, dg, db, None, None, None, None, None
+
+
+def batchnorm_rows(x, bn, relu=False):
+    """Apply an nn.BatchNorm1d module (train: batch stats + running-stat update with its momentum; eval: running stats)."""
+    training = bn.training or bn.running_mean is None
+    y, mean, var_unb = BatchNormRowsFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, training, relu)
+    if bn.training and bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var_unb, alpha=mom)
+    return y

@@ -500,3 +500,35 @@ def conv3d_k3_wgrad(u, dz, padding):
     _call("vb200_conv3d_k3_wgrad", _p(_act(u, "u")), _p(_act(dz, "dz")), _p(dw), g, cin, Co, L.dtype_code(u.dtype))
     # [co, (kd,kh), kw, ci] -> [co, ci, kd, kh, kw]
     return dw.view(Co, 3, 3, 3, 8).permute(0, 4, 1, 2, 3)
+
+
+# ----------------------------------------------------------------------------------------------
+# ContrastiveEncoder pooled head / projection MLP
+def bn_rows_fwd(x, gamma, beta, run_mean, run_var, eps, training, relu):
+    """x [B,C] 16-bit -> (y, mean [C], rstd [C], unbiased batch var [C] or None)"""
+    _act(x, "x")
+    B, Cc = x.shape
+    y = torch.empty_like(x)
+    st = torch.empty((3, Cc), device=x.device, dtype=torch.float32)
+    _call("vb200_bn_rows_fwd", _p(x), _p(_f32(gamma, "weight")), _p(_f32(beta, "bias")), _p(run_mean), _p(run_var), _p(y),
+          _p(st[0]), _p(st[1]), _p(st[2]) if training else _p(None), B, Cc, C.c_float(eps), int(training), int(relu),
+          L.dtype_code(x.dtype))
+    return y, st[0], st[1], (st[2] if training else None)
+
+
+def bn_rows_bwd(dy, x, y, gamma, mean, rstd, training, relu):
+    B, Cc = x.shape
+    dx = torch.empty_like(x)
+    g = torch.empty((2, Cc), device=x.device, dtype=torch.float32)
+    _call("vb200_bn_rows_bwd", _p(_act(dy, "dy")), _p(x), _p(y), _p(_f32(gamma, "weight")), _p(mean), _p(rstd), _p(dx),
+          _p(g[0]), _p(g[1]), B, Cc, int(training), int(relu), L.dtype_code(x.dtype))
+    return dx, g[0], g[1]
+
+
+def bcast_rows(src, R, scale):
+    """src [B,C] 16-bit -> [B,R,C] = src * scale"""
+    _act(src, "src")
+    B, Cc = src.shape
+    out = torch.empty((B, R, Cc), device=src.device, dtype=src.dtype)
+    _call("vb200_bcast_rows", _p(src), _p(out), B, R, Cc, C.c_float(scale), L.dtype_code(src.dtype))
+    return out

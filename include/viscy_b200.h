@@ -152,6 +152,27 @@ int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t s
 /* fp32 [R,Cc] -> 16-bit (weight packing); transpose != 0 writes [Cc,R] */
 int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype, vb200_stream_t stream);
 
+/* ---- 3-D U-Net family: UNet3DBase / Unet3d (VM/unet/unet3d_base.py:145-198, VM/unet/blocks.py:88-113) ---- */
+/* model boundary: x (N,C,S) [x_dtype 0 bf16 | 1 fp16 | 2 fp32] -> y (N,S,Cpad) 16-bit channels-last, zero channel padding */
+int vb200_to_channels_last(const void* x, int x_dtype, void* y, int64_t N, int C, int Cpad, int64_t S, int dtype,
+                           vb200_stream_t stream);
+int vb200_from_channels_last(const void* y, void* x, int64_t N, int C, int Cpad, int64_t S, vb200_stream_t stream);
+/* y = act(x * scale[c] + shift[c]) on rows [M,C]: nn.BatchNorm3d (folded statistics) + nn.ReLU of Block.forward */
+int vb200_affine_act(const void* x, const float* scale, const float* shift, void* y, int64_t M, int C, int relu, int dtype,
+                     vb200_stream_t stream);
+/* BatchNorm backward: s1[c] += sum dy', s2[c] += sum dy' * xhat (dy' = dy masked by y > 0 when relu); s1, s2 pre-zeroed */
+int vb200_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean, const float* rstd, float* s1,
+                        float* s2, int64_t M, int C, int relu, int dtype, vb200_stream_t stream);
+/* dx = g[c] * (dy' - m1[c] - xhat * m2[c]) */
+int vb200_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* mean, const float* rstd, const float* g,
+                       const float* m1, const float* m2, void* dx, int64_t M, int C, int relu, int dtype,
+                       vb200_stream_t stream);
+/* torch.cat([a, b], 1) on channels-last rows (inverse != 0: split out back into a and b) */
+int vb200_cat2(void* a, void* b, void* out, int64_t M, int Ca, int Cb, int inverse, vb200_stream_t stream);
+/* y = x (+ other) (+ bias[c]) on rows [M,C] */
+int vb200_add_rows(const void* x, const void* other, const float* bias, void* y, int64_t M, int C, int dtype,
+                   vb200_stream_t stream);
+
 /* ---- ContrastiveEncoder pooled head + projection MLP (VM/contrastive/encoder.py:114-124,138-154) ---- */
 /* nn.BatchNorm1d over rows of x [B,C] 16-bit (+ optional fused ReLU); training: batch statistics, var_unbiased (for the
  * running-var update) written when non-NULL; eval: run_mean / run_var are used */

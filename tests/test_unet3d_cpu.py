@@ -1,0 +1,57 @@
+"""Unet3d / UNet3DBase / Unet25d host mirrors (CPU, fp32) against golden vectors from the reference's own code
+(BASELINE configs 1 and 5 at reduced size)."""
+from pathlib import Path
+
+import pytest
+import torch
+
+from viscy_b200 import Unet3d, Unet25d, UNet3DBase
+from viscy_b200.unet3d import ConvBottleneck3D
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.mark.parametrize("name,cls", [("unet3d", Unet3d), ("unet25d", Unet25d)])
+def test_cpu_matches_reference_golden(name, cls):
+    g = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    torch.manual_seed(g["seed"])  # same RNG consumption as the reference constructor -> identical weights
+    m = cls(**g["cfg"])
+    assert len(m.state_dict()) == g["n_keys"]
+    out = m(g["x"])
+    torch.testing.assert_close(out, g["outs"][0], rtol=1e-5, atol=1e-6)
+    loss = torch.nn.functional.mse_loss(out, g["targets"][0])
+    loss.backward()
+    assert abs(loss.item() - g["loss"]) < 1e-5
+    for n, p in m.named_parameters():
+        if p.grad is None:  # ConvBlock3D.resid_conv is registered but unused when residual=False (reference behaviour)
+            assert n not in g["grad_norms"]
+            continue
+        ref = g["grad_norms"][n]
+        assert abs(p.grad.norm().item() - ref) <= 1e-4 * max(ref, 1e-3), n
+
+
+def test_key_counts_pinned_by_reference():
+    """test_state_dict_compat.py:286 (Unet25d = 147) and the 146 keys of Unet3d(3,3,4,32)."""
+    sd = Unet25d().state_dict()
+    assert len(sd) == 147
+    for k in ["down_conv_block_2.Conv3d_1.weight", "up_conv_block_3.resid_conv.bias"]:
+        assert k in sd
+    assert len(Unet3d(3, 3, 4, 32).state_dict()) == 146
+    assert Unet3d(1, 1, depth=2, mult_chan=4).num_blocks == 2 and Unet3d().downsamples_z
+
+
+def test_unet3d_validation_errors():
+    m = Unet3d(1, 1, depth=3, mult_chan=4)
+    with pytest.raises(ValueError, match="must be divisible by 8"):
+        m(torch.randn(1, 1, 12, 16, 16))
+    with pytest.raises(ValueError, match="must equal"):
+        UNet3DBase(1, 1, dims=[4, 8], num_res_block=[1, 1], bottleneck=ConvBottleneck3D(8))
+    # F-Net initialisation: conv weights ~ N(0, 0.02)
+    assert abs(m.inconv.weight.std().item() - 0.02) < 0.01
+
+
+def test_unet25d_rejects_cuda_clearly():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA tensor")
+    with pytest.raises(NotImplementedError):
+        Unet25d().cuda()(torch.randn(1, 1, 5, 32, 32, device="cuda"))

@@ -7,9 +7,11 @@ architecture registries.
 """
 
 from .contrastive import ContrastiveEncoder  # noqa: F401
+from .unet25d import ConvBlock3D, Unet25d  # noqa: F401
+from .unet3d import UNet3DBase, Unet3d  # noqa: F401
 from .unext2 import UNeXt2  # noqa: F401
 
-__all__ = ["UNeXt2", "ContrastiveEncoder"]
+__all__ = ["UNeXt2", "ContrastiveEncoder", "Unet3d", "UNet3DBase", "Unet25d", "ConvBlock3D"]
 
 
 def patch_viscy() -> list[str]:
@@ -27,6 +29,9 @@ def patch_viscy() -> list[str]:
         reg = getattr(mod, attr, None)
         if isinstance(reg, dict) and "UNeXt2" in reg:
             reg["UNeXt2"] = UNeXt2
+            for key, cls in (("FNet3D", Unet3d), ("2.5D", Unet25d)):
+                if key in reg:
+                    reg[key] = cls
             patched.append(f"{mod_name}.{attr}")
     return patched
 

@@ -502,3 +502,231 @@ def batchnorm_rows(x, bn, relu=False):
             bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
             bn.running_var.mul_(1 - mom).add_(var_unb, alpha=mom)
     return y
+
+
+# --------------------------------------------------------------------------------------------------
+# 3-D U-Net family (UNet3DBase / Unet3d): channels-last [N,D,H,W,C] 16-bit activations
+def _pad8(c: int) -> int:
+    return -(-c // 8) * 8
+
+
+class ToChannelsLast3dFn(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.c = x.shape[1]
+        return ops.to_channels_last_3d(x, dtype, _pad8(x.shape[1]))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return ops.from_channels_last_3d(dy.contiguous(), ctx.c).float(), None
+
+
+def to_channels_last_3d(x, dtype):
+    if x.requires_grad:
+        return ToChannelsLast3dFn.apply(x, dtype)
+    return ops.to_channels_last_3d(x, dtype, _pad8(x.shape[1]))
+
+
+class FromChannelsLast3dFn(Function):
+    @staticmethod
+    def forward(ctx, y, c):
+        ctx.cpad = y.shape[-1]
+        return ops.from_channels_last_3d(y, c)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dx):
+        return ops.to_channels_last_3d(dx, dx.dtype, ctx.cpad), None
+
+
+def from_channels_last_3d(y, c):
+    return FromChannelsLast3dFn.apply(y, c)
+
+
+def _conv_weight_rows(w, cin_pad, cout_pad):
+    """nn.Conv3d weight [Co,Ci,kd,kh,kw] -> fp32 [cout_pad, (kd,kh,kw,cin_pad)] (zero padded)"""
+    Co, Ci = w.shape[:2]
+    wk = w.permute(0, 2, 3, 4, 1)
+    if cin_pad != Ci or cout_pad != Co:
+        wk = torch.nn.functional.pad(wk, (0, cin_pad - Ci, 0, 0, 0, 0, 0, 0, 0, cout_pad - Co))
+    return wk.reshape(cout_pad, -1).contiguous()
+
+
+class Conv3dFn(Function):
+    """nn.Conv3d (any kernel / stride / padding, groups=1) on channels-last rows: im2col3d + tcgen05 GEMM (+bias).
+    The patch matrix is rebuilt in backward instead of being kept alive."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        N, D, H, W, Cp = x.shape
+        Co = w.shape[0]
+        Cop = _pad8(Co)
+        ks = tuple(w.shape[2:])
+        geom = ops.conv3d_geom((N, D, H, W, Cp), ks, stride, padding)
+        pointwise = ks == (1, 1, 1) and tuple(stride) == (1, 1, 1) and tuple(padding) == (0, 0, 0)
+        col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
+        wk = _conv_weight_rows(w.detach(), Cp, Cop)
+        bias = None
+        if b is not None:
+            bias = b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))
+        out = ops.gemm(col, ops.cast_pack(wk, x.dtype), bias=bias)
+        ctx.save_for_backward(x, w)
+        ctx.meta = (geom, pointwise, Cop, b is not None)
+        return out.view(N, geom[14], geom[15], geom[16], Cop)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        geom, pointwise, Cop, has_bias = ctx.meta
+        N, D, H, W, Cp = x.shape
+        Co, Ci = w.shape[:2]
+        do2 = dout.contiguous().view(-1, Cop)
+        col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
+        wk = _conv_weight_rows(w, Cp, Cop)
+        dcol, dwk, db = linear_bwd(do2, col, wk, need_da=ctx.needs_input_grad[0], need_db=has_bias)
+        dx = None
+        if dcol is not None:
+            dx = dcol.view(x.shape) if pointwise else ops.col2im3d(dcol, geom)
+        dw = dwk.view(Cop, *w.shape[2:], Cp)[:Co, ..., :Ci].permute(0, 4, 1, 2, 3)
+        return dx, dw, (db[:Co] if has_bias else None), None, None
+
+
+def conv3d_cl(x, conv):
+    if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1) or conv.padding_mode != "zeros":
+        raise NotImplementedError("sm_100a conv3d: groups=1, dilation=1, zero padding only")
+    return Conv3dFn.apply(x, conv.weight, conv.bias, tuple(conv.stride), tuple(conv.padding))
+
+
+class ConvTranspose3dFn(Function):
+    """nn.ConvTranspose3d on channels-last rows = the data gradient of the matching strided conv:
+    rows @ W -> patch gradients -> col2im3d gather (+ bias)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding, output_padding):
+        N, d, h, wd, Cip = x.shape
+        Ci, Co = w.shape[:2]
+        Cop = _pad8(Co)
+        ks = tuple(w.shape[2:])
+        out_sp = tuple((i - 1) * s - 2 * p + k + op for i, s, p, k, op in zip((d, h, wd), stride, padding, ks, output_padding))
+        geom = ops.conv3d_geom((N, *out_sp, Cop), ks, stride, padding)
+        if (geom[14], geom[15], geom[16]) != (d, h, wd):
+            raise NotImplementedError("sm_100a conv_transpose3d: geometry is not the adjoint of a strided conv")
+        wt = _convT_weight_rows(w.detach(), Cip, Cop)  # [(kd,kh,kw,co), ci]
+        dcol = ops.gemm(x.view(-1, Cip), ops.cast_pack(wt, x.dtype))
+        out = ops.col2im3d(dcol, geom)
+        if b is not None:
+            bias = b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))
+            out = ops.add_rows(out, None, bias.contiguous())
+        ctx.save_for_backward(x, w)
+        ctx.meta = (geom, Cop, b is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        geom, Cop, has_bias = ctx.meta
+        Cip = x.shape[-1]
+        Ci, Co = w.shape[:2]
+        dout = dout.contiguous()
+        col = ops.im2col3d(dout, geom)  # [M_in, (kd,kh,kw,co)]
+        wt = _convT_weight_rows(w, Cip, Cop)
+        x2 = x.view(-1, Cip)
+        # dx = col @ wt ; dW^T[(tap,co), ci] = col^T @ x
+        dx = ops.gemm(col, ops.cast_pack(wt, x.dtype, transpose=True)).view(x.shape)
+        dwt = ops.gemm(col, x2, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(col.shape[1], Cip, col.shape[0]))
+        dw = dwt.view(*w.shape[2:], Cop, Cip)[..., :Co, :Ci].permute(4, 3, 0, 1, 2)
+        db = ops.colreduce(dout.view(1, -1, Cop), 0).view(Cop)[:Co] if has_bias else None
+        return dx, dw, db, None, None, None
+
+
+def _convT_weight_rows(w, cin_pad, cout_pad):
+    """nn.ConvTranspose3d weight [Ci,Co,kd,kh,kw] -> fp32 [(kd,kh,kw,cout_pad), cin_pad]"""
+    Ci, Co = w.shape[:2]
+    wt = w.permute(2, 3, 4, 1, 0)  # [kd,kh,kw,Co,Ci]
+    if cin_pad != Ci or cout_pad != Co:
+        wt = torch.nn.functional.pad(wt, (0, cin_pad - Ci, 0, cout_pad - Co))
+    return wt.reshape(-1, cin_pad).contiguous()
+
+
+def conv_transpose3d_cl(x, conv):
+    if conv.groups != 1 or tuple(conv.dilation) != (1, 1, 1):
+        raise NotImplementedError("sm_100a conv_transpose3d: groups=1, dilation=1 only")
+    return ConvTranspose3dFn.apply(x, conv.weight, conv.bias, tuple(conv.stride), tuple(conv.padding),
+                                   tuple(conv.output_padding))
+
+
+class BatchNormActFn(Function):
+    """nn.BatchNorm3d (+ ReLU) on channels-last rows; batch statistics from the vectorised column reductions."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run_mean, run_var, eps, training, relu):
+        Cc = x.shape[-1]
+        M = x.numel() // Cc
+        if training:
+            xs = x.view(1, M, Cc)
+            mean = ops.colreduce(xs, 0).view(Cc) / M
+            var = (ops.colreduce(xs, 1).view(Cc) / M - mean * mean).clamp_min_(0.0)
+        else:
+            mean, var = run_mean, run_var
+        rstd = torch.rsqrt(var + eps)
+        scale = (weight.detach() * rstd).contiguous()
+        shift = (bias.detach() - mean * scale).contiguous()
+        y = ops.affine_act(x, scale, shift, relu)
+        ctx.save_for_backward(x, y, weight, mean.contiguous(), rstd.contiguous())
+        ctx.flags = (training, relu)
+        var_unb = var * (M / max(M - 1, 1))
+        ctx.mark_non_differentiable(mean, var_unb)
+        return y, mean, var_unb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _m, _v):
+        x, y, weight, mean, rstd = ctx.saved_tensors
+        training, relu = ctx.flags
+        dx, dg, db = ops.bn_bwd(dy.contiguous(), x, y, mean, rstd, weight, relu, training)
+        return dx, dg, db, None, None, None, None, None
+
+
+def batchnorm_act_cl(x, bn, relu):
+    training = bn.training or bn.running_mean is None
+    y, mean, var_unb = BatchNormActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, training, relu)
+    if bn.training and bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var_unb, alpha=mom)
+    return y
+
+
+class Cat2Fn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.c = (a.shape[-1], b.shape[-1])
+        return ops.cat2(a, b)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        return ops.split2(dout.contiguous(), *ctx.c)
+
+
+def cat_cl(a, b):
+    return Cat2Fn.apply(a, b)
+
+
+class AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.add_rows(a, b)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return dout, dout
+
+
+def add_cl(a, b):
+    return AddFn.apply(a, b)

@@ -532,3 +532,75 @@ def bcast_rows(src, R, scale):
     out = torch.empty((B, R, Cc), device=src.device, dtype=src.dtype)
     _call("vb200_bcast_rows", _p(src), _p(out), B, R, Cc, C.c_float(scale), L.dtype_code(src.dtype))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# 3-D U-Net family helpers (channels-last rows)
+def to_channels_last_3d(x, dtype, cpad):
+    """x (N,C,D,H,W) fp32/16-bit -> [N,D,H,W,cpad] 16-bit (zero channel padding)."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    N, Cc, D, H, W = x.shape
+    y = torch.empty((N, D, H, W, cpad), device=x.device, dtype=dtype)
+    _call("vb200_to_channels_last", _p(x), _XDT[x.dtype], _p(y), C.c_int64(N), Cc, cpad, C.c_int64(D * H * W),
+          L.dtype_code(dtype))
+    return y
+
+
+def from_channels_last_3d(y, c):
+    """[N,D,H,W,cpad] 16-bit -> (N,c,D,H,W) 16-bit"""
+    _act(y, "y")
+    N, D, H, W, cpad = y.shape
+    x = torch.empty((N, c, D, H, W), device=y.device, dtype=y.dtype)
+    _call("vb200_from_channels_last", _p(y), _p(x), C.c_int64(N), c, cpad, C.c_int64(D * H * W))
+    return x
+
+
+def affine_act(x, scale, shift, relu):
+    _act(x, "x")
+    Cc = x.shape[-1]
+    y = torch.empty_like(x)
+    _call("vb200_affine_act", _p(x), _p(_f32(scale, "scale")), _p(_f32(shift, "shift")), _p(y),
+          C.c_int64(x.numel() // Cc), Cc, int(relu), L.dtype_code(x.dtype))
+    return y
+
+
+def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training):
+    """BatchNorm (+ReLU) backward on rows [..., C] -> (dx, dgamma, dbeta)"""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    dt = L.dtype_code(x.dtype)
+    s = torch.zeros((2, Cc), device=x.device, dtype=torch.float32)
+    _call("vb200_bn_bwd_reduce", _p(_act(dy, "dy")), _p(x), _p(y), _p(mean), _p(rstd), _p(s[0]), _p(s[1]),
+          C.c_int64(M), Cc, int(relu), dt)
+    g = (gamma * rstd).contiguous()
+    m = (s / M) if training else torch.zeros_like(s)
+    dx = torch.empty_like(x)
+    _call("vb200_bn_bwd_apply", _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(m[0]), _p(m[1]), _p(dx),
+          C.c_int64(M), Cc, int(relu), dt)
+    return dx, s[1], s[0]
+
+
+def cat2(a, b):
+    _act(a, "a"), _act(b, "b")
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    out = torch.empty((*a.shape[:-1], Ca + Cb), device=a.device, dtype=a.dtype)
+    _call("vb200_cat2", _p(a), _p(b), _p(out), C.c_int64(a.numel() // Ca), Ca, Cb, 0)
+    return out
+
+
+def split2(dout, Ca, Cb):
+    _act(dout, "dout")
+    M = dout.numel() // (Ca + Cb)
+    a = torch.empty((*dout.shape[:-1], Ca), device=dout.device, dtype=dout.dtype)
+    b = torch.empty((*dout.shape[:-1], Cb), device=dout.device, dtype=dout.dtype)
+    _call("vb200_cat2", _p(a), _p(b), _p(dout), C.c_int64(M), Ca, Cb, 1)
+    return a, b
+
+
+def add_rows(x, other=None, bias=None):
+    _act(x, "x")
+    Cc = x.shape[-1]
+    y = torch.empty_like(x)
+    _call("vb200_add_rows", _p(x), _p(other), _p(bias), _p(y), C.c_int64(x.numel() // Cc), Cc, L.dtype_code(x.dtype))
+    return y

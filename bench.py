@@ -221,13 +221,34 @@ def run_gpu(args):
     yh = y.cpu().pin_memory()
     xd, yd = torch.empty_like(x), torch.empty_like(y)
 
-    def e2e_step():
-        if graphed is not None:  # pinned host buffers are copied straight into the graph's static inputs
-            return graphed(xh, yh).item()
-        xd.copy_(xh, non_blocking=True)
-        yd.copy_(yh, non_blocking=True)
-        return step(xd, yd).item()
+    # Host inputs of step i+1 are copied (pinned host -> device staging buffers, separate stream) while step i runs;
+    # each step then moves staging -> the graph's static inputs (device copy), replays, and reads the loss back.
+    copy_stream = torch.cuda.Stream()
+    xs, ys = torch.empty_like(x), torch.empty_like(y)
+    ready, consumed = torch.cuda.Event(), torch.cuda.Event()
 
+    def prefetch():
+        copy_stream.wait_event(consumed)  # staging buffers have been drained into the static inputs
+        with torch.cuda.stream(copy_stream):
+            xs.copy_(xh, non_blocking=True)
+            ys.copy_(yh, non_blocking=True)
+            ready.record(copy_stream)
+
+    def e2e_step():
+        main = torch.cuda.current_stream()
+        main.wait_event(ready)
+        if graphed is not None:
+            graphed.copy_inputs(xs, ys)  # device copy staging -> static inputs
+        else:
+            xd.copy_(xs)
+            yd.copy_(ys)
+        consumed.record(main)
+        prefetch()  # next step's host->device copy overlaps this step's kernels
+        loss = graphed.replay() if graphed is not None else step(xd, yd)
+        return loss.item()
+
+    consumed.record(torch.cuda.current_stream())
+    prefetch()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 

@@ -38,9 +38,16 @@ class GraphedStep:
             self.static_output = step_fn(*self.static_inputs)
         self.launches_per_replay = _lib.launch_count() - n0
 
-    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+    def copy_inputs(self, *inputs: torch.Tensor) -> None:
+        """Copy fresh inputs into the graph's static buffers (current stream)."""
         for dst, src in zip(self.static_inputs, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
         self.graph.replay()
         return self.static_output
+
+    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        self.copy_inputs(*inputs)
+        return self.replay()

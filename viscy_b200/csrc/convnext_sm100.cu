@@ -24,7 +24,7 @@ __device__ __forceinline__ float2 ldpair(const uint32_t* p, int off, bool ok) {
   return H16<BF16>::unpack(raw);
 }
 
-template <bool BF16, int DW_TH, int DW_TW>
+template <bool BF16, int DW_TH, int DW_TW, bool SMEM_W>
 __global__ void __launch_bounds__(128)
 dwconv7_kernel(const uint32_t* __restrict__ x, const float* __restrict__ wt,
                const float* __restrict__ bias, const uint32_t* __restrict__ add,
@@ -33,11 +33,13 @@ dwconv7_kernel(const uint32_t* __restrict__ x, const float* __restrict__ wt,
   const int cp0 = blockIdx.y * 128;
   const int cp = cp0 + threadIdx.x;
   const int C = C2 * 2;
-  for (int i = threadIdx.x; i < 49 * 128; i += 128) {
-    const int tap = i >> 7, c = cp0 + (i & 127);
-    sw[i] = c < C2 ? __ldg(reinterpret_cast<const float2*>(wt + tap * C) + c) : make_float2(0.f, 0.f);
+  if constexpr (SMEM_W) {  // big tiles: stage the block's 49 x 128 taps once (50 KB)
+    for (int i = threadIdx.x; i < 49 * 128; i += 128) {
+      const int tap = i >> 7, c = cp0 + (i & 127);
+      sw[i] = c < C2 ? __ldg(reinterpret_cast<const float2*>(wt + tap * C) + c) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (cp >= C2) return;
   const int wtiles = (W + DW_TW - 1) / DW_TW, htiles = (H + DW_TH - 1) / DW_TH;
   int t = blockIdx.x;
@@ -77,7 +79,9 @@ dwconv7_kernel(const uint32_t* __restrict__ x, const float* __restrict__ wt,
       if (kh >= 0 && kh < 7) {
 #pragma unroll
         for (int kw = 0; kw < 7; ++kw) {
-          const float2 wv = swl[(kh * 7 + kw) * 128];
+          // small tiles read the taps through L1 instead: staging 50 KB per block would dominate
+          const float2 wv = SMEM_W ? swl[(kh * 7 + kw) * 128]
+                                   : __ldg(reinterpret_cast<const float2*>(wt + (kh * 7 + kw) * C) + cp);
 #pragma unroll
           for (int j = 0; j < DW_TW; ++j) acc[r][j] = __ffma2_rn(in[j + kw], wv, acc[r][j]);
         }
@@ -221,9 +225,111 @@ layernorm_fwd_kernel(const uint32_t* __restrict__ x, const float* __restrict__ g
   }
 }
 
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;  dgamma += dy * xhat; dbeta += dy
-// Each warp walks rows with a grid stride and keeps its dgamma/dbeta partials in registers
-// (NP channel pairs per lane), reduced through shared memory and one atomicAdd per block and channel.
+// LayerNorm backward, split in two HBM-friendly kernels:
+//  rows:    dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma   (one warp per row, 16-byte loads)
+//  columns: dgamma[c] += sum_rows dy * xhat, dbeta[c] += sum_rows dy             (128 x 4 thread blocks, smem combine)
+template <bool BF16, int NV>  // NV = 16-byte vectors per lane (C <= 256 * NV)
+__global__ void __launch_bounds__(256)
+layernorm_bwd_rows_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ gamma, uint4* __restrict__ dx,
+                          long long M, int C8) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+  float g[NV][8], xh[NV][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = lane + 32 * v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[v][k] = xh[v][k] = 0.f;
+    if (i < C8) {
+      const uint4 qd = __ldg(dy + row * C8 + i), qx = __ldg(x + row * C8 + i);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wx[4] = {qx.x, qx.y, qx.z, qx.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 d = H16<BF16>::unpack(wd[k]), xv = H16<BF16>::unpack(wx[k]);
+        xh[v][2 * k] = (xv.x - mu) * rs;
+        xh[v][2 * k + 1] = (xv.y - mu) * rs;
+        g[v][2 * k] = d.x * gm[2 * k];
+        g[v][2 * k + 1] = d.y * gm[2 * k + 1];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s1 += g[v][k];
+        s2 = fmaf(g[v][k], xh[v][k], s2);
+      }
+    }
+  }
+  const float inv_c = 1.0f / (8.0f * C8);
+  s1 = warp_sum(s1) * inv_c;
+  s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = lane + 32 * v;
+    if (i < C8) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = rs * (g[v][k] - s1 - xh[v][k] * s2);
+      dx[row * C8 + i] = make_uint4(H16<BF16>::pack(o[0], o[1]), H16<BF16>::pack(o[2], o[3]),
+                                    H16<BF16>::pack(o[4], o[5]), H16<BF16>::pack(o[6], o[7]));
+    }
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(512)
+layernorm_bwd_cols_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                          long long M, int C8, int rows_per_block) {
+  __shared__ float red[2][4][4 * 128];
+  const int c8 = blockIdx.x * 128 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  if (c8 < C8) {
+#pragma unroll 2
+    for (long long r = r0 + threadIdx.y; r < r1; r += 4) {
+      const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+      const uint4 qd = __ldg(dy + r * C8 + c8), qx = __ldg(x + r * C8 + c8);
+      const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wx[4] = {qx.x, qx.y, qx.z, qx.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 d = H16<BF16>::unpack(wd[k]), xv = H16<BF16>::unpack(wx[k]);
+        a[2 * k] = fmaf(d.x, (xv.x - mu) * rs, a[2 * k]);
+        a[2 * k + 1] = fmaf(d.y, (xv.y - mu) * rs, a[2 * k + 1]);
+        b[2 * k] += d.x;
+        b[2 * k + 1] += d.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      red[0][threadIdx.y][k * 128 + threadIdx.x] = a[half * 4 + k];
+      red[1][threadIdx.y][k * 128 + threadIdx.x] = b[half * 4 + k];
+    }
+    __syncthreads();
+    const int i = threadIdx.y * 128 + threadIdx.x;
+    const int k = i >> 7, cl = i & 127;
+    const int cc = blockIdx.x * 128 + cl;
+    if (cc < C8) {
+      atomicAdd(dgamma + cc * 8 + half * 4 + k, red[0][0][i] + red[0][1][i] + red[0][2][i] + red[0][3][i]);
+      atomicAdd(dbeta + cc * 8 + half * 4 + k, red[1][0][i] + red[1][1][i] + red[1][2][i] + red[1][3][i]);
+    }
+  }
+}
+
+// legacy single-kernel variant (C not a multiple of 8): each warp walks rows with a grid stride and keeps its
+// dgamma/dbeta partials in registers (NP channel pairs per lane)
 template <bool BF16, int NP>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const uint32_t* __restrict__ dy, const uint32_t* __restrict__ x,
@@ -634,16 +740,16 @@ using namespace vb;
     else return vb::fail(VB200_ERR_UNSUPPORTED, "dtype %d", (int)(dtype));   \
   } while (0)
 
-template <bool BF, int TH, int TW>
+template <bool BF, int TH, int TW, bool SW>
 static void dwconv7_launch(const void* x, const float* wt, const float* bias, const void* add, void* y, int B, int H,
                            int W, int C2, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(dwconv7_kernel<BF, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+    cudaFuncSetAttribute(dwconv7_kernel<BF, TH, TW, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
     configured = true;
   }
   dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B), (unsigned)((C2 + 127) / 128));
-  dwconv7_kernel<BF, TH, TW><<<grid, 128, DW_SMEM, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
+  dwconv7_kernel<BF, TH, TW, SW><<<grid, 128, SW ? DW_SMEM : 0, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
                                                         (uint32_t*)y, B, H, W, C2);
 }
 
@@ -656,9 +762,9 @@ extern "C" int vb200_dwconv7(const void* x, const float* wt, const float* bias, 
   // small feature maps: 2x4-pixel tiles so that enough blocks exist to fill the SMs
   const long long big_blocks = (long long)((W + 7) / 8) * ((H + 3) / 4) * B * ((C2 + 127) / 128);
   if (big_blocks >= 2 * 148) {
-    DISPATCH_DT(dtype, (dwconv7_launch<BF, 4, 8>(x, wt, bias, add, y, B, H, W, C2, st)));
+    DISPATCH_DT(dtype, (dwconv7_launch<BF, 4, 8, true>(x, wt, bias, add, y, B, H, W, C2, st)));
   } else {
-    DISPATCH_DT(dtype, (dwconv7_launch<BF, 2, 4>(x, wt, bias, add, y, B, H, W, C2, st)));
+    DISPATCH_DT(dtype, (dwconv7_launch<BF, 2, 4, false>(x, wt, bias, add, y, B, H, W, C2, st)));
   }
   return check_launch("vb200_dwconv7");
 }
@@ -703,12 +809,38 @@ static void ln_bwd_launch(const void* dy, const void* x, const float* mean, cons
       (const uint32_t*)dy, (const uint32_t*)x, mean, rstd, gamma, (uint32_t*)dx, dgamma, dbeta, M, C / 2);
 }
 
+template <bool BF, int NV>
+static void ln_bwd_rows_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                               void* dx, int64_t M, int C8, cudaStream_t st) {
+  layernorm_bwd_rows_kernel<BF, NV><<<(unsigned)((M + 7) / 8), 256, 0, st>>>((const uint4*)dy, (const uint4*)x, mean, rstd,
+                                                                             gamma, (uint4*)dx, M, C8);
+}
+
 extern "C" int vb200_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                                    const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t M,
                                    int C, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "null pointer");
   VB_SUPPORTED(C % 2 == 0 && C <= 3072, "C (%d) must be even and <= 3072", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if (C % 8 == 0 && C <= 2048) {
+    const int C8 = C / 8, nv = (C8 + 31) / 32;
+#define LN_ROWS(NV) DISPATCH_DT(dtype, (ln_bwd_rows_launch<BF, NV>(dy, x, mean, rstd, gamma, dx, M, C8, st)))
+    if (nv <= 1) LN_ROWS(1);
+    else if (nv <= 2) LN_ROWS(2);
+    else if (nv <= 3) LN_ROWS(3);
+    else if (nv <= 4) LN_ROWS(4);
+    else LN_ROWS(8);
+#undef LN_ROWS
+    if (int rc = check_launch("vb200_layernorm_bwd(rows)")) return rc;
+    const int colb = (C8 + 127) / 128;
+    long long rpb = (M * colb + 148 * 2 - 1) / (148 * 2);
+    if (rpb < 32) rpb = 32;
+    if (rpb > M) rpb = M;
+    dim3 grid(colb, (unsigned)((M + rpb - 1) / rpb)), block(128, 4);
+    DISPATCH_DT(dtype, layernorm_bwd_cols_kernel<BF><<<grid, block, 0, st>>>((const uint4*)dy, (const uint4*)x, mean, rstd,
+                                                                            dgamma, dbeta, M, C8, (int)rpb));
+    return check_launch("vb200_layernorm_bwd(cols)");
+  }
   const int np = (C / 2 + 31) / 32;
 #define LN_BWD(NP) DISPATCH_DT(dtype, (ln_bwd_launch<BF, NP>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, C, st)))
   if (np <= 3) LN_BWD(3);

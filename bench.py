@@ -148,6 +148,7 @@ def run_gpu(args):
 
     torch.manual_seed(1234)
     model = UNeXt2(**CFG).to(dev)
+    model.batch_streams = args.batch_streams
     net = model
     exchange = None
     if ddp and args.ddp == "torch":
@@ -314,7 +315,7 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"dp{world}",
-                       "cuda_graph": graphed is not None,
+                       "cuda_graph": graphed is not None, "batch_streams": args.batch_streams,
                        "grad_exchange": ("none" if not ddp else
                                          "torch DDP (bucketed NCCL all-reduce)" if args.ddp == "torch" else
                                          "flat fp32 NCCL all-reduce recorded in the step graph"),
@@ -349,6 +350,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
                     help="N>1 gradient exchange: flat all-reduce inside the CUDA graph (default) or stock torch DDP (eager)")
+    ap.add_argument("--batch-streams", type=int, default=1,
+                    help="split the per-GPU batch into this many chunks on concurrent CUDA streams (exact: per-sample norms)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup

@@ -24,10 +24,11 @@ OVERLAP_WGRAD = True
 
 
 def _side_stream(device: torch.device) -> torch.cuda.Stream:
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    st = _SIDE.get(idx)
+    """The helper stream paired with the CURRENT stream (one per main stream, so batch-chunk streams stay independent)."""
+    key = torch.cuda.current_stream(device).cuda_stream
+    st = _SIDE.get(key)
     if st is None:
-        st = _SIDE[idx] = torch.cuda.Stream(device=device)
+        st = _SIDE[key] = torch.cuda.Stream(device=device)
     return st
 
 

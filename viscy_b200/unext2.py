@@ -86,6 +86,11 @@ class UNeXt2(nn.Module):
         )
         self.out_stack_depth = out_stack_depth
         self.compute_dtype: torch.dtype | None = None
+        # sm_100a path: split the batch into this many chunks that run on concurrent CUDA streams.  Every norm in
+        # this model is per-sample (LayerNorm, GRN, InstanceNorm), so chunking is exact; it keeps the SMs busy on
+        # the small, latency-bound feature maps of the deep stages.
+        self.batch_streams: int = 1
+        self._chunk_streams: list[torch.cuda.Stream] = []
 
     @property
     def num_blocks(self) -> int:
@@ -102,11 +107,28 @@ class UNeXt2(nn.Module):
         x = self.decoder(x)
         return self.head(x)
 
+    def _forward_chunk(self, x: Tensor, dt: torch.dtype) -> Tensor:
+        f = self.stem.forward_cl(x, dt)
+        feats = self.encoder_stages.forward_cl(f)
+        feats.reverse()
+        f = self.decoder.forward_cl(feats)
+        return self.head.forward_cl(f)
+
     def _forward_sm100(self, x: Tensor) -> Tensor:
         dt = resolve_compute_dtype(x, self.compute_dtype)
+        n = self.batch_streams
         with torch.autocast("cuda", enabled=False):
-            f = self.stem.forward_cl(x, dt)
-            feats = self.encoder_stages.forward_cl(f)
-            feats.reverse()
-            f = self.decoder.forward_cl(feats)
-            return self.head.forward_cl(f)
+            if n <= 1 or x.shape[0] < n or x.shape[0] % n:
+                return self._forward_chunk(x, dt)
+            main = torch.cuda.current_stream(x.device)
+            while len(self._chunk_streams) < n:
+                self._chunk_streams.append(torch.cuda.Stream(device=x.device))
+            outs = []
+            for st, xc in zip(self._chunk_streams, x.chunk(n)):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    outs.append(self._forward_chunk(xc.contiguous(), dt))
+            for st, o in zip(self._chunk_streams, outs):
+                main.wait_stream(st)
+                o.record_stream(main)
+            return torch.cat(outs)

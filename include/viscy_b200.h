@@ -149,6 +149,10 @@ int vb200_im2col3d(const void* u, void* col, const int32_t* geom, vb200_stream_t
 int vb200_col2im3d(const void* dcol, void* du, const int32_t* geom, int dtype, vb200_stream_t stream);
 /* conv_dw.weight [C,1,7,7] -> tap-major wt [49][C] and flipped wtf [49][C] (fp32) */
 int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t stream);
+/* all weight packs of a step in one launch.  table (device, int64[n_items][7]) = {src, dst, dst2, R, Cc, kind, first_block}:
+ * kind 0 cast [R,Cc]; 1 cast + transpose; 2 depthwise taps (src [C=R][49] -> dst, dst2 fp32 [49][C], dst2 flipped);
+ * each block converts 1024 elements */
+int vb200_pack_multi(const void* table, int n_items, int64_t total_blocks, int dtype, vb200_stream_t stream);
 /* fp32 [R,Cc] -> 16-bit (weight packing); transpose != 0 writes [Cc,R] */
 int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype, vb200_stream_t stream);
 

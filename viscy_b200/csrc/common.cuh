@@ -122,4 +122,42 @@ __device__ __forceinline__ float dgelu_f(float u) {
   return fmaf(u, pdf, cdf);
 }
 
+// ---- column reductions over rows of [M, C] tensors (8 channels per thread) ------------------------------------------
+// Block = 512 threads arranged as CW column threads x (512 / CW) row lanes, CW = power of two >= min(C/8, 128), so that
+// narrow tensors (C = 96: 12 vectors) still use every thread.  colred_combine sums the row lanes through shared
+// memory and issues one atomicAdd per (block, channel) and quantity.
+struct ColRedShape {
+  int cw_log2;  // log2(CW)
+  int colb;     // column blocks
+  __host__ static ColRedShape make(int C8) {
+    ColRedShape s;
+    s.cw_log2 = 4;
+    while ((1 << s.cw_log2) < C8 && s.cw_log2 < 7) ++s.cw_log2;
+    s.colb = (C8 + (1 << s.cw_log2) - 1) >> s.cw_log2;
+    return s;
+  }
+};
+
+template <int NQ>
+__device__ __forceinline__ void colred_combine(const float (&acc)[NQ][8], float* red /* [NQ*8][512] */, int cw_log2,
+                                               int c8_base, int C8, float* const (&out)[NQ]) {
+  const int tid = threadIdx.x;
+  const int CW = 1 << cw_log2, RL = 512 >> cw_log2;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[(q * 8 + k) * 512 + tid] = acc[q][k];
+  __syncthreads();
+  for (int o = tid; o < NQ * 8 * CW; o += 512) {
+    const int cx = o & (CW - 1);
+    const int qk = o >> cw_log2;
+    const int c8 = c8_base + cx;
+    if (c8 < C8) {
+      float s = 0.f;
+      for (int r = 0; r < RL; ++r) s += red[qk * 512 + r * CW + cx];
+      atomicAdd(out[qk >> 3] + (long long)c8 * 8 + (qk & 7), s);
+    }
+  }
+}
+
 }  // namespace vb

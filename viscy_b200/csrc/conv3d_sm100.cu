@@ -58,13 +58,13 @@ struct ConvParams {
   void* out;           // fwd/dgrad: [N,OD,OH,OW,co_store] 16-bit;  wgrad: fp32 [CO][9][3*8] accumulated (atomics)
 };
 
-__device__ __forceinline__ void tile_coords(const ConvParams& p, long long t, int& n, int& oz, int& oy, int& x0) {
-  x0 = (int)(t % p.xtiles) * 128;
+__device__ __forceinline__ void tile_coords(const ConvParams& p, int t, int& n, int& oz, int& oy, int& x0) {
+  x0 = (t % p.xtiles) * 128;  // 32-bit: the host rejects problems with >= 2^31 tiles
   t /= p.xtiles;
-  oy = (int)(t % p.OH);
+  oy = t % p.OH;
   t /= p.OH;
-  oz = (int)(t % p.OD);
-  n = (int)(t / p.OD);
+  oz = t % p.OD;
+  n = t / p.OD;
 }
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad
@@ -125,14 +125,14 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmU, const ConvParams p) {
     if (lane == 0) {  // ===================== TMA producer: 9*CCH line boxes per tile
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
         int n, oz, oy, x0;
         tile_coords(p, t, n, oz, oy, x0);
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], C::LINES * LINE_BYTES);
         uint8_t* sbase = smem + stage * C::STAGE_BYTES;
-#pragma unroll 1
-        for (int l = 0; l < C::LINES; ++l) {
+#pragma unroll
+        for (int l = 0; l < C::LINES; ++l) {  // fully unrolled: tap / chunk indices are compile-time constants
           const int c = l % CCH, kh = (l / CCH) % 3, kd = l / (3 * CCH);
           tma_load_5d(sbase + l * LINE_PITCH, &tmU, &full_bar[stage], c * 8, x0 - p.pw, oy + kh - p.ph,
                       oz + kd - p.pd, n);
@@ -150,14 +150,14 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmU, const ConvParams p) {
       const uint32_t z_addr = smem_u32(zero_line);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * CO);
-#pragma unroll 1
-        for (int i = 0; i < C::KCH / 2; ++i) {
+#pragma unroll
+        for (int i = 0; i < C::KCH / 2; ++i) {  // fully unrolled: descriptor offsets fold to constants
           // K chunk q -> (line = q / 3, kw = q % 3) with K order (kd, kh, chunk, kw); the padding chunk reads zeros
           const int q0 = 2 * i, q1 = 2 * i + 1;
           const uint32_t a0 = sbase + (q0 / 3) * LINE_PITCH + (q0 % 3) * 16;
@@ -182,7 +182,7 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmU, const ConvParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool bf16 = p.bf16 != 0;
-    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
       int n, oz, oy, x0;
       tile_coords(p, t, n, oz, oy, x0);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -298,16 +298,16 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
         int n, oz, oy, x0;
         tile_coords(p, t, n, oz, oy, x0);
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], COCH * WG_A_CHUNK + 9 * LINE_BYTES);
         uint8_t* sa = smem + stage * C::STAGE_BYTES;
         uint8_t* sl = sa + C::A_BYTES;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < COCH; ++c) tma_load_5d(sa + c * WG_A_CHUNK, &tmDz, &full_bar[stage], c * 8, x0, oy, oz, n);
-#pragma unroll 1
+#pragma unroll
         for (int l = 0; l < 9; ++l)
           tma_load_5d(sl + l * LINE_PITCH, &tmU, &full_bar[stage], 0, x0 - p.pw, oy + (l % 3) - p.ph,
                       oz + (l / 3) - p.pd, n);
@@ -323,12 +323,12 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
         const uint32_t sl = sa + C::A_BYTES;
-#pragma unroll 1
+#pragma unroll
         for (int l = 0; l < 9; ++l) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
@@ -461,6 +461,7 @@ static int fill_params(ConvParams* p, const int32_t* g, int dtype) {
   p->bf16 = dtype == VB200_BF16;
   p->xtiles = (p->OW + 127) / 128;
   p->tiles = (long long)p->N * p->OD * p->OH * p->xtiles;
+  if (p->tiles >= (1LL << 31)) return fail(VB200_ERR_UNSUPPORTED, "conv3d: too many tiles");
   return VB200_OK;
 }
 

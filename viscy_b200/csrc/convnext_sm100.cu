@@ -285,47 +285,33 @@ template <bool BF16>
 __global__ void __launch_bounds__(512)
 layernorm_bwd_cols_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ mean,
                           const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                          long long M, int C8, int rows_per_block) {
-  __shared__ float red[2][4][4 * 128];
-  const int c8 = blockIdx.x * 128 + threadIdx.x;
+                          long long M, int C8, int rows_per_block, int cw_log2) {
+  __shared__ float red[16 * 512];
+  const int cx = threadIdx.x & ((1 << cw_log2) - 1), ry = threadIdx.x >> cw_log2, RL = 512 >> cw_log2;
+  const int c8 = (blockIdx.x << cw_log2) + cx;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
-  float a[8], b[8];
+  float a[2][8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  for (int k = 0; k < 8; ++k) a[0][k] = a[1][k] = 0.f;
   if (c8 < C8) {
 #pragma unroll 2
-    for (long long r = r0 + threadIdx.y; r < r1; r += 4) {
+    for (long long r = r0 + ry; r < r1; r += RL) {
       const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
       const uint4 qd = __ldg(dy + r * C8 + c8), qx = __ldg(x + r * C8 + c8);
       const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wx[4] = {qx.x, qx.y, qx.z, qx.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 d = H16<BF16>::unpack(wd[k]), xv = H16<BF16>::unpack(wx[k]);
-        a[2 * k] = fmaf(d.x, (xv.x - mu) * rs, a[2 * k]);
-        a[2 * k + 1] = fmaf(d.y, (xv.y - mu) * rs, a[2 * k + 1]);
-        b[2 * k] += d.x;
-        b[2 * k + 1] += d.y;
+        a[0][2 * k] = fmaf(d.x, (xv.x - mu) * rs, a[0][2 * k]);
+        a[0][2 * k + 1] = fmaf(d.y, (xv.y - mu) * rs, a[0][2 * k + 1]);
+        a[1][2 * k] += d.x;
+        a[1][2 * k + 1] += d.y;
       }
     }
   }
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      red[0][threadIdx.y][k * 128 + threadIdx.x] = a[half * 4 + k];
-      red[1][threadIdx.y][k * 128 + threadIdx.x] = b[half * 4 + k];
-    }
-    __syncthreads();
-    const int i = threadIdx.y * 128 + threadIdx.x;
-    const int k = i >> 7, cl = i & 127;
-    const int cc = blockIdx.x * 128 + cl;
-    if (cc < C8) {
-      atomicAdd(dgamma + cc * 8 + half * 4 + k, red[0][0][i] + red[0][1][i] + red[0][2][i] + red[0][3][i]);
-      atomicAdd(dbeta + cc * 8 + half * 4 + k, red[1][0][i] + red[1][1][i] + red[1][2][i] + red[1][3][i]);
-    }
-  }
+  float* const outs[2] = {dgamma, dbeta};
+  colred_combine<2>(a, red, cw_log2, blockIdx.x << cw_log2, C8, outs);
 }
 
 // legacy single-kernel variant (C not a multiple of 8): each warp walks rows with a grid stride and keeps its
@@ -571,46 +557,39 @@ colsum_kernel(const uint32_t* __restrict__ x, float* __restrict__ out, long long
   atomicAdd(out + 2 * cp + 1, a.y);
 }
 
-// ---- 16-byte vectorised column reductions: block = 128 column-threads (8 channels each) x 4 row lanes;
-// the row lanes are combined through shared memory, then one atomicAdd per (block, channel).
+// ---- 16-byte vectorised column reductions (block shape: see ColRedShape in common.cuh)
 // MODE 0: out[n,c] += sum x ; MODE 1: out[n,c] += sum x^2
 template <bool BF16, int MODE>
 __global__ void __launch_bounds__(512)
-colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, int R, int C8, int rows_per_block) {
-  __shared__ float red[4][128 * 8];
-  const int c8 = blockIdx.x * 128 + threadIdx.x;
+colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, int R, int C8, int rows_per_block, int cw_log2) {
+  __shared__ float red[8 * 512];
+  const int cx = threadIdx.x & ((1 << cw_log2) - 1), ry = threadIdx.x >> cw_log2, RL = 512 >> cw_log2;
+  const int c8 = (blockIdx.x << cw_log2) + cx;
   const int n = blockIdx.z;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float a[1][8] = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
   if (c8 < C8) {
     const uint4* xp = x + ((long long)n * R) * C8 + c8;
 #pragma unroll 4
-    for (int r = r0 + threadIdx.y; r < r1; r += 4) {
+    for (int r = r0 + ry; r < r1; r += RL) {
       const uint4 q = __ldg(xp + (long long)r * C8);
       const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = H16<BF16>::unpack(w4[k]);
         if (MODE == 0) {
-          a[2 * k] += f.x;
-          a[2 * k + 1] += f.y;
+          a[0][2 * k] += f.x;
+          a[0][2 * k + 1] += f.y;
         } else {
-          a[2 * k] = fmaf(f.x, f.x, a[2 * k]);
-          a[2 * k + 1] = fmaf(f.y, f.y, a[2 * k + 1]);
+          a[0][2 * k] = fmaf(f.x, f.x, a[0][2 * k]);
+          a[0][2 * k + 1] = fmaf(f.y, f.y, a[0][2 * k + 1]);
         }
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) red[threadIdx.y][k * 128 + threadIdx.x] = a[k];
-  __syncthreads();
-  // 1024 sums per block; 512 threads take two each
-  for (int i = threadIdx.y * 128 + threadIdx.x; i < 1024; i += 512) {
-    const int k = i >> 7, cl = i & 127;
-    const int cc = blockIdx.x * 128 + cl;
-    if (cc < C8) atomicAdd(out + ((long long)n * C8 + cc) * 8 + k, red[0][i] + red[1][i] + red[2][i] + red[3][i]);
-  }
+  float* const outs[1] = {out + (long long)n * C8 * 8};
+  colred_combine<1>(a, red, cw_log2, blockIdx.x << cw_log2, C8, outs);
 }
 
 // per-sample GRN-scaled fc2 weights: out[n][j][k] = W2[j][k] * s[n][k]; thread = 8 consecutive k of one row j, all n
@@ -832,13 +811,14 @@ extern "C" int vb200_layernorm_bwd(const void* dy, const void* x, const float* m
     else LN_ROWS(8);
 #undef LN_ROWS
     if (int rc = check_launch("vb200_layernorm_bwd(rows)")) return rc;
-    const int colb = (C8 + 127) / 128;
-    long long rpb = (M * colb + 148 * 2 - 1) / (148 * 2);
-    if (rpb < 32) rpb = 32;
+    const ColRedShape sh = ColRedShape::make(C8);
+    long long rpb = (M * sh.colb + 148 * 2 - 1) / (148 * 2);
+    const long long min_rows = 4LL * (512 >> sh.cw_log2);
+    if (rpb < min_rows) rpb = min_rows;
     if (rpb > M) rpb = M;
-    dim3 grid(colb, (unsigned)((M + rpb - 1) / rpb)), block(128, 4);
-    DISPATCH_DT(dtype, layernorm_bwd_cols_kernel<BF><<<grid, block, 0, st>>>((const uint4*)dy, (const uint4*)x, mean, rstd,
-                                                                            dgamma, dbeta, M, C8, (int)rpb));
+    dim3 grid(sh.colb, (unsigned)((M + rpb - 1) / rpb));
+    DISPATCH_DT(dtype, layernorm_bwd_cols_kernel<BF><<<grid, 512, 0, st>>>((const uint4*)dy, (const uint4*)x, mean, rstd,
+                                                                          dgamma, dbeta, M, C8, (int)rpb, sh.cw_log2));
     return check_launch("vb200_layernorm_bwd(cols)");
   }
   const int np = (C / 2 + 31) / 32;
@@ -932,17 +912,19 @@ extern "C" int vb200_colreduce(const void* x, float* out, int B, int64_t R, int 
                                vb200_stream_t stream) {
   VB_REQUIRE(x && out, "null pointer");
   VB_SUPPORTED(C % 8 == 0 && R < (1LL << 31), "C (%d) %% 8", C);
-  const int C8 = C / 8, colb = (C8 + 127) / 128;
-  // ~2 blocks of 512 threads per SM, at least 32 rows per block
-  long long rpb = (R * colb * B + 148 * 2 - 1) / (148 * 2);
-  if (rpb < 32) rpb = 32;
+  const int C8 = C / 8;
+  const ColRedShape sh = ColRedShape::make(C8);
+  // ~2 blocks of 512 threads per SM, at least 4 rows per row lane
+  long long rpb = (R * sh.colb * B + 148 * 2 - 1) / (148 * 2);
+  const long long min_rows = 4LL * (512 >> sh.cw_log2);
+  if (rpb < min_rows) rpb = min_rows;
   if (rpb > R) rpb = R;
-  dim3 grid(colb, (unsigned)((R + rpb - 1) / rpb), B), block(128, 4);
+  dim3 grid(sh.colb, (unsigned)((R + rpb - 1) / rpb), B);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0)
-    DISPATCH_DT(dtype, colreduce8_kernel<BF, 0><<<grid, block, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb));
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 0><<<grid, 512, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb, sh.cw_log2));
   else
-    DISPATCH_DT(dtype, colreduce8_kernel<BF, 1><<<grid, block, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb));
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 1><<<grid, 512, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb, sh.cw_log2));
   return check_launch("vb200_colreduce");
 }
 

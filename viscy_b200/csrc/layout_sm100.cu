@@ -465,3 +465,62 @@ extern "C" int vb200_bcast_rows(const void* src, void* out, int B, int R, int C,
     return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
   return check_launch("vb200_bcast_rows");
 }
+
+// ------------------------------------------------------------------------------ per-step weight packing, one launch
+// table[item] = {src, dst, dst2, R, Cc, kind, first_block}: kind 0 = cast [R,Cc], 1 = cast + transpose -> [Cc,R],
+// 2 = depthwise taps: src [C=R][49] -> dst fp32 [49][C] and flipped dst2 fp32 [49][C].  1024 elements per block.
+namespace vb {
+constexpr int PM_FIELDS = 7;
+constexpr int PM_PER_BLOCK = 1024;
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+pack_multi_kernel(const long long* __restrict__ table, int n_items) {
+  __shared__ int s_item;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_items - 1;  // last item whose first_block <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid * PM_FIELDS + 6] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_item = lo;
+  }
+  __syncthreads();
+  const long long* it = table + s_item * PM_FIELDS;
+  const float* src = reinterpret_cast<const float*>(it[0]);
+  const long long R = it[3], Cc = it[4];
+  const int kind = (int)it[5];
+  const long long base = ((long long)blockIdx.x - it[6]) * PM_PER_BLOCK;
+  const long long total = kind == 2 ? 49 * R : R * Cc;
+#pragma unroll
+  for (int k = 0; k < PM_PER_BLOCK / 256; ++k) {
+    const long long idx = base + k * 256 + threadIdx.x;
+    if (idx >= total) break;
+    if (kind == 2) {
+      const long long tap = idx / R, c = idx % R;
+      const float v = src[c * 49 + tap];
+      reinterpret_cast<float*>(it[1])[idx] = v;
+      reinterpret_cast<float*>(it[2])[(48 - tap) * R + c] = v;
+    } else {
+      long long s = idx;
+      if (kind == 1) {
+        const long long c = idx / R, r = idx % R;
+        s = r * Cc + c;
+      }
+      typename H16<BF16>::T hv = H16<BF16>::from_f(src[s]);
+      reinterpret_cast<uint16_t*>(it[1])[idx] = *reinterpret_cast<uint16_t*>(&hv);
+    }
+  }
+}
+}  // namespace vb
+
+extern "C" int vb200_pack_multi(const void* table, int n_items, int64_t total_blocks, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(table && n_items > 0 && total_blocks > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_BF16)
+    pack_multi_kernel<true><<<(unsigned)total_blocks, 256, 0, st>>>((const long long*)table, n_items);
+  else if (dtype == VB200_FP16)
+    pack_multi_kernel<false><<<(unsigned)total_blocks, 256, 0, st>>>((const long long*)table, n_items);
+  else
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return check_launch("vb200_pack_multi");
+}

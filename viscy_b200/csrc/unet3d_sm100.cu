@@ -60,25 +60,26 @@ affine_act_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, 
 }
 
 // BatchNorm backward reductions over rows: s1[c] += sum dy', s2[c] += sum dy' * xhat, dy' = dy * (y > 0 if relu)
-// block = 128 column threads (8 channels each) x 4 row lanes (same decomposition as colreduce8_kernel)
+// (block shape: see ColRedShape in common.cuh)
 template <bool BF16>
 __global__ void __launch_bounds__(512)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ s1,
-                     float* __restrict__ s2, long long M, int C8, int relu, int rows_per_block) {
-  __shared__ float red[2][4][4 * 128];  // two rounds of 4 channels: [s1|s2][row lane][k * 128 + column thread]
-  const int c8 = blockIdx.x * 128 + threadIdx.x;
+                     float* __restrict__ s2, long long M, int C8, int relu, int rows_per_block, int cw_log2) {
+  __shared__ float red[16 * 512];
+  const int cx = threadIdx.x & ((1 << cw_log2) - 1), ry = threadIdx.x >> cw_log2, RL = 512 >> cw_log2;
+  const int c8 = (blockIdx.x << cw_log2) + cx;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
-  float a[8], b[8], mu[8], rs[8];
+  float a[2][8], mu[8], rs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    a[k] = b[k] = 0.f;
+    a[0][k] = a[1][k] = 0.f;
     mu[k] = c8 < C8 ? mean[c8 * 8 + k] : 0.f;
     rs[k] = c8 < C8 ? rstd[c8 * 8 + k] : 0.f;
   }
   if (c8 < C8) {
-    for (long long r = r0 + threadIdx.y; r < r1; r += 4) {
+    for (long long r = r0 + ry; r < r1; r += RL) {
       const uint4 qd = __ldg(dy + r * C8 + c8), qx = __ldg(x + r * C8 + c8);
       uint4 qy = make_uint4(0, 0, 0, 0);
       if (relu) qy = __ldg(y + r * C8 + c8);
@@ -92,32 +93,15 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
           if (!(yv.x > 0.f)) d.x = 0.f;
           if (!(yv.y > 0.f)) d.y = 0.f;
         }
-        a[2 * k] += d.x;
-        a[2 * k + 1] += d.y;
-        b[2 * k] = fmaf(d.x, (xv.x - mu[2 * k]) * rs[2 * k], b[2 * k]);
-        b[2 * k + 1] = fmaf(d.y, (xv.y - mu[2 * k + 1]) * rs[2 * k + 1], b[2 * k + 1]);
+        a[0][2 * k] += d.x;
+        a[0][2 * k + 1] += d.y;
+        a[1][2 * k] = fmaf(d.x, (xv.x - mu[2 * k]) * rs[2 * k], a[1][2 * k]);
+        a[1][2 * k + 1] = fmaf(d.y, (xv.y - mu[2 * k + 1]) * rs[2 * k + 1], a[1][2 * k + 1]);
       }
     }
   }
-  // two rounds of 4 channels each through shared memory
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      red[0][threadIdx.y][k * 128 + threadIdx.x] = a[half * 4 + k];
-      red[1][threadIdx.y][k * 128 + threadIdx.x] = b[half * 4 + k];
-    }
-    __syncthreads();
-    for (int i = threadIdx.y * 128 + threadIdx.x; i < 512; i += 512) {
-      const int k = i >> 7, cl = i & 127;
-      const int cc = blockIdx.x * 128 + cl;
-      if (cc < C8) {
-        atomicAdd(s1 + cc * 8 + half * 4 + k, red[0][0][i] + red[0][1][i] + red[0][2][i] + red[0][3][i]);
-        atomicAdd(s2 + cc * 8 + half * 4 + k, red[1][0][i] + red[1][1][i] + red[1][2][i] + red[1][3][i]);
-      }
-    }
-  }
+  float* const outs[2] = {s1, s2};
+  colred_combine<2>(a, red, cw_log2, blockIdx.x << cw_log2, C8, outs);
 }
 
 // dx = g[c] * (dy' - m1[c] - xhat * m2[c]),  g = gamma * rstd, m1 = s1/M, m2 = s2/M (training) or 0 (eval)
@@ -252,13 +236,15 @@ extern "C" int vb200_bn_bwd_reduce(const void* dy, const void* x, const void* y,
                                    float* s1, float* s2, int64_t M, int C, int relu, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(dy && x && mean && rstd && s1 && s2 && (y || !relu), "null pointer");
   VB_SUPPORTED(C % 8 == 0, "C (%d) %% 8", C);
-  const int C8 = C / 8, colb = (C8 + 127) / 128;
-  long long rpb = (M * colb + 148 * 2 - 1) / (148 * 2);
-  if (rpb < 32) rpb = 32;
+  const int C8 = C / 8;
+  const ColRedShape sh = ColRedShape::make(C8);
+  long long rpb = (M * sh.colb + 148 * 2 - 1) / (148 * 2);
+  const long long min_rows = 4LL * (512 >> sh.cw_log2);
+  if (rpb < min_rows) rpb = min_rows;
   if (rpb > M) rpb = M;
-  dim3 grid(colb, (unsigned)((M + rpb - 1) / rpb)), block(128, 4);
+  dim3 grid(sh.colb, (unsigned)((M + rpb - 1) / rpb));
   cudaStream_t st = (cudaStream_t)stream;
-  DT_SWITCH(dtype, bn_bwd_reduce_kernel<BF><<<grid, block, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y, mean, rstd, s1, s2, M, C8, relu, (int)rpb));
+  DT_SWITCH(dtype, bn_bwd_reduce_kernel<BF><<<grid, 512, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y, mean, rstd, s1, s2, M, C8, relu, (int)rpb, sh.cw_log2));
   return check_launch("vb200_bn_bwd_reduce");
 }
 

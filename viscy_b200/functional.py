@@ -43,7 +43,7 @@ def _wgrad_splits(n_out: int, k_in: int, pixels: int) -> int:
 
 def linear_fwd(a2d, w, bias, *, residual=None, act=L.ACT_NONE, epilogue=L.EPI_STORE):
     """a2d [M,K] 16-bit, w fp32 [N,K,...] -> [M,N] 16-bit."""
-    wp = ops.cast_pack(w, a2d.dtype)
+    wp = ops.packed(w, a2d.dtype)
     return ops.gemm(a2d, wp, bias=bias, residual=residual, act=act, epilogue=epilogue)
 
 
@@ -56,14 +56,14 @@ def linear_bwd(dout2d, a2d, w, *, need_da=True, need_db=True):
     db = ops.colreduce(dout2d.view(1, M, N), 0).view(N) if (need_db and N % 8 == 0) else (ops.colsum(dout2d) if need_db else None)
     da = None
     if need_da:
-        wt = ops.cast_pack(w, dout2d.dtype, transpose=True)  # [K, N]
+        wt = ops.packed(w, dout2d.dtype, transpose=True)  # [K, N]
         da = ops.gemm(dout2d, wt)
     return da, dw.view(w.shape), db
 
 
 def _dw_taps(w):
     """conv_dw.weight [C,1,7,7] fp32 -> (tap-major [49,C], flipped tap-major [49,C])"""
-    return ops.dw_pack(w)
+    return ops.dw_taps(w)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -105,7 +105,7 @@ class ConvNeXtBlockFn(Function):
             h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP)  # h := gelu'(u)
             sumsq = s = None
         # ConvNeXt-V1 layer scale: out = gamma * (y W2^T + b2) + x, gamma applied in fp32 in the epilogue
-        out = ops.gemm(y2, ops.cast_pack(fc2_w.detach().reshape(C, C4), x.dtype), bias=fc2_b.detach(),
+        out = ops.gemm(y2, ops.packed(fc2_w, x.dtype).view(C, C4), bias=fc2_b.detach(),
                        svec=None if gamma is None else gamma.detach(), residual=x.view(M, C))
         ctx.fused = False
         ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma)
@@ -135,7 +135,7 @@ class ConvNeXtBlockFn(Function):
             dgw = ar.take(C4)
             ops._call("vb200_grn_coef_bwd", ops._p(sumsq), ops._p(S1), ops._p(grn_w), ops._p(t), ops._p(dgw), B, C4,
                       ops.C.c_float(1e-6))
-            w2t = ops.cast_pack(w2, x.dtype, transpose=True)  # [C4, C]
+            w2t = ops.packed(fc2_w, x.dtype, transpose=True)  # [C4, C]
             dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux=y2, aux2=h, tvec=t, svec=s, rows_per_sample=R)
             dw2 = dw2.view(fc2_w.shape)
             dgamma = None
@@ -172,7 +172,7 @@ class ConvNeXtBlockFn(Function):
                 db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
             dw1 = ops.gemm(dh2, l.view(M, C), mn_major=True, epilogue=L.EPI_F32,
                            k_splits=_wgrad_splits(C4, C, M)).view(fc1_w.shape)
-        dl = ops.gemm(dh2, ops.cast_pack(fc1_w, x.dtype, transpose=True))
+        dl = ops.gemm(dh2, ops.packed(fc1_w, x.dtype, transpose=True))
         dd, dlnw, dlnb = ops.layernorm_bwd(dl.view(B, H, W, C), d, mean, rstd, ln_w, ar)
         if side is not main:
             side.wait_stream(main)

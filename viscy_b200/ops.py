@@ -604,3 +604,85 @@ def add_rows(x, other=None, bias=None):
     y = torch.empty_like(x)
     _call("vb200_add_rows", _p(x), _p(other), _p(bias), _p(y), C.c_int64(x.numel() // Cc), Cc, L.dtype_code(x.dtype))
     return y
+
+
+# ----------------------------------------------------------------------------------------------
+# per-step weight packing in one launch
+class WeightPacks:
+    """16-bit GEMM operand copies ([N,K] and [K,N]) of Linear / 1x1-conv weights and tap-major depthwise filters of a
+    set of modules, refreshed by ONE kernel launch per step (`refresh`), looked up by parameter (`get`)."""
+
+    def __init__(self, linear_weights, dw_weights, dtype):
+        self.dtype = dtype
+        dev = linear_weights[0].device if linear_weights else dw_weights[0].device
+        n16 = sum(2 * w.numel() for w in linear_weights)
+        n32 = sum(2 * 49 * w.shape[0] for w in dw_weights)
+        self.buf16 = torch.empty((n16,), device=dev, dtype=dtype)
+        self.buf32 = torch.empty((n32,), device=dev, dtype=torch.float32)
+        self.views: dict[tuple[int, str], torch.Tensor] = {}
+        import weakref
+        self._refs = [(weakref.ref(w), w.data_ptr()) for w in list(linear_weights) + list(dw_weights)]
+        self._alive = {ptr: ref for ref, ptr in self._refs}
+        rows, off16, off32, blk = [], 0, 0, 0
+        per = 1024
+        for w in linear_weights:
+            R, Cc = w.shape[0], w.numel() // w.shape[0]
+            for kind, name, shape in ((0, "n", (R, Cc)), (1, "t", (Cc, R))):
+                v = self.buf16[off16:off16 + R * Cc].view(shape)
+                off16 += R * Cc
+                self.views[(w.data_ptr(), name)] = v
+                rows.append([w.data_ptr(), v.data_ptr(), 0, R, Cc, kind, blk])
+                blk += -(-R * Cc // per)
+        for w in dw_weights:
+            Cc = w.shape[0]
+            a = self.buf32[off32:off32 + 49 * Cc].view(49, Cc)
+            b = self.buf32[off32 + 49 * Cc:off32 + 98 * Cc].view(49, Cc)
+            off32 += 98 * Cc
+            self.views[(w.data_ptr(), "dw")] = a
+            self.views[(w.data_ptr(), "dwf")] = b
+            rows.append([w.data_ptr(), a.data_ptr(), b.data_ptr(), Cc, 49, 2, blk])
+            blk += -(-49 * Cc // per)
+        self.total_blocks = blk
+        self.table = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self.n_items = len(rows)
+
+    def stale(self) -> bool:
+        """True when a registered parameter has been freed or re-allocated (the table holds raw pointers)."""
+        for ref, ptr in self._refs:
+            p = ref()
+            if p is None or p.data_ptr() != ptr:
+                return True
+        return False
+
+    def refresh(self) -> None:
+        _call("vb200_pack_multi", _p(self.table), self.n_items, C.c_int64(self.total_blocks), L.dtype_code(self.dtype))
+
+    def get(self, w, kind):
+        ptr = w.data_ptr()
+        ref = self._alive.get(ptr)
+        if ref is None:
+            return None
+        owner = ref()
+        if owner is None or owner.data_ptr() != ptr:  # the registered parameter is gone: never serve its pack
+            return None
+        return self.views.get((ptr, kind))
+
+
+ACTIVE_PACKS: WeightPacks | None = None
+
+
+def packed(w, dtype, transpose=False):
+    """16-bit operand copy of fp32 weight `w`: from the step's WeightPacks when registered, else a direct cast."""
+    if ACTIVE_PACKS is not None and ACTIVE_PACKS.dtype == dtype:
+        v = ACTIVE_PACKS.get(w, "t" if transpose else "n")
+        if v is not None:
+            return v
+    return cast_pack(w, dtype, transpose)
+
+
+def dw_taps(w):
+    if ACTIVE_PACKS is not None:
+        a = ACTIVE_PACKS.get(w, "dw")
+        if a is not None:
+            return a, ACTIVE_PACKS.get(w, "dwf")
+    return dw_pack(w)

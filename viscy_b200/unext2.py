@@ -91,6 +91,7 @@ class UNeXt2(nn.Module):
         # the small, latency-bound feature maps of the deep stages.
         self.batch_streams: int = 1
         self._chunk_streams: list[torch.cuda.Stream] = []
+        self._packs = None
 
     @property
     def num_blocks(self) -> int:
@@ -114,8 +115,20 @@ class UNeXt2(nn.Module):
         f = self.decoder.forward_cl(feats)
         return self.head.forward_cl(f)
 
+    def _weight_packs(self, dt: torch.dtype):
+        """One-launch refresh of the 16-bit operand copies of every ConvNeXt block's fc1 / fc2 / conv_dw weights."""
+        from . import ops
+        from .components import ConvNeXtBlock
+        if self._packs is None or self._packs.dtype != dt or self._packs.stale():
+            blocks = [m for m in self.modules() if isinstance(m, ConvNeXtBlock)]
+            lin = [w for b in blocks for w in (b.mlp.fc1.weight, b.mlp.fc2.weight)]
+            self._packs = ops.WeightPacks(lin, [b.conv_dw.weight for b in blocks], dt)
+        self._packs.refresh()
+        ops.ACTIVE_PACKS = self._packs
+
     def _forward_sm100(self, x: Tensor) -> Tensor:
         dt = resolve_compute_dtype(x, self.compute_dtype)
+        self._weight_packs(dt)
         n = self.batch_streams
         with torch.autocast("cuda", enabled=False):
             if n <= 1 or x.shape[0] < n or x.shape[0] % n:

@@ -46,6 +46,10 @@ for e in prof.events():
         agg[name][0] += 1
         agg[name][1] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
         tot += agg[name][1] * 0
+if len(sys.argv) > 1:
+    sel = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and sys.argv[1] in e.name]
+    sel = sel[: len(sel) // N]
+    print(sys.argv[1], [round(e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total, 1) for e in sel])
 tot = sum(v[1] for v in agg.values())
 print(f"sum of kernel time per step: {tot / N:.1f} us")
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:

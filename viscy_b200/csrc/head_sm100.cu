@@ -9,96 +9,139 @@ namespace vb {
 
 // S[n, cm, 2h+i, 2w+j] = dec[n,h,w, cm*4 + i*2 + j];  P = pool ? avg2x2(pad_left_top(S)) : S
 // u[n, dz, Y, X, c] = P[n, c*Dz + dz, Y, X]  (c < Cc; zero for Cc <= c < Cu)
+//
+// One block = one decoder row h (output rows 2h, 2h+1) x 16 decoder pixels (32 output columns).
+// Phase 1: thread = (decoder pixel, cm): four 8-byte loads (the 2x2 sub-pixels of cm at (h-1..h, w-1..w)) give the four
+//          pooled outputs of that pixel; results go to shared memory [row][x][cm].
+// Phase 2: thread = (row, dz, x): gathers the Cu channels c*Dz+dz from shared memory and writes one 16-byte voxel.
+__device__ __forceinline__ uint32_t lo16(uint32_t v) { return v & 0xffffu; }
+__device__ __forceinline__ uint32_t hi16(uint32_t v) { return v >> 16; }
+
+template <bool BF16>
+__device__ __forceinline__ float h2f(uint32_t raw16) {
+  const uint16_t r = static_cast<uint16_t>(raw16);
+  return H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&r));
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t f2h(float v) {
+  typename H16<BF16>::T hv = H16<BF16>::from_f(v);
+  return *reinterpret_cast<uint16_t*>(&hv);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 head_shuffle_pool_fwd_kernel(const uint16_t* __restrict__ dec, uint16_t* __restrict__ u, int h, int w,
                              int Cm, int Dz, int Cc, int Cu, int pool) {
-  extern __shared__ uint16_t sm[];  // [32][Cm]
-  const int X0 = blockIdx.x * 32, Y = blockIdx.y;
+  extern __shared__ uint16_t sm[];  // [2][32][Cm]
+  const int w0 = blockIdx.x * 16, hh = blockIdx.y;
   const long long n = blockIdx.z;
-  const int Cd = Cm * 4;
   const int Hs = 2 * h, Ws = 2 * w;
-  for (int idx = threadIdx.x; idx < 32 * Cm; idx += blockDim.x) {
-    const int xl = idx / Cm, cm = idx % Cm;
-    const int X = X0 + xl;
-    float acc = 0.f;
-    if (X < Ws) {
+  const uint2* dec2 = reinterpret_cast<const uint2*>(dec);  // one uint2 = the 4 sub-pixels of one cm
+  for (int idx = threadIdx.x; idx < 16 * Cm; idx += blockDim.x) {
+    const int wl = idx / Cm, cm = idx - wl * Cm;
+    const int ww = w0 + wl;
+    float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;  // P[2h+i][2w+j]
+    if (ww < w) {
+      auto ld = [&](int a, int b) -> uint2 {  // decoder pixel (hh - a, ww - b) or zeros outside
+        if (hh - a < 0 || ww - b < 0) return make_uint2(0u, 0u);
+        return __ldg(dec2 + ((n * h + hh - a) * w + ww - b) * Cm + cm);
+      };
+      const uint2 c = ld(0, 0);
+      const float s00 = h2f<BF16>(lo16(c.x)), s01 = h2f<BF16>(hi16(c.x)), s10 = h2f<BF16>(lo16(c.y)), s11 = h2f<BF16>(hi16(c.y));
       if (pool) {
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int yy = Y - a, xx = X - b;
-            if (yy >= 0 && xx >= 0) {
-              const uint16_t raw = __ldg(dec + ((n * h + (yy >> 1)) * w + (xx >> 1)) * Cd + cm * 4 + (yy & 1) * 2 + (xx & 1));
-              acc += H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&raw));
-            }
-          }
-        acc *= 0.25f;
+        const uint2 l = ld(0, 1), t = ld(1, 0), tl = ld(1, 1);
+        const float l01 = h2f<BF16>(hi16(l.x)), l11 = h2f<BF16>(hi16(l.y));      // S[2h+i][2w-1]
+        const float t10 = h2f<BF16>(lo16(t.y)), t11 = h2f<BF16>(hi16(t.y));      // S[2h-1][2w+j]
+        const float tl11 = h2f<BF16>(hi16(tl.y));                                // S[2h-1][2w-1]
+        p00 = 0.25f * (s00 + l01 + t10 + tl11);
+        p01 = 0.25f * (s01 + s00 + t11 + t10);
+        p10 = 0.25f * (s10 + l11 + s00 + l01);
+        p11 = 0.25f * (s11 + s10 + s01 + s00);
       } else {
-        const uint16_t raw = __ldg(dec + ((n * h + (Y >> 1)) * w + (X >> 1)) * Cd + cm * 4 + (Y & 1) * 2 + (X & 1));
-        acc = H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&raw));
+        p00 = s00; p01 = s01; p10 = s10; p11 = s11;
       }
     }
-    typename H16<BF16>::T hv = H16<BF16>::from_f(acc);
-    sm[idx] = *reinterpret_cast<uint16_t*>(&hv);
+    sm[(0 * 32 + 2 * wl) * Cm + cm] = f2h<BF16>(p00);
+    sm[(0 * 32 + 2 * wl + 1) * Cm + cm] = f2h<BF16>(p01);
+    sm[(1 * 32 + 2 * wl) * Cm + cm] = f2h<BF16>(p10);
+    sm[(1 * 32 + 2 * wl + 1) * Cm + cm] = f2h<BF16>(p11);
   }
   __syncthreads();
-  const int per_dz = 32 * Cu;
-  for (int idx = threadIdx.x; idx < Dz * per_dz; idx += blockDim.x) {
-    const int dz = idx / per_dz;
-    const int rem = idx % per_dz;
-    const int xl = rem / Cu, c = rem % Cu;
-    const int X = X0 + xl;
-    if (X < Ws) {
-      const uint16_t v = c < Cc ? sm[xl * Cm + c * Dz + dz] : (uint16_t)0;
-      u[(((n * Dz + dz) * Hs + Y) * Ws + X) * (long long)Cu + c] = v;
+  const int C8 = Cu / 8;
+  for (int idx = threadIdx.x; idx < 2 * Dz * 32 * C8; idx += blockDim.x) {
+    const int c8 = idx % C8;
+    int t = idx / C8;
+    const int xl = t & 31;
+    t >>= 5;
+    const int dz = t % Dz, r = t / Dz;
+    const int X = 2 * w0 + xl, Y = 2 * hh + r;
+    if (X < Ws && Y < Hs) {
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ca = c8 * 8 + 2 * k, cb = ca + 1;
+        const uint32_t va = ca < Cc ? sm[(r * 32 + xl) * Cm + ca * Dz + dz] : 0u;
+        const uint32_t vb = cb < Cc ? sm[(r * 32 + xl) * Cm + cb * Dz + dz] : 0u;
+        o[k] = va | (vb << 16);
+      }
+      *reinterpret_cast<uint4*>(u + ((((n * Dz + dz) * Hs + Y) * Ws + X) * (long long)Cu + c8 * 8)) =
+          make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
 
 // ddec[n,h,w, cm*4+i*2+j] = dS[n,cm,2h+i,2w+j];  dS[Y,X] = pool ? 0.25*(dP[Y,X]+dP[Y,X+1]+dP[Y+1,X]+dP[Y+1,X+1]) : dP
+// Phase 1: 16-byte loads of du rows 2h..2h+2, columns 2w0..2w0+32 into shared memory [r][x][cm];
+// Phase 2: thread = (decoder pixel, cm): 9 shared reads -> the 4 sub-pixel gradients -> one 8-byte store.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 head_shuffle_pool_bwd_kernel(const uint16_t* __restrict__ du, uint16_t* __restrict__ ddec, int h, int w,
                              int Cm, int Dz, int Cc, int Cu, int pool) {
-  extern __shared__ uint16_t sm[];  // [3][33][Cm]  (rows 2h..2h+2, columns 2w0..2w0+32)
+  extern __shared__ uint16_t sm[];  // [3][33][Cm]
   const int w0 = blockIdx.x * 16, hh = blockIdx.y;
   const long long n = blockIdx.z;
   const int Hs = 2 * h, Ws = 2 * w;
-  const int Cd = Cm * 4;
-  // load: iterate (r, dz, xl, c) with c fastest (c < Cu contiguous in u)
-  const int per_r = Dz * 33 * Cu;
-  for (int idx = threadIdx.x; idx < 3 * per_r; idx += blockDim.x) {
-    const int r = idx / per_r;
-    int rem = idx % per_r;
-    const int dz = rem / (33 * Cu);
-    rem %= 33 * Cu;
-    const int xl = rem / Cu, c = rem % Cu;
-    if (c >= Cc) continue;
+  const int C8 = Cu / 8;
+  for (int idx = threadIdx.x; idx < 3 * Dz * 33 * C8; idx += blockDim.x) {
+    const int c8 = idx % C8;
+    int t = idx / C8;
+    const int xl = t % 33;
+    t /= 33;
+    const int dz = t % Dz, r = t / Dz;
     const int Y = 2 * hh + r, X = 2 * w0 + xl;
-    uint16_t v = 0;
-    if (Y < Hs && X < Ws) v = __ldg(du + (((n * Dz + dz) * Hs + Y) * Ws + X) * (long long)Cu + c);
-    sm[(r * 33 + xl) * Cm + c * Dz + dz] = v;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (Y < Hs && X < Ws) q = __ldg(reinterpret_cast<const uint4*>(du + ((((n * Dz + dz) * Hs + Y) * Ws + X) * (long long)Cu + c8 * 8)));
+    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ca = c8 * 8 + 2 * k, cb = ca + 1;
+      if (ca < Cc) sm[(r * 33 + xl) * Cm + ca * Dz + dz] = static_cast<uint16_t>(lo16(w4[k]));
+      if (cb < Cc) sm[(r * 33 + xl) * Cm + cb * Dz + dz] = static_cast<uint16_t>(hi16(w4[k]));
+    }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 16 * Cd; idx += blockDim.x) {
-    const int wl = idx / Cd, cd = idx % Cd;
+  uint2* out2 = reinterpret_cast<uint2*>(ddec);
+  for (int idx = threadIdx.x; idx < 16 * Cm; idx += blockDim.x) {
+    const int wl = idx / Cm, cm = idx - wl * Cm;
     const int ww = w0 + wl;
     if (ww >= w) continue;
-    const int cm = cd >> 2, i = (cd >> 1) & 1, j = cd & 1;
-    const int r = i, xl = 2 * wl + j;
-    auto at = [&](int rr, int xx) {
-      const uint16_t raw = sm[(rr * 33 + xx) * Cm + cm];
-      return H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&raw));
-    };
-    float v;
-    if (pool)
-      v = 0.25f * (at(r, xl) + at(r, xl + 1) + at(r + 1, xl) + at(r + 1, xl + 1));
-    else
-      v = at(r, xl);
-    typename H16<BF16>::T hv = H16<BF16>::from_f(v);
-    ddec[((n * h + hh) * w + ww) * (long long)Cd + cd] = *reinterpret_cast<uint16_t*>(&hv);
+    auto at = [&](int rr, int xx) { return h2f<BF16>(sm[(rr * 33 + xx) * Cm + cm]); };
+    const int x0 = 2 * wl;
+    float g00, g01, g10, g11;
+    if (pool) {
+      const float a00 = at(0, x0), a01 = at(0, x0 + 1), a02 = at(0, x0 + 2);
+      const float a10 = at(1, x0), a11 = at(1, x0 + 1), a12 = at(1, x0 + 2);
+      const float a20 = at(2, x0), a21 = at(2, x0 + 1), a22 = at(2, x0 + 2);
+      g00 = 0.25f * (a00 + a01 + a10 + a11);
+      g01 = 0.25f * (a01 + a02 + a11 + a12);
+      g10 = 0.25f * (a10 + a11 + a20 + a21);
+      g11 = 0.25f * (a11 + a12 + a21 + a22);
+    } else {
+      g00 = at(0, x0); g01 = at(0, x0 + 1); g10 = at(1, x0); g11 = at(1, x0 + 1);
+    }
+    const uint32_t lo = f2h<BF16>(g00) | (static_cast<uint32_t>(f2h<BF16>(g01)) << 16);
+    const uint32_t hi = f2h<BF16>(g10) | (static_cast<uint32_t>(f2h<BF16>(g11)) << 16);
+    out2[((n * h + hh) * w + ww) * Cm + cm] = make_uint2(lo, hi);
   }
 }
 
@@ -408,8 +451,8 @@ extern "C" int vb200_head_shuffle_pool(const void* src, void* dst, int B, int h,
   VB_REQUIRE(Cu >= Cc && Cu % 8 == 0, "Cu (%d) must be a multiple of 8 >= %d", Cu, Cc);
   cudaStream_t st = (cudaStream_t)stream;
   if (!backward) {
-    dim3 grid((2 * w + 31) / 32, 2 * h, B);
-    const size_t smem = (size_t)32 * Cm * 2;
+    dim3 grid((w + 15) / 16, h, B);
+    const size_t smem = (size_t)2 * 32 * Cm * 2;
     VB_SUPPORTED(smem <= 48 * 1024, "head: Cm (%d) too large", Cm);
     if (dtype == VB200_BF16)
       head_shuffle_pool_fwd_kernel<true><<<grid, 256, smem, st>>>((const uint16_t*)src, (uint16_t*)dst, h, w, Cm, Dz, Cc, Cu, pool);

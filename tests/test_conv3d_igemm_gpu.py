@@ -1,0 +1,111 @@
+"""Implicit-GEMM Conv3d (TMA boxes at tap-shifted coordinates -> tcgen05) vs torch's fp32 conv3d on the same 16-bit
+inputs: forward (+bias, +ReLU, +residual), data gradient, weight gradient.  Tolerances: 16-bit outputs 2e-3 rel-L2
+(fp16) / 8e-3 (bf16); fp32 weight gradients 2e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+# (N, D, H, W, Cin, Cout, kernel, padding)
+CASES = [
+    (1, 8, 16, 16, 64, 64, (3, 3, 3), (1, 1, 1)),     # box (16, 8, 1, 1)
+    (2, 4, 8, 8, 64, 32, (3, 3, 3), (1, 1, 1)),       # box (8, 8, 2, 1), Cout < tile
+    (1, 2, 4, 128, 128, 96, (3, 3, 3), (1, 1, 1)),    # box (128, 1, 1, 1), two channel chunks per tap
+    (1, 4, 4, 256, 64, 64, (3, 3, 3), (1, 1, 1)),     # OW > 128: two tiles per row
+    (1, 8, 8, 8, 32, 32, (3, 3, 3), (1, 1, 1)),       # 32-channel operands: SWIZZLE_64B rows
+    (1, 8, 8, 16, 96, 64, (3, 3, 3), (1, 1, 1)),      # 96 = 3 x 32: SWIZZLE_64B, three chunks per tap
+    (4, 4, 4, 4, 64, 320, (3, 3, 3), (1, 1, 1)),      # box (4, 4, 4, 2): tile spans samples; Cout > 256
+    (1, 2, 2, 8, 64, 64, (3, 3, 3), (1, 1, 1)),       # 32 voxels: tile larger than the tensor
+    (1, 5, 16, 16, 64, 64, (1, 3, 3), (0, 1, 1)),     # Unet25d decoder filter
+    (1, 5, 8, 16, 64, 64, (5, 1, 1), (0, 0, 0)),      # Unet25d skip / bottom filter: valid in Z -> OD = 1
+    (1, 10, 16, 16, 64, 32, (3, 3, 3), (0, 1, 1)),    # valid in Z (head style): OD = 8
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_igemm_forward_dgrad_wgrad(cuda, case, dtype):
+    from viscy_b200 import _lib as L, ops
+    N, D, H, W, Ci, Co, ks, pad = case
+    tol = 2e-3 if dtype == torch.float16 else 8e-3
+    g = torch.Generator(device=cuda).manual_seed(1)
+    x = torch.randn(N, D, H, W, Ci, device=cuda, generator=g).to(dtype)
+    w = (torch.randn(Co, Ci, *ks, device=cuda, generator=g) / (Ci * ks[0] * ks[1] * ks[2]) ** 0.5)
+    b = torch.randn(Co, device=cuda, generator=g)
+    assert ops.conv3d_igemm_supported((N, D, H, W, Ci), Co, ks, pad)
+    w16 = w.permute(0, 2, 3, 4, 1).reshape(Co, -1).contiguous().to(dtype)
+    xf = x.float().permute(0, 4, 1, 2, 3)
+    wf = w16.float().view(Co, *ks, Ci).permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(xf, wf, b, padding=pad)
+    y = ops.conv3d_igemm(x, w16, b, ks, pad)
+    assert y.shape == (N, *ref.shape[2:], Co)
+    assert rel(y.float().permute(0, 4, 1, 2, 3), ref) < tol
+    # fused ReLU + residual
+    res = torch.randn_like(y)
+    y2 = ops.conv3d_igemm(x, w16, b, ks, pad, act=L.ACT_RELU, residual=res)
+    assert rel(y2.float().permute(0, 4, 1, 2, 3), F.relu(ref) + res.float().permute(0, 4, 1, 2, 3)) < tol
+    # data gradient = conv of dout with the flipped / transposed filter, padding k-1-p
+    dy = torch.randn(y.shape, device=cuda, generator=g).to(dtype)
+    dyf = dy.float().permute(0, 4, 1, 2, 3)
+    gx = torch.nn.grad.conv3d_input(xf.shape, wf, dyf, padding=pad)
+    gw = torch.nn.grad.conv3d_weight(xf, wf.shape, dyf, padding=pad)
+    bpad = tuple(k - 1 - p for k, p in zip(ks, pad))
+    if Co % 32 == 0 and ops.conv3d_igemm_supported(tuple(dy.shape), Ci, ks, bpad):
+        wflip = w16.view(Co, *ks, Ci).flip(1, 2, 3).permute(4, 1, 2, 3, 0).reshape(Ci, -1).contiguous()
+        dx = ops.conv3d_igemm(dy, wflip, None, ks, bpad)
+        assert dx.shape == x.shape
+        assert rel(dx.float().permute(0, 4, 1, 2, 3), gx) < tol
+    assert ops.conv3d_igemm_supported((N, D, H, W, Ci), Co, ks, pad, wgrad=True)
+    for splits in (0, 1, 3):
+        dw = ops.conv3d_igemm_wgrad(x, dy, ks, pad, k_splits=splits)
+        assert rel(dw.view(Co, *ks, Ci).permute(0, 4, 1, 2, 3), gw) < 2e-3, splits
+
+
+def test_igemm_wgrad_narrow_channels(cuda):
+    """weight gradient with Cin = 8 / 24 (below the forward form's 32-channel granule): zero-filled channel boxes"""
+    from viscy_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(2)
+    for Ci, Co in ((8, 32), (24, 8), (160, 16)):
+        x = torch.randn(1, 4, 8, 16, Ci, device=cuda, generator=g).half()
+        dy = torch.randn(1, 4, 8, 16, Co, device=cuda, generator=g).half()
+        gw = torch.nn.grad.conv3d_weight(x.float().permute(0, 4, 1, 2, 3), (Co, Ci, 3, 3, 3),
+                                         dy.float().permute(0, 4, 1, 2, 3), padding=1)
+        dw = ops.conv3d_igemm_wgrad(x, dy, (3, 3, 3), (1, 1, 1))
+        assert rel(dw.view(Co, 3, 3, 3, Ci).permute(0, 4, 1, 2, 3), gw) < 2e-3, (Ci, Co)
+
+
+def test_conv3d_cl_uses_igemm_and_matches_torch(cuda):
+    """Conv3dFn picks the implicit-GEMM form for box-shaped geometries; same results as torch autograd."""
+    from viscy_b200 import _lib, functional as VF
+    torch.manual_seed(0)
+    conv = torch.nn.Conv3d(64, 48, 3, padding=1).to(cuda)
+    x = torch.randn(2, 64, 8, 8, 16, device=cuda).half()
+    xc = x.permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    n0 = _lib.launch_count()
+    y = VF.conv3d_cl(xc, conv)
+    assert _lib.launch_count() - n0 == 2  # weight cast + one implicit-GEMM launch: no im2col
+    xf = x.float().requires_grad_(True)
+    wf = conv.weight.detach().half().float().requires_grad_(True)
+    ref = F.conv3d(xf, wf, conv.bias, padding=1)
+    assert rel(y.permute(0, 4, 1, 2, 3), ref) < 2e-3
+    dy = torch.randn_like(ref).half()
+    gx, gw = torch.autograd.grad(ref, [xf, wf], dy.float())
+    y.backward(dy.permute(0, 2, 3, 4, 1).contiguous())
+    assert rel(xc.grad.permute(0, 4, 1, 2, 3), gx) < 2e-3
+    assert rel(conv.weight.grad, gw) < 2e-3
+    assert rel(conv.bias.grad, dy.float().sum((0, 2, 3, 4))) < 2e-3
+
+
+def test_igemm_rejects_unboxable_geometry(cuda):
+    from viscy_b200 import ops
+    assert not ops.conv3d_igemm_supported((1, 7, 12, 20, 64), 64, (3, 3, 3), (1, 1, 1))
+    x = torch.randn(1, 7, 12, 20, 64, device=cuda).half()
+    w16 = torch.randn(64, 27 * 64, device=cuda).half()
+    with pytest.raises(NotImplementedError):
+        ops.conv3d_igemm(x, w16, None, (3, 3, 3), (1, 1, 1))

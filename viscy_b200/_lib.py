@@ -34,6 +34,21 @@ class GemmDesc(C.Structure):
     ]
 
 
+class Conv3dDesc(C.Structure):
+    """struct vb200_conv3d_desc (include/viscy_b200.h), field for field."""
+
+    _fields_ = [
+        ("N", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32),
+        ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("pd", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
+        ("dtype", C.c_int32), ("act", C.c_int32), ("k_splits", C.c_int32), ("reserved", C.c_int32),
+        ("ldo", C.c_int64), ("ldr", C.c_int64),
+        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
+        ("dout", C.c_void_p), ("dw", C.c_void_p),
+    ]
+
+
 _lib = None
 
 

@@ -24,12 +24,18 @@ constexpr int BK = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
-template <int BN>
+// Operand forms.  The two CONV forms are the implicit-GEMM 3-D convolution: one operand is the channels-last activation
+// tensor seen through a 5-D tensor map (C, X, Y, Z, N); a K block (CONVK) / an N tile (CONVMN) belongs to one filter tap
+// and its box is fetched at the tap-shifted voxel coordinate, TMA zero-filling whatever falls outside (= the padding).
+enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3 };
+
+// BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
+template <int BN, int BKE = BK>
 struct Cfg {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int A_BYTES = BM * BKE * 2;
+  static constexpr int B_BYTES = BN * BKE * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = BKE == 64 ? ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12));
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int COLV_BYTES = 2 * 3 * BN * 4;  // [2 tiles in flight][bias, s, t][BN] fp32
   static constexpr int STG_BYTES = NUM_EPI_WARPS * 2048;  // per-warp 32 rows x 64 B store-staging tile
@@ -55,7 +61,29 @@ struct GemmParams {
   const void* aux2;
   const float* tvec;
   const float* svec;
+  // implicit-GEMM conv forms: output extent, filter extent, padding, channel chunks per tap (CONVK) / channel tiles per
+  // tap (CONVMN), channels of the activation operand
+  int cOW, cOH, cOD, cKW, cKH, cpw, cph, cpd, cchunks, ccin;
 };
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// flattened output-voxel index -> (x, y, z, n)
+__device__ __forceinline__ void voxel_coords(const GemmParams& p, int v, int& x, int& y, int& z, int& n) {
+  x = v % p.cOW;
+  v /= p.cOW;
+  y = v % p.cOH;
+  v /= p.cOH;
+  z = v % p.cOD;
+  n = v / p.cOD;
+}
 
 template <bool BF16>
 __device__ __forceinline__ void load8(const void* p, float* v) {
@@ -209,11 +237,13 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
   }
 }
 
-template <int BN, bool MN_MAJOR, int EPI>
+template <int BN, int MODE, int EPI, int BKE = BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, BKE>;
+  constexpr bool MN_MAJOR = MODE == MODE_MNMAJOR || MODE == MODE_CONVMN;
+  static_assert(BKE == 64 || (BKE == 32 && MODE == MODE_CONVK), "BKE = 32 is the 32-channel conv form only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -263,12 +293,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n0 = (t % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        // conv forms: CONVK walks (tap, channel chunk) along K for a fixed 128-voxel box; CONVMN walks 64-voxel boxes
+        // along K for a fixed (tap, channel tile)
+        int cx = 0, cy = 0, cz = 0, cn = 0, tap = 0, chunk = 0, ci0 = 0;
+        if constexpr (MODE == MODE_CONVK) {
+          voxel_coords(p, m0, cx, cy, cz, cn);
+          tap = kb0 / p.cchunks;
+          chunk = kb0 - tap * p.cchunks;
+        }
+        if constexpr (MODE == MODE_CONVMN) {
+          const int tn = t % p.tiles_n;
+          tap = tn / p.cchunks;
+          ci0 = (tn - tap * p.cchunks) * BN;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          if constexpr (!MN_MAJOR) {
+          if constexpr (MODE == MODE_CONVK) {
+            const int kw = tap % p.cKW, t2 = tap / p.cKW;
+            const int kh = t2 % p.cKH, kd = t2 / p.cKH;
+            tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw - p.cpw, cy + kh - p.cph, cz + kd - p.cpd, cn);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BKE, n0);
+            if (++chunk == p.cchunks) {
+              chunk = 0;
+              ++tap;
+            }
+          } else if constexpr (MODE == MODE_CONVMN) {
+            const int kw = tap % p.cKW, t2 = tap / p.cKW;
+            const int kh = t2 % p.cKH, kd = t2 / p.cKH;
+            voxel_coords(p, kb * BK, cx, cy, cz, cn);
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (64 * BK * 2), &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_5d(sb + j * (64 * BK * 2), &tmB, &full_bar[stage], ci0 + j * 64, cx + kw - p.cpw,
+                          cy + kh - p.cph, cz + kd - p.cpd, cn);
+          } else if constexpr (!MN_MAJOR) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
             const int brow = p.b_batch_rows > 0 ? (m0 / p.b_batch_rows) * p.N + n0 : n0;
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, brow);
@@ -305,9 +368,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
+          for (int k = 0; k < BKE / 16; ++k) {
             uint64_t da, db;
-            if constexpr (!MN_MAJOR) {
+            if constexpr (BKE == 32) {
+              // K-major SW64: rows of 64 B, 8-row groups 512 B apart; step 16 elements (32 B) inside the row
+              da = make_smem_desc_sw64(sa + k * 32, 0, 512);
+              db = make_smem_desc_sw64(sb + k * 32, 0, 512);
+            } else if constexpr (!MN_MAJOR) {
               // K-major SW128: 8-row groups 1024 B apart; step 16 elements (32 B) inside the row
               da = make_smem_desc(sa + k * 32, 0, 1024);
               db = make_smem_desc(sb + k * 32, 0, 1024);
@@ -342,7 +409,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int split = unit / tiles;
       const int t = unit - split * tiles;
       const int m0 = (t / p.tiles_n) * BM;
-      const int n0 = (t % p.tiles_n) * BN;
+      int n0 = (t % p.tiles_n) * BN;
+      int n_lim = p.N;
+      if constexpr (MODE == MODE_CONVMN) {  // N tile = (tap, channel tile): columns [tap*cin + ci0, (tap+1)*cin)
+        const int tn = t % p.tiles_n;
+        const int tap = tn / p.cchunks;
+        n0 = tap * p.ccin + (tn - tap * p.cchunks) * BN;
+        n_lim = (tap + 1) * p.ccin;
+      }
       // stage this tile's per-column vectors (bias and, for the fused GRN backward, s and t of the tile's sample)
       float* cv = colv + acc * 3 * BN;
       if (et < BN) {
@@ -368,7 +442,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int c = 0; c < NCH; ++c) {
         const int cc = half * (BN / 2) + c * 32;
         const int col0 = n0 + cc;
-        if (col0 < p.N) {  // warp-uniform
+        if (col0 < n_lim) {  // warp-uniform
           uint32_t r[32];
           tmem_ld32(t_addr + cc, r);
           if (c + 1 < NCH) load_aux<EPI>(p, row, col0 + 32, row_ok, aux[(c + 1) & 1]);
@@ -376,7 +450,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // this warp's 32 rows x 32 columns: math per row, then row-contiguous stores through the staging tile
           const long long row0 = m0 + quarter * 32;
           const int rows_valid = (int)min(32LL, (long long)p.M - row0);
-          const int cols8_valid = min(4, (p.N - col0) >> 3);
+          const int cols8_valid = min(4, (n_lim - col0) >> 3);
           if (rows_valid > 0) {
             uint4 o1[4], o2[4];
             float f32buf[32];
@@ -403,7 +477,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int g = 0; g < 4; ++g)
                   q[g] = make_uint4(__float_as_uint(f32buf[hh * 16 + g * 4]), __float_as_uint(f32buf[hh * 16 + g * 4 + 1]),
                                     __float_as_uint(f32buf[hh * 16 + g * 4 + 2]), __float_as_uint(f32buf[hh * 16 + g * 4 + 3]));
-                const int c4v = min(4, (p.N - (col0 + hh * 16)) >> 2);
+                const int c4v = min(4, max(0, (n_lim - (col0 + hh * 16)) >> 2));
                 if (p.atomic_out)
                   stage_store<true>(stg, lane, q, ob, p.ldo * 4, row0, rows_valid, (long long)(col0 + hh * 16) * 4, c4v);
                 else
@@ -456,7 +530,7 @@ static EncodeTiledFn get_encode() {
 
 // 2-D row-major 16-bit tensor [rows, cols] with leading dimension ld (elements); box = {box_c, box_r}
 int make_tmap_2d(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld,
-                 int box_c, int box_r, bool bf16) {
+                 int box_c, int box_r, bool bf16, bool sw64 = false) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) return fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0)
@@ -467,10 +541,53 @@ int make_tmap_2d(CUtensorMap* m, const void* base, long long rows, long long col
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return VB200_OK;
+}
+
+// channels-last activation [N, D, H, W, C] as a 5-D map (C, X, Y, Z, N); box = box_c channels x (bx, by, bz, bn) voxels.
+// In shared memory the box is rows of box_c channels (128 B, or 64 B with SWIZZLE_64B) in (n, z, y, x) order: exactly
+// the K-major / MN-major swizzled operand tile of the 2-D forms.
+static int make_tmap_conv(CUtensorMap* m, const void* base, int N, int D, int H, int W, int Cc, int box_c,
+                          const int* vbox, bool bf16, bool sw64) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || Cc % 8 != 0)
+    return fail(VB200_ERR_UNSUPPORTED, "conv operand needs a 16-byte aligned base and C %% 8 == 0 (C=%d)", Cc);
+  cuuint64_t dims[5] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2,
+                           (cuuint64_t)D * H * W * Cc * 2};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)vbox[0], (cuuint32_t)vbox[1], (cuuint32_t)vbox[2],
+                       (cuuint32_t)vbox[3]};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled (5-D conv operand) failed (%d)", (int)r);
+  return VB200_OK;
+}
+
+// `rows` consecutive voxels of the flattened (n, z, y, x) output order form one box iff each extent divides / is divided
+// by what is left of `rows`; a tile larger than the whole tensor spills into zero-filled samples.
+static bool conv_box(int rows, int OW, int OH, int OD, int NB, int* box) {
+  const int dims[4] = {OW, OH, OD, NB};
+  int rem = rows;
+  for (int i = 0; i < 4; ++i) {
+    if (rem >= dims[i]) {
+      if (rem % dims[i]) return false;
+      box[i] = dims[i];
+      rem /= dims[i];
+    } else {
+      if (dims[i] % rem) return false;
+      box[i] = rem;
+      rem = 1;
+    }
+  }
+  if (rem > 1) box[3] *= rem;
+  return box[0] <= 256 && box[1] <= 256 && box[2] <= 256 && box[3] <= 256;
 }
 
 int sm_count() {
@@ -484,18 +601,18 @@ int sm_count() {
   return n;
 }
 
-template <int BN, bool MN_MAJOR, int EPI>
+template <int BN, int MODE, int EPI, int BKE = BK>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                   cudaStream_t st) {
   static bool configured = false;  // per instantiation
-  auto kern = gemm_kernel<BN, MN_MAJOR, EPI>;
+  auto kern = gemm_kernel<BN, MODE, EPI, BKE>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN>::SMEM_BYTES);
+                                         Cfg<BN, BKE>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, NUM_THREADS, Cfg<BN, BKE>::SMEM_BYTES, st>>>(ta, tb, p);
   return check_launch("vb200_gemm");
 }
 
@@ -503,16 +620,16 @@ template <int BN, bool MN_MAJOR>
 static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                       int grid, cudaStream_t st) {
   if constexpr (MN_MAJOR) {
-    if (epi == VB200_EPI_F32) return launch<BN, true, VB200_EPI_F32>(ta, tb, p, grid, st);
+    if (epi == VB200_EPI_F32) return launch<BN, MODE_MNMAJOR, VB200_EPI_F32>(ta, tb, p, grid, st);
     return fail(VB200_ERR_UNSUPPORTED, "mn_major GEMM supports EPI_F32 only");
   } else {
     switch (epi) {
-      case VB200_EPI_STORE: return launch<BN, false, VB200_EPI_STORE>(ta, tb, p, grid, st);
-      case VB200_EPI_GELU_DUAL: return launch<BN, false, VB200_EPI_GELU_DUAL>(ta, tb, p, grid, st);
-      case VB200_EPI_DGELU: return launch<BN, false, VB200_EPI_DGELU>(ta, tb, p, grid, st);
-      case VB200_EPI_DGELU_GRN: return launch<BN, false, VB200_EPI_DGELU_GRN>(ta, tb, p, grid, st);
-      case VB200_EPI_GELU_GP: return launch<BN, false, VB200_EPI_GELU_GP>(ta, tb, p, grid, st);
-      case VB200_EPI_F32: return launch<BN, false, VB200_EPI_F32>(ta, tb, p, grid, st);
+      case VB200_EPI_STORE: return launch<BN, MODE_KMAJOR, VB200_EPI_STORE>(ta, tb, p, grid, st);
+      case VB200_EPI_GELU_DUAL: return launch<BN, MODE_KMAJOR, VB200_EPI_GELU_DUAL>(ta, tb, p, grid, st);
+      case VB200_EPI_DGELU: return launch<BN, MODE_KMAJOR, VB200_EPI_DGELU>(ta, tb, p, grid, st);
+      case VB200_EPI_DGELU_GRN: return launch<BN, MODE_KMAJOR, VB200_EPI_DGELU_GRN>(ta, tb, p, grid, st);
+      case VB200_EPI_GELU_GP: return launch<BN, MODE_KMAJOR, VB200_EPI_GELU_GP>(ta, tb, p, grid, st);
+      case VB200_EPI_F32: return launch<BN, MODE_KMAJOR, VB200_EPI_F32>(ta, tb, p, grid, st);
     }
     return fail(VB200_ERR_INVALID, "unknown epilogue %d", epi);
   }
@@ -601,6 +718,126 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
     if (bn == 128) return launch_epi<128, true>(epi, ta, tb, p, grid, st);
     return launch_epi<64, true>(epi, ta, tb, p, grid, st);
   }
+}
+
+// ------------------------------------------------------------------------------------- implicit-GEMM conv3d
+struct ConvShape {
+  int OD, OH, OW, taps;
+  long long pixels;
+};
+static int conv_shape(const vb200_conv3d_desc* d, ConvShape* s) {
+  VB_REQUIRE(d != nullptr, "null descriptor");
+  VB_REQUIRE(d->N > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->cin > 0 && d->cout > 0, "bad conv3d extent");
+  VB_REQUIRE(d->kd > 0 && d->kh > 0 && d->kw > 0 && d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "bad conv3d filter");
+  VB_SUPPORTED(d->dtype == VB200_BF16 || d->dtype == VB200_FP16, "dtype %d", d->dtype);
+  s->OD = d->D + 2 * d->pd - d->kd + 1;
+  s->OH = d->H + 2 * d->ph - d->kh + 1;
+  s->OW = d->W + 2 * d->pw - d->kw + 1;
+  VB_REQUIRE(s->OD > 0 && s->OH > 0 && s->OW > 0, "conv3d: empty output");
+  s->taps = d->kd * d->kh * d->kw;
+  s->pixels = (long long)d->N * s->OD * s->OH * s->OW;
+  VB_SUPPORTED(s->pixels < (1LL << 31) - 256, "conv3d: too many output voxels");
+  VB_SUPPORTED(d->cout % 8 == 0, "conv3d: cout (%d) must be a multiple of 8", d->cout);
+  return VB200_OK;
+}
+
+static void conv_geom(GemmParams* p, const vb200_conv3d_desc* d, const ConvShape& s) {
+  p->cOW = s.OW; p->cOH = s.OH; p->cOD = s.OD;
+  p->cKW = d->kw; p->cKH = d->kh;
+  p->cpw = d->pw; p->cph = d->ph; p->cpd = d->pd;
+  p->ccin = d->cin;
+}
+
+extern "C" int vb200_conv3d_igemm_supported(const vb200_conv3d_desc* d, int wgrad) {
+  ConvShape s;
+  if (conv_shape(d, &s)) return 0;
+  int box[4];
+  if (wgrad) return d->cin % 8 == 0 && conv_box(BK, s.OW, s.OH, s.OD, d->N, box) ? 1 : 0;
+  return d->cin % 32 == 0 && conv_box(BM, s.OW, s.OH, s.OD, d->N, box) ? 1 : 0;
+}
+
+extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t stream) {
+  ConvShape s;
+  if (int rc = conv_shape(d, &s)) return rc;
+  VB_REQUIRE(d->x && d->w && d->out, "null operand pointer");
+  VB_SUPPORTED(d->cin % 32 == 0, "conv3d_igemm: cin (%d) must be a multiple of 32", d->cin);
+  int box[4];
+  VB_SUPPORTED(conv_box(BM, s.OW, s.OH, s.OD, d->N, box),
+               "conv3d_igemm: 128 consecutive output voxels of %dx%dx%d are not a box", s.OD, s.OH, s.OW);
+  const bool bf16 = d->dtype == VB200_BF16;
+  const int bke = d->cin % 64 == 0 ? 64 : 32;
+  const int sms = sm_count();
+  const int M = (int)s.pixels, N = d->cout, K = s.taps * d->cin;
+  const int tiles_m = (M + BM - 1) / BM;
+  int bn = 256;
+  if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else if ((long long)tiles_m * ((N + 255) / 256) < sms) bn = (long long)tiles_m * ((N + 127) / 128) < sms ? 64 : 128;
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_conv(&ta, d->x, d->N, d->D, d->H, d->W, d->cin, bke, box, bf16, bke == 32)) return rc;
+  if (int rc = make_tmap_2d(&tb, d->w, N, K, K, bke, bn, bf16, bke == 32)) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = tiles_m; p.tiles_n = (N + bn - 1) / bn; p.k_splits = 1;
+  p.kb_total = K / bke; p.kb_per_split = p.kb_total;
+  p.bf16 = bf16 ? 1 : 0;
+  p.act = d->act;
+  p.ldo = d->ldo > 0 ? d->ldo : N;
+  p.ldr = d->ldr > 0 ? d->ldr : N;
+  VB_REQUIRE(p.ldo % 8 == 0 && p.ldr % 8 == 0, "conv3d_igemm: ldo / ldr must be multiples of 8");
+  p.out = d->out; p.bias = d->bias; p.residual = d->residual;
+  conv_geom(&p, d, s);
+  p.cchunks = d->cin / bke;
+  const long long units = (long long)p.tiles_m * p.tiles_n;
+  const int grid = (int)(units < sms ? units : sms);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bke == 64) {
+    if (bn == 256) return launch<256, MODE_CONVK, VB200_EPI_STORE, 64>(ta, tb, p, grid, st);
+    if (bn == 128) return launch<128, MODE_CONVK, VB200_EPI_STORE, 64>(ta, tb, p, grid, st);
+    return launch<64, MODE_CONVK, VB200_EPI_STORE, 64>(ta, tb, p, grid, st);
+  }
+  if (bn == 256) return launch<256, MODE_CONVK, VB200_EPI_STORE, 32>(ta, tb, p, grid, st);
+  if (bn == 128) return launch<128, MODE_CONVK, VB200_EPI_STORE, 32>(ta, tb, p, grid, st);
+  return launch<64, MODE_CONVK, VB200_EPI_STORE, 32>(ta, tb, p, grid, st);
+}
+
+extern "C" int vb200_conv3d_igemm_wgrad(const vb200_conv3d_desc* d, vb200_stream_t stream) {
+  ConvShape s;
+  if (int rc = conv_shape(d, &s)) return rc;
+  VB_REQUIRE(d->x && d->dout && d->dw, "null operand pointer");
+  VB_SUPPORTED(d->cin % 8 == 0, "conv3d_igemm_wgrad: cin (%d) must be a multiple of 8", d->cin);
+  int box[4];
+  VB_SUPPORTED(conv_box(BK, s.OW, s.OH, s.OD, d->N, box),
+               "conv3d_igemm_wgrad: 64 consecutive output voxels of %dx%dx%d are not a box", s.OD, s.OH, s.OW);
+  const bool bf16 = d->dtype == VB200_BF16;
+  const int sms = sm_count();
+  const int bn = d->cin >= 256 ? 256 : (d->cin >= 128 ? 128 : 64);
+  const int ctiles = (d->cin + bn - 1) / bn;
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_2d(&ta, d->dout, s.pixels, d->cout, d->cout, 64, BK, bf16)) return rc;
+  if (int rc = make_tmap_conv(&tb, d->x, d->N, d->D, d->H, d->W, d->cin, 64, box, bf16, false)) return rc;
+  GemmParams p{};
+  p.M = d->cout; p.N = s.taps * d->cin; p.K = (int)s.pixels;
+  p.tiles_m = (d->cout + BM - 1) / BM; p.tiles_n = s.taps * ctiles;
+  p.kb_total = (p.K + BK - 1) / BK;
+  const long long tiles = (long long)p.tiles_m * p.tiles_n;
+  int splits = d->k_splits > 0 ? d->k_splits : (int)((2LL * sms + tiles - 1) / tiles);
+  if (splits > p.kb_total / 8) splits = p.kb_total / 8;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.bf16 = bf16 ? 1 : 0;
+  p.atomic_out = 1;
+  p.ldo = p.N;
+  p.out = d->dw;
+  conv_geom(&p, d, s);
+  p.cchunks = ctiles;
+  const long long units = tiles * p.k_splits;
+  const int grid = (int)(units < sms ? units : sms);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch<256, MODE_CONVMN, VB200_EPI_F32>(ta, tb, p, grid, st);
+  if (bn == 128) return launch<128, MODE_CONVMN, VB200_EPI_F32>(ta, tb, p, grid, st);
+  return launch<64, MODE_CONVMN, VB200_EPI_F32>(ta, tb, p, grid, st);
 }
 
 extern "C" int vb200_last_error(char* buf, size_t n) {

@@ -157,6 +157,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// SWIZZLE_64B variant (layout type 4): rows of 64 B, used by the 32-channel implicit-GEMM conv operands
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr, uint32_t lbo_bytes,
+                                                        uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
 // ---- instruction descriptor (32-bit) for kind::f16 ---------------------------------------------
 // [4,6) D fmt (1=f32)  [7,10) A fmt (0=f16,1=bf16)  [10,13) B fmt  [15] A major (1 = MN-major)
 // [16] B major  [17,23) N>>3  [24,29) M>>4

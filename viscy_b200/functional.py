@@ -554,9 +554,19 @@ def _conv_weight_rows(w, cin_pad, cout_pad):
     return wk.reshape(cout_pad, -1).contiguous()
 
 
+def _conv_weight_rows_flipped(w, cin_pad, cout_pad):
+    """nn.Conv3d weight [Co,Ci,kd,kh,kw] -> fp32 [cin_pad, (kd,kh,kw flipped, cout_pad)]: the filter of the data gradient"""
+    Co, Ci = w.shape[:2]
+    wk = w.flip(2, 3, 4).permute(1, 2, 3, 4, 0)
+    if cin_pad != Ci or cout_pad != Co:
+        wk = torch.nn.functional.pad(wk, (0, cout_pad - Co, 0, 0, 0, 0, 0, 0, 0, cin_pad - Ci))
+    return wk.reshape(cin_pad, -1).contiguous()
+
+
 class Conv3dFn(Function):
-    """nn.Conv3d (any kernel / stride / padding, groups=1) on channels-last rows: im2col3d + tcgen05 GEMM (+bias).
-    The patch matrix is rebuilt in backward instead of being kept alive."""
+    """nn.Conv3d (groups=1) on channels-last rows.  Stride-1 convs whose geometry tiles into TMA boxes run as implicit
+    GEMMs (`ops.conv3d_igemm*`: no patch matrix in HBM) for forward, dgrad and wgrad; anything else (strided convs, odd
+    extents, < 32 channels) goes through im2col3d + the same tcgen05 GEMM, the patch matrix rebuilt in backward."""
 
     @staticmethod
     def forward(ctx, x, w, b, stride, padding):
@@ -566,32 +576,52 @@ class Conv3dFn(Function):
         ks = tuple(w.shape[2:])
         geom = ops.conv3d_geom((N, D, H, W, Cp), ks, stride, padding)
         pointwise = ks == (1, 1, 1) and tuple(stride) == (1, 1, 1) and tuple(padding) == (0, 0, 0)
-        col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
+        unit = tuple(stride) == (1, 1, 1) and not pointwise
+        igemm = unit and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding)
         wk = _conv_weight_rows(w.detach(), Cp, Cop)
         bias = None
         if b is not None:
             bias = b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))
-        out = ops.gemm(col, ops.cast_pack(wk, x.dtype), bias=bias)
+        if igemm:
+            out = ops.conv3d_igemm(x, ops.cast_pack(wk, x.dtype), bias, ks, padding)
+        else:
+            col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
+            out = ops.gemm(col, ops.cast_pack(wk, x.dtype), bias=bias)
         ctx.save_for_backward(x, w)
-        ctx.meta = (geom, pointwise, Cop, b is not None)
+        ctx.meta = (geom, pointwise, unit, Cop, b is not None, tuple(padding))
         return out.view(N, geom[14], geom[15], geom[16], Cop)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         x, w = ctx.saved_tensors
-        geom, pointwise, Cop, has_bias = ctx.meta
+        geom, pointwise, unit, Cop, has_bias, padding = ctx.meta
         N, D, H, W, Cp = x.shape
         Co, Ci = w.shape[:2]
-        do2 = dout.contiguous().view(-1, Cop)
-        col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
-        wk = _conv_weight_rows(w, Cp, Cop)
-        dcol, dwk, db = linear_bwd(do2, col, wk, need_da=ctx.needs_input_grad[0], need_db=has_bias)
-        dx = None
-        if dcol is not None:
-            dx = dcol.view(x.shape) if pointwise else ops.col2im3d(dcol, geom)
-        dw = dwk.view(Cop, *w.shape[2:], Cp)[:Co, ..., :Ci].permute(0, 4, 1, 2, 3)
-        return dx, dw, (db[:Co] if has_bias else None), None, None
+        ks = tuple(w.shape[2:])
+        dout = dout.contiguous()
+        do2 = dout.view(-1, Cop)
+        need_dx = ctx.needs_input_grad[0]
+        dx = dwk = col = None
+        # data gradient: the stride-1 conv of dout with the flipped, transposed filter and padding k-1-p
+        bpad = tuple(k - 1 - p for k, p in zip(ks, padding))
+        if need_dx and unit and ops.conv3d_igemm_supported(tuple(dout.shape), Cp, ks, bpad):
+            wf = _conv_weight_rows_flipped(w, Cp, Cop)
+            dx = ops.conv3d_igemm(dout, ops.cast_pack(wf, x.dtype), None, ks, bpad)
+            need_dx = False
+        if unit and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, wgrad=True):
+            dwk = ops.conv3d_igemm_wgrad(x, dout, ks, padding)
+        if need_dx or dwk is None:
+            col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
+            wk = _conv_weight_rows(w, Cp, Cop)
+            dcol, dwk2, _ = linear_bwd(do2, col, wk, need_da=need_dx, need_db=False)
+            if dwk is None:
+                dwk = dwk2
+            if dcol is not None:
+                dx = dcol.view(x.shape) if pointwise else ops.col2im3d(dcol, geom)
+        db = ops.colreduce(do2.view(1, -1, Cop), 0).view(Cop)[:Co] if has_bias else None
+        dw = dwk.view(Cop, *ks, Cp)[:Co, ..., :Ci].permute(0, 4, 1, 2, 3)
+        return dx, dw, db, None, None
 
 
 def conv3d_cl(x, conv):

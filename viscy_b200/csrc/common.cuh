@@ -111,6 +111,40 @@ __device__ __forceinline__ void gelu_parts2(float2 u, float2& cdf, float2& pdf) 
   pdf = __fmul2_rn(e, make_float2(0.3989422804014327f, 0.3989422804014327f));
 }
 
+// raw MUFU ops: no range fix-up code around them (the arguments here are always in range)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// u -> d = gelu'(u), g = gelu(u) for two elements, one exp and one reciprocal each, everything else on the packed
+// fp32x2 pipe.  With q = erfc(|u|/sqrt2)/2 (Abramowitz-Stegun 7.1.26, coefficients pre-scaled by -1/2) and h = 1/2 - q:
+//   cdf = 1/2 + sgn(u) h,   gelu = u/2 + |u| h,   gelu' = cdf + u pdf = 1/2 + sgn(u) (h + |u| pdf)
+__device__ __forceinline__ void gelu_gp2(float2 u, float2& d, float2& g) {
+  const float2 uu = __fmul2_rn(u, u);
+  const float2 ea = __fmul2_rn(uu, make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));  // exp(-u^2/2)
+  const float2 x = make_float2(fabsf(u.x), fabsf(u.y));
+  const float2 den = __ffma2_rn(x, make_float2(0.23164190541f, 0.23164190541f), make_float2(1.f, 1.f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 poly = __ffma2_rn(t, make_float2(-0.5307027145f, -0.5307027145f), make_float2(0.7265760135f, 0.7265760135f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.7107068705f, -0.7107068705f));
+  poly = __ffma2_rn(poly, t, make_float2(0.142248368f, 0.142248368f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.127414796f, -0.127414796f));
+  poly = __fmul2_rn(poly, t);                                       // -q / e
+  const float2 h = __ffma2_rn(poly, e, make_float2(0.5f, 0.5f));    // 1/2 - q
+  const float2 pdf = __fmul2_rn(e, make_float2(0.3989422804014327f, 0.3989422804014327f));
+  const float2 s = __ffma2_rn(x, pdf, h);
+  d.x = 0.5f + copysignf(s.x, u.x);
+  d.y = 0.5f + copysignf(s.y, u.y);
+  g = __ffma2_rn(x, h, __fmul2_rn(u, make_float2(0.5f, 0.5f)));
+}
+
 __device__ __forceinline__ float gelu_f(float u) {
   float cdf, pdf;
   gelu_parts(u, cdf, pdf);

@@ -102,74 +102,124 @@ __device__ __forceinline__ void store8(void* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = q;
 }
 
-__device__ __forceinline__ void unpack8(bool bf16, const uint4& q, float* v) {
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& q, float* v) {
   const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float2 f = bf16 ? H16<true>::unpack(w4[k]) : H16<false>::unpack(w4[k]);
+    const float2 f = H16<BF16>::unpack(w4[k]);
     v[2 * k] = f.x;
     v[2 * k + 1] = f.y;
   }
 }
-__device__ __forceinline__ uint4 pack8(bool bf16, const float* v) {
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 q;
-  if (bf16) {
-    q.x = H16<true>::pack(v[0], v[1]); q.y = H16<true>::pack(v[2], v[3]);
-    q.z = H16<true>::pack(v[4], v[5]); q.w = H16<true>::pack(v[6], v[7]);
-  } else {
-    q.x = H16<false>::pack(v[0], v[1]); q.y = H16<false>::pack(v[2], v[3]);
-    q.z = H16<false>::pack(v[4], v[5]); q.w = H16<false>::pack(v[6], v[7]);
-  }
+  q.x = H16<BF16>::pack(v[0], v[1]); q.y = H16<BF16>::pack(v[2], v[3]);
+  q.z = H16<BF16>::pack(v[4], v[5]); q.w = H16<BF16>::pack(v[6], v[7]);
   return q;
 }
 
-// Auxiliary 16-bit operands of one 32-column chunk of one row, fetched ahead of the accumulator drain.
+// Auxiliary 16-bit operands of one 32-column chunk of this warp's 32 rows, fetched ahead of the accumulator drain.
+// Loads are row-contiguous: lane l fetches, for i = 0..3, the 16-byte group (l & 3) of row (l >> 2) + 8 i, so one
+// instruction covers 8 rows x 64 B; `unstage` transposes through the warp's staging tile into the row-per-lane order
+// of the TMEM accumulator (lane = row, 4 groups of 8 columns).
 struct AuxRegs {
   uint4 a[4];  // residual (EPI_STORE) | u (EPI_DGELU) | g (EPI_DGELU_GRN)
   uint4 b[4];  // gp (EPI_DGELU_GRN)
 };
 
 template <int EPI>
-__device__ __forceinline__ void load_aux(const GemmParams& p, long long row, int col0, bool row_ok, AuxRegs& x) {
+__device__ __forceinline__ const uint16_t* aux_a_ptr(const GemmParams& p, long long& lda) {
   const uint16_t* pa = nullptr;
-  long long lda = 0;
+  lda = 0;
   if constexpr (EPI == VB200_EPI_STORE) { pa = reinterpret_cast<const uint16_t*>(p.residual); lda = p.ldr; }
   if constexpr (EPI == VB200_EPI_DGELU) { pa = reinterpret_cast<const uint16_t*>(p.aux); lda = p.ldaux; }
   if constexpr (EPI == VB200_EPI_DGELU_GRN) {
     if (p.tvec != nullptr) { pa = reinterpret_cast<const uint16_t*>(p.aux); lda = p.ldaux; }
   }
+  return pa;
+}
+
+template <int EPI>
+__device__ __forceinline__ void load_aux(const GemmParams& p, long long row0, int col0, int lane, AuxRegs& x) {
+  long long lda;
+  const uint16_t* pa = aux_a_ptr<EPI>(p, lda);
+  const int col = col0 + (lane & 3) * 8;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int col = col0 + g * 8;
-    const bool ok = row_ok && col < p.N;
-    x.a[g] = make_uint4(0, 0, 0, 0);
-    if (pa != nullptr && ok) x.a[g] = __ldg(reinterpret_cast<const uint4*>(pa + row * lda + col));
+  for (int i = 0; i < 4; ++i) {
+    const long long row = row0 + (lane >> 2) + 8 * i;
+    const bool ok = row < p.M && col < p.N;
+    x.a[i] = make_uint4(0, 0, 0, 0);
+    if (pa != nullptr && ok) x.a[i] = __ldg(reinterpret_cast<const uint4*>(pa + row * lda + col));
     if constexpr (EPI == VB200_EPI_DGELU_GRN) {
-      x.b[g] = make_uint4(0, 0, 0, 0);
-      if (ok) x.b[g] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux2) + row * p.ldaux2 + col));
+      x.b[i] = make_uint4(0, 0, 0, 0);
+      if (ok) x.b[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux2) + row * p.ldaux2 + col));
     }
   }
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lds_f8(uint32_t addr, float* f) {  // 8 consecutive fp32 (32-byte aligned)
+  const uint4 a = lds128(addr), b = lds128(addr + 16);
+  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+  f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+}
+
+// (8 rows x 4 groups per register) -> (row = lane, group g in register g), through the 32 x 64 B staging tile
+// (stg = shared-space address of this warp's tile)
+__device__ __forceinline__ void unstage(uint32_t stg, int lane, uint4* v) {
+  __syncwarp();
+  const int ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = (lane >> 2) + 8 * i;
+    sts128(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4), v[i]);
+  }
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) v[g] = lds128(stg + lane * 64 + ((g ^ sw) << 4));
 }
 
 // Store one 32-row x 64-byte tile (this warp's rows, 16 B per lane and group) through a swizzled shared-memory
 // staging tile so that global stores are row-contiguous: 4 lanes cover one row's 64 B, one instruction covers 8 rows.
 // `vals` = this lane's row: 4 x uint4.  ATOMIC: red.add.v4.f32 instead of a store (fp32 data).
 template <bool ATOMIC>
-__device__ __forceinline__ void stage_store(uint8_t* stg, int lane, const uint4* vals, void* gbase, long long ld_bytes,
+__device__ __forceinline__ void stage_store(uint32_t stg, int lane, const uint4* vals, void* gbase, long long ld_bytes,
                                             long long row0, int rows_valid, long long col_byte0, int cols16_valid) {
   __syncwarp();
   const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ sw) << 4)) = vals[g];
+  for (int g = 0; g < 4; ++g) sts128(stg + lane * 64 + ((g ^ sw) << 4), vals[g]);
   __syncwarp();
   const int ch = lane & 3;
+  uint8_t* dst0 = reinterpret_cast<uint8_t*>(gbase) + (row0 + (lane >> 2)) * ld_bytes + col_byte0 + ch * 16;
+  if (!ATOMIC && rows_valid == 32 && cols16_valid == 4) {  // interior tile: no per-row predicates
+    uint4 q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 2) + 8 * i;
+      q[i] = lds128(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst0 + 8 * i * ld_bytes) = q[i];
+    return;
+  }
   if (ch < cols16_valid) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int rr = (lane >> 2) + 8 * i;
       if (rr < rows_valid) {
-        const uint4 q = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-        uint8_t* dst = reinterpret_cast<uint8_t*>(gbase) + (row0 + rr) * ld_bytes + col_byte0 + ch * 16;
+        const uint4 q = lds128(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+        uint8_t* dst = dst0 + 8 * i * ld_bytes;
         if constexpr (ATOMIC) {
           atomicAdd(reinterpret_cast<float4*>(dst), make_float4(__uint_as_float(q.x), __uint_as_float(q.y),
                                                                  __uint_as_float(q.z), __uint_as_float(q.w)));
@@ -181,18 +231,23 @@ __device__ __forceinline__ void stage_store(uint8_t* stg, int lane, const uint4*
   }
 }
 
-// Epilogue math for 8 consecutive columns of one row.  cv = staged [bias | s | t] of the tile (fp32, smem).
-// v: accumulators in, primary result out; w: secondary result (dual-output epilogues).
-template <int EPI, int BN>
-__device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, float* w, int cl, const float* cv,
+// Epilogue math for 8 consecutive columns of one row.  cv = shared-space address of the staged [bias | s | t] of the
+// tile (fp32).  v: accumulators in, primary result out; w: secondary result (dual-output epilogues).
+template <int EPI, int BN, bool BF16>
+__device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, float* w, int cl, uint32_t cv,
                                                const uint4& xa, const uint4& xb) {
-  const bool bf16 = p.bf16 != 0;
+  {
+    float b8[8];
+    lds_f8(cv + cl * 4, b8);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] += cv[cl + j];
+    for (int j = 0; j < 8; ++j) v[j] += b8[j];
+  }
   if constexpr (EPI == VB200_EPI_STORE) {
     if (p.svec != nullptr) {  // per-column fp32 scale (ConvNeXt-V1 layer scale gamma): (acc + bias) * s
+      float s8[8];
+      lds_f8(cv + (BN + cl) * 4, s8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= cv[BN + cl + j];
+      for (int j = 0; j < 8; ++j) v[j] *= s8[j];
     }
     if (p.act == VB200_ACT_RELU) {
 #pragma unroll
@@ -203,7 +258,7 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
     }
     if (p.residual != nullptr) {
       float q[8];
-      unpack8(bf16, xa, q);
+      unpack8<BF16>(xa, q);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += q[j];
     }
@@ -214,30 +269,31 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
     // v = gelu'(u), w = gelu(u): the backward never needs u itself
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      float2 cdf, pdf;
-      const float2 u = make_float2(v[j], v[j + 1]);
-      gelu_parts2(u, cdf, pdf);
-      const float2 d = __ffma2_rn(u, pdf, cdf);
-      const float2 gl = __fmul2_rn(u, cdf);
+      float2 d, gl;
+      gelu_gp2(make_float2(v[j], v[j + 1]), d, gl);
       v[j] = d.x; v[j + 1] = d.y;
       w[j] = gl.x; w[j + 1] = gl.y;
     }
   } else if constexpr (EPI == VB200_EPI_DGELU) {
     float u[8];
-    unpack8(bf16, xa, u);
+    unpack8<BF16>(xa, u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= dgelu_f(u[j]);
   } else if constexpr (EPI == VB200_EPI_DGELU_GRN) {
     // dh = (acc * s[n,col] + g * t[n,col]) * gp:  g = aux, gp = aux2 = gelu'(u) saved by the forward epilogue
-    float g[8], gp[8];
-    unpack8(bf16, xa, g);
-    unpack8(bf16, xb, gp);
+    float g[8], gp[8], s8[8], t8[8];
+    unpack8<BF16>(xa, g);
+    unpack8<BF16>(xb, gp);
+    lds_f8(cv + (BN + cl) * 4, s8);
+    lds_f8(cv + (2 * BN + cl) * 4, t8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(g[j], cv[2 * BN + cl + j], v[j] * cv[BN + cl + j]) * gp[j];
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(g[j], t8[j], v[j] * s8[j]) * gp[j];
   }
 }
 
-template <int BN, int MODE, int EPI, int BKE = BK>
+// BF16: element type of the 16-bit epilogue operands / outputs (compile-time so that the unrolled epilogue of a chunk is
+// one basic block; the MMA element type comes from the instruction descriptor, p.bf16)
+template <int BN, int MODE, int EPI, int BKE = BK, bool BF16 = true>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
@@ -401,7 +457,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = e >> 2;       // which half of the BN columns
     const int et = threadIdx.x - 64;
     float* colv = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-    uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES + 256 + C::COLV_BYTES + e * 2048;
+    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256 + C::COLV_BYTES + e * 2048);
     constexpr int NCH = BN / 64;   // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -418,38 +474,57 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         n_lim = (tap + 1) * p.ccin;
       }
       // stage this tile's per-column vectors (bias and, for the fused GRN backward, s and t of the tile's sample)
-      float* cv = colv + acc * 3 * BN;
+      float* cvp = colv + acc * 3 * BN;
+      const uint32_t cv = smem_u32(cvp);
       if (et < BN) {
         const int col = n0 + et;
         const bool ok = col < p.N;
-        cv[et] = (p.bias != nullptr && split == 0 && ok) ? __ldg(p.bias + col) : 0.0f;
+        cvp[et] = (p.bias != nullptr && split == 0 && ok) ? __ldg(p.bias + col) : 0.0f;
         if constexpr (EPI == VB200_EPI_DGELU_GRN || EPI == VB200_EPI_STORE) {
           const long long ns = p.rows_per_sample > 0 ? m0 / p.rows_per_sample : 0;
-          cv[BN + et] = (p.svec != nullptr && ok) ? __ldg(p.svec + ns * p.N + col) : 1.0f;
-          cv[2 * BN + et] = (p.tvec != nullptr && ok) ? __ldg(p.tvec + ns * p.N + col) : 0.0f;
+          cvp[BN + et] = (p.svec != nullptr && ok) ? __ldg(p.svec + ns * p.N + col) : 1.0f;
+          cvp[2 * BN + et] = (p.tvec != nullptr && ok) ? __ldg(p.tvec + ns * p.N + col) : 0.0f;
         }
       }
-      const long long row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const long long row0 = m0 + quarter * 32;
+      long long lda_unused;
+      const bool has_a = aux_a_ptr<EPI>(p, lda_unused) != nullptr;  // warp-uniform
       AuxRegs aux[2];
-      load_aux<EPI>(p, row, n0 + half * (BN / 2), row_ok, aux[0]);
+      const int cc0 = half * (BN / 2);
+      load_aux<EPI>(p, row0, n0 + cc0, lane, aux[0]);
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // cv visible to all epilogue warps
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      // accumulator chunks are fetched one ahead of the math (two register buffers); the TMEM buffer is handed back
+      // to the MMA warp as soon as this warp's last chunk sits in registers
+      // (not for EPI_DGELU_GRN, whose two double-buffered aux operands already fill the register file)
+      constexpr bool TPRE = EPI != VB200_EPI_DGELU_GRN;
+      uint32_t r[TPRE ? 2 : 1][32];
+      const int rows_valid = (int)min(32LL, (long long)p.M - row0);
+      bool released = false;
+      if (TPRE && n0 + cc0 < n_lim) tmem_ld32(t_addr + cc0, r[0]);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const int cc = half * (BN / 2) + c * 32;
+        const int cc = cc0 + c * 32;
         const int col0 = n0 + cc;
         if (col0 < n_lim) {  // warp-uniform
-          uint32_t r[32];
-          tmem_ld32(t_addr + cc, r);
-          if (c + 1 < NCH) load_aux<EPI>(p, row, col0 + 32, row_ok, aux[(c + 1) & 1]);
+          const bool more = c + 1 < NCH && col0 + 32 < n_lim;
+          if constexpr (!TPRE) tmem_ld32(t_addr + cc, r[0]);
+          if (more) load_aux<EPI>(p, row0, col0 + 32, lane, aux[(c + 1) & 1]);
+          if (has_a) unstage(stg, lane, aux[c & 1].a);
+          if constexpr (EPI == VB200_EPI_DGELU_GRN) unstage(stg, lane, aux[c & 1].b);
           tmem_ld_wait();
+          if (TPRE && more) {
+            tmem_ld32(t_addr + cc + 32, r[(c + 1) & 1]);
+          } else if (!more) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            released = true;
+          }
           // this warp's 32 rows x 32 columns: math per row, then row-contiguous stores through the staging tile
-          const long long row0 = m0 + quarter * 32;
-          const int rows_valid = (int)min(32LL, (long long)p.M - row0);
           const int cols8_valid = min(4, (n_lim - col0) >> 3);
           if (rows_valid > 0) {
             uint4 o1[4], o2[4];
@@ -458,14 +533,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int g = 0; g < 4; ++g) {
               float v[8], w[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              epilogue_math8<EPI, BN>(p, v, w, cc + g * 8, cv, aux[c & 1].a[g], aux[c & 1].b[g]);
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[TPRE ? (c & 1) : 0][g * 8 + j]);
+              epilogue_math8<EPI, BN, BF16>(p, v, w, cc + g * 8, cv, aux[c & 1].a[g], aux[c & 1].b[g]);
               if constexpr (EPI == VB200_EPI_F32) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f32buf[g * 8 + j] = v[j];
               } else {
-                o1[g] = pack8(p.bf16 != 0, v);
-                if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP) o2[g] = pack8(p.bf16 != 0, w);
+                o1[g] = pack8<BF16>(v);
+                if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP) o2[g] = pack8<BF16>(w);
               }
             }
             if constexpr (EPI == VB200_EPI_F32) {
@@ -491,9 +566,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (!released) {  // this warp's column range lies past the tile's valid columns
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -601,11 +678,11 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int MODE, int EPI, int BKE = BK>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                  cudaStream_t st) {
+template <int BN, int MODE, int EPI, int BKE, bool BF16>
+static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                     cudaStream_t st) {
   static bool configured = false;  // per instantiation
-  auto kern = gemm_kernel<BN, MODE, EPI, BKE>;
+  auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<BN, BKE>::SMEM_BYTES);
@@ -614,6 +691,17 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   }
   kern<<<grid, NUM_THREADS, Cfg<BN, BKE>::SMEM_BYTES, st>>>(ta, tb, p);
   return check_launch("vb200_gemm");
+}
+
+template <int BN, int MODE, int EPI, int BKE = BK>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                  cudaStream_t st) {
+  if constexpr (EPI == VB200_EPI_F32) {  // fp32 output: no 16-bit epilogue operand, one instantiation serves both
+    return launch_dt<BN, MODE, EPI, BKE, true>(ta, tb, p, grid, st);
+  } else {
+    return p.bf16 ? launch_dt<BN, MODE, EPI, BKE, true>(ta, tb, p, grid, st)
+                  : launch_dt<BN, MODE, EPI, BKE, false>(ta, tb, p, grid, st);
+  }
 }
 
 template <int BN, bool MN_MAJOR>

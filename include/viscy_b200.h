@@ -211,6 +211,21 @@ int vb200_cat2(void* a, void* b, void* out, int64_t M, int Ca, int Cb, int inver
 int vb200_add_rows(const void* x, const void* other, const float* bias, void* y, int64_t M, int C, int dtype,
                    vb200_stream_t stream);
 
+/* ---- 2.5-D U-Net: Unet25d / ConvBlock3D (VM/unet/unet25d.py:206-251, VM/components/conv_block_3d.py:261-298) on
+ * channels-last rows [N,D,H,W,C], C % 8 == 0.  The block convolutions are vb200_conv3d_igemm* / vb200_gemm. ---- */
+/* nn.Dropout3d (scale [N,C] fp32 = keep mask / (1-p), NULL = none) fused with nn.ReLU (conv_block_3d.py:268-272):
+ * forward (gate == NULL): y = relu?(x * scale[n,c]);  backward (gate = forward output): y = x * scale[n,c] * (gate > 0) */
+int vb200_scale_relu(const void* x, const void* gate, const float* scale, void* y, int64_t N, int64_t rows_per_sample,
+                     int C, int relu, int dtype, vb200_stream_t stream);
+/* nn.AvgPool3d((1,2,2), stride (1,2,2)) (unet25d.py:104-112) on P = N*D planes [P,H,W,C] -> [P,H/2,W/2,C];
+ * backward != 0: src = dy [P,H/2,W/2,C], dst = dx [P,H,W,C] */
+int vb200_avgpool_hw2(const void* src, void* dst, int64_t P, int H, int W, int C, int backward, int dtype,
+                      vb200_stream_t stream);
+/* nn.Upsample(scale_factor=(1,2,2), mode="trilinear", align_corners=False) (unet25d.py:114-116): [P,H,W,C] -> [P,2H,2W,C];
+ * backward != 0: src = dy [P,2H,2W,C], dst = dx [P,H,W,C] (the adjoint) */
+int vb200_upsample2x_hw(const void* src, void* dst, int64_t P, int H, int W, int C, int backward, int dtype,
+                        vb200_stream_t stream);
+
 /* ---- ContrastiveEncoder pooled head + projection MLP (VM/contrastive/encoder.py:114-124,138-154) ---- */
 /* nn.BatchNorm1d over rows of x [B,C] 16-bit (+ optional fused ReLU); training: batch statistics, var_unbiased (for the
  * running-var update) written when non-NULL; eval: run_mean / run_var are used */

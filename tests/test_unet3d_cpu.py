@@ -50,8 +50,13 @@ def test_unet3d_validation_errors():
     assert abs(m.inconv.weight.std().item() - 0.02) < 0.01
 
 
-def test_unet25d_rejects_cuda_clearly():
+def test_unet25d_unsupported_configs_raise_on_cuda():
+    """Configurations without sm_100a kernels raise (never a cuDNN fallback); fp32 input without autocast raises too."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA tensor")
+    from viscy_b200.unet25d import ConvBlock3D
     with pytest.raises(NotImplementedError):
-        Unet25d().cuda()(torch.randn(1, 1, 5, 32, 32, device="cuda"))
+        Unet25d().cuda()(torch.randn(1, 1, 5, 32, 32, device="cuda"))  # fp32, no autocast
+    blk = ConvBlock3D(16, 16, norm="instance").cuda()
+    with pytest.raises(NotImplementedError):
+        blk.forward_cl(torch.randn(1, 4, 8, 8, 16, device="cuda").half())

@@ -723,13 +723,20 @@ class BatchNormActFn(Function):
 
 def batchnorm_act_cl(x, bn, relu):
     training = bn.training or bn.running_mean is None
-    y, mean, var_unb = BatchNormActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, training, relu)
+    Cc, Cn = x.shape[-1], bn.num_features
+    weight, bias, rm, rv = bn.weight, bn.bias, bn.running_mean, bn.running_var
+    if Cn != Cc:  # channel-padded rows (e.g. a 1-channel terminal block): padded channels are all-zero and stay zero
+        pad = (0, Cc - Cn)
+        weight, bias = torch.nn.functional.pad(weight, pad), torch.nn.functional.pad(bias, pad)
+        if rm is not None:
+            rm, rv = torch.nn.functional.pad(rm, pad), torch.nn.functional.pad(rv, pad, value=1.0)
+    y, mean, var_unb = BatchNormActFn.apply(x, weight, bias, rm, rv, bn.eps, training, relu)
     if bn.training and bn.track_running_stats and bn.running_mean is not None:
         with torch.no_grad():
             bn.num_batches_tracked += 1
             mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-            bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
-            bn.running_var.mul_(1 - mom).add_(var_unb, alpha=mom)
+            bn.running_mean.mul_(1 - mom).add_(mean[:Cn], alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var_unb[:Cn], alpha=mom)
     return y
 
 
@@ -761,3 +768,65 @@ class AddFn(Function):
 
 def add_cl(a, b):
     return AddFn.apply(a, b)
+
+
+# --------------------------------------------------------------------------------------------------
+# 2.5-D U-Net (Unet25d / ConvBlock3D): Dropout3d + ReLU, (1,2,2) average pooling, (1,2,2) trilinear upsampling
+class ScaleReluFn(Function):
+    """relu?(x * scale[n, c]): nn.Dropout3d (scale = keep mask / (1 - p) per sample and channel, or None) fused with nn.ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, scale, relu):
+        y = ops.scale_relu(x, scale, relu)
+        ctx.save_for_backward(y if relu else None, scale)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        y, scale = ctx.saved_tensors
+        return ops.scale_relu(dy.contiguous(), scale, ctx.relu, gate=y), None, None
+
+
+def scale_relu_cl(x, scale, relu):
+    return ScaleReluFn.apply(x, scale, relu)
+
+
+def dropout3d_scale(x, p: float, training: bool):
+    """Per-(sample, channel) scale of nn.Dropout3d on channels-last rows, or None when it is the identity."""
+    if not training or p <= 0.0:
+        return None
+    keep = torch.full((x.shape[0], x.shape[-1]), 1.0 - p, device=x.device, dtype=torch.float32)
+    return torch.bernoulli(keep) / (1.0 - p)
+
+
+class AvgPoolHW2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return ops.avgpool_hw2(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return ops.avgpool_hw2(dy.contiguous(), backward_shape=ctx.shape)
+
+
+def avgpool_hw2_cl(x):
+    return AvgPoolHW2Fn.apply(x)
+
+
+class Upsample2xHWFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2x_hw(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return ops.upsample2x_hw(dy.contiguous(), backward=True)
+
+
+def upsample2x_hw_cl(x):
+    return Upsample2xHWFn.apply(x)

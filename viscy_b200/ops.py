@@ -661,6 +661,46 @@ def add_rows(x, other=None, bias=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# 2.5-D U-Net helpers (channels-last rows [N,D,H,W,C])
+def scale_relu(x, scale, relu, gate=None):
+    """forward: relu?(x * scale[n,c]); backward (gate = forward output): x * scale[n,c] * (gate > 0).  scale [N,C] fp32 or None."""
+    _act(x, "x")
+    N, Cc = x.shape[0], x.shape[-1]
+    rows = x.numel() // (N * Cc)
+    y = torch.empty_like(x)
+    _call("vb200_scale_relu", _p(x), _p(gate), _p(None if scale is None else _f32(scale, "scale")), _p(y), C.c_int64(N),
+          C.c_int64(rows), Cc, int(relu), L.dtype_code(x.dtype))
+    return y
+
+
+def avgpool_hw2(x, backward_shape=None):
+    """[N,D,H,W,C] -> [N,D,H//2,W//2,C] (AvgPool3d (1,2,2)); backward_shape = input shape: the gradient of that."""
+    _act(x, "x")
+    if backward_shape is None:
+        N, D, H, W, Cc = x.shape
+        y = torch.empty((N, D, H // 2, W // 2, Cc), device=x.device, dtype=x.dtype)
+        _call("vb200_avgpool_hw2", _p(x), _p(y), C.c_int64(N * D), H, W, Cc, 0, L.dtype_code(x.dtype))
+        return y
+    N, D, H, W, Cc = backward_shape
+    dx = torch.empty(backward_shape, device=x.device, dtype=x.dtype)
+    _call("vb200_avgpool_hw2", _p(x), _p(dx), C.c_int64(N * D), H, W, Cc, 1, L.dtype_code(x.dtype))
+    return dx
+
+
+def upsample2x_hw(x, backward=False):
+    """bilinear x2 in H and W (trilinear, scale (1,2,2), align_corners=False) on [N,D,H,W,C]; backward: the adjoint."""
+    _act(x, "x")
+    N, D, H, W, Cc = x.shape
+    if not backward:
+        y = torch.empty((N, D, 2 * H, 2 * W, Cc), device=x.device, dtype=x.dtype)
+        _call("vb200_upsample2x_hw", _p(x), _p(y), C.c_int64(N * D), H, W, Cc, 0, L.dtype_code(x.dtype))
+        return y
+    dx = torch.empty((N, D, H // 2, W // 2, Cc), device=x.device, dtype=x.dtype)
+    _call("vb200_upsample2x_hw", _p(x), _p(dx), C.c_int64(N * D), H // 2, W // 2, Cc, 1, L.dtype_code(x.dtype))
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
 # per-step weight packing in one launch
 class WeightPacks:
     """16-bit GEMM operand copies ([N,K] and [K,N]) of Linear / 1x1-conv weights and tap-major depthwise filters of a

@@ -1,8 +1,11 @@
 """Unet25d and its ConvBlock3D (VM/unet/unet25d.py:11-251, VM/components/conv_block_3d.py:11-346): same constructor,
 forward, sub-module names and state_dict as the reference.
 
-This family is BASELINE config #1 (CPU, fp32 parity): it runs in plain torch ops.  CUDA tensors are rejected with
-NotImplementedError until its sm_100a kernels land - there is no silent cuDNN fallback.
+CPU tensors (BASELINE config #1, fp32 parity) run in plain torch ops.  CUDA tensors run channels-last 16-bit through the
+sm_100a kernels: every convolution on the tcgen05 GEMM (implicit-GEMM TMA form where the geometry tiles, im2col lowering
+otherwise), Dropout3d + ReLU, BatchNorm3d, (1,2,2) average pooling and trilinear upsampling as HBM-bound kernels.
+Configurations without kernels (InstanceNorm, non-ReLU activations, transposed convs) raise NotImplementedError on CUDA -
+there is no silent cuDNN fallback.
 """
 
 from __future__ import annotations
@@ -12,14 +15,17 @@ import torch
 import torch.nn.functional as TF
 from torch import Tensor, nn
 
+from . import functional as F
+from .unext2 import resolve_compute_dtype
+
 _ACTS = {"relu": nn.ReLU, "leakyrelu": nn.LeakyReLU, "elu": nn.ELU, "selu": nn.SELU}
 
 
 def _reject_cuda(x: Tensor, what: str) -> None:
     if x.is_cuda:
         raise NotImplementedError(
-            f"{what}: no sm_100a kernels yet (BASELINE config 1 is the CPU parity configuration); "
-            "move the module and its input to the CPU"
+            f"{what}: NCDHW CUDA tensors enter through Unet25d.forward (channels-last sm_100a path) or "
+            "ConvBlock3D.forward_cl; there is no cuDNN fallback"
         )
 
 
@@ -99,6 +105,54 @@ class ConvBlock3D(nn.Module):
             self.add_module(f"{name}_{i}", m)
 
     register_modules = _register
+
+    def forward_cl(self, x: Tensor) -> Tensor:
+        """sm_100a path on channels-last rows [N,D,H,W,C] (C padded to a multiple of 8)."""
+        if self.transpose:
+            raise NotImplementedError("sm_100a ConvBlock3D: transpose=True")
+        if self.norm == "instance":
+            raise NotImplementedError("sm_100a ConvBlock3D: norm='instance' (BatchNorm3d / none only)")
+        if self.activation not in ("relu", "linear"):
+            raise NotImplementedError(f"sm_100a ConvBlock3D: activation {self.activation!r} (relu / linear only)")
+        pw, ph, pd = self.padding[0], self.padding[2], self.padding[4]
+        if (self.padding[1], self.padding[3], self.padding[5]) != (pw, ph, pd):
+            raise NotImplementedError("sm_100a ConvBlock3D: asymmetric padding")
+        x0 = x
+        for i in range(self.num_repeats):
+            order = self.layer_order
+            k = 0
+            while k < len(order):
+                layer = order[k]
+                if layer == "c":
+                    conv = self.conv_list[i]
+                    x = F.Conv3dFn.apply(x, conv.weight, conv.bias, (1, 1, 1), (pd, ph, pw))
+                    scale = F.dropout3d_scale(x, self.dropout, self.training) if self.dropout else None
+                    act_next = k + 1 < len(order) and order[k + 1] == "a" and self._has_act(i)
+                    if act_next:  # conv -> dropout -> ReLU in one pass over the tensor
+                        x = F.scale_relu_cl(x, scale, True)
+                        k += 1
+                    elif scale is not None:
+                        x = F.scale_relu_cl(x, scale, False)
+                elif layer == "a":
+                    if self._has_act(i):
+                        x = F.scale_relu_cl(x, None, True)
+                elif layer == "n" and self.norm_list[i] is not None:
+                    x = F.batchnorm_act_cl(x, self.norm_list[i], relu=False)
+                k += 1
+        if self.residual:
+            if self.in_filters > self.out_filters:
+                x0 = F.conv3d_cl(x0, self.resid_conv)
+            elif self.in_filters < self.out_filters:
+                cin_rows, cout_rows = x0.shape[-1], x.shape[-1]
+                if cin_rows != self.in_filters or cout_rows != self.out_filters:
+                    raise NotImplementedError("sm_100a ConvBlock3D: residual channel growth needs channel counts % 8 == 0")
+                zeros = torch.zeros((*x0.shape[:-1], cout_rows - cin_rows), device=x0.device, dtype=x0.dtype)
+                x0 = F.cat_cl(zeros, x0)  # identity lands on the LAST in_filters channels (conv_block_3d.py:281-287)
+            x = F.add_cl(x, x0)
+        return x
+
+    def _has_act(self, i: int) -> bool:
+        return self.activation != "linear" and (i < self.num_repeats - 1 or self.activation != "linear")
 
     def forward(self, x: Tensor) -> Tensor:
         _reject_cuda(x, "ConvBlock3D")
@@ -181,8 +235,28 @@ class Unet25d(nn.Module):
 
     register_modules = _register
 
+    compute_dtype: torch.dtype | None = None  # sm_100a arithmetic type override (default: autocast / input dtype)
+
+    def _forward_sm100(self, x: Tensor) -> Tensor:
+        dt = resolve_compute_dtype(x, self.compute_dtype)
+        F.ops.ACTIVE_PACKS = None  # weight packs are scoped to the model that registered them
+        with torch.autocast("cuda", enabled=False):
+            h = F.to_channels_last_3d(x, dt)
+            skips = []
+            for blk in self.down_conv_blocks:
+                h = blk.forward_cl(h)
+                skips.append(h)
+                h = F.avgpool_hw2_cl(h)
+            h = F.conv3d_cl(h, self.bottom_transition_block)
+            skips = [F.conv3d_cl(s, conv) for conv, s in zip(self.skip_conv_layers, skips)]
+            for i, blk in enumerate(self.up_conv_blocks):
+                h = blk.forward_cl(F.cat_cl(F.upsample2x_hw_cl(h), skips[-(i + 1)]))
+            h = self.terminal_block.forward_cl(h)
+            return F.from_channels_last_3d(h, self.terminal_block.out_filters)
+
     def forward(self, x: Tensor) -> Tensor:
-        _reject_cuda(x, "Unet25d")
+        if x.is_cuda:
+            return self._forward_sm100(x)
         skips = []
         for blk, down in zip(self.down_conv_blocks, self.down_list):
             x = blk(x)

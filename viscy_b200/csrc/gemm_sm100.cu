@@ -21,8 +21,13 @@ std::atomic<long long> g_launches{0};
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+// Epilogue warps per CTA: 8 (two per TMEM lane quarter, half of the tile's columns each), or 16 for the epilogues that
+// are bound by their own instruction latency (GELU'/GELU pair, fused GRN+GELU backward) on 256-wide tiles: twice the
+// warps in flight, each with a quarter of the columns, single-buffered operands to stay under the register ceiling.
+template <int BN, int EPI>
+struct EpiWarps {
+  static constexpr int value = (BN == 256 && (EPI == VB200_EPI_GELU_GP || EPI == VB200_EPI_DGELU_GRN)) ? 16 : 8;
+};
 
 // Operand forms.  The two CONV forms are the implicit-GEMM 3-D convolution: one operand is the channels-last activation
 // tensor seen through a 5-D tensor map (C, X, Y, Z, N); a K block (CONVK) / an N tile (CONVMN) belongs to one filter tap
@@ -30,15 +35,17 @@ constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3 };
 
 // BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
-template <int BN, int BKE = BK>
+template <int BN, int BKE = BK, int EW = 8>
 struct Cfg {
   static constexpr int A_BYTES = BM * BKE * 2;
   static constexpr int B_BYTES = BN * BKE * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BKE == 64 ? ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12));
+  // (the 16-warp epilogues need 32 KB of staging tiles: one operand stage less on the 256-wide tile)
+  static constexpr int STAGES = BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8))
+                                          : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12));
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int COLV_BYTES = 2 * 3 * BN * 4;  // [2 tiles in flight][bias, s, t][BN] fp32
-  static constexpr int STG_BYTES = NUM_EPI_WARPS * 2048;  // per-warp 32 rows x 64 B store-staging tile
+  static constexpr int STG_BYTES = EW * 2048;  // per-warp 32 rows x 64 B store-staging tile
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES + STG_BYTES;
 };
@@ -294,10 +301,12 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
 // BF16: element type of the 16-bit epilogue operands / outputs (compile-time so that the unrolled epilogue of a chunk is
 // one basic block; the MMA element type comes from the instruction descriptor, p.bf16)
 template <int BN, int MODE, int EPI, int BKE = BK, bool BF16 = true>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * EpiWarps<BN, EPI>::value, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
-  using C = Cfg<BN, BKE>;
+  constexpr int NUM_EPI_WARPS = EpiWarps<BN, EPI>::value;
+  using C = Cfg<BN, BKE, NUM_EPI_WARPS>;
+  constexpr int COL_GROUPS = NUM_EPI_WARPS / 4;  // warps sharing a TMEM lane quarter split the tile's columns
   constexpr bool MN_MAJOR = MODE == MODE_MNMAJOR || MODE == MODE_CONVMN;
   static_assert(BKE == 64 || (BKE == 32 && MODE == MODE_CONVK), "BKE = 32 is the 32-channel conv form only");
   extern __shared__ uint8_t smem_raw[];
@@ -454,11 +463,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== epilogue warps =====================
     const int e = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
-    const int half = e >> 2;       // which half of the BN columns
+    const int half = e >> 2;       // which group of BN / COL_GROUPS columns
     const int et = threadIdx.x - 64;
     float* colv = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
     const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256 + C::COLV_BYTES + e * 2048);
-    constexpr int NCH = BN / 64;   // 32-column chunks per warp
+    constexpr int NCH = BN / (32 * COL_GROUPS);  // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -489,8 +498,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long row0 = m0 + quarter * 32;
       long long lda_unused;
       const bool has_a = aux_a_ptr<EPI>(p, lda_unused) != nullptr;  // warp-uniform
-      AuxRegs aux[2];
-      const int cc0 = half * (BN / 2);
+      constexpr bool APRE = NUM_EPI_WARPS == 8;  // aux operands fetched one chunk ahead (second register buffer)
+      AuxRegs aux[APRE ? 2 : 1];
+      const int cc0 = half * (BN / COL_GROUPS);
       load_aux<EPI>(p, row0, n0 + cc0, lane, aux[0]);
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // cv visible to all epilogue warps
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -500,7 +510,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // accumulator chunks are fetched one ahead of the math (two register buffers); the TMEM buffer is handed back
       // to the MMA warp as soon as this warp's last chunk sits in registers
       // (not for EPI_DGELU_GRN, whose two double-buffered aux operands already fill the register file)
-      constexpr bool TPRE = EPI != VB200_EPI_DGELU_GRN;
+      constexpr bool TPRE = EPI != VB200_EPI_DGELU_GRN && NUM_EPI_WARPS == 8;
       uint32_t r[TPRE ? 2 : 1][32];
       const int rows_valid = (int)min(32LL, (long long)p.M - row0);
       bool released = false;
@@ -512,9 +522,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (col0 < n_lim) {  // warp-uniform
           const bool more = c + 1 < NCH && col0 + 32 < n_lim;
           if constexpr (!TPRE) tmem_ld32(t_addr + cc, r[0]);
-          if (more) load_aux<EPI>(p, row0, col0 + 32, lane, aux[(c + 1) & 1]);
-          if (has_a) unstage(stg, lane, aux[c & 1].a);
-          if constexpr (EPI == VB200_EPI_DGELU_GRN) unstage(stg, lane, aux[c & 1].b);
+          const int AB = APRE ? (c & 1) : 0;
+          if constexpr (APRE) {
+            if (more) load_aux<EPI>(p, row0, col0 + 32, lane, aux[(c + 1) & 1]);
+          } else {
+            if (c > 0) load_aux<EPI>(p, row0, col0, lane, aux[0]);
+          }
+          if (has_a) unstage(stg, lane, aux[AB].a);
+          if constexpr (EPI == VB200_EPI_DGELU_GRN) unstage(stg, lane, aux[AB].b);
           tmem_ld_wait();
           if (TPRE && more) {
             tmem_ld32(t_addr + cc + 32, r[(c + 1) & 1]);
@@ -534,7 +549,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float v[8], w[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[TPRE ? (c & 1) : 0][g * 8 + j]);
-              epilogue_math8<EPI, BN, BF16>(p, v, w, cc + g * 8, cv, aux[c & 1].a[g], aux[c & 1].b[g]);
+              epilogue_math8<EPI, BN, BF16>(p, v, w, cc + g * 8, cv, aux[AB].a[g], aux[AB].b[g]);
               if constexpr (EPI == VB200_EPI_F32) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f32buf[g * 8 + j] = v[j];
@@ -685,11 +700,11 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN, BKE>::SMEM_BYTES);
+                                         Cfg<BN, BKE, EpiWarps<BN, EPI>::value>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<BN, BKE>::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value, Cfg<BN, BKE, EpiWarps<BN, EPI>::value>::SMEM_BYTES, st>>>(ta, tb, p);
   return check_launch("vb200_gemm");
 }
 

@@ -10,8 +10,11 @@ from pathlib import Path
 
 import torch
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libviscy_b200.so"
+# VB200_LIB: load another build of the same library (A/B timing of kernel variants); never a different implementation
+LIB_PATH = Path(os.environ["VB200_LIB"]) if os.environ.get("VB200_LIB") else _PKG / "libviscy_b200.so"
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 BF16, FP16 = 0, 1

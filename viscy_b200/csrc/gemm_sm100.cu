@@ -27,6 +27,8 @@ constexpr int BK = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 template <int BN, int EPI>
 struct EpiWarps {
   static constexpr int value = (BN == 256 && (EPI == VB200_EPI_GELU_GP || EPI == VB200_EPI_DGELU_GRN)) ? 16 : 8;
+  // dual-output epilogue: results leave through TMA stores (two staging tiles, two bulk groups in flight per warp)
+  static constexpr bool tma_store = value == 16 && EPI == VB200_EPI_GELU_GP;
 };
 
 // Operand forms.  The two CONV forms are the implicit-GEMM 3-D convolution: one operand is the channels-last activation
@@ -35,7 +37,7 @@ struct EpiWarps {
 enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3 };
 
 // BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
-template <int BN, int BKE = BK, int EW = 8>
+template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BKE * 2;
   static constexpr int B_BYTES = BN * BKE * 2;
@@ -45,7 +47,10 @@ struct Cfg {
                                           : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12));
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int COLV_BYTES = 2 * 3 * BN * 4;  // [2 tiles in flight][bias, s, t][BN] fp32
-  static constexpr int STG_BYTES = EW * 2048;  // per-warp 32 rows x 64 B store-staging tile
+  // per-warp 32 rows x 64 B staging tile(s): one, or two for the 16-warp epilogues whose outputs leave through TMA stores
+  static constexpr int STG_PER_WARP = TWO_TILES ? 4096 : 2048;
+  static constexpr int STG_BYTES = EW * STG_PER_WARP;
+  static_assert(!TWO_TILES || EW == 16, "TMA-store epilogues run 16 warps");
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES + STG_BYTES;
 };
@@ -80,6 +85,39 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// Output tensor maps of the TMA-store epilogues: [M, N] 16-bit, box 32 columns x 32 rows, SWIZZLE_64B -- the layout the
+// epilogue warps already write their staging tile in (16-byte group g of row r at r*64 + ((g ^ (r>>1 & 3)) << 4)).
+struct OutMaps {
+  CUtensorMap o, o2;
+};
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+// one elected lane owns the warp's bulk-store groups: wait until at most PENDING of them still read shared memory,
+// publish the other lanes' staging writes to the async proxy, issue the store
+template <int PENDING>
+__device__ __forceinline__ void tma_stage_store(uint32_t tile, int lane, const uint4* vals, const CUtensorMap* m, int col0,
+                                                long long row0) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + lane * 64 + ((g ^ sw) << 4)), "r"(vals[g].x),
+                 "r"(vals[g].y), "r"(vals[g].z), "r"(vals[g].w)
+                 : "memory");
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(m, tile, col0, (int)row0);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
 }
 
 // flattened output-voxel index -> (x, y, z, n)
@@ -303,9 +341,9 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
 template <int BN, int MODE, int EPI, int BKE = BK, bool BF16 = true>
 __global__ void __launch_bounds__(64 + 32 * EpiWarps<BN, EPI>::value, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const GemmParams p) {
+            const __grid_constant__ OutMaps tmOut, const GemmParams p) {
   constexpr int NUM_EPI_WARPS = EpiWarps<BN, EPI>::value;
-  using C = Cfg<BN, BKE, NUM_EPI_WARPS>;
+  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store>;
   constexpr int COL_GROUPS = NUM_EPI_WARPS / 4;  // warps sharing a TMEM lane quarter split the tile's columns
   constexpr bool MN_MAJOR = MODE == MODE_MNMAJOR || MODE == MODE_CONVMN;
   static_assert(BKE == 64 || (BKE == 32 && MODE == MODE_CONVK), "BKE = 32 is the 32-channel conv form only");
@@ -466,7 +504,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = e >> 2;       // which group of BN / COL_GROUPS columns
     const int et = threadIdx.x - 64;
     float* colv = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256 + C::COLV_BYTES + e * 2048);
+    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256 + C::COLV_BYTES + e * C::STG_PER_WARP);
+    constexpr bool TMA_STORE = EpiWarps<BN, EPI>::tma_store;
     constexpr int NCH = BN / (32 * COL_GROUPS);  // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -573,6 +612,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 else
                   stage_store<false>(stg, lane, q, ob, p.ldo * 4, row0, rows_valid, (long long)(col0 + hh * 16) * 4, c4v);
               }
+            } else if constexpr (TMA_STORE) {
+              if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP) {
+                // two tiles, two stores in flight: each waits only for the store that last read its own tile
+                tma_stage_store<1>(stg, lane, o1, &tmOut.o, col0, row0);
+                tma_stage_store<1>(stg + 2048, lane, o2, &tmOut.o2, col0, row0);
+              }
             } else {
               stage_store<false>(stg, lane, o1, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
               if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP)
@@ -588,6 +633,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (TMA_STORE) {  // the staging tiles must outlive the bulk stores that read them
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
 
@@ -700,11 +748,17 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN, BKE, EpiWarps<BN, EPI>::value>::SMEM_BYTES);
+                                         Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value, Cfg<BN, BKE, EpiWarps<BN, EPI>::value>::SMEM_BYTES, st>>>(ta, tb, p);
+  OutMaps om{};
+  if constexpr (EpiWarps<BN, EPI>::tma_store) {
+    if (int rc = make_tmap_2d(&om.o, p.out, p.M, p.N, p.ldo, 32, 32, BF16, true)) return rc;
+    if (p.out2 != nullptr)
+      if (int rc = make_tmap_2d(&om.o2, p.out2, p.M, p.N, p.ldo2, 32, 32, BF16, true)) return rc;
+  }
+  kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value, Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store>::SMEM_BYTES, st>>>(ta, tb, om, p);
   return check_launch("vb200_gemm");
 }
 

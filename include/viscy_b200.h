@@ -73,13 +73,16 @@ typedef struct vb200_gemm_desc {
 
 int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);
 
-/* ---- implicit-GEMM 3-D convolution on the same tcgen05 pipeline (stride 1, any filter extent, zero padding).
+/* ---- implicit-GEMM 3-D convolution on the same tcgen05 pipeline (any filter extent, stride <= 8, zero padding).
  * im2col is folded into TMA: the channels-last activation is one 5-D tensor map (C, X, Y, Z, N) and each K block of
  * the contraction -- (filter tap, 64- or 32-channel chunk) -- is one box fetched at the tap-shifted voxel coordinate,
  * out-of-range voxels zero-filled by the TMA unit (= the padding).  No patch matrix ever exists in HBM.
- *   forward : out[v, co] = act(bias[co] + sum_{tap,ci} x[v + tap - pad, ci] * w[co, tap, ci]) (+ residual[v, co])
- *   dgrad   : the same entry point on dout with the flipped / transposed filter and padding k-1-p
- *   wgrad   : dw[co, tap, ci] += sum_v dout[v, co] * x[v + tap - pad, ci]   (fp32, red.add; K-split over voxels)
+ *   forward : out[v, co] = act(bias[co] + sum_{tap,ci} x[v*s + tap - pad, ci] * w[co, tap, ci]) (+ residual[v, co])
+ *   dgrad   : (stride 1) the same entry point on dout with the flipped / transposed filter and padding k-1-p
+ *   wgrad   : dw[co, tap, ci] += sum_v dout[v, co] * x[v*s + tap - pad, ci]   (fp32, red.add; K-split over voxels)
+ * Strided convolutions use the tensor map's element strides: a box of s*b voxels per dimension delivers b voxels.
+ * The data gradient of nn.ConvTranspose3d is the strided forward of its adjoint conv, its weight gradient the strided
+ * wgrad with the roles of x and dout exchanged.
  * Replaces nn.Conv3d(k=3, padding=1) of Block.proj (VM/unet/blocks.py:88-113), ResnetBlock / ConvBottleneck3D
  * (VM/unet/blocks.py:116-188,233-292), UNet3DBase inconv / outconv (VM/unet/unet3d_base.py:90-138), the padded Conv3d
  * of ConvBlock3D (VM/components/conv_block_3d.py:261-274) and their autograd dgrad / wgrad (cuDNN today). */
@@ -88,7 +91,8 @@ typedef struct vb200_conv3d_desc {
   int32_t cin;          /* channels of x (= its row pitch); forward: multiple of 32, wgrad: multiple of 8 */
   int32_t cout;         /* output channels (= row pitch of dout and, unless ldo is set, of out); multiple of 8 */
   int32_t kd, kh, kw;   /* filter extent */
-  int32_t pd, ph, pw;   /* zero padding; output extent = in + 2p - k + 1 */
+  int32_t pd, ph, pw;   /* zero padding; output extent = (in + 2p - k) / s + 1 */
+  int32_t sd, sh, sw;   /* stride (0 is read as 1) */
   int32_t dtype;        /* VB200_BF16 | VB200_FP16 */
   int32_t act;          /* VB200_ACT_* applied to the forward output */
   int32_t k_splits;     /* wgrad: split of the voxel range (0 = pick) */

@@ -109,3 +109,69 @@ def test_igemm_rejects_unboxable_geometry(cuda):
     w16 = torch.randn(64, 27 * 64, device=cuda).half()
     with pytest.raises(NotImplementedError):
         ops.conv3d_igemm(x, w16, None, (3, 3, 3), (1, 1, 1))
+
+
+# strided convs: TMA element strides deliver every s-th voxel of a box spanning s*b voxels
+STRIDED = [
+    (1, 16, 16, 16, 64, 64, (3, 3, 3), (1, 1, 1), (2, 2, 2)),
+    (1, 8, 32, 32, 32, 64, (3, 3, 3), (1, 1, 1), (2, 2, 2)),     # 32-channel operand (SWIZZLE_64B)
+    (2, 4, 16, 16, 64, 32, (1, 3, 3), (0, 1, 1), (1, 2, 2)),     # UNet3DBase down_stride (1,2,2)
+    (1, 4, 4, 256, 64, 64, (3, 3, 3), (1, 1, 1), (2, 2, 2)),     # 128 output voxels per row: the 256-voxel box limit
+    (1, 8, 8, 8, 128, 256, (3, 3, 3), (1, 1, 1), (2, 2, 2)),     # 64 output voxels: tile larger than the tensor
+]
+
+
+@pytest.mark.parametrize("case", STRIDED, ids=[str(c) for c in STRIDED])
+def test_igemm_strided_forward_and_wgrad(cuda, case):
+    from viscy_b200 import ops
+    N, D, H, W, Ci, Co, ks, pad, st = case
+    g = torch.Generator(device=cuda).manual_seed(5)
+    x = torch.randn(N, D, H, W, Ci, device=cuda, generator=g).half()
+    w = torch.randn(Co, Ci, *ks, device=cuda, generator=g) / (Ci * ks[0] * ks[1] * ks[2]) ** 0.5
+    b = torch.randn(Co, device=cuda, generator=g)
+    assert ops.conv3d_igemm_supported((N, D, H, W, Ci), Co, ks, pad, stride=st)
+    w16 = w.permute(0, 2, 3, 4, 1).reshape(Co, -1).contiguous().half()
+    xf = x.float().permute(0, 4, 1, 2, 3)
+    wf = w16.float().view(Co, *ks, Ci).permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(xf, wf, b, stride=st, padding=pad)
+    y = ops.conv3d_igemm(x, w16, b, ks, pad, stride=st)
+    assert y.shape == (N, *ref.shape[2:], Co)
+    assert rel(y.float().permute(0, 4, 1, 2, 3), ref) < 2e-3
+    dy = torch.randn(y.shape, device=cuda, generator=g).half()
+    gw = torch.nn.grad.conv3d_weight(xf, wf.shape, dy.float().permute(0, 4, 1, 2, 3), stride=st, padding=pad)
+    assert ops.conv3d_igemm_supported((N, D, H, W, Ci), Co, ks, pad, wgrad=True, stride=st)
+    dw = ops.conv3d_igemm_wgrad(x, dy, ks, pad, stride=st)
+    assert rel(dw.view(Co, *ks, Ci).permute(0, 4, 1, 2, 3), gw) < 2e-3
+
+
+def test_strided_conv_and_transposed_conv_use_igemm(cuda):
+    """Conv3d(stride 2) forward / wgrad and ConvTranspose3d backward run without a patch matrix on box geometries."""
+    from viscy_b200 import functional as VF
+    torch.manual_seed(1)
+    conv = torch.nn.Conv3d(64, 96, 3, stride=2, padding=1).to(cuda)
+    x = torch.randn(1, 64, 16, 16, 16, device=cuda).half()
+    xc = x.permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    y = VF.conv3d_cl(xc, conv)
+    xf = x.float().requires_grad_(True)
+    wf = conv.weight.detach().half().float().requires_grad_(True)
+    ref = F.conv3d(xf, wf, conv.bias, stride=2, padding=1)
+    assert rel(y.permute(0, 4, 1, 2, 3), ref) < 2e-3
+    dy = torch.randn_like(ref).half()
+    gx, gw = torch.autograd.grad(ref, [xf, wf], dy.float())
+    y.backward(dy.permute(0, 2, 3, 4, 1).contiguous())
+    assert rel(xc.grad.permute(0, 4, 1, 2, 3), gx) < 2e-3 and rel(conv.weight.grad, gw) < 2e-3
+
+    ct = torch.nn.ConvTranspose3d(64, 32, kernel_size=3, stride=(2, 2, 2), padding=1, output_padding=1).to(cuda)
+    x = torch.randn(1, 64, 4, 8, 8, device=cuda).half()
+    xc = x.permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    y = VF.conv_transpose3d_cl(xc, ct)
+    xf = x.float().requires_grad_(True)
+    wf = ct.weight.detach().clone().requires_grad_(True)
+    bf = ct.bias.detach().clone().requires_grad_(True)
+    ref = F.conv_transpose3d(xf, wf, bf, stride=2, padding=1, output_padding=1)
+    assert y.shape == (1, 8, 16, 16, 32) and rel(y.permute(0, 4, 1, 2, 3), ref) < 2e-3
+    dy = torch.randn_like(ref).half()
+    ref.backward(dy.float())
+    y.backward(dy.permute(0, 2, 3, 4, 1).contiguous())
+    assert rel(xc.grad.permute(0, 4, 1, 2, 3), xf.grad) < 2e-3
+    assert rel(ct.weight.grad, wf.grad) < 2e-3 and rel(ct.bias.grad, bf.grad) < 2e-3

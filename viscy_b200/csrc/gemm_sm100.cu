@@ -76,6 +76,8 @@ struct GemmParams {
   // implicit-GEMM conv forms: output extent, filter extent, padding, channel chunks per tap (CONVK) / channel tiles per
   // tap (CONVMN), channels of the activation operand
   int cOW, cOH, cOD, cKW, cKH, cpw, cph, cpd, cchunks, ccin;
+  int cbx, cby, cbz, cbn;  // voxel box of one K block (CONVMN): the walk along K advances by one box, no divisions
+  int csw, csh, csd;       // stride: input coordinate = output coordinate * stride + tap - padding
 };
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -376,6 +378,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_alloc(tmem_ptr, C::TMEM_COLS);
     tmem_relinquish();
   }
+  // MN-major forms with M <= 64 (weight gradients of <= 64-channel layers): rows 64..127 of the A tile are all padding.
+  // They are zeroed once here and their TMA box is never issued, which saves a third of the boxes per K block.
+  const bool a_half = MN_MAJOR && p.M <= 64;
+  if (a_half) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      uint4* z = reinterpret_cast<uint4*>(smem + s * C::STAGE_BYTES + 64 * BK * 2);
+      for (int i = threadIdx.x; i < 64 * BK * 2 / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -398,50 +410,74 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         // conv forms: CONVK walks (tap, channel chunk) along K for a fixed 128-voxel box; CONVMN walks 64-voxel boxes
         // along K for a fixed (tap, channel tile)
-        int cx = 0, cy = 0, cz = 0, cn = 0, tap = 0, chunk = 0, ci0 = 0;
+        // (the producer is ONE thread: integer divisions per K block would bound the whole kernel, so tap and voxel
+        //  coordinates are decomposed once per unit and then advanced with carries)
+        int cx = 0, cy = 0, cz = 0, cn = 0, chunk = 0, ci0 = 0, kw = 0, kh = 0, kd = 0;
         if constexpr (MODE == MODE_CONVK) {
           voxel_coords(p, m0, cx, cy, cz, cn);
-          tap = kb0 / p.cchunks;
+          const int tap = kb0 / p.cchunks;
           chunk = kb0 - tap * p.cchunks;
+          kw = tap % p.cKW;
+          kh = (tap / p.cKW) % p.cKH;
+          kd = tap / (p.cKW * p.cKH);
+          cx = cx * p.csw - p.cpw;
+          cy = cy * p.csh - p.cph;
+          cz = cz * p.csd - p.cpd;
         }
         if constexpr (MODE == MODE_CONVMN) {
           const int tn = t % p.tiles_n;
-          tap = tn / p.cchunks;
+          const int tap = tn / p.cchunks;
           ci0 = (tn - tap * p.cchunks) * BN;
+          kw = tap % p.cKW;
+          kh = (tap / p.cKW) % p.cKH;
+          kd = tap / (p.cKW * p.cKH);
+          voxel_coords(p, kb0 * BK, cx, cy, cz, cn);
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], a_half ? C::STAGE_BYTES - 64 * BK * 2 : C::STAGE_BYTES);
           if constexpr (MODE == MODE_CONVK) {
-            const int kw = tap % p.cKW, t2 = tap / p.cKW;
-            const int kh = t2 % p.cKH, kd = t2 / p.cKH;
-            tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw - p.cpw, cy + kh - p.cph, cz + kd - p.cpd, cn);
+            tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw, cy + kh, cz + kd, cn);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BKE, n0);
-            if (++chunk == p.cchunks) {
+            if (++chunk == p.cchunks) {  // next tap
               chunk = 0;
-              ++tap;
+              if (++kw == p.cKW) {
+                kw = 0;
+                if (++kh == p.cKH) {
+                  kh = 0;
+                  ++kd;
+                }
+              }
             }
           } else if constexpr (MODE == MODE_CONVMN) {
-            const int kw = tap % p.cKW, t2 = tap / p.cKW;
-            const int kh = t2 % p.cKH, kd = t2 / p.cKH;
-            voxel_coords(p, kb * BK, cx, cy, cz, cn);
-#pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (64 * BK * 2), &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+            tma_load_2d(sa, &tmA, &full_bar[stage], m0, kb * BK);
+            if (!a_half) tma_load_2d(sa + 64 * BK * 2, &tmA, &full_bar[stage], m0 + 64, kb * BK);
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_5d(sb + j * (64 * BK * 2), &tmB, &full_bar[stage], ci0 + j * 64, cx + kw - p.cpw,
-                          cy + kh - p.cph, cz + kd - p.cpd, cn);
+              tma_load_5d(sb + j * (64 * BK * 2), &tmB, &full_bar[stage], ci0 + j * 64, cx * p.csw + kw - p.cpw,
+                          cy * p.csh + kh - p.cph, cz * p.csd + kd - p.cpd, cn);
+            cx += p.cbx;  // next 64-voxel box of the flattened (n, z, y, x) order
+            if (cx >= p.cOW) {
+              cx = 0;
+              cy += p.cby;
+              if (cy >= p.cOH) {
+                cy = 0;
+                cz += p.cbz;
+                if (cz >= p.cOD) {
+                  cz = 0;
+                  cn += p.cbn;
+                }
+              }
+            }
           } else if constexpr (!MN_MAJOR) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
             const int brow = p.b_batch_rows > 0 ? (m0 / p.b_batch_rows) * p.N + n0 : n0;
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, brow);
           } else {
-#pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (64 * BK * 2), &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+            tma_load_2d(sa, &tmA, &full_bar[stage], m0, kb * BK);
+            if (!a_half) tma_load_2d(sa + 64 * BK * 2, &tmA, &full_bar[stage], m0 + 64, kb * BK);
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(sb + j * (64 * BK * 2), &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
@@ -691,7 +727,7 @@ int make_tmap_2d(CUtensorMap* m, const void* base, long long rows, long long col
 // In shared memory the box is rows of box_c channels (128 B, or 64 B with SWIZZLE_64B) in (n, z, y, x) order: exactly
 // the K-major / MN-major swizzled operand tile of the 2-D forms.
 static int make_tmap_conv(CUtensorMap* m, const void* base, int N, int D, int H, int W, int Cc, int box_c,
-                          const int* vbox, bool bf16, bool sw64) {
+                          const int* vbox, const int* stride /* w, h, d */, bool bf16, bool sw64) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) return fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || Cc % 8 != 0)
@@ -699,9 +735,10 @@ static int make_tmap_conv(CUtensorMap* m, const void* base, int N, int D, int H,
   cuuint64_t dims[5] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2,
                            (cuuint64_t)D * H * W * Cc * 2};
-  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)vbox[0], (cuuint32_t)vbox[1], (cuuint32_t)vbox[2],
-                       (cuuint32_t)vbox[3]};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // strided convs: the box spans s*b voxels and the element stride s makes TMA deliver every s-th one (b voxels)
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(vbox[0] * stride[0]), (cuuint32_t)(vbox[1] * stride[1]),
+                       (cuuint32_t)(vbox[2] * stride[2]), (cuuint32_t)vbox[3]};
+  cuuint32_t estr[5] = {1, (cuuint32_t)stride[0], (cuuint32_t)stride[1], (cuuint32_t)stride[2], 1};
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -880,6 +917,7 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
 // ------------------------------------------------------------------------------------- implicit-GEMM conv3d
 struct ConvShape {
   int OD, OH, OW, taps;
+  int stride[3];  // w, h, d
   long long pixels;
 };
 static int conv_shape(const vb200_conv3d_desc* d, ConvShape* s) {
@@ -887,10 +925,14 @@ static int conv_shape(const vb200_conv3d_desc* d, ConvShape* s) {
   VB_REQUIRE(d->N > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->cin > 0 && d->cout > 0, "bad conv3d extent");
   VB_REQUIRE(d->kd > 0 && d->kh > 0 && d->kw > 0 && d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "bad conv3d filter");
   VB_SUPPORTED(d->dtype == VB200_BF16 || d->dtype == VB200_FP16, "dtype %d", d->dtype);
-  s->OD = d->D + 2 * d->pd - d->kd + 1;
-  s->OH = d->H + 2 * d->ph - d->kh + 1;
-  s->OW = d->W + 2 * d->pw - d->kw + 1;
-  VB_REQUIRE(s->OD > 0 && s->OH > 0 && s->OW > 0, "conv3d: empty output");
+  s->stride[0] = d->sw > 0 ? d->sw : 1;
+  s->stride[1] = d->sh > 0 ? d->sh : 1;
+  s->stride[2] = d->sd > 0 ? d->sd : 1;
+  VB_SUPPORTED(s->stride[0] <= 8 && s->stride[1] <= 8 && s->stride[2] <= 8, "conv3d: stride > 8");
+  VB_REQUIRE(d->D + 2 * d->pd >= d->kd && d->H + 2 * d->ph >= d->kh && d->W + 2 * d->pw >= d->kw, "conv3d: empty output");
+  s->OD = (d->D + 2 * d->pd - d->kd) / s->stride[2] + 1;
+  s->OH = (d->H + 2 * d->ph - d->kh) / s->stride[1] + 1;
+  s->OW = (d->W + 2 * d->pw - d->kw) / s->stride[0] + 1;
   s->taps = d->kd * d->kh * d->kw;
   s->pixels = (long long)d->N * s->OD * s->OH * s->OW;
   VB_SUPPORTED(s->pixels < (1LL << 31) - 256, "conv3d: too many output voxels");
@@ -902,15 +944,22 @@ static void conv_geom(GemmParams* p, const vb200_conv3d_desc* d, const ConvShape
   p->cOW = s.OW; p->cOH = s.OH; p->cOD = s.OD;
   p->cKW = d->kw; p->cKH = d->kh;
   p->cpw = d->pw; p->cph = d->ph; p->cpd = d->pd;
+  p->csw = s.stride[0]; p->csh = s.stride[1]; p->csd = s.stride[2];
   p->ccin = d->cin;
+}
+
+// box of `rows` consecutive output voxels, whose (strided) input box must also respect TMA's 256-element box limit
+static bool conv_box_strided(int rows, const ConvShape& s, int NB, int* box) {
+  if (!conv_box(rows, s.OW, s.OH, s.OD, NB, box)) return false;
+  return box[0] * s.stride[0] <= 256 && box[1] * s.stride[1] <= 256 && box[2] * s.stride[2] <= 256;
 }
 
 extern "C" int vb200_conv3d_igemm_supported(const vb200_conv3d_desc* d, int wgrad) {
   ConvShape s;
   if (conv_shape(d, &s)) return 0;
   int box[4];
-  if (wgrad) return d->cin % 8 == 0 && conv_box(BK, s.OW, s.OH, s.OD, d->N, box) ? 1 : 0;
-  return d->cin % 32 == 0 && conv_box(BM, s.OW, s.OH, s.OD, d->N, box) ? 1 : 0;
+  if (wgrad) return d->cin % 8 == 0 && conv_box_strided(BK, s, d->N, box) ? 1 : 0;
+  return d->cin % 32 == 0 && conv_box_strided(BM, s, d->N, box) ? 1 : 0;
 }
 
 extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t stream) {
@@ -919,7 +968,7 @@ extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t str
   VB_REQUIRE(d->x && d->w && d->out, "null operand pointer");
   VB_SUPPORTED(d->cin % 32 == 0, "conv3d_igemm: cin (%d) must be a multiple of 32", d->cin);
   int box[4];
-  VB_SUPPORTED(conv_box(BM, s.OW, s.OH, s.OD, d->N, box),
+  VB_SUPPORTED(conv_box_strided(BM, s, d->N, box),
                "conv3d_igemm: 128 consecutive output voxels of %dx%dx%d are not a box", s.OD, s.OH, s.OW);
   const bool bf16 = d->dtype == VB200_BF16;
   const int bke = d->cin % 64 == 0 ? 64 : 32;
@@ -931,7 +980,7 @@ extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t str
   else if (N <= 128) bn = 128;
   else if ((long long)tiles_m * ((N + 255) / 256) < sms) bn = (long long)tiles_m * ((N + 127) / 128) < sms ? 64 : 128;
   CUtensorMap ta, tb;
-  if (int rc = make_tmap_conv(&ta, d->x, d->N, d->D, d->H, d->W, d->cin, bke, box, bf16, bke == 32)) return rc;
+  if (int rc = make_tmap_conv(&ta, d->x, d->N, d->D, d->H, d->W, d->cin, bke, box, s.stride, bf16, bke == 32)) return rc;
   if (int rc = make_tmap_2d(&tb, d->w, N, K, K, bke, bn, bf16, bke == 32)) return rc;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
@@ -964,7 +1013,7 @@ extern "C" int vb200_conv3d_igemm_wgrad(const vb200_conv3d_desc* d, vb200_stream
   VB_REQUIRE(d->x && d->dout && d->dw, "null operand pointer");
   VB_SUPPORTED(d->cin % 8 == 0, "conv3d_igemm_wgrad: cin (%d) must be a multiple of 8", d->cin);
   int box[4];
-  VB_SUPPORTED(conv_box(BK, s.OW, s.OH, s.OD, d->N, box),
+  VB_SUPPORTED(conv_box_strided(BK, s, d->N, box),
                "conv3d_igemm_wgrad: 64 consecutive output voxels of %dx%dx%d are not a box", s.OD, s.OH, s.OW);
   const bool bf16 = d->dtype == VB200_BF16;
   const int sms = sm_count();
@@ -972,13 +1021,14 @@ extern "C" int vb200_conv3d_igemm_wgrad(const vb200_conv3d_desc* d, vb200_stream
   const int ctiles = (d->cin + bn - 1) / bn;
   CUtensorMap ta, tb;
   if (int rc = make_tmap_2d(&ta, d->dout, s.pixels, d->cout, d->cout, 64, BK, bf16)) return rc;
-  if (int rc = make_tmap_conv(&tb, d->x, d->N, d->D, d->H, d->W, d->cin, 64, box, bf16, false)) return rc;
+  if (int rc = make_tmap_conv(&tb, d->x, d->N, d->D, d->H, d->W, d->cin, 64, box, s.stride, bf16, false)) return rc;
   GemmParams p{};
   p.M = d->cout; p.N = s.taps * d->cin; p.K = (int)s.pixels;
   p.tiles_m = (d->cout + BM - 1) / BM; p.tiles_n = s.taps * ctiles;
   p.kb_total = (p.K + BK - 1) / BK;
   const long long tiles = (long long)p.tiles_m * p.tiles_n;
-  int splits = d->k_splits > 0 ? d->k_splits : (int)((2LL * sms + tiles - 1) / tiles);
+  // K-split so that the units fill (at most) two whole waves of CTAs: a third partial wave would cost 50 %
+  int splits = d->k_splits > 0 ? d->k_splits : (int)((2LL * sms) / tiles);
   if (splits > p.kb_total / 8) splits = p.kb_total / 8;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
@@ -989,6 +1039,7 @@ extern "C" int vb200_conv3d_igemm_wgrad(const vb200_conv3d_desc* d, vb200_stream
   p.out = d->dw;
   conv_geom(&p, d, s);
   p.cchunks = ctiles;
+  p.cbx = box[0]; p.cby = box[1]; p.cbz = box[2]; p.cbn = box[3];
   const long long units = tiles * p.k_splits;
   const int grid = (int)(units < sms ? units : sms);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

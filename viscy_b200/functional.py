@@ -564,9 +564,10 @@ def _conv_weight_rows_flipped(w, cin_pad, cout_pad):
 
 
 class Conv3dFn(Function):
-    """nn.Conv3d (groups=1) on channels-last rows.  Stride-1 convs whose geometry tiles into TMA boxes run as implicit
-    GEMMs (`ops.conv3d_igemm*`: no patch matrix in HBM) for forward, dgrad and wgrad; anything else (strided convs, odd
-    extents, < 32 channels) goes through im2col3d + the same tcgen05 GEMM, the patch matrix rebuilt in backward."""
+    """nn.Conv3d (groups=1) on channels-last rows.  Convs whose geometry tiles into TMA boxes run as implicit GEMMs
+    (`ops.conv3d_igemm*`: no patch matrix in HBM): forward and weight gradient at any stride, data gradient at stride 1.
+    Anything else (odd extents, < 32 channels) goes through im2col3d + the same tcgen05 GEMM, the patch matrix rebuilt in
+    backward; the data gradient of a strided conv is the GEMM + col2im3d scatter."""
 
     @staticmethod
     def forward(ctx, x, w, b, stride, padding):
@@ -574,51 +575,51 @@ class Conv3dFn(Function):
         Co = w.shape[0]
         Cop = _pad8(Co)
         ks = tuple(w.shape[2:])
+        stride, padding = tuple(stride), tuple(padding)
         geom = ops.conv3d_geom((N, D, H, W, Cp), ks, stride, padding)
-        pointwise = ks == (1, 1, 1) and tuple(stride) == (1, 1, 1) and tuple(padding) == (0, 0, 0)
-        unit = tuple(stride) == (1, 1, 1) and not pointwise
-        igemm = unit and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding)
+        pointwise = ks == (1, 1, 1) and stride == (1, 1, 1) and padding == (0, 0, 0)
+        igemm = not pointwise and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, stride=stride)
         wk = _conv_weight_rows(w.detach(), Cp, Cop)
         bias = None
         if b is not None:
             bias = b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))
         if igemm:
-            out = ops.conv3d_igemm(x, ops.cast_pack(wk, x.dtype), bias, ks, padding)
+            out = ops.conv3d_igemm(x, ops.cast_pack(wk, x.dtype), bias, ks, padding, stride=stride)
         else:
             col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
             out = ops.gemm(col, ops.cast_pack(wk, x.dtype), bias=bias)
         ctx.save_for_backward(x, w)
-        ctx.meta = (geom, pointwise, unit, Cop, b is not None, tuple(padding))
+        ctx.meta = (geom, pointwise, stride, Cop, b is not None, padding)
         return out.view(N, geom[14], geom[15], geom[16], Cop)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         x, w = ctx.saved_tensors
-        geom, pointwise, unit, Cop, has_bias, padding = ctx.meta
+        geom, pointwise, stride, Cop, has_bias, padding = ctx.meta
         N, D, H, W, Cp = x.shape
         Co, Ci = w.shape[:2]
         ks = tuple(w.shape[2:])
         dout = dout.contiguous()
         do2 = dout.view(-1, Cop)
         need_dx = ctx.needs_input_grad[0]
-        dx = dwk = col = None
-        # data gradient: the stride-1 conv of dout with the flipped, transposed filter and padding k-1-p
+        unit = stride == (1, 1, 1) and not pointwise
+        dx = dwk = None
+        # data gradient at stride 1: the conv of dout with the flipped, transposed filter and padding k-1-p
         bpad = tuple(k - 1 - p for k, p in zip(ks, padding))
         if need_dx and unit and ops.conv3d_igemm_supported(tuple(dout.shape), Cp, ks, bpad):
             wf = _conv_weight_rows_flipped(w, Cp, Cop)
             dx = ops.conv3d_igemm(dout, ops.cast_pack(wf, x.dtype), None, ks, bpad)
             need_dx = False
-        if unit and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, wgrad=True):
-            dwk = ops.conv3d_igemm_wgrad(x, dout, ks, padding)
-        if need_dx or dwk is None:
+        if not pointwise and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, wgrad=True, stride=stride):
+            dwk = ops.conv3d_igemm_wgrad(x, dout, ks, padding, stride=stride)
+        if need_dx:
+            wt = ops.cast_pack(_conv_weight_rows(w, Cp, Cop), x.dtype, transpose=True)  # [K, Cop]
+            dcol = ops.gemm(do2, wt)
+            dx = dcol.view(x.shape) if pointwise else ops.col2im3d(dcol, geom)
+        if dwk is None:
             col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
-            wk = _conv_weight_rows(w, Cp, Cop)
-            dcol, dwk2, _ = linear_bwd(do2, col, wk, need_da=need_dx, need_db=False)
-            if dwk is None:
-                dwk = dwk2
-            if dcol is not None:
-                dx = dcol.view(x.shape) if pointwise else ops.col2im3d(dcol, geom)
+            dwk = ops.gemm(do2, col, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(Cop, col.shape[1], col.shape[0]))
         db = ops.colreduce(do2.view(1, -1, Cop), 0).view(Cop)[:Co] if has_bias else None
         dw = dwk.view(Cop, *ks, Cp)[:Co, ..., :Ci].permute(0, 4, 1, 2, 3)
         return dx, dw, db, None, None
@@ -661,14 +662,27 @@ class ConvTranspose3dFn(Function):
         geom, Cop, has_bias = ctx.meta
         Cip = x.shape[-1]
         Ci, Co = w.shape[:2]
+        ks = tuple(w.shape[2:])
+        stride, padding = tuple(geom[8:11]), tuple(geom[11:14])
         dout = dout.contiguous()
-        col = ops.im2col3d(dout, geom)  # [M_in, (kd,kh,kw,co)]
-        wt = _convT_weight_rows(w, Cip, Cop)
+        wt = _convT_weight_rows(w, Cip, Cop)  # [(kd,kh,kw,co), ci]
         x2 = x.view(-1, Cip)
-        # dx = col @ wt ; dW^T[(tap,co), ci] = col^T @ x
-        dx = ops.gemm(col, ops.cast_pack(wt, x.dtype, transpose=True)).view(x.shape)
-        dwt = ops.gemm(col, x2, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(col.shape[1], Cip, col.shape[0]))
-        dw = dwt.view(*w.shape[2:], Cop, Cip)[..., :Co, :Ci].permute(4, 3, 0, 1, 2)
+        col = None
+        # dx = the strided forward conv of dout (adjoint of this transposed conv): implicit GEMM when the geometry tiles
+        if ops.conv3d_igemm_supported(tuple(dout.shape), Cip, ks, padding, stride=stride):
+            dx = ops.conv3d_igemm(dout, ops.cast_pack(wt, x.dtype, transpose=True), None, ks, padding, stride=stride)
+        else:
+            col = ops.im2col3d(dout, geom)  # [M_in, (kd,kh,kw,co)]
+            dx = ops.gemm(col, ops.cast_pack(wt, x.dtype, transpose=True)).view(x.shape)
+        # dW[ci, (tap, co)] = sum_v x[v, ci] * dout[v*s + tap - p, co]: the strided weight gradient with x as "dout"
+        if ops.conv3d_igemm_supported(tuple(dout.shape), Cip, ks, padding, wgrad=True, stride=stride):
+            dwc = ops.conv3d_igemm_wgrad(dout, x, ks, padding, stride=stride)  # [Cip, (kd,kh,kw,Cop)]
+            dw = dwc.view(Cip, *ks, Cop)[:Ci, ..., :Co].permute(0, 4, 1, 2, 3)
+        else:
+            if col is None:
+                col = ops.im2col3d(dout, geom)
+            dwt = ops.gemm(col, x2, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(col.shape[1], Cip, col.shape[0]))
+            dw = dwt.view(*ks, Cop, Cip)[..., :Co, :Ci].permute(4, 3, 0, 1, 2)
         db = ops.colreduce(dout.view(1, -1, Cop), 0).view(Cop)[:Co] if has_bias else None
         return dx, dw, db, None, None, None
 

@@ -328,24 +328,29 @@ def conv3d_geom(shape, kernel, stride, padding):
     return [N, D, H, W, Cc, kd, kh, kw, sd, sh, sw, pd, ph, pw, OD, OH, OW]
 
 
-def _conv3d_desc(shape, cout, kernel, padding, dtype_code=L.BF16):
+def _conv3d_desc(shape, cout, kernel, padding, dtype_code=L.BF16, stride=(1, 1, 1)):
     d = L.Conv3dDesc()
     d.N, d.D, d.H, d.W, d.cin = shape
     d.cout = cout
     d.kd, d.kh, d.kw = kernel
     d.pd, d.ph, d.pw = padding
+    d.sd, d.sh, d.sw = stride
     d.dtype = dtype_code
     return d
 
 
-def conv3d_igemm_supported(shape, cout, kernel, padding, wgrad=False) -> bool:
-    """Host-only geometry query: does the TMA implicit-GEMM form cover this stride-1 conv ([N,D,H,W,C] input)?"""
+def _conv3d_out(shape, kernel, padding, stride):
+    return tuple((i + 2 * p - k) // s + 1 for i, k, p, s in zip(shape, kernel, padding, stride))
+
+
+def conv3d_igemm_supported(shape, cout, kernel, padding, wgrad=False, stride=(1, 1, 1)) -> bool:
+    """Host-only geometry query: does the TMA implicit-GEMM form cover this conv ([N,D,H,W,C] input)?"""
     fn = L.lib().vb200_conv3d_igemm_supported
-    return bool(fn(C.byref(_conv3d_desc(shape, cout, kernel, padding)), int(wgrad)))
+    return bool(fn(C.byref(_conv3d_desc(shape, cout, kernel, padding, stride=stride)), int(wgrad)))
 
 
-def conv3d_igemm(x, w16, bias, kernel, padding, act=L.ACT_NONE, residual=None, out=None):
-    """Stride-1 Conv3d as an implicit GEMM on tcgen05: x [N,D,H,W,Cin] 16-bit, w16 [Cout, (kd,kh,kw,Cin)] 16-bit K-major.
+def conv3d_igemm(x, w16, bias, kernel, padding, act=L.ACT_NONE, residual=None, out=None, stride=(1, 1, 1)):
+    """Conv3d as an implicit GEMM on tcgen05: x [N,D,H,W,Cin] 16-bit, w16 [Cout, (kd,kh,kw,Cin)] 16-bit K-major.
     Returns [N,OD,OH,OW,Cout].  The patch matrix is never materialised (TMA boxes at tap-shifted coordinates)."""
     _act(x, "x")
     N, D, H, W, Ci = x.shape
@@ -353,8 +358,8 @@ def conv3d_igemm(x, w16, bias, kernel, padding, act=L.ACT_NONE, residual=None, o
     kd, kh, kw = kernel
     if w16.dtype != x.dtype or w16.shape[1] != kd * kh * kw * Ci or not w16.is_contiguous():
         raise ValueError(f"w16 must be contiguous {x.dtype} [Cout, {kd * kh * kw * Ci}], got {tuple(w16.shape)} {w16.dtype}")
-    d = _conv3d_desc((N, D, H, W, Ci), Co, kernel, padding, L.dtype_code(x.dtype))
-    OD, OH, OW = D + 2 * d.pd - kd + 1, H + 2 * d.ph - kh + 1, W + 2 * d.pw - kw + 1
+    d = _conv3d_desc((N, D, H, W, Ci), Co, kernel, padding, L.dtype_code(x.dtype), stride)
+    OD, OH, OW = _conv3d_out((D, H, W), kernel, padding, stride)
     if out is None:
         out = torch.empty((N, OD, OH, OW, Co), device=x.device, dtype=x.dtype)
     d.act = act
@@ -367,14 +372,16 @@ def conv3d_igemm(x, w16, bias, kernel, padding, act=L.ACT_NONE, residual=None, o
     return out
 
 
-def conv3d_igemm_wgrad(x, dout, kernel, padding, k_splits=0):
-    """dw[co, (kd,kh,kw,ci)] (fp32) = sum over output voxels of dout[v, co] * x[v + tap - pad, ci]."""
+def conv3d_igemm_wgrad(x, dout, kernel, padding, k_splits=0, stride=(1, 1, 1)):
+    """dw[co, (kd,kh,kw,ci)] (fp32) = sum over output voxels of dout[v, co] * x[v * stride + tap - pad, ci]."""
     _act(x, "x")
     _act(dout, "dout")
     N, D, H, W, Ci = x.shape
     Co = dout.shape[-1]
     kd, kh, kw = kernel
-    d = _conv3d_desc((N, D, H, W, Ci), Co, kernel, padding, L.dtype_code(x.dtype))
+    d = _conv3d_desc((N, D, H, W, Ci), Co, kernel, padding, L.dtype_code(x.dtype), stride)
+    if tuple(dout.shape[1:4]) != _conv3d_out((D, H, W), kernel, padding, stride):
+        raise ValueError(f"dout extent {tuple(dout.shape[1:4])} does not match the conv geometry")
     d.k_splits = k_splits
     dw = torch.zeros((Co, kd * kh * kw * Ci), device=x.device, dtype=torch.float32)
     d.x, d.dout, d.dw = x.data_ptr(), dout.data_ptr(), dw.data_ptr()

@@ -110,6 +110,11 @@ int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t stream);
 int vb200_conv3d_igemm_wgrad(const vb200_conv3d_desc* d, vb200_stream_t stream);
 /* host-only geometry query (no launch): 1 when the forward (wgrad = 0) / weight-gradient (wgrad = 1) form applies */
 int vb200_conv3d_igemm_supported(const vb200_conv3d_desc* d, int wgrad);
+/* weight gradient for few-channel stride-1 convs with kh == 3 (same descriptor, same dw layout): a K block is an 8 x 8
+ * voxel patch, the x patch carries a y halo and the three kh taps are row-shifted views of that one box, accumulated in
+ * three TMEM accumulators (conv3d_wgrad_sm100.cu).  Needs OH % 8 == 0 and OW % 8 == 0. */
+int vb200_conv3d_wgrad_kh3(const vb200_conv3d_desc* d, vb200_stream_t stream);
+int vb200_conv3d_wgrad_kh3_supported(const vb200_conv3d_desc* d);
 
 /* ---- ConvNeXt / ConvNeXt-V2 block pieces (timm ConvNeXtBlock as composed by VM/unet/unext2.py:40-49,
  * VM/components/blocks.py:54-74, VM/contrastive/encoder.py:93-99).  All activations channels-last 16-bit. ---- */

@@ -175,3 +175,33 @@ def test_strided_conv_and_transposed_conv_use_igemm(cuda):
     y.backward(dy.permute(0, 2, 3, 4, 1).contiguous())
     assert rel(xc.grad.permute(0, 4, 1, 2, 3), xf.grad) < 2e-3
     assert rel(ct.weight.grad, wf.grad) < 2e-3 and rel(ct.bias.grad, bf.grad) < 2e-3
+
+
+# (N, D, H, W, Cin, Cout, kernel, padding): few-channel patch-form weight gradient (kh taps = views of one haloed box)
+KH3 = [
+    (1, 4, 16, 16, 32, 32, (3, 3, 3), (1, 1, 1)),
+    (2, 3, 8, 24, 64, 32, (3, 3, 3), (1, 1, 1)),
+    (1, 2, 16, 8, 8, 16, (3, 3, 3), (1, 1, 1)),       # 8-channel input (padded stem): zero-filled channel box
+    (1, 4, 8, 8, 96, 160, (3, 3, 3), (1, 1, 1)),      # two channel tiles, two M tiles
+    (1, 5, 16, 16, 48, 16, (1, 3, 3), (0, 1, 1)),     # Unet25d decoder filter
+    (1, 6, 10, 16, 32, 64, (3, 3, 3), (0, 0, 1)),     # valid in Z and Y: output rows 8
+]
+
+
+@pytest.mark.parametrize("case", KH3, ids=[str(c) for c in KH3])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_wgrad_kh3_vs_torch(cuda, case, dtype):
+    from viscy_b200 import ops
+    N, D, H, W, Ci, Co, ks, pad = case
+    g = torch.Generator(device=cuda).manual_seed(9)
+    x = torch.randn(N, D, H, W, Ci, device=cuda, generator=g).to(dtype)
+    assert ops.conv3d_wgrad_kh3_supported((N, D, H, W, Ci), Co, ks, pad)
+    od, oh, ow = (D + 2 * pad[0] - ks[0] + 1, H + 2 * pad[1] - ks[1] + 1, W + 2 * pad[2] - ks[2] + 1)
+    dy = torch.randn(N, od, oh, ow, Co, device=cuda, generator=g).to(dtype)
+    gw = torch.nn.grad.conv3d_weight(x.float().permute(0, 4, 1, 2, 3), (Co, Ci, *ks), dy.float().permute(0, 4, 1, 2, 3),
+                                     padding=pad)
+    for splits in (0, 1, 5):
+        dw = ops.conv3d_wgrad_kh3(x, dy, ks, pad, k_splits=splits)
+        assert rel(dw.view(Co, *ks, Ci).permute(0, 4, 1, 2, 3), gw) < 2e-3, splits
+    assert not ops.conv3d_wgrad_kh3_supported((N, D, H, W, Ci), Co, ks, pad, stride=(1, 2, 2))
+    assert not ops.conv3d_wgrad_kh3_supported((N, D, H + 3, W, Ci), Co, ks, pad)

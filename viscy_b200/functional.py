@@ -611,7 +611,9 @@ class Conv3dFn(Function):
             wf = _conv_weight_rows_flipped(w, Cp, Cop)
             dx = ops.conv3d_igemm(dout, ops.cast_pack(wf, x.dtype), None, ks, bpad)
             need_dx = False
-        if not pointwise and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, wgrad=True, stride=stride):
+        if unit and Cp <= 128 and ops.conv3d_wgrad_kh3_supported((N, D, H, W, Cp), Cop, ks, padding):
+            dwk = ops.conv3d_wgrad_kh3(x, dout, ks, padding)  # few channels: patch form, kh taps share one haloed box
+        elif not pointwise and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, wgrad=True, stride=stride):
             dwk = ops.conv3d_igemm_wgrad(x, dout, ks, padding, stride=stride)
         if need_dx:
             wt = ops.cast_pack(_conv_weight_rows(w, Cp, Cop), x.dtype, transpose=True)  # [K, Cop]

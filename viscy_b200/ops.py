@@ -389,6 +389,29 @@ def conv3d_igemm_wgrad(x, dout, kernel, padding, k_splits=0, stride=(1, 1, 1)):
     return dw
 
 
+def conv3d_wgrad_kh3_supported(shape, cout, kernel, padding, stride=(1, 1, 1)) -> bool:
+    fn = L.lib().vb200_conv3d_wgrad_kh3_supported
+    return bool(fn(C.byref(_conv3d_desc(shape, cout, kernel, padding, stride=stride))))
+
+
+def conv3d_wgrad_kh3(x, dout, kernel, padding, k_splits=0):
+    """Few-channel stride-1 weight gradient (8 x 8 voxel patches, kh taps as views of one haloed box); same result
+    layout as `conv3d_igemm_wgrad`: fp32 [Cout, (kd,kh,kw,Cin)]."""
+    _act(x, "x")
+    _act(dout, "dout")
+    N, D, H, W, Ci = x.shape
+    Co = dout.shape[-1]
+    kd, kh, kw = kernel
+    d = _conv3d_desc((N, D, H, W, Ci), Co, kernel, padding, L.dtype_code(x.dtype))
+    if tuple(dout.shape[1:4]) != _conv3d_out((D, H, W), kernel, padding, (1, 1, 1)):
+        raise ValueError(f"dout extent {tuple(dout.shape[1:4])} does not match the conv geometry")
+    d.k_splits = k_splits
+    dw = torch.zeros((Co, kd * kh * kw * Ci), device=x.device, dtype=torch.float32)
+    d.x, d.dout, d.dw = x.data_ptr(), dout.data_ptr(), dw.data_ptr()
+    L.check(L.lib().vb200_conv3d_wgrad_kh3(C.byref(d), L.stream_ptr()), "vb200_conv3d_wgrad_kh3")
+    return dw
+
+
 def im2col3d(u, geom):
     _act(u, "u")
     g = (C.c_int32 * 17)(*geom)

@@ -82,7 +82,9 @@ int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);
  *   wgrad   : dw[co, tap, ci] += sum_v dout[v, co] * x[v*s + tap - pad, ci]   (fp32, red.add; K-split over voxels)
  * Strided convolutions use the tensor map's element strides: a box of s*b voxels per dimension delivers b voxels.
  * The data gradient of nn.ConvTranspose3d is the strided forward of its adjoint conv, its weight gradient the strided
- * wgrad with the roles of x and dout exchanged.
+ * wgrad with the roles of x and dout exchanged.  nn.ConvTranspose3d forward (and the data gradient of a strided conv)
+ * is one forward launch per output parity class r = o mod s: a stride-1 conv over the taps {k : (k - r - p) mod s == 0}
+ * (tapmap into the full filter), written to the strided sub-lattice of the output (out_pitch) -- no column matrix.
  * Replaces nn.Conv3d(k=3, padding=1) of Block.proj (VM/unet/blocks.py:88-113), ResnetBlock / ConvBottleneck3D
  * (VM/unet/blocks.py:116-188,233-292), UNet3DBase inconv / outconv (VM/unet/unet3d_base.py:90-138), the padded Conv3d
  * of ConvBlock3D (VM/components/conv_block_3d.py:261-274) and their autograd dgrad / wgrad (cuDNN today). */
@@ -96,8 +98,13 @@ typedef struct vb200_conv3d_desc {
   int32_t dtype;        /* VB200_BF16 | VB200_FP16 */
   int32_t act;          /* VB200_ACT_* applied to the forward output */
   int32_t k_splits;     /* wgrad: split of the voxel range (0 = pick) */
+  int32_t w_taps;       /* forward: taps held by w when a tapmap selects among them (0 = kd*kh*kw) */
+  int32_t xd, xh, xw;   /* extra output extent per dimension (asymmetric high-side padding); 0 */
   int32_t reserved;
   int64_t ldo, ldr;     /* row pitch (elements) of out / residual; 0 = cout */
+  int64_t out_pitch[4]; /* forward, optional: output voxel (n,z,y,x) is written at out + n*p[3] + z*p[2] + y*p[1] + x*p[0]
+                           (elements): a transposed conv runs as one launch per output parity class.  0 = dense rows */
+  const int32_t* tapmap; /* forward, optional (host memory): tap t of this launch uses weight columns of tap tapmap[t] */
   const void* x;        /* [N,D,H,W,cin] 16-bit */
   const void* w;        /* forward: [cout, kd*kh*kw*cin] 16-bit, K order (kd, kh, kw, ci) */
   const float* bias;    /* [cout] or NULL */

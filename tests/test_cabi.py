@@ -44,9 +44,12 @@ def test_conv3d_desc_layout_matches_header():
     body = header[header.index("typedef struct vb200_conv3d_desc {"):header.index("} vb200_conv3d_desc;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
-    for decl in re.findall(r"(?:int32_t|int64_t|const void\*|void\*|const float\*|float\*)\s+([^;]+);", body):
-        fields += [f.strip() for f in decl.split(",")]
+    for decl in re.findall(r"(?:const int32_t\*|int32_t|int64_t|const void\*|void\*|const float\*|float\*)\s+([^;]+);", body):
+        fields += [re.sub(r"\[\d+\]", "", f).strip() for f in decl.split(",")]
     assert fields == [f[0] for f in _lib.Conv3dDesc._fields_]
+    import ctypes as C
+    # natural C layout: 24 int32 (one of them alignment padding), 6 int64, 8 pointers
+    assert C.sizeof(_lib.Conv3dDesc) == 96 + 48 + 64
 
 
 def test_conv3d_igemm_geometry_query_is_host_only():

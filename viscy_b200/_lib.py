@@ -46,8 +46,9 @@ class Conv3dDesc(C.Structure):
         ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("pd", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
         ("sd", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
-        ("dtype", C.c_int32), ("act", C.c_int32), ("k_splits", C.c_int32), ("reserved", C.c_int32),
-        ("ldo", C.c_int64), ("ldr", C.c_int64),
+        ("dtype", C.c_int32), ("act", C.c_int32), ("k_splits", C.c_int32), ("w_taps", C.c_int32),
+        ("xd", C.c_int32), ("xh", C.c_int32), ("xw", C.c_int32), ("reserved", C.c_int32),
+        ("ldo", C.c_int64), ("ldr", C.c_int64), ("out_pitch", C.c_int64 * 4), ("tapmap", C.POINTER(C.c_int32)),
         ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
         ("dout", C.c_void_p), ("dw", C.c_void_p),
     ]

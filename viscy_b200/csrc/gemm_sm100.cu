@@ -78,6 +78,12 @@ struct GemmParams {
   int cOW, cOH, cOD, cKW, cKH, cpw, cph, cpd, cchunks, ccin;
   int cbx, cby, cbz, cbn;  // voxel box of one K block (CONVMN): the walk along K advances by one box, no divisions
   int csw, csh, csd;       // stride: input coordinate = output coordinate * stride + tap - padding
+  // CONVK output scatter (transposed convs as parity-class sub-convolutions): when opx != 0 output voxel (n, z, y, x)
+  // of this launch lives at out + n*opn + z*opz + y*opy + x*opx (elements) instead of at row m of a dense matrix
+  long long opx, opy, opz, opn;
+  // CONVK tap selection: K block tap t reads weight columns [ctap[t]*cin, (ctap[t]+1)*cin) (ntap == 0: t itself)
+  int ntap;
+  int ctap[27];
 };
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -239,15 +245,30 @@ __device__ __forceinline__ void unstage(uint32_t stg, int lane, uint4* v) {
 // Store one 32-row x 64-byte tile (this warp's rows, 16 B per lane and group) through a swizzled shared-memory
 // staging tile so that global stores are row-contiguous: 4 lanes cover one row's 64 B, one instruction covers 8 rows.
 // `vals` = this lane's row: 4 x uint4.  ATOMIC: red.add.v4.f32 instead of a store (fp32 data).
+// `rowoff` (optional): byte offsets of this lane's four rows (lane >> 2) + 8 i relative to gbase, for scattered outputs.
 template <bool ATOMIC>
 __device__ __forceinline__ void stage_store(uint32_t stg, int lane, const uint4* vals, void* gbase, long long ld_bytes,
-                                            long long row0, int rows_valid, long long col_byte0, int cols16_valid) {
+                                            long long row0, int rows_valid, long long col_byte0, int cols16_valid,
+                                            const long long* rowoff = nullptr) {
   __syncwarp();
   const int sw = (lane >> 1) & 3;
 #pragma unroll
   for (int g = 0; g < 4; ++g) sts128(stg + lane * 64 + ((g ^ sw) << 4), vals[g]);
   __syncwarp();
   const int ch = lane & 3;
+  if (rowoff != nullptr) {
+    if (ch < cols16_valid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        if (rr < rows_valid) {
+          const uint4 q = lds128(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbase) + rowoff[i] + col_byte0 + ch * 16) = q;
+        }
+      }
+    }
+    return;
+  }
   uint8_t* dst0 = reinterpret_cast<uint8_t*>(gbase) + (row0 + (lane >> 2)) * ld_bytes + col_byte0 + ch * 16;
   if (!ATOMIC && rows_valid == 32 && cols16_valid == 4) {  // interior tile: no per-row predicates
     uint4 q[4];
@@ -412,10 +433,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // along K for a fixed (tap, channel tile)
         // (the producer is ONE thread: integer divisions per K block would bound the whole kernel, so tap and voxel
         //  coordinates are decomposed once per unit and then advanced with carries)
-        int cx = 0, cy = 0, cz = 0, cn = 0, chunk = 0, ci0 = 0, kw = 0, kh = 0, kd = 0;
+        int cx = 0, cy = 0, cz = 0, cn = 0, chunk = 0, ci0 = 0, kw = 0, kh = 0, kd = 0, tapi = 0;
         if constexpr (MODE == MODE_CONVK) {
           voxel_coords(p, m0, cx, cy, cz, cn);
           const int tap = kb0 / p.cchunks;
+          tapi = tap;
           chunk = kb0 - tap * p.cchunks;
           kw = tap % p.cKW;
           kh = (tap / p.cKW) % p.cKH;
@@ -440,9 +462,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_expect_tx(&full_bar[stage], a_half ? C::STAGE_BYTES - 64 * BK * 2 : C::STAGE_BYTES);
           if constexpr (MODE == MODE_CONVK) {
             tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw, cy + kh, cz + kd, cn);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BKE, n0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], (p.ntap ? p.ctap[tapi] : tapi) * p.ccin + chunk * BKE, n0);
             if (++chunk == p.cchunks) {  // next tap
               chunk = 0;
+              ++tapi;
               if (++kw == p.cKW) {
                 kw = 0;
                 if (++kh == p.cKH) {
@@ -571,6 +594,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       const long long row0 = m0 + quarter * 32;
+      long long rowoff[4];
+      bool scatter = false;
+      if constexpr (MODE == MODE_CONVK && EPI == VB200_EPI_STORE) {
+        scatter = p.opx != 0;
+        if (scatter) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int vx, vy, vz, vn;
+            voxel_coords(p, (int)min(row0 + (lane >> 2) + 8 * i, (long long)p.M - 1), vx, vy, vz, vn);
+            rowoff[i] = (vn * p.opn + vz * p.opz + vy * p.opy + vx * p.opx) * 2;
+          }
+        }
+      }
       long long lda_unused;
       const bool has_a = aux_a_ptr<EPI>(p, lda_unused) != nullptr;  // warp-uniform
       constexpr bool APRE = NUM_EPI_WARPS == 8;  // aux operands fetched one chunk ahead (second register buffer)
@@ -655,7 +691,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tma_stage_store<1>(stg + 2048, lane, o2, &tmOut.o2, col0, row0);
               }
             } else {
-              stage_store<false>(stg, lane, o1, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
+              stage_store<false>(stg, lane, o1, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid,
+                                 scatter ? rowoff : nullptr);
               if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP)
                 stage_store<false>(stg, lane, o2, p.out2, p.ldo2 * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
             }
@@ -930,9 +967,10 @@ static int conv_shape(const vb200_conv3d_desc* d, ConvShape* s) {
   s->stride[2] = d->sd > 0 ? d->sd : 1;
   VB_SUPPORTED(s->stride[0] <= 8 && s->stride[1] <= 8 && s->stride[2] <= 8, "conv3d: stride > 8");
   VB_REQUIRE(d->D + 2 * d->pd >= d->kd && d->H + 2 * d->ph >= d->kh && d->W + 2 * d->pw >= d->kw, "conv3d: empty output");
-  s->OD = (d->D + 2 * d->pd - d->kd) / s->stride[2] + 1;
-  s->OH = (d->H + 2 * d->ph - d->kh) / s->stride[1] + 1;
-  s->OW = (d->W + 2 * d->pw - d->kw) / s->stride[0] + 1;
+  VB_REQUIRE(d->xd >= 0 && d->xh >= 0 && d->xw >= 0, "conv3d: negative extra extent");
+  s->OD = (d->D + 2 * d->pd - d->kd) / s->stride[2] + 1 + d->xd;
+  s->OH = (d->H + 2 * d->ph - d->kh) / s->stride[1] + 1 + d->xh;
+  s->OW = (d->W + 2 * d->pw - d->kw) / s->stride[0] + 1 + d->xw;
   s->taps = d->kd * d->kh * d->kw;
   s->pixels = (long long)d->N * s->OD * s->OH * s->OW;
   VB_SUPPORTED(s->pixels < (1LL << 31) - 256, "conv3d: too many output voxels");
@@ -974,6 +1012,10 @@ extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t str
   const int bke = d->cin % 64 == 0 ? 64 : 32;
   const int sms = sm_count();
   const int M = (int)s.pixels, N = d->cout, K = s.taps * d->cin;
+  const int wtaps = d->w_taps > 0 ? d->w_taps : s.taps;  // taps held by the weight matrix (tap selection: > s.taps)
+  VB_REQUIRE(d->tapmap == nullptr || (s.taps <= 27 && d->w_taps > 0), "conv3d_igemm: tapmap needs w_taps and <= 27 taps");
+  const bool scatter = d->out_pitch[0] != 0;
+  VB_REQUIRE(!scatter || d->residual == nullptr, "conv3d_igemm: scattered output excludes the residual operand");
   const int tiles_m = (M + BM - 1) / BM;
   int bn = 256;
   if (N <= 64) bn = 64;
@@ -981,9 +1023,21 @@ extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t str
   else if ((long long)tiles_m * ((N + 255) / 256) < sms) bn = (long long)tiles_m * ((N + 127) / 128) < sms ? 64 : 128;
   CUtensorMap ta, tb;
   if (int rc = make_tmap_conv(&ta, d->x, d->N, d->D, d->H, d->W, d->cin, bke, box, s.stride, bf16, bke == 32)) return rc;
-  if (int rc = make_tmap_2d(&tb, d->w, N, K, K, bke, bn, bf16, bke == 32)) return rc;
+  if (int rc = make_tmap_2d(&tb, d->w, N, (long long)wtaps * d->cin, (long long)wtaps * d->cin, bke, bn, bf16, bke == 32))
+    return rc;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
+  if (d->tapmap != nullptr) {
+    p.ntap = s.taps;
+    for (int i = 0; i < s.taps; ++i) {
+      VB_REQUIRE(d->tapmap[i] >= 0 && d->tapmap[i] < wtaps, "conv3d_igemm: tapmap[%d] out of range", i);
+      p.ctap[i] = d->tapmap[i];
+    }
+  }
+  if (scatter) {
+    p.opx = d->out_pitch[0]; p.opy = d->out_pitch[1]; p.opz = d->out_pitch[2]; p.opn = d->out_pitch[3];
+    VB_REQUIRE(p.opx % 8 == 0 && p.opy % 8 == 0 && p.opz % 8 == 0 && p.opn % 8 == 0, "conv3d_igemm: out_pitch %% 8");
+  }
   p.tiles_m = tiles_m; p.tiles_n = (N + bn - 1) / bn; p.k_splits = 1;
   p.kb_total = K / bke; p.kb_per_split = p.kb_total;
   p.bf16 = bf16 ? 1 : 0;

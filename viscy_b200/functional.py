@@ -615,6 +615,11 @@ class Conv3dFn(Function):
             dwk = ops.conv3d_wgrad_kh3(x, dout, ks, padding)  # few channels: patch form, kh taps share one haloed box
         elif not pointwise and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, wgrad=True, stride=stride):
             dwk = ops.conv3d_igemm_wgrad(x, dout, ks, padding, stride=stride)
+        if need_dx and not unit and not pointwise:
+            # strided conv: dx is the transposed conv of dout = one stride-1 sub-convolution per parity class of dx
+            rows = ops.cast_pack(_convT_weight_rows_fwd(w, Cop, Cp), x.dtype)
+            dx = conv_transpose3d_igemm(dout, rows, None, ks, stride, padding, (D, H, W), Cp)
+            need_dx = dx is None
         if need_dx:
             wt = ops.cast_pack(_conv_weight_rows(w, Cp, Cop), x.dtype, transpose=True)  # [K, Cop]
             dcol = ops.gemm(do2, wt)
@@ -633,6 +638,74 @@ def conv3d_cl(x, conv):
     return Conv3dFn.apply(x, conv.weight, conv.bias, tuple(conv.stride), tuple(conv.padding))
 
 
+def _parity_classes(k: int, s: int, p: int, n_in: int, n_out: int):
+    """Transposed conv along one dimension: output o = i*s - p + kk.  For each parity class r = o mod s returns
+    (r, taps kk sorted by input offset, pad_lo, extra) such that the class is the stride-1 correlation
+    out[s*j + r] = sum_t x[j + t - pad_lo] w[taps[t]], j in [0, J_r), J_r = n_in + 2*pad_lo - len(taps) + 1 + extra.
+    None when a class cannot be expressed that way."""
+    out = []
+    for r in range(s):
+        J = -(-(n_out - r) // s)
+        if J <= 0:
+            continue
+        kks = [kk for kk in range(k) if (kk - r - p) % s == 0]
+        if not kks:
+            return None  # a class without taps is bias only: leave it to the scatter lowering
+        deltas = sorted(((r + p - kk) // s, kk) for kk in kks)
+        dmin, dmax = deltas[0][0], deltas[-1][0]
+        if [d for d, _ in deltas] != list(range(dmin, dmax + 1)):
+            return None
+        pad_lo = -dmin
+        K = len(deltas)
+        if pad_lo < 0:
+            return None
+        extra = J - (n_in + 2 * pad_lo - K + 1)
+        if extra < 0:
+            return None
+        out.append((r, [kk for _, kk in deltas], pad_lo, extra))
+    return out
+
+
+def conv_transpose3d_igemm(x, wrows16, bias, ks, stride, padding, out_sp, Cop):
+    """ConvTranspose3d forward (= data gradient of the strided conv) without a column matrix: one implicit-GEMM launch
+    per output parity class, each a stride-1 sub-convolution over its own taps (tapmap into the full filter `wrows16`
+    [Cop, (kd,kh,kw,Cin)]), written straight to the class's sub-lattice of the output.  Returns None when the geometry
+    does not fit (the caller then uses GEMM + col2im3d)."""
+    N, d, h, w, Cip = x.shape
+    if Cip % 32 != 0:
+        return None
+    per_dim = [_parity_classes(k, s, p, n, o) for k, s, p, n, o in zip(ks, stride, padding, (d, h, w), out_sp)]
+    if any(c is None for c in per_dim):
+        return None
+    OD, OH, OW = out_sp
+    plans = []
+    for rz, tz, pz, ez in per_dim[0]:
+        for ry, ty, py, ey in per_dim[1]:
+            for rx, tx, px, ex in per_dim[2]:
+                kern = (len(tz), len(ty), len(tx))
+                if not ops.conv3d_igemm_supported((N, d, h, w, Cip), Cop, kern, (pz, py, px), extra=(ez, ey, ex)):
+                    return None
+                tapmap = [(a * ks[1] + b) * ks[2] + c for a in tz for b in ty for c in tx]
+                plans.append(((rz, ry, rx), kern, (pz, py, px), (ez, ey, ex), tapmap))
+    out = torch.empty((N, OD, OH, OW, Cop), device=x.device, dtype=x.dtype)
+    sd, sh, sw = stride
+    pitch = (sw * Cop, sh * OW * Cop, sd * OH * OW * Cop, OD * OH * OW * Cop)
+    for (rz, ry, rx), kern, pad, extra, tapmap in plans:
+        view = out[:, rz:, ry:, rx:]  # base pointer of the class's sub-lattice
+        ops.conv3d_igemm(x, wrows16, bias, kern, pad, out=view, extra=extra, tapmap=tapmap, out_pitch=pitch)
+    return out
+
+
+def _convT_weight_rows_fwd(w, cin_pad, cout_pad):
+    """transposed-conv filter [Cin, Cout, kd,kh,kw] (= nn.ConvTranspose3d.weight, or nn.Conv3d.weight read as the filter
+    of its data gradient) -> fp32 [cout_pad, (kd,kh,kw,cin_pad)]: rows of the per-parity-class sub-convolutions"""
+    Ci, Co = w.shape[:2]
+    wk = w.permute(1, 2, 3, 4, 0)
+    if cin_pad != Ci or cout_pad != Co:
+        wk = torch.nn.functional.pad(wk, (0, cin_pad - Ci, 0, 0, 0, 0, 0, 0, 0, cout_pad - Co))
+    return wk.reshape(cout_pad, -1).contiguous()
+
+
 class ConvTranspose3dFn(Function):
     """nn.ConvTranspose3d on channels-last rows = the data gradient of the matching strided conv:
     rows @ W -> patch gradients -> col2im3d gather (+ bias)."""
@@ -647,12 +720,18 @@ class ConvTranspose3dFn(Function):
         geom = ops.conv3d_geom((N, *out_sp, Cop), ks, stride, padding)
         if (geom[14], geom[15], geom[16]) != (d, h, wd):
             raise NotImplementedError("sm_100a conv_transpose3d: geometry is not the adjoint of a strided conv")
-        wt = _convT_weight_rows(w.detach(), Cip, Cop)  # [(kd,kh,kw,co), ci]
-        dcol = ops.gemm(x.view(-1, Cip), ops.cast_pack(wt, x.dtype))
-        out = ops.col2im3d(dcol, geom)
+        bias = None
         if b is not None:
-            bias = b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))
-            out = ops.add_rows(out, None, bias.contiguous())
+            bias = (b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))).contiguous()
+        # one implicit-GEMM sub-convolution per output parity class when the geometry tiles, else GEMM + col2im scatter
+        out = conv_transpose3d_igemm(x, ops.cast_pack(_convT_weight_rows_fwd(w.detach(), Cip, Cop), x.dtype), bias, ks,
+                                     stride, padding, out_sp, Cop)
+        if out is None:
+            wt = _convT_weight_rows(w.detach(), Cip, Cop)  # [(kd,kh,kw,co), ci]
+            dcol = ops.gemm(x.view(-1, Cip), ops.cast_pack(wt, x.dtype))
+            out = ops.col2im3d(dcol, geom)
+            if bias is not None:
+                out = ops.add_rows(out, None, bias)
         ctx.save_for_backward(x, w)
         ctx.meta = (geom, Cop, b is not None)
         return out

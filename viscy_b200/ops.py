@@ -343,23 +343,44 @@ def _conv3d_out(shape, kernel, padding, stride):
     return tuple((i + 2 * p - k) // s + 1 for i, k, p, s in zip(shape, kernel, padding, stride))
 
 
-def conv3d_igemm_supported(shape, cout, kernel, padding, wgrad=False, stride=(1, 1, 1)) -> bool:
+def conv3d_igemm_supported(shape, cout, kernel, padding, wgrad=False, stride=(1, 1, 1), extra=(0, 0, 0)) -> bool:
     """Host-only geometry query: does the TMA implicit-GEMM form cover this conv ([N,D,H,W,C] input)?"""
     fn = L.lib().vb200_conv3d_igemm_supported
-    return bool(fn(C.byref(_conv3d_desc(shape, cout, kernel, padding, stride=stride)), int(wgrad)))
+    d = _conv3d_desc(shape, cout, kernel, padding, stride=stride)
+    d.xd, d.xh, d.xw = extra
+    return bool(fn(C.byref(d), int(wgrad)))
 
 
-def conv3d_igemm(x, w16, bias, kernel, padding, act=L.ACT_NONE, residual=None, out=None, stride=(1, 1, 1)):
+def conv3d_igemm(x, w16, bias, kernel, padding, act=L.ACT_NONE, residual=None, out=None, stride=(1, 1, 1),
+                 extra=(0, 0, 0), tapmap=None, out_pitch=None):
     """Conv3d as an implicit GEMM on tcgen05: x [N,D,H,W,Cin] 16-bit, w16 [Cout, (kd,kh,kw,Cin)] 16-bit K-major.
-    Returns [N,OD,OH,OW,Cout].  The patch matrix is never materialised (TMA boxes at tap-shifted coordinates)."""
+    Returns [N,OD,OH,OW,Cout].  The patch matrix is never materialised (TMA boxes at tap-shifted coordinates).
+    `extra`: additional output extent per dimension (asymmetric high-side padding).  `tapmap`: tap t of `kernel` uses
+    the weight columns of tap tapmap[t] of a wider w16.  `out_pitch` (x, y, z, n element pitches): scatter the output
+    voxels into `out` (required then), e.g. one parity class of a transposed conv."""
     _act(x, "x")
     N, D, H, W, Ci = x.shape
     Co = w16.shape[0]
     kd, kh, kw = kernel
-    if w16.dtype != x.dtype or w16.shape[1] != kd * kh * kw * Ci or not w16.is_contiguous():
-        raise ValueError(f"w16 must be contiguous {x.dtype} [Cout, {kd * kh * kw * Ci}], got {tuple(w16.shape)} {w16.dtype}")
+    wtaps = w16.shape[1] // Ci
+    if w16.dtype != x.dtype or w16.shape[1] != wtaps * Ci or not w16.is_contiguous() or \
+            (tapmap is None and wtaps != kd * kh * kw):
+        raise ValueError(f"w16 must be contiguous {x.dtype} [Cout, taps * {Ci}], got {tuple(w16.shape)} {w16.dtype}")
     d = _conv3d_desc((N, D, H, W, Ci), Co, kernel, padding, L.dtype_code(x.dtype), stride)
-    OD, OH, OW = _conv3d_out((D, H, W), kernel, padding, stride)
+    d.xd, d.xh, d.xw = extra
+    OD, OH, OW = (o + e for o, e in zip(_conv3d_out((D, H, W), kernel, padding, stride), extra))
+    keep = None
+    if tapmap is not None:
+        if len(tapmap) != kd * kh * kw:
+            raise ValueError("tapmap needs one entry per tap of `kernel`")
+        keep = (C.c_int32 * len(tapmap))(*tapmap)
+        d.tapmap = C.cast(keep, C.POINTER(C.c_int32))
+        d.w_taps = wtaps
+    if out_pitch is not None:
+        if out is None:
+            raise ValueError("out_pitch needs the destination tensor `out`")
+        for i, v in enumerate(out_pitch):
+            d.out_pitch[i] = v
     if out is None:
         out = torch.empty((N, OD, OH, OW, Co), device=x.device, dtype=x.dtype)
     d.act = act

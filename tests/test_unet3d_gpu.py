@@ -104,3 +104,24 @@ def test_batchnorm_relu_cat_cl(cuda):
     assert torch.equal(c, torch.cat([a, b], -1))
     c.backward(torch.ones_like(c))
     assert a.grad.shape == a.shape and b.grad.shape == b.shape
+
+
+def test_boundary_convs_3_to_32_and_32_to_3(cuda):
+    """UNet3DBase inconv / outconv (3 <-> 32 channels, padded to 8): line-kernel forward / data gradient, no patch matrix."""
+    from viscy_b200 import functional as VF
+    torch.manual_seed(2)
+    for cin, cout in ((3, 32), (32, 3)):
+        conv = torch.nn.Conv3d(cin, cout, 3, padding=1).to(cuda)
+        x = torch.randn(1, cin, 8, 16, 32, device=cuda).half()
+        xc = VF.to_channels_last_3d(x, torch.float16).requires_grad_(True)
+        y = VF.conv3d_cl(xc, conv)
+        xf = x.float().requires_grad_(True)
+        wf = conv.weight.detach().half().float().requires_grad_(True)
+        ref = F.conv3d(xf, wf, conv.bias, padding=1)
+        assert rel(y.permute(0, 4, 1, 2, 3)[:, :cout], ref) < 2e-3
+        dy = torch.randn_like(ref).half()
+        gx, gw = torch.autograd.grad(ref, [xf, wf], dy.float())
+        dyc = VF.to_channels_last_3d(dy, torch.float16)
+        y.backward(dyc)
+        assert rel(xc.grad.permute(0, 4, 1, 2, 3)[:, :cin], gx) < 2e-3
+        assert rel(conv.weight.grad, gw) < 2e-3

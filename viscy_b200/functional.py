@@ -563,6 +563,12 @@ def _conv_weight_rows_flipped(w, cin_pad, cout_pad):
     return wk.reshape(cin_pad, -1).contiguous()
 
 
+def _small_k3(ks, stride, cin_rows, cout_rows) -> bool:
+    """3x3x3 stride-1 conv with 8 / 16 input channels and <= 32 output channels (below the 32-channel granule of the
+    implicit GEMM): served by the line kernel of conv3d_sm100.cu."""
+    return ks == (3, 3, 3) and tuple(stride) == (1, 1, 1) and cin_rows in (8, 16) and cout_rows <= 32
+
+
 class Conv3dFn(Function):
     """nn.Conv3d (groups=1) on channels-last rows.  Convs whose geometry tiles into TMA boxes run as implicit GEMMs
     (`ops.conv3d_igemm*`: no patch matrix in HBM): forward and weight gradient at any stride, data gradient at stride 1.
@@ -585,6 +591,10 @@ class Conv3dFn(Function):
             bias = b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))
         if igemm:
             out = ops.conv3d_igemm(x, ops.cast_pack(wk, x.dtype), bias, ks, padding, stride=stride)
+        elif _small_k3(ks, stride, Cp, Cop):
+            # model-boundary convs (3 -> 32 channels): the 130-voxel-line kernel, taps as views of resident lines
+            cpad = 16 if Cop <= 16 else 32
+            out = ops.conv3d_k3(x, ops.conv3d_pack_weights(w, x.dtype, Cp, cpad), bias, padding, cpad, Cop)
         else:
             col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
             out = ops.gemm(col, ops.cast_pack(wk, x.dtype), bias=bias)
@@ -615,6 +625,12 @@ class Conv3dFn(Function):
             dwk = ops.conv3d_wgrad_kh3(x, dout, ks, padding)  # few channels: patch form, kh taps share one haloed box
         elif not pointwise and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, wgrad=True, stride=stride):
             dwk = ops.conv3d_igemm_wgrad(x, dout, ks, padding, stride=stride)
+        if need_dx and _small_k3(ks, stride, Cop, Cp):
+            # few-channel data gradient (e.g. the 32 -> 3 output conv): line kernel with the flipped, transposed filter
+            cpad = 16 if Cp <= 16 else 32
+            wpt = ops.conv3d_pack_weights(w, x.dtype, Cop, cpad, transpose_flip=True)
+            dx = ops.conv3d_k3(dout, wpt, None, bpad, cpad, Cp)
+            need_dx = False
         if need_dx and not unit and not pointwise:
             # strided conv: dx is the transposed conv of dout = one stride-1 sub-convolution per parity class of dx
             rows = ops.cast_pack(_convT_weight_rows_fwd(w, Cop, Cp), x.dtype)

@@ -129,6 +129,78 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ secondary evidence
+def _event_ms(fn, reps, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def secondary_evidence(dev, tf_sus):
+    """3-D conv blocks of BASELINE config 5 through the implicit-GEMM kernels (forward launch of each level of
+    Unet3d(3,3,4,32) at 128^3, fp16; algorithmic FLOP = 2 * voxels * 27 * Cin * Cout) and one eager training step of
+    configs 5 and 4.  Reported next to the headline, never mixed into it."""
+    from viscy_b200 import ContrastiveEncoder, Unet3d, ops
+    from viscy_b200.loss import NTXentLoss
+    out = {"conv3d_igemm_fwd": {}}
+    g = torch.Generator(device=dev).manual_seed(11)
+    for S, ci, co in ((128, 32, 32), (64, 64, 64), (32, 128, 128), (16, 256, 256)):
+        x = torch.randn((1, S, S, S, ci), device=dev, generator=g).half()
+        w = (torch.randn((co, 27 * ci), device=dev, generator=g) * 0.02).half()
+        y = torch.empty((1, S, S, S, co), device=dev, dtype=torch.float16)
+        ms = _event_ms(lambda: ops.conv3d_igemm(x, w, None, (3, 3, 3), (1, 1, 1), out=y), 10, 3)
+        tf = 2.0 * S ** 3 * 27 * ci * co / (ms * 1e-3) / 1e12
+        out["conv3d_igemm_fwd"][f"{ci}->{co}@{S}^3"] = {"ms": ms, "tflops": tf, "frac_of_sustained_tensor_peak": tf / tf_sus}
+        del x, w, y
+    torch.manual_seed(0)
+    m = Unet3d(3, 3, 4, 32).to(dev)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True)
+    x = torch.randn(1, 3, 128, 128, 128, device=dev)
+    y = torch.randn(1, 3, 128, 128, 128, device=dev)
+
+    def step5():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            loss = torch.nn.functional.mse_loss(m(x).float(), y)
+        loss.backward()
+        opt.step()
+
+    ms = _event_ms(step5, 5, 2)
+    out["config5_unet3d_128_fp16_b1"] = {"ms_per_step": ms, "samples_per_s": 1e3 / ms, "algorithmic_tflops": 3.696 / (ms * 1e-3),
+                                         "mode": "eager (no CUDA graph)"}
+    del m, opt, x, y
+    torch.cuda.empty_cache()
+    m = ContrastiveEncoder("convnext_tiny", in_channels=2, in_stack_depth=15).to(dev)
+    opt = torch.optim.AdamW(m.parameters(), lr=2e-4, fused=True)
+    a = torch.randn(64, 2, 15, 224, 224, device=dev)
+    p = torch.randn(64, 2, 15, 224, 224, device=dev)
+    labels = torch.cat([torch.arange(64), torch.arange(64)]).to(dev)
+    crit = NTXentLoss(temperature=0.07)
+
+    def step4():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, pa = m(a)
+            _, pp = m(p)
+        loss = crit(torch.cat([pa, pp]).float(), labels)
+        loss.backward()
+        opt.step()
+
+    ms = _event_ms(step4, 5, 2)
+    out["config4_contrastive_2x64_bf16"] = {"ms_per_step": ms, "samples_per_s": 128e3 / ms,
+                                            "algorithmic_tflops": 3.448 / (ms * 1e-3), "mode": "eager (no CUDA graph)"}
+    del m, opt, a, p
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch.distributed as dist
@@ -295,12 +367,21 @@ def run_gpu(args):
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
                 # dram__bytes_read+write per launch, mean of the four launches, from the committed `ncu --set full`
-                # capture of this same command (profiles/r1_gemm_dec2_ncu_summary.txt)
+                # capture of these launches (profiles/r1_v5_gemm_dec2_ncu_summary.txt: 385 / 315 / 608 / 228 MB)
                 "traffic": 384.0e6,
                 "kernel": "gemm_kernel<256,K-major,*>: decoder-stage-2 GEMMs M=32768, 736<->2944 (142 GFLOP per launch)",
                 "per_launch_ms": per, "avg_ms": avg_ms, "launches_timed": reps * len(per),
                 "peak_source": f"bf16_tflops_sustained ({src})"}
         del a_c, a_c4, o_c4a, o_c4b, o_c
+
+    # ---- secondary evidence (N=1 only, never part of `value`): the implicit-GEMM 3-D conv launches of BASELINE config 5
+    #      (Unet3d 128^3 fp16) timed alone, and one eager training step of configs 4 and 5
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            secondary = secondary_evidence(dev, tf_sus)
+        except Exception as exc:  # evidence only: never fail the headline line
+            secondary = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         value = world * BATCH * args.steps / (ms * 1e-3)
@@ -327,6 +408,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if ddp:
@@ -348,6 +430,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-4/5 evidence block")
     ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
                     help="N>1 gradient exchange: flat all-reduce inside the CUDA graph (default) or stock torch DDP (eager)")
     ap.add_argument("--batch-streams", type=int, default=1,

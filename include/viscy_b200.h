@@ -161,7 +161,8 @@ int vb200_grn_apply_bwd(const void* h, const void* dy, const float* s, const flo
 
 /* ---- fused GRN path (pixels-per-sample % 128 == 0): the GRN scale is folded into per-sample fc2 weights so the
  * hidden tensor y = GRN(g) is never materialised, and the GRN + GELU backward rides in the fc2-dgrad epilogue ---- */
-/* mode 0: out[n,c] += sum_r x[n,r,c]; mode 1: sum of squares.  x [B,R,C] 16-bit, C % 8 == 0, out pre-zeroed */
+/* mode 0: out[n,c] += sum_r x[n,r,c]; mode 1: sum of squares; mode 2: both in one pass (out [2,B,C]: sums, then sums of
+ * squares -- BatchNorm statistics).  x [B,R,C] 16-bit, C % 8 == 0, out pre-zeroed */
 int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode, int dtype, vb200_stream_t stream);
 /* out[n][j][k] = W2[j][k] * s[n][k] (16-bit) */
 int vb200_grn_pack_w2(const float* W2, const float* s, void* out, int nb, int C, int C4, int dtype,

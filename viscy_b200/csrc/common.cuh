@@ -157,15 +157,15 @@ __device__ __forceinline__ float dgelu_f(float u) {
 }
 
 // ---- column reductions over rows of [M, C] tensors (8 channels per thread) ------------------------------------------
-// Block = 512 threads arranged as CW column threads x (512 / CW) row lanes, CW = power of two >= min(C/8, 128), so that
-// narrow tensors (C = 96: 12 vectors) still use every thread.  colred_combine sums the row lanes through shared
+// Block = 512 threads arranged as CW column threads x (512 / CW) row lanes, CW = power of two in [4, 128] >= min(C/8, 128),
+// so that narrow tensors (C = 32: 4 vectors, C = 96: 12 vectors) still use every thread.  colred_combine sums the row lanes through shared
 // memory and issues one atomicAdd per (block, channel) and quantity.
 struct ColRedShape {
   int cw_log2;  // log2(CW)
   int colb;     // column blocks
   __host__ static ColRedShape make(int C8) {
     ColRedShape s;
-    s.cw_log2 = 4;
+    s.cw_log2 = 2;  // narrow tensors (C = 32: 4 vectors): 4 column threads x 128 row lanes, every thread loads
     while ((1 << s.cw_log2) < C8 && s.cw_log2 < 7) ++s.cw_log2;
     s.colb = (C8 + (1 << s.cw_log2) - 1) >> s.cw_log2;
     return s;

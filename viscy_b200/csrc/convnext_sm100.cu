@@ -561,14 +561,20 @@ colsum_kernel(const uint32_t* __restrict__ x, float* __restrict__ out, long long
 // MODE 0: out[n,c] += sum x ; MODE 1: out[n,c] += sum x^2
 template <bool BF16, int MODE>
 __global__ void __launch_bounds__(512)
-colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, int R, int C8, int rows_per_block, int cw_log2) {
-  __shared__ float red[8 * 512];
+colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, float* __restrict__ out2, int R, int C8,
+                  int rows_per_block, int cw_log2) {
+  constexpr int NQ = MODE == 2 ? 2 : 1;  // MODE 2: sums and sums of squares in one pass (BatchNorm statistics)
+  __shared__ float red[NQ * 8 * 512];
   const int cx = threadIdx.x & ((1 << cw_log2) - 1), ry = threadIdx.x >> cw_log2, RL = 512 >> cw_log2;
   const int c8 = (blockIdx.x << cw_log2) + cx;
   const int n = blockIdx.z;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
-  float a[1][8] = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
+  float a[NQ][8];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[q][k] = 0.f;
   if (c8 < C8) {
     const uint4* xp = x + ((long long)n * R) * C8 + c8;
 #pragma unroll 4
@@ -578,18 +584,24 @@ colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, int R, i
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = H16<BF16>::unpack(w4[k]);
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 2) {
           a[0][2 * k] += f.x;
           a[0][2 * k + 1] += f.y;
-        } else {
-          a[0][2 * k] = fmaf(f.x, f.x, a[0][2 * k]);
-          a[0][2 * k + 1] = fmaf(f.y, f.y, a[0][2 * k + 1]);
+        }
+        if (MODE == 1 || MODE == 2) {
+          a[NQ - 1][2 * k] = fmaf(f.x, f.x, a[NQ - 1][2 * k]);
+          a[NQ - 1][2 * k + 1] = fmaf(f.y, f.y, a[NQ - 1][2 * k + 1]);
         }
       }
     }
   }
-  float* const outs[1] = {out + (long long)n * C8 * 8};
-  colred_combine<1>(a, red, cw_log2, blockIdx.x << cw_log2, C8, outs);
+  if constexpr (NQ == 2) {
+    float* const outs[2] = {out + (long long)n * C8 * 8, out2 + (long long)n * C8 * 8};
+    colred_combine<2>(a, red, cw_log2, blockIdx.x << cw_log2, C8, outs);
+  } else {
+    float* const outs[1] = {out + (long long)n * C8 * 8};
+    colred_combine<1>(a, red, cw_log2, blockIdx.x << cw_log2, C8, outs);
+  }
 }
 
 // per-sample GRN-scaled fc2 weights: out[n][j][k] = W2[j][k] * s[n][k]; thread = 8 consecutive k of one row j, all n
@@ -907,7 +919,8 @@ extern "C" int vb200_colsum(const void* x, float* out, int64_t M, int C, int dty
   return check_launch("vb200_colsum");
 }
 
-/* MODE 0: out[n,c] += sum_r x[n,r,c];  MODE 1: out[n,c] += sum_r x[n,r,c]^2   (x [B,R,C], C % 8 == 0, out pre-zeroed) */
+/* MODE 0: out[n,c] += sum_r x[n,r,c];  MODE 1: out[n,c] += sum_r x[n,r,c]^2;  MODE 2: both in one pass, sums into
+ * out[0:B*C], sums of squares into out[B*C:2*B*C]   (x [B,R,C], C % 8 == 0, out pre-zeroed) */
 extern "C" int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode, int dtype,
                                vb200_stream_t stream) {
   VB_REQUIRE(x && out, "null pointer");
@@ -922,9 +935,13 @@ extern "C" int vb200_colreduce(const void* x, float* out, int B, int64_t R, int 
   dim3 grid(sh.colb, (unsigned)((R + rpb - 1) / rpb), B);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0)
-    DISPATCH_DT(dtype, colreduce8_kernel<BF, 0><<<grid, 512, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb, sh.cw_log2));
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 0><<<grid, 512, 0, st>>>((const uint4*)x, out, nullptr, (int)R, C8, (int)rpb, sh.cw_log2));
+  else if (mode == 1)
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 1><<<grid, 512, 0, st>>>((const uint4*)x, out, nullptr, (int)R, C8, (int)rpb, sh.cw_log2));
+  else if (mode == 2)
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 2><<<grid, 512, 0, st>>>((const uint4*)x, out, out + (long long)B * C, (int)R, C8, (int)rpb, sh.cw_log2));
   else
-    DISPATCH_DT(dtype, colreduce8_kernel<BF, 1><<<grid, 512, 0, st>>>((const uint4*)x, out, (int)R, C8, (int)rpb, sh.cw_log2));
+    return fail(VB200_ERR_INVALID, "colreduce mode %d", mode);
   return check_launch("vb200_colreduce");
 }
 

@@ -808,9 +808,9 @@ class BatchNormActFn(Function):
         Cc = x.shape[-1]
         M = x.numel() // Cc
         if training:
-            xs = x.view(1, M, Cc)
-            mean = ops.colreduce(xs, 0).view(Cc) / M
-            var = (ops.colreduce(xs, 1).view(Cc) / M - mean * mean).clamp_min_(0.0)
+            st = ops.colreduce(x.view(1, M, Cc), 2).view(2, Cc) / M  # sums and sums of squares in one pass
+            mean = st[0]
+            var = (st[1] - mean * mean).clamp_min_(0.0)
         else:
             mean, var = run_mean, run_var
         rstd = torch.rsqrt(var + eps)

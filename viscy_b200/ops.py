@@ -517,10 +517,12 @@ def head_tail_bwd(z, mean, rstd, alpha, W1, dout, Dz, H, W):
 # ----------------------------------------------------------------------------------------------
 # fused GRN path helpers
 def colreduce(x, mode, arena=None):
-    """x [B,R,C] 16-bit -> fp32 [B,C]: mode 0 column sums, mode 1 column sums of squares."""
+    """x [B,R,C] 16-bit -> fp32 [B,C]: mode 0 column sums, mode 1 column sums of squares; mode 2: both in one pass,
+    fp32 [2,B,C]."""
     _act(x, "x")
     B, R, Cc = x.shape
-    out = arena.take(B, Cc) if arena is not None else torch.zeros((B, Cc), device=x.device, dtype=torch.float32)
+    shape = (2, B, Cc) if mode == 2 else (B, Cc)
+    out = arena.take(*shape) if arena is not None else torch.zeros(shape, device=x.device, dtype=torch.float32)
     _call("vb200_colreduce", _p(x), _p(out), B, C.c_int64(R), Cc, mode, L.dtype_code(x.dtype))
     return out
 

@@ -25,6 +25,11 @@ CASES = [
     (1, 5, 16, 16, 64, 64, (1, 3, 3), (0, 1, 1)),     # Unet25d decoder filter
     (1, 5, 8, 16, 64, 64, (5, 1, 1), (0, 0, 0)),      # Unet25d skip / bottom filter: valid in Z -> OD = 1
     (1, 10, 16, 16, 64, 32, (3, 3, 3), (0, 1, 1)),    # valid in Z (head style): OD = 8
+    # extents in whole 16 x 8 patches + kh == 3: the patch form (one y-haloed box serves the three kh taps)
+    (1, 4, 32, 32, 32, 32, (3, 3, 3), (1, 1, 1)),     # 32-channel operand, 4 patches per plane
+    (1, 2, 16, 32, 64, 128, (3, 3, 3), (1, 1, 1)),    # 128-wide output tile
+    (2, 3, 8, 16, 128, 96, (3, 3, 3), (1, 1, 1)),     # two channel chunks, two samples
+    (1, 3, 24, 32, 64, 64, (3, 3, 1), (1, 1, 0)),     # kw == 1
 ]
 
 

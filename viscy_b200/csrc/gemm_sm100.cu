@@ -34,17 +34,24 @@ struct EpiWarps {
 // Operand forms.  The two CONV forms are the implicit-GEMM 3-D convolution: one operand is the channels-last activation
 // tensor seen through a 5-D tensor map (C, X, Y, Z, N); a K block (CONVK) / an N tile (CONVMN) belongs to one filter tap
 // and its box is fetched at the tap-shifted voxel coordinate, TMA zero-filling whatever falls outside (= the padding).
-enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3 };
+// MODE_CONVKP is the patch variant of CONVK for 3-row filters (kh == 3): the M tile is a 16 x 8 voxel patch of one
+// z-plane, a K block = (kd, kw, channel chunk) fetches ONE box of 16 x 10 voxels (y halo) and the three kh taps are
+// that box viewed at row offsets 0 / 16 / 32 (swizzle phase survives shifts by multiples of 8 rows), each against its
+// own weight sub-tile: 160 + 3 BN box rows per three taps instead of 3 (128 + BN).
+enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4 };
 
 // BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
-template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false>
+template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false>
 struct Cfg {
-  static constexpr int A_BYTES = BM * BKE * 2;
-  static constexpr int B_BYTES = BN * BKE * 2;
+  static constexpr int A_BYTES = (PATCH ? 160 : BM) * BKE * 2;
+  static constexpr int B_TAP_BYTES = BN * BKE * 2;
+  static constexpr int B_BYTES = (PATCH ? 3 : 1) * B_TAP_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // (the 16-warp epilogues need 32 KB of staging tiles: one operand stage less on the 256-wide tile)
-  static constexpr int STAGES = BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8))
-                                          : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12));
+  static constexpr int STAGES =
+      PATCH ? (BKE == 64 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 8 : 5))
+            : (BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12)));
+  static_assert(!PATCH || BN <= 128, "patch conv form: tiles up to 128 output channels");
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int COLV_BYTES = 2 * 3 * BN * 4;  // [2 tiles in flight][bias, s, t][BN] fp32
   // per-warp 32 rows x 64 B staging tile(s): one, or two for the 16-warp epilogues whose outputs leave through TMA stores
@@ -84,6 +91,7 @@ struct GemmParams {
   // CONVK tap selection: K block tap t reads weight columns [ctap[t]*cin, (ctap[t]+1)*cin) (ntap == 0: t itself)
   int ntap;
   int ctap[27];
+  int cpxn, cpyn;  // CONVKP: 16 x 8 voxel patches per output row / column
 };
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -366,10 +374,11 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<BN, EPI>::value, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ OutMaps tmOut, const GemmParams p) {
   constexpr int NUM_EPI_WARPS = EpiWarps<BN, EPI>::value;
-  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store>;
+  constexpr bool PATCH = MODE == MODE_CONVKP;
+  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH>;
   constexpr int COL_GROUPS = NUM_EPI_WARPS / 4;  // warps sharing a TMEM lane quarter split the tile's columns
   constexpr bool MN_MAJOR = MODE == MODE_MNMAJOR || MODE == MODE_CONVMN;
-  static_assert(BKE == 64 || (BKE == 32 && MODE == MODE_CONVK), "BKE = 32 is the 32-channel conv form only");
+  static_assert(BKE == 64 || (BKE == 32 && (MODE == MODE_CONVK || PATCH)), "BKE = 32 is the 32-channel conv form only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -434,6 +443,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // (the producer is ONE thread: integer divisions per K block would bound the whole kernel, so tap and voxel
         //  coordinates are decomposed once per unit and then advanced with carries)
         int cx = 0, cy = 0, cz = 0, cn = 0, chunk = 0, ci0 = 0, kw = 0, kh = 0, kd = 0, tapi = 0;
+        if constexpr (PATCH) {  // M tile -> (n, z, patch row, patch column); K blocks walk (kd, kw, chunk)
+          int mt = t / p.tiles_n;
+          cx = (mt % p.cpxn) * 16 - p.cpw;
+          mt /= p.cpxn;
+          cy = (mt % p.cpyn) * 8 - p.cph;
+          mt /= p.cpyn;
+          cz = mt % p.cOD - p.cpd;
+          cn = mt / p.cOD;
+        }
         if constexpr (MODE == MODE_CONVK) {
           voxel_coords(p, m0, cx, cy, cz, cn);
           const int tap = kb0 / p.cchunks;
@@ -460,7 +478,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_expect_tx(&full_bar[stage], a_half ? C::STAGE_BYTES - 64 * BK * 2 : C::STAGE_BYTES);
-          if constexpr (MODE == MODE_CONVK) {
+          if constexpr (PATCH) {
+            tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw, cy, cz + kd, cn);
+#pragma unroll
+            for (int h = 0; h < 3; ++h)
+              tma_load_2d(sb + h * C::B_TAP_BYTES, &tmB, &full_bar[stage],
+                          ((kd * 3 + h) * p.cKW + kw) * p.ccin + chunk * BKE, n0);
+            if (++chunk == p.cchunks) {
+              chunk = 0;
+              if (++kw == p.cKW) {
+                kw = 0;
+                ++kd;
+              }
+            }
+          } else if constexpr (MODE == MODE_CONVK) {
             tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw, cy + kh, cz + kd, cn);
             tma_load_2d(sb, &tmB, &full_bar[stage], (p.ntap ? p.ctap[tapi] : tapi) * p.ccin + chunk * BKE, n0);
             if (++chunk == p.cchunks) {  // next tap
@@ -529,6 +560,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
+          if constexpr (PATCH) {
+            // three kh taps: the haloed A box viewed 16 voxel rows (one patch line) further down, its own B sub-tile
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+#pragma unroll
+              for (int k = 0; k < BKE / 16; ++k) {
+                const uint32_t a_addr = sa + h * 16 * (BKE * 2) + k * 32;
+                const uint32_t b_addr = sb + h * C::B_TAP_BYTES + k * 32;
+                const uint64_t da = BKE == 32 ? make_smem_desc_sw64(a_addr, 0, 512) : make_smem_desc(a_addr, 0, 1024);
+                const uint64_t db = BKE == 32 ? make_smem_desc_sw64(b_addr, 0, 512) : make_smem_desc(b_addr, 0, 1024);
+                tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || h > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BKE / 16; ++k) {
             uint64_t da, db;
@@ -547,6 +592,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               db = make_smem_desc(sb + k * 2048, 64 * BK * 2, 1024);
             }
             tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -596,6 +642,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long row0 = m0 + quarter * 32;
       long long rowoff[4];
       bool scatter = false;
+      if constexpr (PATCH) {  // rows of the tile = voxels of a 16 x 8 patch: each goes to its own output row
+        scatter = true;
+        int mt = t / p.tiles_n;
+        const int px = mt % p.cpxn;
+        mt /= p.cpxn;
+        const int py = mt % p.cpyn;
+        mt /= p.cpyn;  // = n * OD + z
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = quarter * 32 + (lane >> 2) + 8 * i;
+          const long long row = ((long long)mt * p.cOH + py * 8 + (r >> 4)) * p.cOW + px * 16 + (r & 15);
+          rowoff[i] = row * p.ldo * 2;
+        }
+      }
       if constexpr (MODE == MODE_CONVK && EPI == VB200_EPI_STORE) {
         scatter = p.opx != 0;
         if (scatter) {
@@ -822,7 +882,7 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store>::SMEM_BYTES);
+                                         Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store, MODE == MODE_CONVKP>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -832,7 +892,8 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     if (p.out2 != nullptr)
       if (int rc = make_tmap_2d(&om.o2, p.out2, p.M, p.N, p.ldo2, 32, 32, BF16, true)) return rc;
   }
-  kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value, Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store>::SMEM_BYTES, st>>>(ta, tb, om, p);
+  kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value,
+         Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store, MODE == MODE_CONVKP>::SMEM_BYTES, st>>>(ta, tb, om, p);
   return check_launch("vb200_gemm");
 }
 
@@ -1048,9 +1109,31 @@ extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t str
   p.out = d->out; p.bias = d->bias; p.residual = d->residual;
   conv_geom(&p, d, s);
   p.cchunks = d->cin / bke;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // patch form (see MODE_CONVKP): 3-row filters at stride 1 on extents in whole 16 x 8 patches, up to 128 output channels
+  const bool patch = d->kh == 3 && s.stride[0] == 1 && s.stride[1] == 1 && s.stride[2] == 1 && bn <= 128 &&
+                     s.OW % 16 == 0 && s.OH % 8 == 0 && d->xh == 0 && d->xw == 0 && d->xd == 0 && !scatter &&
+                     d->tapmap == nullptr && d->residual == nullptr;
+  if (patch) {
+    const int pbox[4] = {16, 10, 1, 1};
+    const int one[3] = {1, 1, 1};
+    if (int rc = make_tmap_conv(&ta, d->x, d->N, d->D, d->H, d->W, d->cin, bke, pbox, one, bf16, bke == 32)) return rc;
+    p.cpxn = s.OW / 16;
+    p.cpyn = s.OH / 8;
+    p.tiles_m = d->N * s.OD * p.cpyn * p.cpxn;
+    p.kb_total = d->kd * d->kw * p.cchunks;
+    p.kb_per_split = p.kb_total;
+    const long long punits = (long long)p.tiles_m * p.tiles_n;
+    const int pgrid = (int)(punits < sms ? punits : sms);
+    if (bke == 64) {
+      if (bn == 128) return launch<128, MODE_CONVKP, VB200_EPI_STORE, 64>(ta, tb, p, pgrid, st);
+      return launch<64, MODE_CONVKP, VB200_EPI_STORE, 64>(ta, tb, p, pgrid, st);
+    }
+    if (bn == 128) return launch<128, MODE_CONVKP, VB200_EPI_STORE, 32>(ta, tb, p, pgrid, st);
+    return launch<64, MODE_CONVKP, VB200_EPI_STORE, 32>(ta, tb, p, pgrid, st);
+  }
   const long long units = (long long)p.tiles_m * p.tiles_n;
   const int grid = (int)(units < sms ? units : sms);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (bke == 64) {
     if (bn == 256) return launch<256, MODE_CONVK, VB200_EPI_STORE, 64>(ta, tb, p, grid, st);
     if (bn == 128) return launch<128, MODE_CONVK, VB200_EPI_STORE, 64>(ta, tb, p, grid, st);

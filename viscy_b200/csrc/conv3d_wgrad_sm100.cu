@@ -5,11 +5,14 @@
 // The generic implicit-GEMM weight gradient (gemm_sm100.cu, MODE_CONVMN) fetches one box of dout and one of x per
 // (tap, 64 voxels); with <= 64 channels a box row carries 64-128 bytes and the kernel is bound by the number of box rows
 // the TMA unit can deliver, not by the tensor pipe.  Here a K block is an 8 x 8 voxel patch of one z-plane:
-//   A = dout patch            : box (64 co, 8, 8, 1, 1)  -> 64 rows, MN-major SWIZZLE_128B
-//   B = x patch with y halo   : box (64 ci, 8, 10, 1, 1) -> 80 rows; the three kh taps are the SAME box viewed at row
-//                               offsets 0 / 8 / 16 (shifts by 8 rows keep the 128-byte swizzle phase)
-// so one unit = (kd, kw, channel tile, K split) accumulates THREE taps in three TMEM accumulators from 144 box rows per
-// 64 voxels instead of 3 x 128.  Replaces the autograd weight gradient of nn.Conv3d(k=3, padding=1) in Block.proj /
+//   A = x patch with y halo   : box (64 ci, 8, 11, 1, 1) -> 88 rows, MN-major SWIZZLE_128B; a kh tap is the SAME box
+//                               viewed 8 rows further down (shifts by 8 rows keep the 128-byte swizzle phase), and the two
+//                               64-wide M atoms of one MMA are two consecutive kh views (LBO = one voxel row = 1024 B):
+//                               M = 128 = (kh, kh+1) x 64 input channels
+//   B = dout patch            : box (64 co, 8, 8, 1, 1)  -> 64 rows; N = 32 or 64 output channels
+// so one unit = (co tile, kd, kw, ci tile, K split) accumulates the three kh taps in two TMEM accumulators ((0,1) and
+// (2, unused)) from 152 box rows and 8 MMAs per 64 voxels instead of 3 x 128 rows and 12 MMAs with 3/4 of the M rows
+// padding: measured, the tensor pipe waits on shared-memory operand reads, so bytes per useful MAC is what counts.  Replaces the autograd weight gradient of nn.Conv3d(k=3, padding=1) in Block.proj /
 // ResnetBlock (VM/unet/blocks.py:88-188) and ConvBlock3D (VM/components/conv_block_3d.py:261-274) (cuDNN today).
 #include <cuda.h>
 
@@ -22,11 +25,11 @@ int sm_count();  // gemm_sm100.cu
 
 namespace wg3 {
 
-constexpr int A_BYTES = 2 * 64 * 128;   // two 64-channel atoms x 64 voxel rows (M = 128)
-constexpr int B_BYTES = 80 * 128;       // 64 channels x (8 x 10) voxel rows
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 26 KB
-constexpr int STAGES = 7;
-constexpr int TMEM_COLS = 512;          // 2 buffers x 3 taps x 64 columns = 384 -> next power of two
+constexpr int A_BYTES = 88 * 128;       // x: 64 channels x (8 x 11) voxel rows
+constexpr int B_BYTES = 64 * 128;       // dout: 64 channels x (8 x 8) voxel rows
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 19 KB
+constexpr int STAGES = 10;
+constexpr int TMEM_COLS = 256;          // 2 buffers x 2 accumulators x 64 columns
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 
 struct Params {
@@ -35,7 +38,7 @@ struct Params {
   int pd, ph, pw;
   int cin, cout;          // channels of x / dout (row pitches)
   int ctiles;             // ceil(cin / 64)
-  int tiles_m;            // ceil(cout / 128)
+  int tiles_m;            // ceil(cout / 64): output-channel tiles (the MMA N)
   int px_n, py_n;         // patches per row / column
   long long patches;      // N * OD * py_n * px_n  (K blocks)
   int k_splits, kb_per_split;
@@ -66,7 +69,7 @@ __device__ __forceinline__ Unit decode(const Params& p, int unit) {
   u.kw = t % p.KW;
   t /= p.KW;
   u.kd = t % p.KD;
-  u.m0 = (t / p.KD) * 128;
+  u.m0 = (t / p.KD) * 64;  // first output channel of the tile
   return u;
 }
 
@@ -82,15 +85,6 @@ conv3d_wgrad_kh3_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_c
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool a_half = p.cout <= 64;  // rows 64..127 of A are padding: zeroed once, their box is never issued
-
-  if (a_half) {
-    for (int s = 0; s < STAGES; ++s) {
-      uint4* z = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + 64 * 128);
-      for (int i = threadIdx.x; i < 64 * 128 / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    fence_proxy_async_smem();
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDz);
     tma_prefetch_desc(&tmX);
@@ -135,10 +129,9 @@ conv3d_wgrad_kh3_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_c
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], (a_half ? 64 * 128 : A_BYTES) + B_BYTES);
-          tma_load_5d(sa, &tmDz, &full_bar[stage], u.m0, px * 8, py * 8, z, n);
-          if (!a_half) tma_load_5d(sa + 64 * 128, &tmDz, &full_bar[stage], u.m0 + 64, px * 8, py * 8, z, n);
-          tma_load_5d(sb, &tmX, &full_bar[stage], u.ci0, px * 8 + u.kw - p.pw, py * 8 - p.ph, z + u.kd - p.pd, n);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_5d(sa, &tmX, &full_bar[stage], u.ci0, px * 8 + u.kw - p.pw, py * 8 - p.ph, z + u.kd - p.pd, n);
+          tma_load_5d(sb, &tmDz, &full_bar[stage], u.m0, px * 8, py * 8, z, n);
           if (++px == p.px_n) {
             px = 0;
             if (++py == p.py_n) {
@@ -157,31 +150,32 @@ conv3d_wgrad_kh3_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===================== MMA issuer: 3 taps x 4 K steps per K block
-      const uint32_t idesc = make_idesc(128, 64, p.bf16 != 0, true, true);
+    if (lane == 0) {  // ===================== MMA issuer: 2 kh pairs x 4 K steps per K block
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const Unit u = decode(p, unit);
         const long long kb0 = (long long)u.split * p.kb_per_split;
         const long long kb1 = min(p.patches, kb0 + p.kb_per_split);
+        const int ncols = p.cout - u.m0 <= 32 ? 32 : 64;  // MMA N: output channels of this tile
+        const uint32_t idesc = make_idesc(128, ncols, p.bf16 != 0, true, true);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * 192);
+        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * 128);
         for (long long kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
+          for (int pair = 0; pair < 2; ++pair) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              // MN-major SW128: 64-wide MN atoms LBO apart, 8-row K groups 1024 B apart; 16 K rows = 2048 B per step.
-              // tap kh = the x box shifted by kh voxel rows of 8 voxels = 1024 B
-              const uint64_t da = make_smem_desc(sa + k * 2048, 64 * 128, 1024);
-              const uint64_t db = make_smem_desc(sb + kh * 1024 + k * 2048, 0, 1024);
-              tc_mma_f16(d0 + kh * 64, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              // MN-major SW128: 8-row K groups 1024 B apart (SBO), 16 K rows = 2048 B per step.  A: the second 64-wide
+              // M atom is the next kh view = 8 voxel rows = 1024 B further (LBO); pair 1's second atom is unused.
+              const uint64_t da = make_smem_desc(sa + pair * 2048 + k * 2048, 1024, 1024);
+              const uint64_t db = make_smem_desc(sb + k * 2048, 0, 1024);
+              tc_mma_f16(d0 + pair * 64, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
           tc_commit(&empty_bar[stage]);
@@ -195,36 +189,33 @@ conv3d_wgrad_kh3_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_c
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {  // ===================== epilogue: 4 warps, lane = output channel row, red.add into dw
+  } else {  // ===================== epilogue: 4 warps; lane = (kh of the pair, input channel), columns = output channels
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int taps_row = p.KD * p.KH * p.KW * p.cin;  // row pitch of dw
+    const long long taps_row = (long long)p.KD * p.KH * p.KW * p.cin;  // row pitch of dw
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
       const Unit u = decode(p, unit);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int co = u.m0 + quarter * 32 + lane;
-      const bool warp_live = u.m0 + quarter * 32 < p.cout;  // warp-uniform
+      const int ci = u.ci0 + (quarter & 1) * 32 + lane;
+      const int nco = min(64, p.cout - u.m0);
 #pragma unroll 1
-      for (int kh = 0; kh < 3; ++kh) {
+      for (int pair = 0; pair < 2; ++pair) {
+        const int kh = pair * 2 + (quarter >> 1);
+        const bool live = kh < 3 && u.ci0 + (quarter & 1) * 32 < p.cin;  // warp-uniform
         const int tap = (u.kd * p.KH + kh) * p.KW + u.kw;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-          const int ci = u.ci0 + c * 32;
-          if (warp_live && ci < p.cin) {
+          if (live && c * 32 < nco) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 192 + kh * 64 + c * 32, r);
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + pair * 64 + c * 32, r);
             tmem_ld_wait();
-            if (co < p.cout) {
-              float* o = p.dw + (long long)co * taps_row + (long long)tap * p.cin + ci;
+            if (ci < p.cin) {
+              float* o = p.dw + (long long)(u.m0 + c * 32) * taps_row + (long long)tap * p.cin + ci;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (ci + j < p.cin)
-                  atomicAdd(reinterpret_cast<float4*>(o + j),
-                            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                        __uint_as_float(r[j + 3])));
-              }
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < nco) atomicAdd(o + j * taps_row, __uint_as_float(r[j]));
             }
           }
         }
@@ -302,7 +293,7 @@ extern "C" int vb200_conv3d_wgrad_kh3(const vb200_conv3d_desc* d, vb200_stream_t
   p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
   p.cin = d->cin; p.cout = d->cout;
   p.ctiles = (d->cin + 63) / 64;
-  p.tiles_m = (d->cout + 127) / 128;
+  p.tiles_m = (d->cout + 63) / 64;
   p.px_n = p.OW / 8; p.py_n = p.OH / 8;
   p.patches = (long long)p.N * p.OD * p.py_n * p.px_n;
   p.bf16 = d->dtype == VB200_BF16;
@@ -317,7 +308,7 @@ extern "C" int vb200_conv3d_wgrad_kh3(const vb200_conv3d_desc* d, vb200_stream_t
   VB_SUPPORTED(tiles * p.k_splits < (1LL << 30), "conv3d_wgrad_kh3: too many units");
   CUtensorMap tmDz, tmX;
   if (int rc = wg3::make_tmap_patch(&tmDz, d->dout, p.N, p.OD, p.OH, p.OW, d->cout, 8, p.bf16 != 0)) return rc;
-  if (int rc = wg3::make_tmap_patch(&tmX, d->x, d->N, d->D, d->H, d->W, d->cin, 10, p.bf16 != 0)) return rc;
+  if (int rc = wg3::make_tmap_patch(&tmX, d->x, d->N, d->D, d->H, d->W, d->cin, 11, p.bf16 != 0)) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(wg3::conv3d_wgrad_kh3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -30,6 +30,10 @@ CASES = [
     (1, 2, 16, 32, 64, 128, (3, 3, 3), (1, 1, 1)),    # 128-wide output tile
     (2, 3, 8, 16, 128, 96, (3, 3, 3), (1, 1, 1)),     # two channel chunks, two samples
     (1, 3, 24, 32, 64, 64, (3, 3, 1), (1, 1, 0)),     # kw == 1
+    # >= 2 patches per CTA and a filter <= 112 KB: the resident-filter variant (weights fetched once per CTA)
+    (1, 8, 64, 128, 32, 32, (3, 3, 3), (1, 1, 1)),    # 32-row weight sub-tiles, MMA N = 32; dgrad the same form
+    (1, 5, 64, 128, 64, 32, (3, 3, 3), (1, 1, 1)),    # 64 -> 32; its dgrad is the 32 -> 64 form (64-row sub-tiles)
+    (2, 3, 64, 64, 32, 16, (1, 3, 3), (0, 1, 1)),     # 9 taps, two samples
 ]
 
 

@@ -38,18 +38,22 @@ struct EpiWarps {
 // z-plane, a K block = (kd, kw, channel chunk) fetches ONE box of 16 x 10 voxels (y halo) and the three kh taps are
 // that box viewed at row offsets 0 / 16 / 32 (swizzle phase survives shifts by multiples of 8 rows), each against its
 // own weight sub-tile: 160 + 3 BN box rows per three taps instead of 3 (128 + BN).
-enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4 };
+// MODE_CONVKPW: CONVKP with the whole filter resident in shared memory (fetched once per CTA, <= 110 KB: Cin x Cout up to
+// 64 x 32 / 32 x 64 at 27 taps), so that a K block is the 160 A rows only -- the weight sub-tiles were over half of the
+// box rows the TMA unit had to deliver per K block.
+enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4, MODE_CONVKPW = 5 };
 
 // BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
-template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false>
+template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false, bool WRES = false>
 struct Cfg {
   static constexpr int A_BYTES = (PATCH ? 160 : BM) * BKE * 2;
   static constexpr int B_TAP_BYTES = BN * BKE * 2;
-  static constexpr int B_BYTES = (PATCH ? 3 : 1) * B_TAP_BYTES;
+  static constexpr int B_BYTES = WRES ? 0 : (PATCH ? 3 : 1) * B_TAP_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // (the 16-warp epilogues need 32 KB of staging tiles: one operand stage less on the 256-wide tile)
   static constexpr int STAGES =
-      PATCH ? (BKE == 64 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 8 : 5))
+      WRES  ? (BKE == 64 ? 4 : 8)
+      : PATCH ? (BKE == 64 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 8 : 5))
             : (BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12)));
   static_assert(!PATCH || BN <= 128, "patch conv form: tiles up to 128 output channels");
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
@@ -60,6 +64,8 @@ struct Cfg {
   static_assert(!TWO_TILES || EW == 16, "TMA-store epilogues run 16 warps");
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES + STG_BYTES;
+  // WRES: the resident filter follows (1024-byte aligned), its size is a launch parameter
+  static constexpr int W_OFFSET = (STAGES * STAGE_BYTES + 256 + COLV_BYTES + STG_BYTES + 1023) / 1024 * 1024;
 };
 
 struct GemmParams {
@@ -92,6 +98,8 @@ struct GemmParams {
   int ntap;
   int ctap[27];
   int cpxn, cpyn;  // CONVKP: 16 x 8 voxel patches per output row / column
+  int cwbytes;     // CONVKPW: bytes of the resident filter (taps x chunks sub-tiles of cwrows x BKE)
+  int cwrows;      // CONVKPW: output channels per sub-tile = MMA N (32 or 64)
 };
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -374,11 +382,13 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<BN, EPI>::value, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ OutMaps tmOut, const GemmParams p) {
   constexpr int NUM_EPI_WARPS = EpiWarps<BN, EPI>::value;
-  constexpr bool PATCH = MODE == MODE_CONVKP;
-  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH>;
+  constexpr bool WRES = MODE == MODE_CONVKPW;
+  constexpr bool PATCH = MODE == MODE_CONVKP || WRES;
+  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH, WRES>;
   constexpr int COL_GROUPS = NUM_EPI_WARPS / 4;  // warps sharing a TMEM lane quarter split the tile's columns
   constexpr bool MN_MAJOR = MODE == MODE_MNMAJOR || MODE == MODE_CONVMN;
   static_assert(BKE == 64 || (BKE == 32 && (MODE == MODE_CONVK || PATCH)), "BKE = 32 is the 32-channel conv form only");
+  static_assert(!WRES || BN == 64, "resident-filter form: one 64-wide output tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -387,6 +397,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* w_bar = tmem_empty + 3;             // CONVKPW: resident filter landed
+  uint8_t* wres = smem + C::W_OFFSET;           // CONVKPW: [tap][chunk][BN x BKE] sub-tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -402,6 +414,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
     }
+    if constexpr (WRES) mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -431,6 +444,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (WRES) {  // the whole filter, once: one box per (tap, channel chunk)
+        mbar_expect_tx(w_bar, p.cwbytes);
+        const int sub = p.cwrows * BKE * 2;
+        for (int i = 0; i * sub < p.cwbytes; ++i) tma_load_2d(wres + i * sub, &tmB, w_bar, i * BKE, 0);
+      }
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const int split = unit / tiles;
         const int t = unit - split * tiles;
@@ -480,10 +498,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_expect_tx(&full_bar[stage], a_half ? C::STAGE_BYTES - 64 * BK * 2 : C::STAGE_BYTES);
           if constexpr (PATCH) {
             tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw, cy, cz + kd, cn);
+            if constexpr (!WRES) {
 #pragma unroll
-            for (int h = 0; h < 3; ++h)
-              tma_load_2d(sb + h * C::B_TAP_BYTES, &tmB, &full_bar[stage],
-                          ((kd * 3 + h) * p.cKW + kw) * p.ccin + chunk * BKE, n0);
+              for (int h = 0; h < 3; ++h)
+                tma_load_2d(sb + h * C::B_TAP_BYTES, &tmB, &full_bar[stage],
+                            ((kd * 3 + h) * p.cKW + kw) * p.ccin + chunk * BKE, n0);
+            }
             if (++chunk == p.cchunks) {
               chunk = 0;
               if (++kw == p.cKW) {
@@ -543,11 +563,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      const uint32_t idesc = make_idesc(BM, BN, p.bf16 != 0, MN_MAJOR, MN_MAJOR);
+      const uint32_t idesc = make_idesc(BM, WRES ? p.cwrows : BN, p.bf16 != 0, MN_MAJOR, MN_MAJOR);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (WRES) {
+        mbar_wait(w_bar, 0);
+        tc_fence_after();
+      }
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const int split = unit / tiles;
         const int kb0 = split * p.kb_per_split;
@@ -555,6 +579,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        int wkd = 0, wkw = 0, wchunk = 0;  // CONVKPW: (kd, kw, chunk) of the K block, walked like the producer does
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -567,10 +592,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int k = 0; k < BKE / 16; ++k) {
                 const uint32_t a_addr = sa + h * 16 * (BKE * 2) + k * 32;
-                const uint32_t b_addr = sb + h * C::B_TAP_BYTES + k * 32;
+                // weights: this stage's sub-tile of tap (kd, h, kw), or its resident copy [tap][chunk]
+                const uint32_t b_addr =
+                    (WRES ? smem_u32(wres) + ((((wkd * 3 + h) * p.cKW + wkw) * p.cchunks + wchunk) * (p.cwrows * BKE * 2))
+                          : sb + h * C::B_TAP_BYTES) + k * 32;
                 const uint64_t da = BKE == 32 ? make_smem_desc_sw64(a_addr, 0, 512) : make_smem_desc(a_addr, 0, 1024);
                 const uint64_t db = BKE == 32 ? make_smem_desc_sw64(b_addr, 0, 512) : make_smem_desc(b_addr, 0, 1024);
                 tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || h > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            if constexpr (WRES) {
+              if (++wchunk == p.cchunks) {
+                wchunk = 0;
+                if (++wkw == p.cKW) {
+                  wkw = 0;
+                  ++wkd;
+                }
               }
             }
           } else {
@@ -880,9 +917,12 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
                      cudaStream_t st) {
   static bool configured = false;  // per instantiation
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
+  using LC = Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store,
+                 MODE == MODE_CONVKP || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW>;
+  const int smem_bytes = MODE == MODE_CONVKPW ? LC::W_OFFSET + 1024 + p.cwbytes : LC::SMEM_BYTES;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store, MODE == MODE_CONVKP>::SMEM_BYTES);
+                                         MODE == MODE_CONVKPW ? 232448 : LC::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -892,8 +932,8 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     if (p.out2 != nullptr)
       if (int rc = make_tmap_2d(&om.o2, p.out2, p.M, p.N, p.ldo2, 32, 32, BF16, true)) return rc;
   }
-  kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value,
-         Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store, MODE == MODE_CONVKP>::SMEM_BYTES, st>>>(ta, tb, om, p);
+  if (smem_bytes > 232448) return fail(VB200_ERR_UNSUPPORTED, "resident filter does not fit shared memory (%d B)", smem_bytes);
+  kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value, smem_bytes, st>>>(ta, tb, om, p);
   return check_launch("vb200_gemm");
 }
 
@@ -1125,6 +1165,16 @@ extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t str
     p.kb_per_split = p.kb_total;
     const long long punits = (long long)p.tiles_m * p.tiles_n;
     const int pgrid = (int)(punits < sms ? punits : sms);
+    // the whole filter fits next to the A ring: keep it resident (one fetch per CTA instead of three sub-tiles per K block)
+    const int wrows = N <= 32 ? 32 : 64;
+    const long long wbytes = (long long)s.taps * p.cchunks * wrows * bke * 2;
+    if (bn == 64 && wbytes <= 112 * 1024 && p.tiles_m >= 2 * pgrid) {
+      p.cwbytes = (int)wbytes;
+      p.cwrows = wrows;
+      if (int rc = make_tmap_2d(&tb, d->w, N, K, K, bke, wrows, bf16, bke == 32)) return rc;
+      return bke == 64 ? launch<64, MODE_CONVKPW, VB200_EPI_STORE, 64>(ta, tb, p, pgrid, st)
+                       : launch<64, MODE_CONVKPW, VB200_EPI_STORE, 32>(ta, tb, p, pgrid, st);
+    }
     if (bke == 64) {
       if (bn == 128) return launch<128, MODE_CONVKP, VB200_EPI_STORE, 64>(ta, tb, p, pgrid, st);
       return launch<64, MODE_CONVKP, VB200_EPI_STORE, 64>(ta, tb, p, pgrid, st);

@@ -150,44 +150,49 @@ conv3d_wgrad_kh3_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===================== MMA issuer: 2 kh pairs x 4 K steps per K block
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const Unit u = decode(p, unit);
-        const long long kb0 = (long long)u.split * p.kb_per_split;
-        const long long kb1 = min(p.patches, kb0 + p.kb_per_split);
-        const int ncols = p.cout - u.m0 <= 32 ? 32 : 64;  // MMA N: output channels of this tile
-        const uint32_t idesc = make_idesc(128, ncols, p.bf16 != 0, true, true);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer: 2 kh pairs x 4 K steps per K block.  The whole warp walks the loops (uniform
+    // control flow, uniform-datapath address arithmetic); one lane, elected once, issues tcgen05.mma / commit.
+    // MN-major SW128 descriptors: 8-row K groups 1024 B apart (SBO), 16 K rows = 2048 B per step.  A: the second 64-wide
+    // M atom is the next kh view = 8 voxel rows = 1024 B further (LBO); pair 1's second atom is unused.
+    const bool leader = elect_one();
+    const uint64_t desc_a0 = make_smem_desc(0, 1024, 1024), desc_b0 = make_smem_desc(0, 0, 1024);
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const Unit u = decode(p, unit);
+      const long long kb0 = (long long)u.split * p.kb_per_split;
+      const long long kb1 = min(p.patches, kb0 + p.kb_per_split);
+      const int ncols = p.cout - u.m0 <= 32 ? 32 : 64;  // MMA N: output channels of this tile
+      const uint32_t idesc = make_idesc(128, ncols, p.bf16 != 0, true, true);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * 128);
+      for (long long kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * 128);
-        for (long long kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+        const uint32_t sa = smem0 + stage * STAGE_BYTES;
+        const uint64_t da_s = desc_a0 + (sa >> 4), db_s = desc_b0 + ((sa + A_BYTES) >> 4);
+        if (leader) {
 #pragma unroll
           for (int pair = 0; pair < 2; ++pair) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // MN-major SW128: 8-row K groups 1024 B apart (SBO), 16 K rows = 2048 B per step.  A: the second 64-wide
-              // M atom is the next kh view = 8 voxel rows = 1024 B further (LBO); pair 1's second atom is unused.
-              const uint64_t da = make_smem_desc(sa + pair * 2048 + k * 2048, 1024, 1024);
-              const uint64_t db = make_smem_desc(sb + k * 2048, 0, 1024);
-              tc_mma_f16(d0 + pair * 64, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(d0 + pair * 64, da_s + ((pair * 2048 + k * 2048) >> 4), db_s + ((k * 2048) >> 4), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        tc_commit(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (leader) tc_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {  // ===================== epilogue: 4 warps; lane = (kh of the pair, input channel), columns = output channels
     const int quarter = warp & 3;

@@ -561,83 +561,80 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc = make_idesc(BM, WRES ? p.cwrows : BN, p.bf16 != 0, MN_MAJOR, MN_MAJOR);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if constexpr (WRES) {
-        mbar_wait(w_bar, 0);
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loops (warp-uniform control flow keeps the address arithmetic on the uniform datapath);
+    // one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are built once per stage and advanced by
+    // adding byte offsets >> 4 to their address field: with 16-32-cycle MMAs (N = 32 / 64 tiles) the issue loop of this
+    // single thread, not the tensor pipe, was the measured limit.
+    const uint32_t idesc = make_idesc(BM, WRES ? p.cwrows : BN, p.bf16 != 0, MN_MAJOR, MN_MAJOR);
+    const uint64_t desc_a0 = BKE == 32 ? make_smem_desc_sw64(0, 0, 512)
+                             : (MN_MAJOR ? make_smem_desc(0, 64 * BK * 2, 1024) : make_smem_desc(0, 0, 1024));
+    const uint64_t desc_b0 = desc_a0;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t wres0 = smem_u32(wres);
+    const bool leader = elect_one();  // elected once: tcgen05.commit tracks the MMAs of the thread that issues it
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if constexpr (WRES) {
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+    }
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int split = unit / tiles;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      // CONVKPW: resident sub-tile index of tap (kd, h = 0, kw), chunk: +1 per K block, +2 filter rows when kw wraps
+      int widx = 0, winplane = 0;
+      const int wplane = p.cKW * p.cchunks;
+      const uint32_t wsub = static_cast<uint32_t>(p.cwrows) * BKE * 2;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-      }
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const int split = unit / tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        int wkd = 0, wkw = 0, wchunk = 0;  // CONVKPW: (kd, kw, chunk) of the K block, walked like the producer does
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
+        const uint32_t sa = smem0 + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + C::A_BYTES;
+        const uint64_t da_s = desc_a0 + (sa >> 4);
+        const uint64_t db_s = desc_b0 + (sb >> 4);
+        if (leader) {
           if constexpr (PATCH) {
             // three kh taps: the haloed A box viewed 16 voxel rows (one patch line) further down, its own B sub-tile
 #pragma unroll
             for (int h = 0; h < 3; ++h) {
+              // weights: this stage's sub-tile of tap (kd, h, kw), or its resident copy [tap][chunk]
+              const uint64_t db_h = WRES ? desc_b0 + ((wres0 + static_cast<uint32_t>(widx + h * wplane) * wsub) >> 4)
+                                         : db_s + ((h * C::B_TAP_BYTES) >> 4);
 #pragma unroll
-              for (int k = 0; k < BKE / 16; ++k) {
-                const uint32_t a_addr = sa + h * 16 * (BKE * 2) + k * 32;
-                // weights: this stage's sub-tile of tap (kd, h, kw), or its resident copy [tap][chunk]
-                const uint32_t b_addr =
-                    (WRES ? smem_u32(wres) + ((((wkd * 3 + h) * p.cKW + wkw) * p.cchunks + wchunk) * (p.cwrows * BKE * 2))
-                          : sb + h * C::B_TAP_BYTES) + k * 32;
-                const uint64_t da = BKE == 32 ? make_smem_desc_sw64(a_addr, 0, 512) : make_smem_desc(a_addr, 0, 1024);
-                const uint64_t db = BKE == 32 ? make_smem_desc_sw64(b_addr, 0, 512) : make_smem_desc(b_addr, 0, 1024);
-                tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || h > 0 || k > 0) ? 1u : 0u);
-              }
-            }
-            if constexpr (WRES) {
-              if (++wchunk == p.cchunks) {
-                wchunk = 0;
-                if (++wkw == p.cKW) {
-                  wkw = 0;
-                  ++wkd;
-                }
-              }
+              for (int k = 0; k < BKE / 16; ++k)
+                tc_mma_f16(d_tmem, da_s + ((h * 16 * (BKE * 2) + k * 32) >> 4), db_h + ((k * 32) >> 4), idesc,
+                           (kb > kb0 || h > 0 || k > 0) ? 1u : 0u);
             }
           } else {
+            // K-major: step 16 elements (32 B) inside the swizzled row; MN-major: step 16 k rows = 2048 B
+            constexpr int KSTEP = MN_MAJOR ? 2048 : 32;
 #pragma unroll
-          for (int k = 0; k < BKE / 16; ++k) {
-            uint64_t da, db;
-            if constexpr (BKE == 32) {
-              // K-major SW64: rows of 64 B, 8-row groups 512 B apart; step 16 elements (32 B) inside the row
-              da = make_smem_desc_sw64(sa + k * 32, 0, 512);
-              db = make_smem_desc_sw64(sb + k * 32, 0, 512);
-            } else if constexpr (!MN_MAJOR) {
-              // K-major SW128: 8-row groups 1024 B apart; step 16 elements (32 B) inside the row
-              da = make_smem_desc(sa + k * 32, 0, 1024);
-              db = make_smem_desc(sb + k * 32, 0, 1024);
-            } else {
-              // MN-major SW128: 64-wide MN atoms (one TMA box each) 64*BK*2 B apart (LBO),
-              // 8-row k groups 1024 B apart (SBO); step 16 k rows = 2048 B
-              da = make_smem_desc(sa + k * 2048, 64 * BK * 2, 1024);
-              db = make_smem_desc(sb + k * 2048, 64 * BK * 2, 1024);
-            }
-            tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+            for (int k = 0; k < BKE / 16; ++k)
+              tc_mma_f16(d_tmem, da_s + ((k * KSTEP) >> 4), db_s + ((k * KSTEP) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if constexpr (WRES) {
+          ++widx;
+          if (++winplane == wplane) {
+            winplane = 0;
+            widx += 2 * wplane;
+          }
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (leader) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ===================== epilogue warps =====================

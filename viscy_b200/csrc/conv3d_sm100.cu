@@ -144,38 +144,48 @@ conv3d_k3_kernel(const __grid_constant__ CUtensorMap tmU, const ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===================== MMA issuer
-      const uint32_t idesc = make_idesc(128, CO, p.bf16 != 0, false, false);
-      const uint32_t w_addr = smem_u32(wsm);
-      const uint32_t z_addr = smem_u32(zero_line);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * CO);
+    // ===================== MMA issuer: the whole warp walks the loop (uniform control flow keeps the descriptor
+    // arithmetic on the uniform datapath), one lane elected once issues; descriptors = per-stage base + constants
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, CO, p.bf16 != 0, false, false);
+    const uint32_t w_addr = smem_u32(wsm);
+    const uint32_t z_addr = smem_u32(zero_line);
+    const uint32_t s0 = smem_u32(smem);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sbase = s0 + stage * C::STAGE_BYTES;
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * CO);
+      // A: 8-row groups 128 B apart (SBO), the two K chunks of an MMA (a1 - a0) apart (LBO); B: chunks CO*16 B apart
+      const uint64_t db0 = make_desc_noswz(w_addr, CO * 16, 128);
+      if (leader) {
 #pragma unroll
         for (int i = 0; i < C::KCH / 2; ++i) {  // fully unrolled: descriptor offsets fold to constants
           // K chunk q -> (line = q / 3, kw = q % 3) with K order (kd, kh, chunk, kw); the padding chunk reads zeros
           const int q0 = 2 * i, q1 = 2 * i + 1;
-          const uint32_t a0 = sbase + (q0 / 3) * LINE_PITCH + (q0 % 3) * 16;
-          const uint32_t a1 = q1 < 27 * CCH ? sbase + (q1 / 3) * LINE_PITCH + (q1 % 3) * 16 : z_addr;
-          // A: 8-row groups 128 B apart (SBO), the two K chunks (a1 - a0) apart (LBO); zero chunk sits above the stages
-          const uint64_t da = make_desc_noswz(a0, a1 - a0, 128);
-          const uint64_t db = make_desc_noswz(w_addr + q0 * (CO * 16), CO * 16, 128);
-          tc_mma_f16(d_tmem, da, db, idesc, i > 0 ? 1u : 0u);
+          const uint32_t o0 = (q0 / 3) * LINE_PITCH + (q0 % 3) * 16;
+          uint64_t da;
+          if (q1 < 27 * CCH) {
+            const uint32_t o1 = (q1 / 3) * LINE_PITCH + (q1 % 3) * 16;
+            da = make_desc_noswz(0, o1 - o0, 128) + ((sbase + o0) >> 4);
+          } else {  // zero chunk sits above the stages
+            da = make_desc_noswz(sbase + o0, z_addr - (sbase + o0), 128);
+          }
+          tc_mma_f16(d_tmem, da, db0 + ((q0 * (CO * 16)) >> 4), idesc, i > 0 ? 1u : 0u);
         }
         tc_commit(&empty_bar[stage]);
         tc_commit(&tmem_full[acc]);
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
+      __syncwarp();
+      if (++stage == C::STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {  // ===================== epilogue: 4 warps, thread = output voxel (row), CO columns
     const int quarter = warp & 3;
@@ -318,35 +328,39 @@ conv3d_k3_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, 32, p.bf16 != 0, true, true);
-      int stage = 0;
-      uint32_t phase = 0;
-      bool first = true;
-      for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint32_t sl = sa + C::A_BYTES;
+    // MMA issuer (whole warp walks the loop, one lane elected once issues; see conv3d_k3_kernel)
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, 32, p.bf16 != 0, true, true);
+    // MN-major, no swizzle: MN chunks SBO apart, 8-row K groups LBO = 128 B apart; 16 K rows = 256 B per step
+    const uint64_t da0 = make_desc_noswz(0, 128, WG_A_CHUNK), db0 = make_desc_noswz(0, 128, 16);
+    const uint32_t s0 = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int t = blockIdx.x; t < (int)p.tiles; t += gridDim.x) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = s0 + stage * C::STAGE_BYTES;
+      const uint64_t da_s = da0 + (sa >> 4), db_s = db0 + ((sa + C::A_BYTES) >> 4);
+      if (leader) {
 #pragma unroll
         for (int l = 0; l < 9; ++l) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            // MN-major, no swizzle: MN chunks SBO apart, 8-row K groups LBO = 128 B apart; 16 K rows = 256 B per step
-            const uint64_t da = make_desc_noswz(sa + ks * 256, 128, WG_A_CHUNK);
-            const uint64_t db = make_desc_noswz(sl + l * LINE_PITCH + ks * 256, 128, 16);
-            tc_mma_f16(tmem_base + l * 32, da, db, idesc, (!first || ks > 0) ? 1u : 0u);
-          }
+          for (int ks = 0; ks < 8; ++ks)
+            tc_mma_f16(tmem_base + l * 32, da_s + ((ks * 256) >> 4), db_s + ((l * LINE_PITCH + ks * 256) >> 4), idesc,
+                       (!first || ks > 0) ? 1u : 0u);
         }
-        first = false;
         tc_commit(&empty_bar[stage]);
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
-      tc_commit(done_bar);
+      __syncwarp();
+      first = false;
+      if (++stage == C::STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
+    if (leader) tc_commit(done_bar);
+    __syncwarp();
   } else {
     // epilogue after the last tile: rows (co) 0 .. 8*COCH-1 of the accumulator -> global atomics
     const int quarter = warp & 3;

@@ -367,7 +367,7 @@ def run_gpu(args):
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
                 # dram__bytes_read+write per launch, mean of the four launches, from the committed `ncu --set full`
-                # capture of these launches (profiles/r1_v5_gemm_dec2_ncu_summary.txt: 385 / 315 / 608 / 228 MB)
+                # capture of these launches (profiles/r1_v7_gemm_dec2_ncu_summary.txt: 385 / 314 / 609 / 228 MB)
                 "traffic": 384.0e6,
                 "kernel": "gemm_kernel<256,K-major,*>: decoder-stage-2 GEMMs M=32768, 736<->2944 (142 GFLOP per launch)",
                 "per_launch_ms": per, "avg_ms": avg_ms, "launches_timed": reps * len(per),

@@ -404,8 +404,13 @@ class HeadFn(Function):
                 side.wait_stream(main)
             with torch.cuda.stream(side):
                 dconv_w = ops.conv3d_k3_wgrad(u, dz5, (0, 1, 1))[:, :Cc]
-            wpt = ops.conv3d_pack_weights(conv_w, dz.dtype, Cmid, 16, transpose_flip=True)
-            du = ops.conv3d_k3(dz5, wpt, None, (2, 1, 1), 16, 8)
+            if Cmid % 32 == 0 and ops.conv3d_igemm_supported(tuple(dz5.shape), 8, (3, 3, 3), (2, 1, 1)):
+                # data gradient on the patch-form implicit GEMM (filter resident in shared memory)
+                du = ops.conv3d_igemm(dz5, ops.cast_pack(_conv_weight_rows_flipped(conv_w, 8, Cmid), dz.dtype), None,
+                                      (3, 3, 3), (2, 1, 1))
+            else:
+                wpt = ops.conv3d_pack_weights(conv_w, dz.dtype, Cmid, 16, transpose_flip=True)
+                du = ops.conv3d_k3(dz5, wpt, None, (2, 1, 1), 16, 8)
             if side is not main:
                 main.wait_stream(side)
         else:

@@ -289,7 +289,7 @@ extern "C" int vb200_conv3d_wgrad_kh3_supported(const vb200_conv3d_desc* d) {
 extern "C" int vb200_conv3d_wgrad_kh3(const vb200_conv3d_desc* d, vb200_stream_t stream) {
   VB_REQUIRE(d != nullptr && d->x && d->dout && d->dw, "null pointer");
   VB_SUPPORTED(vb200_conv3d_wgrad_kh3_supported(d), "conv3d_wgrad_kh3: needs stride 1, kh == 3 and an output extent in 8 x 8 patches");
-  wg3::Params p;
+  wg3::Params p{};
   p.N = d->N;
   p.OD = d->D + 2 * d->pd - d->kd + 1;
   p.OH = d->H + 2 * d->ph - 2;

@@ -1023,7 +1023,7 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
     if ((rc = make_tmap_2d(&ta, d->A, d->K, d->M, d->lda, 64, BK, bf16))) return rc;
     if ((rc = make_tmap_2d(&tb, d->B, d->K, d->N, d->ldb, 64, BK, bf16))) return rc;
   }
-  GemmParams p;
+  GemmParams p{};  // conv-only fields stay zero
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.k_splits = splits;
   p.kb_total = kb_total; p.kb_per_split = kb_per;

@@ -62,10 +62,12 @@ struct Cfg {
   static constexpr int STG_PER_WARP = TWO_TILES ? 4096 : 2048;
   static constexpr int STG_BYTES = EW * STG_PER_WARP;
   static_assert(!TWO_TILES || EW == 16, "TMA-store epilogues run 16 warps");
-  static constexpr int SMEM_BYTES =
-      STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLV_BYTES + STG_BYTES;
+  // The staging tiles that TMA stores read (SWIZZLE_64B output maps) must sit on the swizzle period: the hardware
+  // derives the XOR pattern from absolute shared-memory address bits, the epilogue warps from the row index.
+  static constexpr int STG_OFFSET = (STAGES * STAGE_BYTES + 256 + COLV_BYTES + 1023) / 1024 * 1024;
+  static constexpr int SMEM_BYTES = STG_OFFSET + 1024 /*align slack*/ + STG_BYTES;
   // WRES: the resident filter follows (1024-byte aligned), its size is a launch parameter
-  static constexpr int W_OFFSET = (STAGES * STAGE_BYTES + 256 + COLV_BYTES + STG_BYTES + 1023) / 1024 * 1024;
+  static constexpr int W_OFFSET = (STG_OFFSET + STG_BYTES + 1023) / 1024 * 1024;
 };
 
 struct GemmParams {
@@ -643,7 +645,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = e >> 2;       // which group of BN / COL_GROUPS columns
     const int et = threadIdx.x - 64;
     float* colv = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256 + C::COLV_BYTES + e * C::STG_PER_WARP);
+    const uint32_t stg = smem_u32(smem + C::STG_OFFSET + e * C::STG_PER_WARP);
     constexpr bool TMA_STORE = EpiWarps<BN, EPI>::tma_store;
     constexpr int NCH = BN / (32 * COL_GROUPS);  // 32-column chunks per warp
     int acc = 0;

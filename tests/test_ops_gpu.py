@@ -23,7 +23,12 @@ def rnd(shape, dev, seed, dtype=None, scale=1.0):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 96), (1, 8, 8, 768), (2, 13, 21, 40), (1, 64, 64, 736)])
+@pytest.mark.parametrize("B,H,W,C", [
+    (2, 16, 16, 96), (1, 8, 8, 768), (2, 13, 21, 40), (1, 64, 64, 736),  # 40 / 736: partial 64-channel chunks
+    (3, 56, 56, 96), (2, 7, 7, 768), (5, 14, 14, 384), (1, 33, 9, 64), (2, 5, 3, 128), (1, 64, 64, 8),
+    (2, 19, 23, 36), (1, 6, 6, 50),  # C % 8 != 0: the register-tile kernels
+    (8, 64, 64, 736),  # decoder stage 2 of BASELINE config 2
+])
 def test_dwconv7_fwd_bwd(cuda, B, H, W, C, dtype):
     from viscy_b200 import ops
     x = rnd((B, H, W, C), cuda, 1, dtype)

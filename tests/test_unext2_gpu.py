@@ -27,7 +27,8 @@ def _pair(cuda, cfg, seed=0):
     return o, m.to(cuda)
 
 
-@pytest.mark.parametrize("dtype,ftol,gtol", [(torch.float16, 2e-3, 6e-2), (torch.bfloat16, 2e-2, 2.5e-1)])
+# absolute bounds; the per-tensor bound relative to stock autocast lives in test_parity_yardstick_gpu.py
+@pytest.mark.parametrize("dtype,ftol,gtol", [(torch.float16, 1.5e-3, 3e-2), (torch.bfloat16, 1e-2, 8e-2)])
 def test_unext2_fwd_bwd_parity(cuda, dtype, ftol, gtol):
     o, m = _pair(cuda, CFG)
     torch.manual_seed(1)
@@ -38,7 +39,10 @@ def test_unext2_fwd_bwd_parity(cuda, dtype, ftol, gtol):
     with torch.autocast("cuda", dtype=dtype):
         out = m(x.to(cuda))
         loss = torch.nn.functional.mse_loss(out.float(), tgt.to(cuda))
-    loss.backward()
+    scale = 65536.0 if dtype == torch.float16 else 1.0  # static GradScaler stand-in
+    (loss * scale).backward()
+    for p in m.parameters():
+        p.grad.div_(scale)
     assert out.shape == ref.shape and out.dtype == dtype
     e = rel(out.float().cpu(), ref)
     print(f"\n[{dtype}] forward rel-L2 {e:.3e}")
@@ -76,21 +80,39 @@ def test_unext2_requires_16bit(cuda):
 
 
 def test_unext2_full_config_step(cuda):
-    """BASELINE config 2 shape: one fwd+bwd at B=8, 21x256x256 bf16 must run and stay finite."""
+    """BASELINE config 2 shape (B=8, 21x256x256 bf16): forward against the fp32 oracle moved to the GPU (TF32 off), loss
+    against its loss, finite gradients, and a second step on the same buffers gives the same result."""
+    from oracle import models as OM
     from viscy_b200 import UNeXt2
+    cfg = dict(in_channels=1, out_channels=2, in_stack_depth=21, backbone="convnextv2_tiny",
+               stem_kernel_size=(7, 4, 4), head_pool=True)
     torch.manual_seed(0)
-    m = UNeXt2(in_channels=1, out_channels=2, in_stack_depth=21, backbone="convnextv2_tiny",
-               stem_kernel_size=(7, 4, 4), head_pool=True).to(cuda)
+    o = OM.UNeXt2(**cfg)
+    m = UNeXt2(**cfg)
+    m.load_state_dict(o.state_dict())
+    m, o = m.to(cuda), o.to(cuda)
     x = torch.randn(8, 1, 21, 256, 256, device=cuda)
     tgt = torch.randn(8, 2, 21, 256, 256, device=cuda)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref = torch.cat([o(x[i:i + 2]) for i in range(0, 8, 2)])
+    ref_loss = torch.nn.functional.mse_loss(ref, tgt).item()
+    outs = []
     for _ in range(2):
+        m.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = m(x)
             loss = torch.nn.functional.mse_loss(out.float(), tgt)
         loss.backward()
+        outs.append(out.float())
     torch.cuda.synchronize()
     assert out.shape == (8, 2, 21, 256, 256)
-    assert torch.isfinite(loss)
+    e = rel(out.float().cpu(), ref.cpu())
+    print(f"\nfull-config forward rel-L2 vs fp32 oracle: {e:.3e}; loss {loss.item():.6f} vs {ref_loss:.6f}")
+    assert e < 8e-3
+    assert abs(loss.item() - ref_loss) < 2e-3 * abs(ref_loss)
+    assert torch.equal(outs[0], outs[1])  # deterministic forward
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
 
 

@@ -56,16 +56,19 @@ def run_fp32(o, x, tgt):
     return out.detach(), {n: p.grad.detach().clone() for n, p in o.named_parameters()}
 
 
-def run_autocast(model, x, tgt, dtype):
+def run_autocast(model, x, tgt, dtype, loss_scale: float = 1.0):
+    """`loss_scale`: static stand-in for torch.amp.GradScaler (fp16 gradients of a mean-reduced loss underflow
+    without it, for the stock path and for ours alike); gradients are returned unscaled."""
     model.zero_grad(set_to_none=True)
     with torch.autocast("cuda", dtype=dtype):
         out = model(x)
         loss = torch.nn.functional.mse_loss(out.float(), tgt)
-    loss.backward()
-    return out.detach().float(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
+    (loss * loss_scale).backward()
+    return out.detach().float(), {n: p.grad.detach().float() / loss_scale for n, p in model.named_parameters()}
 
 
-def yardstick(cfg: dict, batch: int, hw: int, dtype: torch.dtype, seed: int = 0, fp32_on: str = "cpu"):
+def yardstick(cfg: dict, batch: int, hw: int, dtype: torch.dtype, seed: int = 0, fp32_on: str = "cpu",
+              loss_scale: float = 1.0):
     """-> dict(out=(ours, stock), grads={name: (ours, stock)}): rel-L2 errors vs the fp32 oracle."""
     import copy
     dev = torch.device("cuda:0")
@@ -82,9 +85,9 @@ def yardstick(cfg: dict, batch: int, hw: int, dtype: torch.dtype, seed: int = 0,
         ref_out, ref_g = run_fp32(o, x.to(dev), tgt.to(dev))
     else:
         ref_out, ref_g = run_fp32(o, x, tgt)
-    s_out, s_g = run_autocast(stock, x.to(dev), tgt.to(dev), dtype)
+    s_out, s_g = run_autocast(stock, x.to(dev), tgt.to(dev), dtype, loss_scale)
     m = m.to(dev)
-    m_out, m_g = run_autocast(m, x.to(dev), tgt.to(dev), dtype)
+    m_out, m_g = run_autocast(m, x.to(dev), tgt.to(dev), dtype, loss_scale)
     res = {"out": (rel(m_out, ref_out), rel(s_out, ref_out)), "grads": {}}
     for n, g in ref_g.items():
         if g.norm().item() < 1e-12:
@@ -98,8 +101,10 @@ def time_incumbent(batch: int, hw: int, steps: int, warmup: int, channels_last: 
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     model = OM.UNeXt2(**CFG).to(dev)
-    if channels_last:
-        model = model.to(memory_format=torch.channels_last)
+    if channels_last:  # 4-D (2-D conv) weights only: the stem / head Conv3d weights are rank 5
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Conv2d):
+                mod.weight.data = mod.weight.data.contiguous(memory_format=torch.channels_last)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
     x = torch.randn(batch, 1, 21, hw, hw, device=dev)
     y = torch.randn(batch, 2, 21, hw, hw, device=dev)
@@ -160,7 +165,7 @@ def main():
             print(json.dumps(doc), flush=True)
     for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
         t0 = time.time()
-        res = yardstick(CFG, args.batch, args.hw, dt)
+        res = yardstick(CFG, args.batch, args.hw, dt, loss_scale=65536.0 if dt == torch.float16 else 1.0)
         doc[f"yardstick_{name}_b{args.batch}_{args.hw}"] = summarize(res)
         doc[f"yardstick_{name}_b{args.batch}_{args.hw}"]["seconds"] = time.time() - t0
         print(json.dumps(doc[f"yardstick_{name}_b{args.batch}_{args.hw}"]), flush=True)

@@ -7,6 +7,11 @@
 
 namespace vb {
 
+int dwconv7_legacy(const void* x, const float* wt, const float* bias, const void* add, void* y, int B, int H, int W,
+                   int C, int dtype, cudaStream_t st);
+int dwconv7_wgrad_legacy(const void* x, const void* dy, float* dwt, float* db, int B, int H, int W, int C, int dtype,
+                         cudaStream_t st);
+
 // ------------------------------------------------------------------------------ depthwise 7x7
 // x [B,H,W,C] 16-bit, wt [49][C] fp32 (tap-major so that channel loads coalesce), bias [C] or null,
 // add [B,H,W,C] 16-bit or null (residual gradient folded into the dgrad call).
@@ -744,12 +749,11 @@ static void dwconv7_launch(const void* x, const float* wt, const float* bias, co
                                                         (uint32_t*)y, B, H, W, C2);
 }
 
-extern "C" int vb200_dwconv7(const void* x, const float* wt, const float* bias, const void* add,
-                             void* y, int B, int H, int W, int C, int dtype, vb200_stream_t stream) {
-  VB_REQUIRE(x && wt && y, "null pointer");
+// register-tile kernels for channel counts the shared-memory tile kernels (dwconv_sm100.cu) do not take (C % 8 != 0)
+int vb::dwconv7_legacy(const void* x, const float* wt, const float* bias, const void* add, void* y, int B, int H, int W,
+                       int C, int dtype, cudaStream_t st) {
   VB_SUPPORTED(C % 2 == 0 && (long long)B * H * W * C < (1LL << 31), "C (%d) must be even, tensor < 2^31 elements", C);
   const int C2 = C / 2;
-  cudaStream_t st = (cudaStream_t)stream;
   // small feature maps: 2x4-pixel tiles so that enough blocks exist to fill the SMs
   const long long big_blocks = (long long)((W + 7) / 8) * ((H + 3) / 4) * B * ((C2 + 127) / 128);
   if (big_blocks >= 2 * 148) {
@@ -760,9 +764,8 @@ extern "C" int vb200_dwconv7(const void* x, const float* wt, const float* bias, 
   return check_launch("vb200_dwconv7");
 }
 
-extern "C" int vb200_dwconv7_wgrad(const void* x, const void* dy, float* dwt, float* db, int B, int H,
-                                   int W, int C, int dtype, vb200_stream_t stream) {
-  VB_REQUIRE(x && dy && dwt, "null pointer");
+int vb::dwconv7_wgrad_legacy(const void* x, const void* dy, float* dwt, float* db, int B, int H, int W, int C,
+                             int dtype, cudaStream_t st) {
   VB_SUPPORTED(C % 2 == 0 && (long long)B * H * W * C < (1LL << 31), "C (%d) must be even, tensor < 2^31 elements", C);
   const int C2 = C / 2;
   const int colb = (C2 + 127) / 128;
@@ -772,7 +775,6 @@ extern "C" int vb200_dwconv7_wgrad(const void* x, const void* dy, float* dwt, fl
   if (rpb > H) rpb = H;
   const int strips = (H + rpb - 1) / rpb;
   dim3 grid((unsigned)(B * strips), (unsigned)colb);
-  cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_DT(dtype, dwconv7_wgrad_kernel<BF><<<grid, 128, 0, st>>>((const uint32_t*)x, (const uint32_t*)dy, dwt,
                                                                    db, B, H, W, C2, rpb));
   return check_launch("vb200_dwconv7_wgrad");

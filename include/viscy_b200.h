@@ -69,6 +69,12 @@ typedef struct vb200_gemm_desc {
   const void* aux2;      /* EPI_DGELU_GRN: gp = gelu'(u), 16-bit [M,ldaux2] */
   const float* tvec;     /* EPI_DGELU_GRN: t [nsamples, N] fp32 or NULL */
   const float* svec;     /* EPI_DGELU_GRN: s [nsamples, N] fp32 or NULL; EPI_STORE: per-column scale [N] or NULL */
+  int32_t n_split;       /* EPI_F32, optional (multiple of 16, < N): columns >= n_split are written to out2 (fp32, row pitch
+                            ldo2) at column - n_split.  With B = [l | 1] the weight-gradient GEMM writes dW to out and the
+                            bias gradient (the ones column) to out2 */
+  int32_t rvec_rows;     /* rows per sample for rvec */
+  const float* rvec;     /* EPI_STORE, optional: per-sample fp32 scale applied to (acc + bias) * s before the residual is
+                            added, row r uses rvec[r / rvec_rows] (timm DropPath / stochastic depth on the residual branch) */
 } vb200_gemm_desc;
 
 int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);
@@ -137,6 +143,12 @@ int vb200_dwconv7_wgrad(const void* x, const void* dy, float* dwt, float* db, in
 /* LayerNorm over the channel dim of [M, C] rows (timm LayerNorm / LayerNorm2d, eps 1e-6) */
 int vb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                         float* rstd, int64_t M, int C, float eps, int dtype, vb200_stream_t stream);
+/* same with a row pitch ldy (elements) for y.  ones != 0: y[:, C:C+8] = {1,0,..,0} (ldy >= C + 8); ones2 != NULL: the
+ * same group at ones2[row * ld2 + col2 ..].  A weight-gradient GEMM against [l | 1] then yields the bias gradient as an
+ * extra column, which replaces the column-sum passes over dh / dout (C % 8 == 0, C <= 2048) */
+int vb200_layernorm_fwd_ld(const void* x, const float* gamma, const float* beta, void* y, int64_t ldy, int ones,
+                           void* ones2, int64_t ld2, int col2, float* mean, float* rstd, int64_t M, int C, float eps,
+                           int dtype, vb200_stream_t stream);
 /* dgamma, dbeta are accumulated into (pre-zeroed by the caller) */
 int vb200_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                         const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t M, int C,
@@ -164,6 +176,10 @@ int vb200_grn_apply_bwd(const void* h, const void* dy, const float* s, const flo
 /* mode 0: out[n,c] += sum_r x[n,r,c]; mode 1: sum of squares; mode 2: both in one pass (out [2,B,C]: sums, then sums of
  * squares -- BatchNorm statistics).  x [B,R,C] 16-bit, C % 8 == 0, out pre-zeroed */
 int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode, int dtype, vb200_stream_t stream);
+/* same on rows with pitch ld >= C (elements, % 8); pivot (fp32 [C] or NULL) is subtracted from every element before
+ * summing (shifted one-pass BatchNorm statistics: mean = p + S1/M, var = S2/M - (S1/M)^2) */
+int vb200_colreduce_ld(const void* x, float* out, int B, int64_t R, int C, int64_t ld, int mode, const float* pivot,
+                       int dtype, vb200_stream_t stream);
 /* out[n][j][k] = W2[j][k] * s[n][k] (16-bit) */
 int vb200_grn_pack_w2(const float* W2, const float* s, void* out, int nb, int C, int C4, int dtype,
                       vb200_stream_t stream);
@@ -175,6 +191,15 @@ int vb200_grn_bias_eff(const float* W2, const float* bgrn, const float* b2, floa
 /* from per-sample wgrad partials P[n][j][k]: dW2 (overwritten), S1 [nb,C4] and dbgrn [C4] (accumulated, pre-zeroed) */
 int vb200_grn_wgrad_finish(const float* P, const float* W2, const float* s, const float* bgrn, const float* db2,
                            float* dW2, float* S1, float* dbgrn, int nb, int C, int C4, vb200_stream_t stream);
+/* same with a row pitch ldp for P; db2_in == NULL: the fc2 bias gradient is column C4 of P summed over samples (the
+ * ones column of the GELU output buffer) and is written to db2_out [C] */
+int vb200_grn_wgrad_finish_ld(const float* P, int64_t ldp, const float* W2, const float* s, const float* bgrn,
+                              const float* db2_in, float* dW2, float* S1, float* dbgrn, float* db2_out, int nb, int C,
+                              int C4, vb200_stream_t stream);
+/* vb200_grn_coef_fwd + vb200_grn_prepare in one launch: s (fp32 [nb,C4], written), w2s, b2e from sumsq */
+int vb200_grn_prepare2(const float* sumsq, const float* gw, const float* gb, const float* W2, const float* b2,
+                       float* s_out, void* w2s, float* b2e, int nb, int C, int C4, float eps, int dtype,
+                       vb200_stream_t stream);
 
 /* out[c] += sum_rows x[r][c]  (bias gradients; out pre-zeroed) */
 int vb200_colsum(const void* x, float* out, int64_t M, int C, int dtype, vb200_stream_t stream);

@@ -122,3 +122,38 @@ def test_gemm_wide_tile_fused_epilogues(cuda, M, N, K, R, dtype):
     P = ops.gemm(dout, gact, mn_major=True, epilogue=L.EPI_F32, k_splits=nb, split_slabs=True)
     Pref = torch.einsum("nrj,nrk->njk", dout.float().view(nb, R, K), gact.float().view(nb, R, N))
     assert _rel(P, Pref) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("P,M,N,splits", [(4096, 2944, 736, 4), (1024, 384, 96, 1), (32768, 384, 96, 16), (520, 768, 192, 3)])
+def test_gemm_wgrad_ones_column_split(cuda, P, M, N, splits, dtype):
+    """dW = A^T [B | 1]: the weight gradient leaves through `out`, the ones column (bias gradient) through `out2`."""
+    from viscy_b200 import ops, _lib as L
+    g = torch.Generator(device=cuda).manual_seed(P + M + N)
+    a = torch.randn(P, M, device=cuda, generator=g).to(dtype)
+    bx = torch.zeros(P, N + 8, device=cuda, dtype=dtype)
+    bx[:, :N] = torch.randn(P, N, device=cuda, generator=g).to(dtype)
+    bx[:, N] = 1.0
+    out = torch.zeros(M, N, device=cuda)
+    out2 = torch.zeros(M, 8, device=cuda)
+    ops.gemm(a, bx, mn_major=True, epilogue=L.EPI_F32, k_splits=splits, out=out, out2=out2, n_split=N, accumulate=True)
+    assert _rel(out, a.float().t() @ bx[:, :N].float()) < 1e-4
+    assert _rel(out2[:, 0], a.float().sum(0)) < 1e-4
+    assert out2[:, 1:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,R", [(8192, 736, 2944, 4096), (3 * 196, 96, 384, 196), (2 * 3136, 96, 384, 3136)])
+def test_gemm_row_scale_per_sample(cuda, M, N, K, R, dtype):
+    """EPI_STORE with rvec: out = (acc + bias) * s[col] * rvec[row / R] + residual (stochastic depth on the branch)."""
+    from viscy_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(M + N)
+    a = torch.randn(M, K, device=cuda, generator=g).to(dtype)
+    b = (torch.randn(N, K, device=cuda, generator=g) / K ** 0.5).to(dtype)
+    bias = torch.randn(N, device=cuda, generator=g)
+    sv = torch.randn(N, device=cuda, generator=g)
+    res = torch.randn(M, N, device=cuda, generator=g).to(dtype)
+    keep = (torch.rand(M // R, device=cuda, generator=g) > 0.4).float() / 0.6
+    out = ops.gemm(a, b, bias=bias, svec=sv, residual=res, rvec=keep, rvec_rows=R)
+    ref = (a.float() @ b.float().t() + bias) * sv * keep.repeat_interleave(R)[:, None] + res.float()
+    assert _rel(out, ref) < (6e-3 if dtype == torch.bfloat16 else 1e-3)

@@ -289,7 +289,7 @@ def test_fused_grn_pieces(cuda, dtype):
     Pref = torch.einsum("nrj,nrk->njk", dout.float().view(nb, R, C), g.float().view(nb, R, C4))
     assert rel(P, Pref) < 1e-4
     db2 = dout.float().sum(0)
-    dW2, S1, dbg = ops.grn_wgrad_finish(P, w2, s, bg, db2)
+    dW2, S1, dbg, _ = ops.grn_wgrad_finish(P, w2, s, bg, db2)
     assert rel(dW2, (Pref * s[:, None, :]).sum(0) + db2[:, None] * bg[None, :]) < 1e-4
     assert rel(S1, (Pref * w2[None]).sum(1)) < 1e-4
     assert rel(dbg, w2.t() @ db2) < 1e-4
@@ -341,3 +341,121 @@ def test_conv3d_k3_implicit_gemm(cuda, shape, pad, Co, dtype):
     assert rel(du.permute(0, 4, 1, 2, 3), uf.grad) < tol(dtype)
     dw = ops.conv3d_k3_wgrad(u, dz, pad)
     assert rel(dw, wf.grad) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,C", [(64, 96), (1000, 192), (4096, 736), (77, 768), (300, 1536), (50, 40)])
+def test_layernorm_fwd_rows_ones_columns(cuda, M, C, dtype):
+    """LayerNorm forward that also plants the ones columns of the bias-gradient trick: l = [LN(x) | 1 0 ... 0] and the
+    same group behind a second matrix."""
+    from viscy_b200 import ops
+    x = rnd((M, C), cuda, 1, dtype) * 3 + 0.5
+    gm, bt = rnd((C,), cuda, 2), rnd((C,), cuda, 3)
+    ref = F.layer_norm(x.float(), (C,), gm, bt, 1e-6)
+    y, mean, rstd = ops.layernorm_fwd(x, gm, bt, 1e-6)
+    assert rel(y, ref) < tol(dtype)
+    assert rel(mean, x.float().mean(1)) < 1e-5
+    assert rel(rstd, (x.float().var(1, unbiased=False) + 1e-6).rsqrt()) < 1e-4
+    other = torch.full((M, 4 * C + 8), 7.0, device=cuda, dtype=dtype)
+    yb, mean2, rstd2 = ops.layernorm_fwd(x, gm, bt, 1e-6, ones=True, ones2=other, ones2_col=4 * C)
+    assert yb.shape == (M, C + 8)
+    assert torch.equal(yb[:, :C], y) and torch.equal(mean, mean2) and torch.equal(rstd, rstd2)
+    assert (yb[:, C] == 1).all() and (yb[:, C + 1:] == 0).all()
+    assert (other[:, 4 * C] == 1).all() and (other[:, 4 * C + 1:] == 0).all() and (other[:, :4 * C] == 7).all()
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_colreduce_pitched_and_finish_from_ones_column(cuda, dtype):
+    from viscy_b200 import ops, _lib as L
+    nb, R, C, C4 = 3, 256, 96, 384
+    M = nb * R
+    gbuf = torch.zeros((M, C4 + 8), device=cuda, dtype=dtype)
+    gbuf[:, :C4] = rnd((M, C4), cuda, 1, dtype)
+    gbuf[:, C4] = 1.0
+    sq = ops.colreduce(gbuf.view(nb, R, C4 + 8), 1, width=C4)
+    assert sq.shape == (nb, C4)
+    assert rel(sq, (gbuf[:, :C4].float() ** 2).view(nb, R, C4).sum(1)) < 1e-4
+    w2 = rnd((C, C4), cuda, 2) * 0.1
+    s = rnd((nb, C4), cuda, 3) * 0.3 + 1.0
+    bg = rnd((C4,), cuda, 4) * 0.2
+    dout = rnd((M, C), cuda, 5, dtype)
+    P = ops.gemm(dout, gbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=nb, split_slabs=True)
+    assert P.shape == (nb, C, C4 + 8)
+    dW2, S1, dbg, db2 = ops.grn_wgrad_finish(P, w2, s, bg, None)
+    Pref = torch.einsum("nrj,nrk->njk", dout.float().view(nb, R, C), gbuf[:, :C4].float().view(nb, R, C4))
+    db2_ref = dout.float().sum(0)
+    assert rel(db2, db2_ref) < 1e-4
+    assert rel(dW2, (Pref * s[:, None, :]).sum(0) + db2_ref[:, None] * bg[None, :]) < 1e-4
+    assert rel(S1, (Pref * w2[None]).sum(1)) < 1e-4
+    assert rel(dbg, w2.t() @ db2_ref) < 1e-4
+    # parallel coefficient kernel of the backward
+    sumsq = rnd((nb, C4), cuda, 6).abs() + 0.1
+    gw = rnd((C4,), cuda, 7) * 0.5
+    t = torch.empty_like(S1)
+    dgw = torch.zeros((C4,), device=cuda)
+    ops._call("vb200_grn_coef_bwd", ops._p(sumsq), ops._p(S1.contiguous()), ops._p(gw), ops._p(t), ops._p(dgw), nb, C4,
+              ops.C.c_float(1e-6))
+    gx = sumsq.sqrt()
+    m = gx.mean(1, keepdim=True)
+    inv = 1.0 / (m + 1e-6)
+    dot = (gw * S1 * gx).sum(1, keepdim=True)
+    dgx = gw * S1 * inv - dot * inv * inv / C4
+    assert rel(t, dgx / gx) < 1e-5
+    assert rel(dgw, (gx * inv * S1).sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("v2,B,HW,C", [(True, 2, 16, 96), (True, 3, 8, 64), (False, 2, 14, 96), (True, 2, 6, 48)])
+def test_convnext_block_stochastic_depth(cuda, v2, B, HW, C, dtype):
+    """ConvNeXt block with a per-sample stochastic-depth scale vs the restated timm block (oracle/ref_timm.py) whose
+    DropPath is replaced by the same mask; forward, input gradient and every parameter gradient."""
+    from oracle import ref_timm
+    from viscy_b200 import components as CM
+    torch.manual_seed(3)
+    ob = ref_timm.ConvNeXtBlock(C, conv_mlp=v2, use_grn=v2, ls_init_value=None if v2 else 0.5).to(cuda)
+    mb = CM.ConvNeXtBlock(C, use_grn=v2, conv_mlp=v2, ls_init_value=None if v2 else 0.5).to(cuda)
+    with torch.no_grad():
+        for n, p in ob.named_parameters():
+            if "grn" in n or n.endswith("bias"):
+                p.normal_(0, 0.3)
+    mb.load_state_dict(ob.state_dict())
+    keep = torch.tensor([0.0, 1.25, 1.25][:B], device=cuda)
+
+    class Mask(torch.nn.Module):
+        def forward(self, x):
+            return x * keep.view(-1, 1, 1, 1)
+
+    ob.drop_path = Mask()
+    x = rnd((B, C, HW, HW), cuda, 5)
+    xo = x.clone().requires_grad_(True)
+    ref = ob(xo)
+    dy = rnd(tuple(ref.shape), cuda, 6)
+    ref.backward(dy)
+    xm = x.permute(0, 2, 3, 1).contiguous().to(dtype).requires_grad_(True)
+    out = mb.forward_cl(xm, keep=keep)
+    out.backward(dy.permute(0, 2, 3, 1).contiguous().to(dtype))
+    t = 2 * tol(dtype)
+    assert rel(out.permute(0, 3, 1, 2), ref) < t
+    assert rel(xm.grad.permute(0, 3, 1, 2), xo.grad) < t
+    og = dict(ob.named_parameters())
+    for n, p in mb.named_parameters():
+        assert rel(p.grad, og[n].grad) < 3 * t, n
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_weight_packs_one_launch(cuda, dtype):
+    """WeightPacks: every registered Linear / 1x1-conv weight as [N,K] and [K,N] 16-bit copies and the depthwise filters
+    tap-major (plain and flipped), refreshed by one launch."""
+    from viscy_b200 import ops
+    lin = [rnd(sh, cuda, 10 + i) for i, sh in enumerate([(384, 96), (96, 384, 1, 1), (2944, 736), (200, 72), (30, 50), (64, 64)])]
+    dws = [rnd((C, 1, 7, 7), cuda, 30 + C) for C in (96, 40, 736)]
+    packs = ops.WeightPacks(lin, dws, dtype)
+    packs.refresh()
+    for w in lin:
+        w2 = w.reshape(w.shape[0], -1)
+        assert torch.equal(packs.get(w, "n"), w2.to(dtype))
+        assert torch.equal(packs.get(w, "t"), w2.t().contiguous().to(dtype))
+    for w in dws:
+        C = w.shape[0]
+        assert torch.equal(packs.get(w, "dw"), w.reshape(C, 49).t().contiguous())
+        assert torch.equal(packs.get(w, "dwf"), w.flip(2, 3).reshape(C, 49).t().contiguous())

@@ -69,7 +69,7 @@ def test_golden_vs_stock_autocast(cuda):
     stock = copy.deepcopy(o).to(cuda)
     m = m.to(cuda)
     x, tgt = g["x"].to(cuda), g["targets"][0].to(cuda)
-    for dt, lim in ((torch.float16, 1e-3), (torch.bfloat16, 8e-3)):
+    for dt, lim in ((torch.float16, 1.2e-3), (torch.bfloat16, 1.2e-2)):  # stock autocast itself: 1.1e-3 / 8.9e-3
         s_out, _ = I.run_autocast(stock, x, tgt, dt)
         m_out, _ = I.run_autocast(m, x, tgt, dt)
         eo, es = I.rel(m_out, g["outs"][0]), I.rel(s_out, g["outs"][0])

@@ -140,10 +140,11 @@ class ConvNeXtBlock(nn.Module):
             x = x * self.gamma.reshape(1, -1, 1, 1)
         return self.drop_path(x) + shortcut
 
-    def forward_cl(self, x: Tensor) -> Tensor:
-        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0:
-            raise NotImplementedError("sm_100a ConvNeXt block: stochastic depth (drop_path_rate > 0) in training mode")
-        return F.convnext_block(x, self)
+    def forward_cl(self, x: Tensor, keep: Tensor | None = None) -> Tensor:
+        """keep: per-sample stochastic-depth scale (fp32 [B]); drawn here like timm's DropPath when not given."""
+        if keep is None and isinstance(self.drop_path, DropPath):
+            keep = F.drop_path_scale(x, self.drop_path.drop_prob, self.training)
+        return F.convnext_block(x, self, keep)
 
 
 class ConvNeXtStage(nn.Module):

@@ -31,6 +31,19 @@ inline int check_launch(const char* what) {
   return VB200_OK;
 }
 
+// Per-device one-time work (cudaFuncSetAttribute opt-ins, attribute queries): function attributes are per device /
+// context, so a process that drives several GPUs must repeat them on each; thread-safe (autograd's backward threads).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static int device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  bool need(int dev) const { return ((mask.load(std::memory_order_acquire) >> dev) & 1ull) == 0; }
+  void done(int dev) { mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+
 #define VB_REQUIRE(cond, ...) \
   do {                        \
     if (!(cond)) return vb::fail(VB200_ERR_INVALID, __VA_ARGS__); \

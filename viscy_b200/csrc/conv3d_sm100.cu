@@ -428,13 +428,14 @@ static int make_tmap_ndhwc(CUtensorMap* m, const void* base, int N, int D, int H
 
 template <int CCH, int CO>
 static int launch_conv(const CUtensorMap& tm, const ConvParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static PerDeviceOnce once;
+  const int dev = PerDeviceOnce::device();
   auto kern = conv3d_k3_kernel<CCH, CO>;
-  if (!configured) {
+  if (once.need(dev)) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<CCH, CO>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "conv3d smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    once.done(dev);
   }
   const int grid = (int)(p.tiles < sm_count() ? p.tiles : sm_count());
   kern<<<grid, 192, ConvCfg<CCH, CO>::SMEM_BYTES, st>>>(tm, p);
@@ -443,12 +444,13 @@ static int launch_conv(const CUtensorMap& tm, const ConvParams& p, cudaStream_t 
 
 template <int COCH>
 static int launch_wgrad(const CUtensorMap& tmU, const CUtensorMap& tmDz, const ConvParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static PerDeviceOnce once;
+  const int dev = PerDeviceOnce::device();
   auto kern = conv3d_k3_wgrad_kernel<COCH>;
-  if (!configured) {
+  if (once.need(dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<COCH>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "conv3d wgrad smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    once.done(dev);
   }
   const int grid = (int)(p.tiles < sm_count() ? p.tiles : sm_count());
   kern<<<grid, 192, WgCfg<COCH>::SMEM_BYTES, st>>>(tmU, tmDz, p);

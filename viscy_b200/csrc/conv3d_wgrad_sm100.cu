@@ -314,12 +314,13 @@ extern "C" int vb200_conv3d_wgrad_kh3(const vb200_conv3d_desc* d, vb200_stream_t
   CUtensorMap tmDz, tmX;
   if (int rc = wg3::make_tmap_patch(&tmDz, d->dout, p.N, p.OD, p.OH, p.OW, d->cout, 8, p.bf16 != 0)) return rc;
   if (int rc = wg3::make_tmap_patch(&tmX, d->x, d->N, d->D, d->H, d->W, d->cin, 11, p.bf16 != 0)) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  const int dev = PerDeviceOnce::device();
+  if (once.need(dev)) {
     cudaError_t e = cudaFuncSetAttribute(wg3::conv3d_wgrad_kh3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          wg3::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "conv3d_wgrad_kh3 smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    once.done(dev);
   }
   const long long units = tiles * p.k_splits;
   const int grid = (int)(units < sms ? units : sms);

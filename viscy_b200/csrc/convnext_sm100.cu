@@ -230,6 +230,79 @@ layernorm_fwd_kernel(const uint32_t* __restrict__ x, const float* __restrict__ g
   }
 }
 
+
+// One warp per row with the row held in registers (NV 16-byte vectors per lane): one HBM read, exact two-pass statistics.
+// y has row pitch ldy8 (in 16-byte vectors).  `ones`: the 8 columns [C, C+8) of y are written {1,0,...,0} -- the weight
+// gradient GEMM dW1 = dh^T [l | 1] then delivers the fc1 bias gradient as its extra column (no column-sum pass over the
+// hidden tensor).  ones2 (row pitch ld2_8, vector column c2_8): a second matrix that receives the same group per row
+// (the block's GELU output buffer: its ones column makes the fc2 weight-gradient GEMM produce the fc2 bias gradient).
+template <bool BF16, int NV>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_rows_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          uint4* __restrict__ y, long long ldy8, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                          long long M, int C8, float eps, int ones, uint4* __restrict__ ones2, long long ld2_8, int c2_8) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < C8) {
+      const uint4 q = __ldg(x + row * C8 + i);
+      const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = H16<BF16>::unpack(w4[j]);
+        v[k][2 * j] = f.x;
+        v[k][2 * j + 1] = f.y;
+        s += f.x + f.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+    }
+  }
+  const float inv_c = 1.0f / (8.0f * C8);
+  const float mean = warp_sum(s) * inv_c;
+  float qs = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (lane + 32 * k < C8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = v[k][j] - mean;
+        qs = fmaf(a, a, qs);
+      }
+    }
+  const float rstd = rsqrtf(warp_sum(qs) * inv_c + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < C8) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * i);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * i + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[k][j] - mean) * rstd, gm[j], bt[j]);
+      y[row * ldy8 + i] = make_uint4(H16<BF16>::pack(o[0], o[1]), H16<BF16>::pack(o[2], o[3]),
+                                     H16<BF16>::pack(o[4], o[5]), H16<BF16>::pack(o[6], o[7]));
+    }
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+    const uint4 one = make_uint4(H16<BF16>::pack(1.0f, 0.0f), 0u, 0u, 0u);
+    if (ones) y[row * ldy8 + C8] = one;
+    if (ones2 != nullptr) ones2[row * ld2_8 + c2_8] = one;
+  }
+}
+
 // LayerNorm backward, split in two HBM-friendly kernels:
 //  rows:    dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma   (one warp per row, 16-byte loads)
 //  columns: dgamma[c] += sum_rows dy * xhat, dbeta[c] += sum_rows dy             (128 x 4 thread blocks, smem combine)
@@ -456,6 +529,8 @@ __global__ void grn_coef_fwd_kernel(const float* __restrict__ sumsq, const float
 // backward coefficients from S1[n,c] = sum_r dy * g:
 //   dNx = w * S1;  dw[c] += Nx * S1;  dGx = dNx/(m+eps) - (1/C) * sum_c'(dNx * Gx) / (m+eps)^2
 //   t[n,c] = dGx / Gx   (so that dg = dy * s + g * t)
+// grid (sample, column chunk of blockDim.x): every block reduces the whole sample row for the two scalars (C4 values:
+// cheap) and writes its own chunk, instead of one block per sample walking all columns.
 __global__ void grn_coef_bwd_kernel(const float* __restrict__ sumsq, const float* __restrict__ S1,
                                     const float* __restrict__ w, float* __restrict__ t,
                                     float* __restrict__ dw, int C, float eps) {
@@ -470,7 +545,8 @@ __global__ void grn_coef_bwd_kernel(const float* __restrict__ sumsq, const float
   const float m = block_sum(pm, scratch) / C;
   const float dot = block_sum(pd, scratch);
   const float inv = 1.0f / (m + eps);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c < C) {
     const float gx = sqrtf(sumsq[(long long)n * C + c]);
     const float s1 = S1[(long long)n * C + c];
     const float dgx = w[c] * s1 * inv - dot * inv * inv / C;
@@ -567,7 +643,7 @@ colsum_kernel(const uint32_t* __restrict__ x, float* __restrict__ out, long long
 template <bool BF16, int MODE>
 __global__ void __launch_bounds__(512)
 colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, float* __restrict__ out2, int R, int C8,
-                  int rows_per_block, int cw_log2) {
+                  int rows_per_block, int cw_log2, long long ld8, const float* __restrict__ pivot) {
   constexpr int NQ = MODE == 2 ? 2 : 1;  // MODE 2: sums and sums of squares in one pass (BatchNorm statistics)
   __shared__ float red[NQ * 8 * 512];
   const int cx = threadIdx.x & ((1 << cw_log2) - 1), ry = threadIdx.x >> cw_log2, RL = 512 >> cw_log2;
@@ -581,14 +657,21 @@ colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, float* _
 #pragma unroll
     for (int k = 0; k < 8; ++k) a[q][k] = 0.f;
   if (c8 < C8) {
-    const uint4* xp = x + ((long long)n * R) * C8 + c8;
+    const uint4* xp = x + ((long long)n * R) * ld8 + c8;
+    // optional per-channel pivot subtracted before summing: one-pass variance E[(x-p)^2] - E[x-p]^2 without the
+    // catastrophic cancellation of E[x^2] - E[x]^2 when |mean| >> std (BatchNorm statistics; p = running mean)
+    float pv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pv[k] = pivot != nullptr ? __ldg(pivot + c8 * 8 + k) : 0.f;
 #pragma unroll 4
     for (int r = r0 + ry; r < r1; r += RL) {
-      const uint4 q = __ldg(xp + (long long)r * C8);
+      const uint4 q = __ldg(xp + (long long)r * ld8);
       const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 f = H16<BF16>::unpack(w4[k]);
+        float2 f = H16<BF16>::unpack(w4[k]);
+        f.x -= pv[2 * k];
+        f.y -= pv[2 * k + 1];
         if (MODE == 0 || MODE == 2) {
           a[0][2 * k] += f.x;
           a[0][2 * k + 1] += f.y;
@@ -661,6 +744,76 @@ grn_prepare_kernel(const float* __restrict__ s, const float* __restrict__ gb, co
   }
 }
 
+// GRN forward coefficients, per-sample scaled fc2 weights and the effective bias in ONE launch:
+//   s[n][k] = 1 + gw[k] * Gx[n][k] / (mean_k Gx[n][:] + eps), Gx = sqrt(sumsq)      (written by block 0)
+//   w2s[n][j][k] = W2[j][k] * s[n][k] (16-bit),  b2e[j] = b2[j] + sum_k W2[j][k] * gb[k]
+// Every block recomputes the nb per-sample means (nb * C4 square roots: far cheaper than a kernel boundary on the
+// latency-bound small stages); one block per GRN_JB rows of W2, thread = 8 consecutive k.
+template <bool BF16, int NB>
+__global__ void __launch_bounds__(256)
+grn_prepare2_kernel(const float* __restrict__ sumsq, const float* __restrict__ gw, const float* __restrict__ gb,
+                    const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ s_out,
+                    uint4* __restrict__ w2s, float* __restrict__ b2e, int nb, int C, int C4, float eps) {
+  __shared__ float wsum[8][NB];
+  __shared__ float inv_m[NB];
+  __shared__ float scratch[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float part[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) part[n] = 0.f;
+  for (int k = threadIdx.x; k < C4; k += 256) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+      if (n < nb) part[n] += sqrtf(__ldg(sumsq + (long long)n * C4 + k));
+  }
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    const float v = warp_sum(part[n]);
+    if (lane == 0) wsum[warp][n] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NB) {
+    float m = 0.f;
+    for (int w = 0; w < 8; ++w) m += wsum[w][threadIdx.x];
+    inv_m[threadIdx.x] = 1.0f / (m / C4 + eps);
+  }
+  __syncthreads();
+  const int C48 = C4 / 8;
+  for (int jj = 0; jj < GRN_JB; ++jj) {
+    const int j = blockIdx.x * GRN_JB + jj;
+    if (j >= C) break;
+    float bacc = 0.f;
+    for (int k8 = threadIdx.x; k8 < C48; k8 += blockDim.x) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W2 + (long long)j * C4) + 2 * k8);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W2 + (long long)j * C4) + 2 * k8 + 1);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gb) + 2 * k8);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gb) + 2 * k8 + 1);
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(gw) + 2 * k8);
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(gw) + 2 * k8 + 1);
+      bacc += w0.x * g0.x + w0.y * g0.y + w0.z * g0.z + w0.w * g0.w + w1.x * g1.x + w1.y * g1.y + w1.z * g1.z + w1.w * g1.w;
+      for (int n = 0; n < nb; ++n) {
+        const float4 u0 = __ldg(reinterpret_cast<const float4*>(sumsq + (long long)n * C4) + 2 * k8);
+        const float4 u1 = __ldg(reinterpret_cast<const float4*>(sumsq + (long long)n * C4) + 2 * k8 + 1);
+        const float im = inv_m[n];
+        float4 s0, s1;
+        s0.x = fmaf(q0.x * sqrtf(u0.x), im, 1.0f); s0.y = fmaf(q0.y * sqrtf(u0.y), im, 1.0f);
+        s0.z = fmaf(q0.z * sqrtf(u0.z), im, 1.0f); s0.w = fmaf(q0.w * sqrtf(u0.w), im, 1.0f);
+        s1.x = fmaf(q1.x * sqrtf(u1.x), im, 1.0f); s1.y = fmaf(q1.y * sqrtf(u1.y), im, 1.0f);
+        s1.z = fmaf(q1.z * sqrtf(u1.z), im, 1.0f); s1.w = fmaf(q1.w * sqrtf(u1.w), im, 1.0f);
+        if (blockIdx.x == 0 && jj == 0) {
+          reinterpret_cast<float4*>(s_out + (long long)n * C4)[2 * k8] = s0;
+          reinterpret_cast<float4*>(s_out + (long long)n * C4)[2 * k8 + 1] = s1;
+        }
+        w2s[((long long)n * C + j) * C48 + k8] =
+            make_uint4(H16<BF16>::pack(w0.x * s0.x, w0.y * s0.y), H16<BF16>::pack(w0.z * s0.z, w0.w * s0.w),
+                       H16<BF16>::pack(w1.x * s1.x, w1.y * s1.y), H16<BF16>::pack(w1.z * s1.z, w1.w * s1.w));
+      }
+    }
+    const float tot = block_sum(bacc, scratch);
+    if (threadIdx.x == 0) b2e[j] = b2[j] + tot;
+  }
+}
+
 // b2eff[j] = b2[j] + sum_k W2[j][k] * bgrn[k]   (one warp per output row)
 __global__ void __launch_bounds__(256)
 grn_bias_eff_kernel(const float* __restrict__ W2, const float* __restrict__ bgrn, const float* __restrict__ b2,
@@ -679,11 +832,14 @@ grn_bias_eff_kernel(const float* __restrict__ W2, const float* __restrict__ bgrn
 //   S1[n][k]  += sum_j W2[j][k] * P[n][j][k]         (= sum_r dy * g with dy = dout W2)
 //   dbgrn[k]  += sum_j W2[j][k] * db2[j]             (= sum_r dy)
 // thread = column k, block = chunk of rows j; NB <= 16 samples per launch.
+// ldp = row pitch of P (>= C4).  db2_in == NULL: the fc2 bias gradient is read from column C4 of P (the ones column of
+// the GELU output buffer: P[n][j][C4] = sum_{rows of n} dout[r][j]) and written to db2_out.
 template <int NB>
 __global__ void __launch_bounds__(128)
 grn_wgrad_finish_kernel(const float* __restrict__ P, const float* __restrict__ W2, const float* __restrict__ s,
-                        const float* __restrict__ bgrn, const float* __restrict__ db2, float* __restrict__ dW2,
-                        float* __restrict__ S1, float* __restrict__ dbgrn, int nb, int C, int C4, int jchunk) {
+                        const float* __restrict__ bgrn, const float* __restrict__ db2_in, float* __restrict__ dW2,
+                        float* __restrict__ S1, float* __restrict__ dbgrn, float* __restrict__ db2_out, int nb, int C,
+                        int C4, long long ldp, int jchunk) {
   const int k = blockIdx.x * 128 + threadIdx.x;
   if (k >= C4) return;
   const int j0 = blockIdx.y * jchunk, j1 = min(C, j0 + jchunk);
@@ -695,16 +851,25 @@ grn_wgrad_finish_kernel(const float* __restrict__ P, const float* __restrict__ W
   }
   const float bg = bgrn[k];
   float dbg = 0.f;
-  const long long per = (long long)C * C4;
+  const long long per = (long long)C * ldp;
+#pragma unroll 2
   for (int j = j0; j < j1; ++j) {
     const float w = W2[(long long)j * C4 + k];
-    const float d = db2[j];
+    float d = 0.f;
+    if (db2_in != nullptr) {
+      d = db2_in[j];
+    } else {
+#pragma unroll
+      for (int n = 0; n < NB; ++n)
+        if (n < nb) d += __ldg(P + n * per + (long long)j * ldp + C4);
+      if (k == 0) db2_out[j] = d;
+    }
     float acc = bg * d;
     dbg = fmaf(w, d, dbg);
 #pragma unroll
     for (int n = 0; n < NB; ++n)
       if (n < nb) {
-        const float pv = P[n * per + (long long)j * C4 + k];
+        const float pv = __ldg(P + n * per + (long long)j * ldp + k);
         acc = fmaf(sv[n], pv, acc);
         s1[n] = fmaf(w, pv, s1[n]);
       }
@@ -739,10 +904,11 @@ using namespace vb;
 template <bool BF, int TH, int TW, bool SW>
 static void dwconv7_launch(const void* x, const float* wt, const float* bias, const void* add, void* y, int B, int H,
                            int W, int C2, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  const int dev = PerDeviceOnce::device();
+  if (once.need(dev)) {
     cudaFuncSetAttribute(dwconv7_kernel<BF, TH, TW, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
-    configured = true;
+    once.done(dev);
   }
   dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B), (unsigned)((C2 + 127) / 128));
   dwconv7_kernel<BF, TH, TW, SW><<<grid, 128, SW ? DW_SMEM : 0, st>>>((const uint32_t*)x, wt, bias, (const uint32_t*)add,
@@ -780,16 +946,45 @@ int vb::dwconv7_wgrad_legacy(const void* x, const void* dy, float* dwt, float* d
   return check_launch("vb200_dwconv7_wgrad");
 }
 
-extern "C" int vb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
-                                   float* mean, float* rstd, int64_t M, int C, float eps, int dtype,
-                                   vb200_stream_t stream) {
+template <bool BF, int NV>
+static void ln_fwd_rows_launch(const void* x, const float* gamma, const float* beta, void* y, long long ldy8, float* mean,
+                               float* rstd, int64_t M, int C8, float eps, int ones, void* ones2, long long ld2_8, int c2_8,
+                               cudaStream_t st) {
+  layernorm_fwd_rows_kernel<BF, NV><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(
+      (const uint4*)x, gamma, beta, (uint4*)y, ldy8, mean, rstd, M, C8, eps, ones, (uint4*)ones2, ld2_8, c2_8);
+}
+
+/* y row pitch ldy (elements, % 8); ones != 0: y[:, C:C+8] = {1,0,...,0} (needs ldy >= C + 8); ones2 != NULL: the same
+ * group written at ones2[row * ld2 + col2 .. +8) */
+extern "C" int vb200_layernorm_fwd_ld(const void* x, const float* gamma, const float* beta, void* y, int64_t ldy, int ones,
+                                      void* ones2, int64_t ld2, int col2, float* mean, float* rstd, int64_t M, int C,
+                                      float eps, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(x && gamma && beta && y && mean && rstd, "null pointer");
-  VB_SUPPORTED(C % 2 == 0, "C (%d) must be even", C);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool plain = ldy == C && !ones && ones2 == nullptr;
+  if (C % 8 == 0 && C <= 2048 && ldy % 8 == 0 && ld2 % 8 == 0 && col2 % 8 == 0) {
+    VB_REQUIRE(ldy >= C + (ones ? 8 : 0), "ldy (%lld) too small", (long long)ldy);
+    const int C8 = C / 8, nv = (C8 + 31) / 32;
+#define LN_FWD(NV) DISPATCH_DT(dtype, (ln_fwd_rows_launch<BF, NV>(x, gamma, beta, y, ldy / 8, mean, rstd, M, C8, eps, ones, ones2, ld2 / 8, col2 / 8, st)))
+    if (nv <= 1) LN_FWD(1);
+    else if (nv <= 2) LN_FWD(2);
+    else if (nv <= 3) LN_FWD(3);
+    else if (nv <= 4) LN_FWD(4);
+    else LN_FWD(8);
+#undef LN_FWD
+    return check_launch("vb200_layernorm_fwd");
+  }
+  VB_SUPPORTED(plain, "layernorm_fwd: pitch / ones columns need C %% 8 == 0 and C <= 2048 (C=%d)", C);
+  VB_SUPPORTED(C % 2 == 0, "C (%d) must be even", C);
   const unsigned grid = (unsigned)((M + 7) / 8);
   DISPATCH_DT(dtype, layernorm_fwd_kernel<BF><<<grid, 256, 0, st>>>((const uint32_t*)x, gamma, beta, (uint32_t*)y,
                                                                    mean, rstd, M, C / 2, eps));
   return check_launch("vb200_layernorm_fwd");
+}
+extern "C" int vb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
+                                   float* mean, float* rstd, int64_t M, int C, float eps, int dtype,
+                                   vb200_stream_t stream) {
+  return vb200_layernorm_fwd_ld(x, gamma, beta, y, C, 0, nullptr, 8, 0, mean, rstd, M, C, eps, dtype, stream);
 }
 
 template <bool BF, int NP>
@@ -893,7 +1088,7 @@ extern "C" int vb200_grn_bwd_reduce(const void* h, const void* dy, float* S1, fl
 extern "C" int vb200_grn_coef_bwd(const float* sumsq, const float* S1, const float* w, float* t, float* dw,
                                   int B, int C, float eps, vb200_stream_t stream) {
   VB_REQUIRE(sumsq && S1 && w && t && dw, "null pointer");
-  grn_coef_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(sumsq, S1, w, t, dw, C, eps);
+  grn_coef_bwd_kernel<<<dim3(B, (C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sumsq, S1, w, t, dw, C, eps);
   return check_launch("vb200_grn_coef_bwd");
 }
 
@@ -922,12 +1117,13 @@ extern "C" int vb200_colsum(const void* x, float* out, int64_t M, int C, int dty
 }
 
 /* MODE 0: out[n,c] += sum_r x[n,r,c];  MODE 1: out[n,c] += sum_r x[n,r,c]^2;  MODE 2: both in one pass, sums into
- * out[0:B*C], sums of squares into out[B*C:2*B*C]   (x [B,R,C], C % 8 == 0, out pre-zeroed) */
-extern "C" int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode, int dtype,
-                               vb200_stream_t stream) {
+ * out[0:B*C], sums of squares into out[B*C:2*B*C]   (x [B,R,C] with row pitch ld >= C, C % 8 == 0, out pre-zeroed) */
+extern "C" int vb200_colreduce_ld(const void* x, float* out, int B, int64_t R, int C, int64_t ld, int mode,
+                                  const float* pivot, int dtype, vb200_stream_t stream) {
   VB_REQUIRE(x && out, "null pointer");
-  VB_SUPPORTED(C % 8 == 0 && R < (1LL << 31), "C (%d) %% 8", C);
+  VB_SUPPORTED(C % 8 == 0 && ld % 8 == 0 && ld >= C && R < (1LL << 31), "C (%d) %% 8, ld (%lld) %% 8", C, (long long)ld);
   const int C8 = C / 8;
+  const long long ld8 = ld / 8;
   const ColRedShape sh = ColRedShape::make(C8);
   // ~2 blocks of 512 threads per SM, at least 4 rows per row lane
   long long rpb = (R * sh.colb * B + 148 * 2 - 1) / (148 * 2);
@@ -937,14 +1133,18 @@ extern "C" int vb200_colreduce(const void* x, float* out, int B, int64_t R, int 
   dim3 grid(sh.colb, (unsigned)((R + rpb - 1) / rpb), B);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0)
-    DISPATCH_DT(dtype, colreduce8_kernel<BF, 0><<<grid, 512, 0, st>>>((const uint4*)x, out, nullptr, (int)R, C8, (int)rpb, sh.cw_log2));
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 0><<<grid, 512, 0, st>>>((const uint4*)x, out, nullptr, (int)R, C8, (int)rpb, sh.cw_log2, ld8, pivot));
   else if (mode == 1)
-    DISPATCH_DT(dtype, colreduce8_kernel<BF, 1><<<grid, 512, 0, st>>>((const uint4*)x, out, nullptr, (int)R, C8, (int)rpb, sh.cw_log2));
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 1><<<grid, 512, 0, st>>>((const uint4*)x, out, nullptr, (int)R, C8, (int)rpb, sh.cw_log2, ld8, pivot));
   else if (mode == 2)
-    DISPATCH_DT(dtype, colreduce8_kernel<BF, 2><<<grid, 512, 0, st>>>((const uint4*)x, out, out + (long long)B * C, (int)R, C8, (int)rpb, sh.cw_log2));
+    DISPATCH_DT(dtype, colreduce8_kernel<BF, 2><<<grid, 512, 0, st>>>((const uint4*)x, out, out + (long long)B * C, (int)R, C8, (int)rpb, sh.cw_log2, ld8, pivot));
   else
     return fail(VB200_ERR_INVALID, "colreduce mode %d", mode);
   return check_launch("vb200_colreduce");
+}
+extern "C" int vb200_colreduce(const void* x, float* out, int B, int64_t R, int C, int mode, int dtype,
+                               vb200_stream_t stream) {
+  return vb200_colreduce_ld(x, out, B, R, C, C, mode, nullptr, dtype, stream);
 }
 
 extern "C" int vb200_grn_pack_w2(const float* W2, const float* s, void* out, int nb, int C, int C4, int dtype,
@@ -965,10 +1165,11 @@ extern "C" int vb200_grn_bias_eff(const float* W2, const float* bgrn, const floa
   return check_launch("vb200_grn_bias_eff");
 }
 
-extern "C" int vb200_grn_wgrad_finish(const float* P, const float* W2, const float* s, const float* bgrn,
-                                      const float* db2, float* dW2, float* S1, float* dbgrn, int nb, int C, int C4,
-                                      vb200_stream_t stream) {
-  VB_REQUIRE(P && W2 && s && bgrn && db2 && dW2 && S1 && dbgrn, "null pointer");
+extern "C" int vb200_grn_wgrad_finish_ld(const float* P, int64_t ldp, const float* W2, const float* s,
+                                         const float* bgrn, const float* db2_in, float* dW2, float* S1, float* dbgrn,
+                                         float* db2_out, int nb, int C, int C4, vb200_stream_t stream) {
+  VB_REQUIRE(P && W2 && s && bgrn && dW2 && S1 && dbgrn, "null pointer");
+  VB_REQUIRE(db2_in != nullptr || (db2_out != nullptr && ldp >= C4 + 1), "db2 from the ones column needs db2_out and ldp > C4");
   VB_SUPPORTED(nb <= 16, "at most 16 samples per call (nb=%d)", nb);
   const int colb = (C4 + 127) / 128;
   int jchunk = (C * colb + 148 * 4 - 1) / (148 * 4);
@@ -976,10 +1177,30 @@ extern "C" int vb200_grn_wgrad_finish(const float* P, const float* W2, const flo
   dim3 grid(colb, (C + jchunk - 1) / jchunk);
   cudaStream_t st = (cudaStream_t)stream;
   if (nb <= 8)
-    grn_wgrad_finish_kernel<8><<<grid, 128, 0, st>>>(P, W2, s, bgrn, db2, dW2, S1, dbgrn, nb, C, C4, jchunk);
+    grn_wgrad_finish_kernel<8><<<grid, 128, 0, st>>>(P, W2, s, bgrn, db2_in, dW2, S1, dbgrn, db2_out, nb, C, C4, ldp, jchunk);
   else
-    grn_wgrad_finish_kernel<16><<<grid, 128, 0, st>>>(P, W2, s, bgrn, db2, dW2, S1, dbgrn, nb, C, C4, jchunk);
+    grn_wgrad_finish_kernel<16><<<grid, 128, 0, st>>>(P, W2, s, bgrn, db2_in, dW2, S1, dbgrn, db2_out, nb, C, C4, ldp, jchunk);
   return check_launch("vb200_grn_wgrad_finish");
+}
+extern "C" int vb200_grn_wgrad_finish(const float* P, const float* W2, const float* s, const float* bgrn,
+                                      const float* db2, float* dW2, float* S1, float* dbgrn, int nb, int C, int C4,
+                                      vb200_stream_t stream) {
+  VB_REQUIRE(db2 != nullptr, "null pointer");
+  return vb200_grn_wgrad_finish_ld(P, C4, W2, s, bgrn, db2, dW2, S1, dbgrn, nullptr, nb, C, C4, stream);
+}
+
+extern "C" int vb200_grn_prepare2(const float* sumsq, const float* gw, const float* gb, const float* W2, const float* b2,
+                                  float* s_out, void* w2s, float* b2e, int nb, int C, int C4, float eps, int dtype,
+                                  vb200_stream_t stream) {
+  VB_REQUIRE(sumsq && gw && gb && W2 && b2 && s_out && w2s && b2e, "null pointer");
+  VB_SUPPORTED(C4 % 8 == 0 && nb <= 16, "grn_prepare2: C4 (%d) %% 8, nb (%d) <= 16", C4, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((C + GRN_JB - 1) / GRN_JB);
+  if (nb <= 8)
+    DISPATCH_DT(dtype, (grn_prepare2_kernel<BF, 8><<<grid, 256, 0, st>>>(sumsq, gw, gb, W2, b2, s_out, (uint4*)w2s, b2e, nb, C, C4, eps)));
+  else
+    DISPATCH_DT(dtype, (grn_prepare2_kernel<BF, 16><<<grid, 256, 0, st>>>(sumsq, gw, gb, W2, b2, s_out, (uint4*)w2s, b2e, nb, C, C4, eps)));
+  return check_launch("vb200_grn_prepare2");
 }
 
 extern "C" int vb200_grn_prepare(const float* s, const float* gb, const float* W2, const float* b2, void* w2s,

@@ -249,12 +249,14 @@ static Plan make_plan(int B, int H, int W, int C, int max_rsw) {
   return p;
 }
 
+constexpr int MAX_SMEM = 112 * 1024;  // two CTAs per SM
 template <typename K>
-static int set_smem(K kern, size_t bytes) {
-  // per-device opt-in above 48 KB; cheap enough to issue on every launch (no process-global flags)
-  if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+static int set_smem(K kern, PerDeviceOnce& once) {
+  const int dev = PerDeviceOnce::device();
+  if (once.need(dev)) {  // opt-in above 48 KB, once per kernel and device
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "dwconv7 smem attribute: %s", cudaGetErrorString(e));
+    once.done(dev);
   }
   return VB200_OK;
 }
@@ -263,7 +265,9 @@ template <bool BF, int WC>
 static int launch_fwd(const void* x, const float* wt, const float* bias, const void* add, void* y, const Geom& g,
                       const Plan& p, cudaStream_t st) {
   auto kern = dwconv7_tile_kernel<BF, WC>;
-  if (int rc = set_smem(kern, p.smem_fwd)) return rc;
+  static PerDeviceOnce once;
+  if (int rc = set_smem(kern, once)) return rc;
+  if (p.smem_fwd > (size_t)MAX_SMEM) return fail(VB200_ERR_UNSUPPORTED, "dwconv7 tile needs %zu B of shared memory", p.smem_fwd);
   dim3 grid((unsigned)(g.B * p.htiles * p.wtiles), (unsigned)p.chunks);
   kern<<<grid, NWARP * 32, p.smem_fwd, st>>>((const uint4*)x, wt, bias, (const uint32_t*)add, (uint32_t*)y, g);
   return VB200_OK;
@@ -273,7 +277,9 @@ template <bool BF, int WC>
 static int launch_wgrad(const void* x, const void* dy, float* dwt, float* db, const Geom& g, const Plan& p,
                         cudaStream_t st) {
   auto kern = dwconv7_wgrad_tile_kernel<BF, WC>;
-  if (int rc = set_smem(kern, p.smem_wgrad)) return rc;
+  static PerDeviceOnce once;
+  if (int rc = set_smem(kern, once)) return rc;
+  if (p.smem_wgrad > (size_t)MAX_SMEM) return fail(VB200_ERR_UNSUPPORTED, "dwconv7 wgrad tile needs %zu B of shared memory", p.smem_wgrad);
   dim3 grid((unsigned)(g.B * p.htiles * p.wtiles), (unsigned)p.chunks);
   kern<<<grid, NWARP * 32, p.smem_wgrad, st>>>((const uint4*)x, (const uint4*)dy, dwt, db, g);
   return VB200_OK;

@@ -78,6 +78,7 @@ struct GemmParams {
   int atomic_out;
   int b_batch_rows;     // > 0: B is [nb][N][K]; tile rows [m0, m0+128) use batch m0 / b_batch_rows
   int rows_per_sample;  // EPI_DGELU_GRN: n = row / rows_per_sample
+  int n_split;          // EPI_F32: columns >= n_split (multiple of 16) go to out2 (fp32, row pitch ldo2) at column - n_split
   long long ldo, ldo2, ldr, ldaux, ldaux2;
   long long split_out_stride;
   void* out;
@@ -88,6 +89,8 @@ struct GemmParams {
   const void* aux2;
   const float* tvec;
   const float* svec;
+  const float* rvec;  // EPI_STORE: per-sample scale of (acc + bias) * s before the residual: rvec[row / rvec_rows]
+  int rvec_rows;
   // implicit-GEMM conv forms: output extent, filter extent, padding, channel chunks per tap (CONVK) / channel tiles per
   // tap (CONVMN), channels of the activation operand
   int cOW, cOH, cOD, cKW, cKH, cpw, cph, cpd, cchunks, ccin;
@@ -321,7 +324,7 @@ __device__ __forceinline__ void stage_store(uint32_t stg, int lane, const uint4*
 // tile (fp32).  v: accumulators in, primary result out; w: secondary result (dual-output epilogues).
 template <int EPI, int BN, bool BF16>
 __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, float* w, int cl, uint32_t cv,
-                                               const uint4& xa, const uint4& xb) {
+                                               const uint4& xa, const uint4& xb, float rs) {
   {
     float b8[8];
     lds_f8(cv + cl * 4, b8);
@@ -341,6 +344,10 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
     } else if (p.act == VB200_ACT_GELU) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
+    }
+    if (p.rvec != nullptr) {  // stochastic depth: the residual branch scaled per sample (row)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= rs;
     }
     if (p.residual != nullptr) {
       float q[8];
@@ -720,6 +727,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr bool TPRE = EPI != VB200_EPI_DGELU_GRN && NUM_EPI_WARPS == 8;
       uint32_t r[TPRE ? 2 : 1][32];
       const int rows_valid = (int)min(32LL, (long long)p.M - row0);
+      float rscale = 1.0f;  // this lane's row: TMEM lane = tile row
+      if constexpr (EPI == VB200_EPI_STORE) {
+        if (p.rvec != nullptr) rscale = __ldg(p.rvec + min(row0 + lane, (long long)p.M - 1) / p.rvec_rows);
+      }
       bool released = false;
       if (TPRE && n0 + cc0 < n_lim) tmem_ld32(t_addr + cc0, r[0]);
 #pragma unroll
@@ -756,7 +767,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float v[8], w[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[TPRE ? (c & 1) : 0][g * 8 + j]);
-              epilogue_math8<EPI, BN, BF16>(p, v, w, cc + g * 8, cv, aux[AB].a[g], aux[AB].b[g]);
+              epilogue_math8<EPI, BN, BF16>(p, v, w, cc + g * 8, cv, aux[AB].a[g], aux[AB].b[g], rscale);
               if constexpr (EPI == VB200_EPI_F32) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f32buf[g * 8 + j] = v[j];
@@ -774,11 +785,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int g = 0; g < 4; ++g)
                   q[g] = make_uint4(__float_as_uint(f32buf[hh * 16 + g * 4]), __float_as_uint(f32buf[hh * 16 + g * 4 + 1]),
                                     __float_as_uint(f32buf[hh * 16 + g * 4 + 2]), __float_as_uint(f32buf[hh * 16 + g * 4 + 3]));
-                const int c4v = min(4, max(0, (n_lim - (col0 + hh * 16)) >> 2));
+                const int colh = col0 + hh * 16;
+                float* dst = ob;
+                long long ldb = p.ldo * 4, cb = (long long)colh * 4;
+                int lim = n_lim;
+                if (p.n_split > 0) {  // second destination for the trailing columns (bias-gradient column of [l | 1])
+                  if (colh >= p.n_split) {
+                    dst = reinterpret_cast<float*>(p.out2);
+                    ldb = p.ldo2 * 4;
+                    cb = (long long)(colh - p.n_split) * 4;
+                  } else {
+                    lim = min(n_lim, p.n_split);
+                  }
+                }
+                const int c4v = min(4, max(0, (lim - colh) >> 2));
                 if (p.atomic_out)
-                  stage_store<true>(stg, lane, q, ob, p.ldo * 4, row0, rows_valid, (long long)(col0 + hh * 16) * 4, c4v);
+                  stage_store<true>(stg, lane, q, dst, ldb, row0, rows_valid, cb, c4v);
                 else
-                  stage_store<false>(stg, lane, q, ob, p.ldo * 4, row0, rows_valid, (long long)(col0 + hh * 16) * 4, c4v);
+                  stage_store<false>(stg, lane, q, dst, ldb, row0, rows_valid, cb, c4v);
               }
             } else if constexpr (TMA_STORE) {
               if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP) {
@@ -900,13 +924,13 @@ static bool conv_box(int rows, int OW, int OH, int OD, int NB, int* box) {
   return box[0] <= 256 && box[1] <= 256 && box[2] <= 256 && box[3] <= 256;
 }
 
-int sm_count() {
-  static int n = 0;
+int sm_count() {  // of the current device (one process may drive several)
+  static std::atomic<int> cache[64];
+  const int dev = PerDeviceOnce::device();
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -914,16 +938,17 @@ int sm_count() {
 template <int BN, int MODE, int EPI, int BKE, bool BF16>
 static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                      cudaStream_t st) {
-  static bool configured = false;  // per instantiation
+  static PerDeviceOnce once;  // per instantiation and device
+  const int dev = PerDeviceOnce::device();
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
   using LC = Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store,
                  MODE == MODE_CONVKP || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW>;
   const int smem_bytes = MODE == MODE_CONVKPW ? LC::W_OFFSET + 1024 + p.cwbytes : LC::SMEM_BYTES;
-  if (!configured) {
+  if (once.need(dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          MODE == MODE_CONVKPW ? 232448 : LC::SMEM_BYTES);
     if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    once.done(dev);
   }
   OutMaps om{};
   if constexpr (EpiWarps<BN, EPI>::tma_store) {
@@ -1034,6 +1059,17 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
   p.atomic_out = d->atomic_out;
   p.ldo = d->ldo; p.ldo2 = d->ldo2; p.ldr = d->ldr; p.ldaux = d->ldaux; p.ldaux2 = d->ldaux2;
   p.b_batch_rows = d->b_batch_rows; p.rows_per_sample = d->rows_per_sample;
+  if (d->rvec != nullptr) {
+    VB_REQUIRE(epi == VB200_EPI_STORE && !d->mn_major && d->rvec_rows > 0, "rvec: K-major EPI_STORE with rvec_rows > 0");
+    p.rvec = d->rvec;
+    p.rvec_rows = d->rvec_rows;
+  }
+  if (d->n_split > 0) {
+    VB_REQUIRE(epi == VB200_EPI_F32 && d->out2 != nullptr && d->n_split % 16 == 0 && d->n_split < d->N &&
+                   d->ldo2 >= d->N - d->n_split && d->ldo2 % 4 == 0 && d->split_out_stride == 0,
+               "n_split: EPI_F32 with out2, n_split %% 16 == 0, ldo2 >= N - n_split");
+    p.n_split = d->n_split;
+  }
   p.aux2 = d->aux2; p.tvec = d->tvec; p.svec = d->svec;
   p.split_out_stride = d->atomic_out ? 0 : d->split_out_stride;
   p.out = d->out; p.out2 = d->out2; p.bias = d->bias; p.residual = d->residual; p.aux = d->aux;

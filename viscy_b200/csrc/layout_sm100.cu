@@ -467,15 +467,20 @@ extern "C" int vb200_bcast_rows(const void* src, void* out, int B, int R, int C,
 }
 
 // ------------------------------------------------------------------------------ per-step weight packing, one launch
-// table[item] = {src, dst, dst2, R, Cc, kind, first_block}: kind 0 = cast [R,Cc], 1 = cast + transpose -> [Cc,R],
-// 2 = depthwise taps: src [C=R][49] -> dst fp32 [49][C] and flipped dst2 fp32 [49][C].  1024 elements per block.
+// table[item] = {src, dst, dst2, R, Cc, kind, first_block}:
+//   kind 0 / 1 (legacy, 1024 elements per block): cast [R,Cc] / cast + transpose -> [Cc,R];
+//   kind 2: depthwise taps src [C=R][49] -> dst fp32 [49][C] and flipped dst2 fp32 [49][C] (1024 elements per block);
+//   kind 3: one 64 x 64 tile of src [R,Cc] per block, read once (coalesced rows), written as BOTH 16-bit operand copies:
+//           dst [R,Cc] (forward, K-major) and dst2 [Cc,R] (data gradient) through a padded shared-memory transpose.
 namespace vb {
 constexpr int PM_FIELDS = 7;
 constexpr int PM_PER_BLOCK = 1024;
+constexpr int PM_TILE = 64;
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 pack_multi_kernel(const long long* __restrict__ table, int n_items) {
   __shared__ int s_item;
+  __shared__ float tile[PM_TILE][PM_TILE + 1];
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_items - 1;  // last item whose first_block <= blockIdx.x
     while (lo < hi) {
@@ -489,6 +494,61 @@ pack_multi_kernel(const long long* __restrict__ table, int n_items) {
   const float* src = reinterpret_cast<const float*>(it[0]);
   const long long R = it[3], Cc = it[4];
   const int kind = (int)it[5];
+  if (kind == 3) {
+    const int tiles_c = (int)((Cc + PM_TILE - 1) / PM_TILE);
+    const int tidx = (int)((long long)blockIdx.x - it[6]);
+    const long long r0 = (long long)(tidx / tiles_c) * PM_TILE, c0 = (long long)(tidx % tiles_c) * PM_TILE;
+    const bool vec = (R % 8 == 0) && (Cc % 8 == 0);
+    uint16_t* dn = reinterpret_cast<uint16_t*>(it[1]);
+    uint16_t* dt = reinterpret_cast<uint16_t*>(it[2]);
+    if (vec) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // 64 rows x 16 float4
+        const int id = threadIdx.x + 256 * k;
+        const int r = id >> 4, c4 = (id & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < R && c0 + c4 < Cc) v = __ldg(reinterpret_cast<const float4*>(src + (r0 + r) * Cc + c0 + c4));
+        tile[r][c4] = v.x; tile[r][c4 + 1] = v.y; tile[r][c4 + 2] = v.z; tile[r][c4 + 3] = v.w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {  // 64 rows x 8 groups of 8 columns
+        const int id = threadIdx.x + 256 * k;
+        const int r = id >> 3, c8 = (id & 7) * 8;
+        if (r0 + r < R && c0 + c8 < Cc) {
+          const float* t = &tile[r][c8];
+          *reinterpret_cast<uint4*>(dn + (r0 + r) * Cc + c0 + c8) =
+              make_uint4(H16<BF16>::pack(t[0], t[1]), H16<BF16>::pack(t[2], t[3]), H16<BF16>::pack(t[4], t[5]),
+                         H16<BF16>::pack(t[6], t[7]));
+        }
+        const int c = id >> 3, r8 = (id & 7) * 8;  // transposed copy: row c of dst2 holds 8 consecutive r
+        if (c0 + c < Cc && r0 + r8 < R) {
+          *reinterpret_cast<uint4*>(dt + (c0 + c) * R + r0 + r8) =
+              make_uint4(H16<BF16>::pack(tile[r8][c], tile[r8 + 1][c]), H16<BF16>::pack(tile[r8 + 2][c], tile[r8 + 3][c]),
+                         H16<BF16>::pack(tile[r8 + 4][c], tile[r8 + 5][c]), H16<BF16>::pack(tile[r8 + 6][c], tile[r8 + 7][c]));
+        }
+      }
+    } else {
+      for (int id = threadIdx.x; id < PM_TILE * PM_TILE; id += 256) {
+        const int r = id >> 6, c = id & 63;
+        tile[r][c] = (r0 + r < R && c0 + c < Cc) ? __ldg(src + (r0 + r) * Cc + c0 + c) : 0.f;
+      }
+      __syncthreads();
+      for (int id = threadIdx.x; id < PM_TILE * PM_TILE; id += 256) {
+        const int r = id >> 6, c = id & 63;
+        if (r0 + r < R && c0 + c < Cc) {
+          typename H16<BF16>::T hv = H16<BF16>::from_f(tile[r][c]);
+          dn[(r0 + r) * Cc + c0 + c] = *reinterpret_cast<uint16_t*>(&hv);
+        }
+        const int c2 = id >> 6, r2 = id & 63;
+        if (r0 + r2 < R && c0 + c2 < Cc) {
+          typename H16<BF16>::T hv = H16<BF16>::from_f(tile[r2][c2]);
+          dt[(c0 + c2) * R + r0 + r2] = *reinterpret_cast<uint16_t*>(&hv);
+        }
+      }
+    }
+    return;
+  }
   const long long base = ((long long)blockIdx.x - it[6]) * PM_PER_BLOCK;
   const long long total = kind == 2 ? 49 * R : R * Cc;
 #pragma unroll

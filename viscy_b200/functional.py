@@ -41,10 +41,10 @@ def _wgrad_splits(n_out: int, k_in: int, pixels: int) -> int:
     return max(1, min(want, kb // 4 if kb >= 4 else 1, 64))
 
 
-def linear_fwd(a2d, w, bias, *, residual=None, act=L.ACT_NONE, epilogue=L.EPI_STORE):
+def linear_fwd(a2d, w, bias, *, residual=None, act=L.ACT_NONE, epilogue=L.EPI_STORE, out2=None):
     """a2d [M,K] 16-bit, w fp32 [N,K,...] -> [M,N] 16-bit."""
     wp = ops.packed(w, a2d.dtype)
-    return ops.gemm(a2d, wp, bias=bias, residual=residual, act=act, epilogue=epilogue)
+    return ops.gemm(a2d, wp, bias=bias, residual=residual, act=act, epilogue=epilogue, out2=out2)
 
 
 def linear_bwd(dout2d, a2d, w, *, need_da=True, need_db=True):
@@ -71,83 +71,109 @@ class ConvNeXtBlockFn(Function):
     """timm ConvNeXtBlock (V2: GRN, no layer scale / V1: layer-scale gamma, no GRN), NHWC in / NHWC out.
 
     forward:  d = dwconv7(x)+b ; l = LN(d) ; h = l W1^T + b1 ; y = GRN(GELU(h)) | GELU(h) ;
-              out = (y W2^T + b2) [* gamma] + x
+              out = keep[n] * ((y W2^T + b2) [* gamma]) + x        (keep: stochastic-depth scale per sample, or None)
+
+    Bias gradients without column-sum passes (`onescol`, C % 16 == 0): LayerNorm writes l as [M, C + 8] with a ones
+    column and plants the same column behind the GELU output g [M, C4 + 8]; the weight-gradient GEMMs dh^T [l | 1] and
+    dout^T [g | 1] then carry d fc1.bias / d fc2.bias as their last column.
     """
 
     @staticmethod
-    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b, grn_w, grn_b, gamma):
+    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b, grn_w, grn_b, gamma, keep):
         B, H, W, C = x.shape
         M = B * H * W
         wt, wt_flip = _dw_taps(dw_w)
         ctx.wt_flip = wt_flip
         d = ops.dwconv7(x, wt, dw_b)
-        l, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS)
-        l2 = l.view(M, C)
         C4 = fc1_w.shape[0]
         use_grn = grn_w is not None
         R = H * W
         fused = use_grn and R % 128 == 0 and B <= 16
+        onescol = (fused or not use_grn) and C % 16 == 0 and C <= 2048 and C4 % 8 == 0
+        if onescol:
+            gbuf = torch.empty((M, C4 + 8), device=x.device, dtype=x.dtype)  # [g | 1 0 0 0 0 0 0 0]
+            lbuf, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS, ones=True, ones2=gbuf, ones2_col=C4)
+            l2, y2 = lbuf[:, :C], gbuf[:, :C4]
+        else:
+            l, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS)
+            lbuf = l2 = l.view(M, C)
+            gbuf = y2 = None
         if fused:
             # gp = gelu'(u) and g = gelu(u) from the fc1 epilogue; GRN scale folded into per-sample fc2 weights
-            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP)
-            sumsq = ops.colreduce(y2.view(B, R, C4), 1)
+            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP, out2=y2)
+            if onescol:
+                sumsq = ops.colreduce(gbuf.view(B, R, C4 + 8), 1, width=C4)
+            else:
+                sumsq = ops.colreduce(y2.view(B, R, C4), 1)
+                gbuf = y2
             w2 = fc2_w.detach().reshape(C, C4)
             s, w2s, b2e = ops.grn_prepare(sumsq, grn_w.detach(), grn_b.detach(), w2, fc2_b.detach(), x.dtype)
-            out = ops.gemm(y2, w2s, bias=b2e, residual=x.view(M, C), b_batch_rows=R)
-            ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, grn_b)
-            ctx.use_grn, ctx.fused = True, True
+            out = ops.gemm(y2, w2s, bias=b2e, residual=x.view(M, C), b_batch_rows=R, rvec=keep, rvec_rows=R)
+            ctx.save_for_backward(x, d, mean, rstd, lbuf, h, gbuf, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, grn_b, keep)
+            ctx.use_grn, ctx.fused, ctx.onescol = True, True, onescol
             return out.view(B, H, W, C)
         if use_grn:
             h = linear_fwd(l2, fc1_w, fc1_b)
             y, sumsq, s = ops.gelu_grn_fwd(h.view(B, H * W, C4), grn_w, grn_b)
-            y2 = y.view(M, C4)
+            gbuf = y2 = y.view(M, C4)
         else:
-            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP)  # h := gelu'(u)
+            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP, out2=y2)  # h := gelu'(u)
+            if not onescol:
+                gbuf = y2
             sumsq = s = None
         # ConvNeXt-V1 layer scale: out = gamma * (y W2^T + b2) + x, gamma applied in fp32 in the epilogue
         out = ops.gemm(y2, ops.packed(fc2_w, x.dtype).view(C, C4), bias=fc2_b.detach(),
-                       svec=None if gamma is None else gamma.detach(), residual=x.view(M, C))
-        ctx.fused = False
-        ctx.save_for_backward(x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma)
+                       svec=None if gamma is None else gamma.detach(), residual=x.view(M, C), rvec=keep, rvec_rows=R)
+        ctx.fused, ctx.onescol = False, onescol
+        ctx.save_for_backward(x, d, mean, rstd, lbuf, h, gbuf, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma, keep)
         ctx.use_grn = use_grn
         return out.view(B, H, W, C)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        x, d, mean, rstd, l, h, y2, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma = ctx.saved_tensors
+        x, d, mean, rstd, lbuf, h, gbuf, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma, keep = ctx.saved_tensors
         B, H, W, C = x.shape
         M = B * H * W
+        R = H * W
         C4 = fc1_w.shape[0]
+        onescol = ctx.onescol
         dout = dout.contiguous()
         do2 = dout.view(M, C)
-        ar = ops.Arena(x.device, [C, (B + 2) * C4, C4, 2 * C, 50 * C])
+        # stochastic depth: the residual branch sees keep[n] * dout, the shortcut sees dout
+        dob = do2 if keep is None else ops.scale_rows(dout, keep).view(M, C)
+        l2 = lbuf[:, :C] if onescol else lbuf
+        y2 = gbuf[:, :C4] if onescol else gbuf
+        ar = ops.Arena(x.device, [C, (B + 2) * C4, C4, 2 * C, 50 * C] + ([C4 * C, 8 * C4] if onescol else []))
         if ctx.fused:
             grn_b = gamma  # the 16th saved tensor is grn.bias on the fused path (V2 blocks carry no layer scale)
             gamma = None
-            R = H * W
             w2 = fc2_w.reshape(C, C4)
-            db2 = ops.colreduce(do2.view(1, M, C), 0, ar).view(C)
-            # per-sample wgrad partials P[n] = dout_n^T g_n  (g = y2 here)
-            P = ops.gemm(do2, y2, mn_major=True, epilogue=L.EPI_F32, k_splits=B, split_slabs=True)
-            dw2, S1, dgb = ops.grn_wgrad_finish(P, w2, s, grn_b, db2, ar)
+            # per-sample wgrad partials P[n] = dout_n^T [g_n | 1]: the ones column carries the fc2 bias gradient
+            db2 = None if onescol else ops.colreduce(dob.view(1, M, C), 0, ar).view(C)
+            P = ops.gemm(dob, gbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=B, split_slabs=True)
+            dw2, S1, dgb, db2 = ops.grn_wgrad_finish(P, w2, s, grn_b, db2, ar)
             t = torch.empty_like(S1)
             dgw = ar.take(C4)
             ops._call("vb200_grn_coef_bwd", ops._p(sumsq), ops._p(S1), ops._p(grn_w), ops._p(t), ops._p(dgw), B, C4,
                       ops.C.c_float(1e-6))
             w2t = ops.packed(fc2_w, x.dtype, transpose=True)  # [C4, C]
-            dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux=y2, aux2=h, tvec=t, svec=s, rows_per_sample=R)
+            dh = ops.gemm(dob, w2t, epilogue=L.EPI_DGELU_GRN, aux=y2, aux2=h, tvec=t, svec=s, rows_per_sample=R)
             dw2 = dw2.view(fc2_w.shape)
             dgamma = None
         else:
             w2 = fc2_w.reshape(C, C4)
             if ctx.use_grn:
-                dy, dw2, db2 = linear_bwd(do2, y2, w2)
+                dy, dw2, db2 = linear_bwd(dob, y2, w2)
                 dw2, dgamma = dw2.view(fc2_w.shape), None
                 dh, dgw, dgb, db1 = ops.gelu_grn_bwd(h.view(B, H * W, C4), dy.view(B, H * W, C4), sumsq, s, grn_w)
             else:
                 # ConvNeXt-V1: GELU backward rides in the fc2-dgrad epilogue (h holds gelu'(u))
-                _, G, db_raw = linear_bwd(do2, y2, w2, need_da=False)  # G = dout^T y (without the layer scale)
+                if onescol:
+                    Gx = ops.gemm(dob, gbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(C, C4 + 8, M))
+                    G, db_raw = Gx[:, :C4], Gx[:, C4]  # G = dout^T y (without the layer scale), its ones column
+                else:
+                    _, G, db_raw = linear_bwd(dob, y2, w2, need_da=False)
                 if gamma is not None:
                     # out = gamma * (y W2^T + b2): weights carry gamma / max|gamma| (16-bit safe), the epilogue the rest
                     gmax = gamma.abs().max().clamp_min(1e-30)
@@ -156,11 +182,12 @@ class ConvNeXtBlockFn(Function):
                     dgamma = (G * w2).sum(1) + db_raw * fc2_b
                     dw2, db2 = (G * gamma[:, None]).view(fc2_w.shape), db_raw * gamma
                 else:
-                    w2n, sv, dgamma, dw2, db2 = w2, None, None, G.view(fc2_w.shape), db_raw
+                    w2n, sv, dgamma, dw2, db2 = w2, None, None, G.reshape(fc2_w.shape), db_raw.contiguous()
                 w2t = ops.cast_pack(w2n, x.dtype, transpose=True)
-                dh = ops.gemm(do2, w2t, epilogue=L.EPI_DGELU_GRN, aux2=h, svec=sv,
+                dh = ops.gemm(dob, w2t, epilogue=L.EPI_DGELU_GRN, aux2=h, svec=sv,
                               rows_per_sample=128 * (-(-M // 128)) if sv is not None else 0)
-                db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
+                if not onescol:
+                    db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
                 dgw = dgb = None
         dh2 = dh.view(M, C4)
         main = torch.cuda.current_stream()
@@ -168,10 +195,18 @@ class ConvNeXtBlockFn(Function):
         if side is not main:
             side.wait_stream(main)
         with torch.cuda.stream(side):
-            if ctx.fused:
-                db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
-            dw1 = ops.gemm(dh2, l.view(M, C), mn_major=True, epilogue=L.EPI_F32,
-                           k_splits=_wgrad_splits(C4, C, M)).view(fc1_w.shape)
+            if onescol:
+                # dW1 = dh^T [l | 1]: the weight gradient to its own buffer, the ones column (= d fc1.bias) to db1x
+                dw1, db1x = ar.take(C4, C), ar.take(C4, 8)
+                ops.gemm(dh2, lbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(C4, C + 8, M),
+                         out=dw1, out2=db1x, n_split=C, accumulate=True)
+                db1 = db1x[:, 0].contiguous()
+                dw1 = dw1.view(fc1_w.shape)
+            else:
+                if ctx.fused:
+                    db1 = ops.colreduce(dh.view(1, M, C4), 0, ar).view(C4)
+                dw1 = ops.gemm(dh2, l2, mn_major=True, epilogue=L.EPI_F32,
+                               k_splits=_wgrad_splits(C4, C, M)).view(fc1_w.shape)
         dl = ops.gemm(dh2, ops.packed(fc1_w, x.dtype, transpose=True))
         dd, dlnw, dlnb = ops.layernorm_bwd(dl.view(B, H, W, C), d, mean, rstd, ln_w, ar)
         if side is not main:
@@ -182,16 +217,29 @@ class ConvNeXtBlockFn(Function):
         if side is not main:
             main.wait_stream(side)
         ddw = dwt.t().reshape(dw_w.shape)
-        return dx, ddw, ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma
+        return dx, ddw, ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma, None
 
 
-def convnext_block(x, blk) -> torch.Tensor:
-    """blk: module with conv_dw, norm, mlp.fc1, mlp.fc2, optional mlp.grn, optional gamma."""
+def drop_path_scale(x: torch.Tensor, drop_prob: float, training: bool):
+    """timm DropPath (scale_by_keep=True): per-sample Bernoulli(keep) / keep as an fp32 [B] vector, or None when the
+    layer is the identity (VM/contrastive/encoder.py:79-90, VM/unet/unext2.py:40-46)."""
+    if drop_prob == 0.0 or not training:
+        return None
+    keep = 1.0 - drop_prob
+    mask = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32).bernoulli_(keep)
+    if keep > 0.0:
+        mask.div_(keep)
+    return mask
+
+
+def convnext_block(x, blk, keep=None) -> torch.Tensor:
+    """blk: module with conv_dw, norm, mlp.fc1, mlp.fc2, optional mlp.grn, optional gamma.  keep: stochastic-depth
+    scale per sample (fp32 [B]) or None."""
     grn = getattr(blk.mlp, "grn", None)
     return ConvNeXtBlockFn.apply(
         x, blk.conv_dw.weight, blk.conv_dw.bias, blk.norm.weight, blk.norm.bias,
         blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias,
-        None if grn is None else grn.weight, None if grn is None else grn.bias, getattr(blk, "gamma", None),
+        None if grn is None else grn.weight, None if grn is None else grn.bias, getattr(blk, "gamma", None), keep,
     )
 
 
@@ -585,6 +633,10 @@ class Conv3dFn(Function):
         N, D, H, W, Cp = x.shape
         Co = w.shape[0]
         Cop = _pad8(Co)
+        if Cp != _pad8(w.shape[1]):
+            raise NotImplementedError(
+                f"sm_100a conv3d: rows carry {Cp} channels but the filter expects {w.shape[1]} (padded {_pad8(w.shape[1])}); "
+                "channel-padded operands must be concatenated with cat_cl(a, b, ca, cb)")
         ks = tuple(w.shape[2:])
         stride, padding = tuple(stride), tuple(padding)
         geom = ops.conv3d_geom((N, D, H, W, Cp), ks, stride, padding)
@@ -736,6 +788,8 @@ class ConvTranspose3dFn(Function):
         N, d, h, wd, Cip = x.shape
         Ci, Co = w.shape[:2]
         Cop = _pad8(Co)
+        if Cip != _pad8(Ci):
+            raise NotImplementedError(f"sm_100a conv_transpose3d: rows carry {Cip} channels, the filter expects {Ci}")
         ks = tuple(w.shape[2:])
         out_sp = tuple((i - 1) * s - 2 * p + k + op for i, s, p, k, op in zip((d, h, wd), stride, padding, ks, output_padding))
         geom = ops.conv3d_geom((N, *out_sp, Cop), ks, stride, padding)
@@ -813,9 +867,12 @@ class BatchNormActFn(Function):
         Cc = x.shape[-1]
         M = x.numel() // Cc
         if training:
-            st = ops.colreduce(x.view(1, M, Cc), 2).view(2, Cc) / M  # sums and sums of squares in one pass
-            mean = st[0]
-            var = (st[1] - mean * mean).clamp_min_(0.0)
+            # sums and sums of squares in one pass, taken about the running mean (a per-channel pivot close to the batch
+            # mean): E[(x-p)^2] - E[x-p]^2 does not cancel catastrophically when |mean| >> std
+            pivot = run_mean.detach().contiguous() if run_mean is not None else None
+            st = ops.colreduce(x.view(1, M, Cc), 2, pivot=pivot).view(2, Cc) / M
+            var = (st[1] - st[0] * st[0]).clamp_min_(0.0)
+            mean = st[0] if pivot is None else st[0] + pivot
         else:
             mean, var = run_mean, run_var
         rstd = torch.rsqrt(var + eps)
@@ -868,8 +925,17 @@ class Cat2Fn(Function):
         return ops.split2(dout.contiguous(), *ctx.c)
 
 
-def cat_cl(a, b):
-    return Cat2Fn.apply(a, b)
+def cat_cl(a, b, ca=None, cb=None):
+    """torch.cat([a, b], channel dim) on channels-last rows.  ca / cb: the REAL channel counts when the rows are padded
+    to a multiple of 8: the result must be [a | b | zero pad] (the layout the next conv's weight rows assume), so
+    padded operands are compacted first (plain torch ops; only channel counts that are not multiples of 8 pay this)."""
+    ca = a.shape[-1] if ca is None else ca
+    cb = b.shape[-1] if cb is None else cb
+    if ca == a.shape[-1] and cb == b.shape[-1]:
+        return Cat2Fn.apply(a, b)
+    out = torch.cat([a[..., :ca], b[..., :cb]], dim=-1)
+    pad = _pad8(ca + cb) - (ca + cb)
+    return torch.nn.functional.pad(out, (0, pad)) if pad else out.contiguous()
 
 
 class AddFn(Function):

@@ -39,6 +39,9 @@ def gemm(
     svec: torch.Tensor | None = None,
     rows_per_sample: int = 0,
     split_slabs: bool = False,
+    n_split: int = 0,
+    rvec: torch.Tensor | None = None,
+    rvec_rows: int = 0,
 ) -> torch.Tensor | tuple[torch.Tensor, torch.Tensor]:
     """tcgen05 GEMM.  K-major form: a [M,K], b [N,K] -> [M,N].  MN-major (wgrad) form: a [P,M], b [P,N]."""
     lda = _rowmajor2d(a, "a")
@@ -75,6 +78,17 @@ def gemm(
         d.A, d.B, d.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
         L.check(L.lib().vb200_gemm(C.byref(d), L.stream_ptr()), "vb200_gemm")
         return out
+    if epilogue == L.EPI_F32 and n_split:
+        # columns >= n_split leave through out2 (fp32 [M, ldo2]): dW to `out` [M, n_split], the ones-column sums to out2
+        if out is None or out2 is None:
+            raise ValueError("n_split needs caller-provided out [M, n_split] and out2 [M, >= N - n_split] (fp32)")
+        d.n_split = n_split
+        d.atomic_out = 1 if (k_splits > 1 or accumulate) else 0
+        d.lda, d.ldb = lda, ldb
+        d.ldo, d.ldo2 = _rowmajor2d(out, "out"), _rowmajor2d(out2, "out2")
+        d.A, d.B, d.out, d.out2 = a.data_ptr(), b.data_ptr(), out.data_ptr(), out2.data_ptr()
+        L.check(L.lib().vb200_gemm(C.byref(d), L.stream_ptr()), "vb200_gemm")
+        return out, out2
     if epilogue == L.EPI_F32:
         if out is None:
             out = (torch.zeros if (k_splits > 1 or accumulate) else torch.empty)(
@@ -113,6 +127,11 @@ def gemm(
         if svec.dtype != torch.float32 or not svec.is_contiguous():
             raise ValueError("svec must be contiguous fp32")
         d.svec = svec.data_ptr()
+    if rvec is not None:
+        if rvec.dtype != torch.float32 or not rvec.is_contiguous() or rvec_rows <= 0 or rvec.numel() * rvec_rows < M:
+            raise ValueError("rvec must be contiguous fp32 with one entry per rvec_rows rows")
+        d.rvec = rvec.data_ptr()
+        d.rvec_rows = rvec_rows
     L.check(L.lib().vb200_gemm(C.byref(d), L.stream_ptr()), "vb200_gemm")
     if epilogue in (L.EPI_GELU_DUAL, L.EPI_GELU_GP):
         return out, out2
@@ -197,16 +216,32 @@ def dwconv7_wgrad(x, dy, want_bias=True, arena=None):
     return dwt, db
 
 
-def layernorm_fwd(x, gamma, beta, eps):
-    """x [..., C] 16-bit rows -> (y, mean, rstd)."""
+def layernorm_fwd(x, gamma, beta, eps, ones=False, ones2=None, ones2_col=0):
+    """x [..., C] 16-bit rows -> (y, mean, rstd).
+
+    ones=True: y is [M, C + 8] with y[:, C] = 1 and y[:, C+1:] = 0 (use y[:, :C] as the normalised rows): a weight
+    gradient GEMM against it yields the bias gradient as an extra column.  ones2 ([M, ld2] 16-bit, ones2_col % 8 == 0):
+    a second matrix that receives the same {1, 0 x 7} group per row."""
     _act(x, "x")
     Cc = x.shape[-1]
     M = x.numel() // Cc
-    y = torch.empty_like(x)
     mean = torch.empty((M,), device=x.device, dtype=torch.float32)
     rstd = torch.empty((M,), device=x.device, dtype=torch.float32)
-    _call("vb200_layernorm_fwd", _p(x), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(y), _p(mean), _p(rstd),
-          C.c_int64(M), Cc, C.c_float(eps), L.dtype_code(x.dtype))
+    if not ones and ones2 is None:
+        y = torch.empty_like(x)
+        _call("vb200_layernorm_fwd", _p(x), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(y), _p(mean), _p(rstd),
+              C.c_int64(M), Cc, C.c_float(eps), L.dtype_code(x.dtype))
+        return y, mean, rstd
+    ldy = Cc + 8 if ones else Cc
+    y = torch.empty((M, ldy), device=x.device, dtype=x.dtype)
+    ld2 = 8
+    if ones2 is not None:
+        if ones2.dtype != x.dtype or ones2.dim() != 2 or ones2.shape[0] != M or ones2.stride(1) != 1:
+            raise ValueError("ones2 must be a [M, ld] matrix of the activation dtype")
+        ld2 = ones2.stride(0)
+    _call("vb200_layernorm_fwd_ld", _p(x), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(y), C.c_int64(ldy),
+          int(ones), _p(ones2), C.c_int64(ld2), int(ones2_col), _p(mean), _p(rstd), C.c_int64(M), Cc, C.c_float(eps),
+          L.dtype_code(x.dtype))
     return y, mean, rstd
 
 
@@ -516,14 +551,17 @@ def head_tail_bwd(z, mean, rstd, alpha, W1, dout, Dz, H, W):
 
 # ----------------------------------------------------------------------------------------------
 # fused GRN path helpers
-def colreduce(x, mode, arena=None):
+def colreduce(x, mode, arena=None, width=None, pivot=None):
     """x [B,R,C] 16-bit -> fp32 [B,C]: mode 0 column sums, mode 1 column sums of squares; mode 2: both in one pass,
-    fp32 [2,B,C]."""
+    fp32 [2,B,C].  width: reduce only the first `width` columns of rows whose pitch is x.shape[-1].  pivot: fp32 [C]
+    subtracted from every element before summing."""
     _act(x, "x")
-    B, R, Cc = x.shape
+    B, R, ld = x.shape
+    Cc = ld if width is None else width
     shape = (2, B, Cc) if mode == 2 else (B, Cc)
     out = arena.take(*shape) if arena is not None else torch.zeros(shape, device=x.device, dtype=torch.float32)
-    _call("vb200_colreduce", _p(x), _p(out), B, C.c_int64(R), Cc, mode, L.dtype_code(x.dtype))
+    _call("vb200_colreduce_ld", _p(x), _p(out), B, C.c_int64(R), Cc, C.c_int64(ld), mode,
+          _p(None if pivot is None else _f32(pivot, "pivot")), L.dtype_code(x.dtype))
     return out
 
 
@@ -537,15 +575,16 @@ def grn_pack_w2(w2, s, dtype):
 
 
 def grn_prepare(sumsq, gw, gb, w2, b2, dtype, eps=1e-6):
-    """-> (s [nb,C4] fp32, w2s [nb*C, C4] 16-bit, b2eff [C] fp32): GRN coefficients, then weights + bias in one launch."""
+    """-> (s [nb,C4] fp32, w2s [nb*C, C4] 16-bit, b2eff [C] fp32): GRN coefficients, per-sample scaled fc2 weights and
+    the effective bias in one launch."""
     nb, C4 = sumsq.shape
     Cc = w2.shape[0]
     s = torch.empty_like(sumsq)
-    _call("vb200_grn_coef_fwd", _p(sumsq), _p(_f32(gw, "grn.weight")), _p(s), nb, C4, C.c_float(eps))
     w2s = torch.empty((nb * Cc, C4), device=w2.device, dtype=dtype)
     b2e = torch.empty((Cc,), device=w2.device, dtype=torch.float32)
-    _call("vb200_grn_prepare", _p(s), _p(_f32(gb, "grn.bias")), _p(_f32(w2, "w2")), _p(_f32(b2, "b2")), _p(w2s), _p(b2e),
-          nb, Cc, C4, L.dtype_code(dtype))
+    _call("vb200_grn_prepare2", _p(_f32(sumsq, "sumsq")), _p(_f32(gw, "grn.weight")), _p(_f32(gb, "grn.bias")),
+          _p(_f32(w2, "w2")), _p(_f32(b2, "b2")), _p(s), _p(w2s), _p(b2e), nb, Cc, C4, C.c_float(eps),
+          L.dtype_code(dtype))
     return s, w2s, b2e
 
 
@@ -557,13 +596,18 @@ def grn_bias_eff(w2, bgrn, b2):
 
 
 def grn_wgrad_finish(P, w2, s, bgrn, db2, arena=None):
-    """P fp32 [nb,C,C4] -> (dW2 [C,C4], S1 [nb,C4], dbgrn [C4])"""
-    nb, Cc, C4 = P.shape
+    """P fp32 [nb,C,ldp] -> (dW2 [C,C4], S1 [nb,C4], dbgrn [C4], db2 [C]).  db2=None: P carries the ones column
+    (ldp > C4, column C4 = per-sample sums of dout) and the fc2 bias gradient is taken from it."""
+    nb, Cc, ldp = P.shape
+    C4 = w2.shape[1]
     dW2 = torch.empty((Cc, C4), device=P.device, dtype=torch.float32)
     acc = arena.take(nb + 1, C4) if arena is not None else torch.zeros((nb + 1, C4), device=P.device, dtype=torch.float32)
-    _call("vb200_grn_wgrad_finish", _p(P), _p(_f32(w2, "w2")), _p(_f32(s, "s")), _p(_f32(bgrn, "bgrn")), _p(_f32(db2, "db2")),
-          _p(dW2), _p(acc[:nb]), _p(acc[nb]), nb, Cc, C4)
-    return dW2, acc[:nb], acc[nb]
+    db2_out = None
+    if db2 is None:
+        db2_out = torch.empty((Cc,), device=P.device, dtype=torch.float32)
+    _call("vb200_grn_wgrad_finish_ld", _p(P), C.c_int64(ldp), _p(_f32(w2, "w2")), _p(_f32(s, "s")), _p(_f32(bgrn, "bgrn")),
+          _p(db2), _p(dW2), _p(acc[:nb]), _p(acc[nb]), _p(db2_out), nb, Cc, C4)
+    return dW2, acc[:nb], acc[nb], (db2 if db2 is not None else db2_out)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -726,6 +770,12 @@ def scale_relu(x, scale, relu, gate=None):
     return y
 
 
+def scale_rows(x, scale):
+    """x [N, ..., C] 16-bit times scale[n] (fp32 [N]): stochastic-depth scaling of a gradient."""
+    N, Cc = x.shape[0], x.shape[-1]
+    return scale_relu(x, scale.view(N, 1).expand(N, Cc).contiguous(), False)
+
+
 def avgpool_hw2(x, backward_shape=None):
     """[N,D,H,W,C] -> [N,D,H//2,W//2,C] (AvgPool3d (1,2,2)); backward_shape = input shape: the gradient of that."""
     _act(x, "x")
@@ -762,7 +812,7 @@ class WeightPacks:
     def __init__(self, linear_weights, dw_weights, dtype):
         self.dtype = dtype
         dev = linear_weights[0].device if linear_weights else dw_weights[0].device
-        n16 = sum(2 * w.numel() for w in linear_weights)
+        n16 = sum(2 * w.numel() + 16 for w in linear_weights)  # both copies, each 16-byte aligned
         n32 = sum(2 * 49 * w.shape[0] for w in dw_weights)
         self.buf16 = torch.empty((n16,), device=dev, dtype=dtype)
         self.buf32 = torch.empty((n32,), device=dev, dtype=torch.float32)
@@ -773,13 +823,16 @@ class WeightPacks:
         rows, off16, off32, blk = [], 0, 0, 0
         per = 1024
         for w in linear_weights:
+            # one 64 x 64 tile per block, read once, written as both operand copies ([R,Cc] and [Cc,R])
             R, Cc = w.shape[0], w.numel() // w.shape[0]
-            for kind, name, shape in ((0, "n", (R, Cc)), (1, "t", (Cc, R))):
-                v = self.buf16[off16:off16 + R * Cc].view(shape)
-                off16 += R * Cc
-                self.views[(w.data_ptr(), name)] = v
-                rows.append([w.data_ptr(), v.data_ptr(), 0, R, Cc, kind, blk])
-                blk += -(-R * Cc // per)
+            sz = -(-R * Cc // 8) * 8
+            vn = self.buf16[off16:off16 + R * Cc].view(R, Cc)
+            vt = self.buf16[off16 + sz:off16 + sz + R * Cc].view(Cc, R)
+            off16 += 2 * sz
+            self.views[(w.data_ptr(), "n")] = vn
+            self.views[(w.data_ptr(), "t")] = vt
+            rows.append([w.data_ptr(), vn.data_ptr(), vt.data_ptr(), R, Cc, 3, blk])
+            blk += -(-R // 64) * -(-Cc // 64)
         for w in dw_weights:
             Cc = w.shape[0]
             a = self.buf32[off32:off32 + 49 * Cc].view(49, Cc)

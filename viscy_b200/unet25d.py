@@ -250,7 +250,9 @@ class Unet25d(nn.Module):
             h = F.conv3d_cl(h, self.bottom_transition_block)
             skips = [F.conv3d_cl(s, conv) for conv, s in zip(self.skip_conv_layers, skips)]
             for i, blk in enumerate(self.up_conv_blocks):
-                h = blk.forward_cl(F.cat_cl(F.upsample2x_hw_cl(h), skips[-(i + 1)]))
+                ch = self.up_conv_blocks[i - 1].out_filters if i > 0 else self.bottom_transition_block.out_channels
+                h = blk.forward_cl(F.cat_cl(F.upsample2x_hw_cl(h), skips[-(i + 1)], ch,
+                                            self.skip_conv_layers[-(i + 1)].out_channels))
             h = self.terminal_block.forward_cl(h)
             return F.from_channels_last_3d(h, self.terminal_block.out_filters)
 

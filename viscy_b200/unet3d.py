@@ -217,13 +217,15 @@ class UNet3DBase(nn.Module):
             for blocks, down in zip(self._encoder_blocks, self._downsamples):
                 for blk in blocks:
                     h = blk.forward_cl(h)
-                    skips.append(h)
+                    skips.append((h, down.in_channels))
                 h = F.conv3d_cl(h, down)
             h = self.bottleneck.forward_cl(h)
             for up, blocks in zip(self._upsamples, self._decoder_blocks):
                 h = F.conv_transpose3d_cl(h, up)
+                ch = up.out_channels
                 for blk in blocks:
-                    h = blk.forward_cl(F.cat_cl(h, skips.pop()))
+                    skip, cs = skips.pop()
+                    h = blk.forward_cl(F.cat_cl(h, skip, ch, cs))  # real channel counts: rows are padded to 8
             return F.from_channels_last_3d(F.conv3d_cl(h, self.outconv), self.outconv.out_channels)
 
 

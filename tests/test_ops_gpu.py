@@ -53,7 +53,8 @@ def test_dwconv7_fwd_bwd(cuda, B, H, W, C, dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("M,C", [(64, 96), (1000, 192), (77, 768), (4096, 736), (33, 144), (16, 1536)])
+@pytest.mark.parametrize("M,C", [(64, 96), (1000, 192), (77, 768), (4096, 736), (33, 144), (16, 1536), (32768, 736),
+                                 (5000, 576), (300, 50), (9, 1024)])
 def test_layernorm_fwd_bwd(cuda, M, C, dtype):
     from viscy_b200 import ops
     x = rnd((M, C), cuda, 1, dtype)

@@ -117,6 +117,7 @@ class ContrastiveEncoder(nn.Module):
     def _forward_sm100(self, x: Tensor) -> tuple[Tensor, Tensor]:
         dt = resolve_compute_dtype(x, self.compute_dtype)
         F.ops.ACTIVE_PACKS = None  # weight packs are scoped to the model that registered them
+        F.ops.STEP.begin(x.device, torch.is_grad_enabled())  # one zero-filled allocation for the step's accumulators
         with torch.autocast("cuda", enabled=False):
             f = self.stem.forward_cl(x, dt)
             emb = self.encoder.forward_cl(f)

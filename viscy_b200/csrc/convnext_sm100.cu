@@ -359,6 +359,92 @@ layernorm_bwd_rows_kernel(const uint4* __restrict__ dy, const uint4* __restrict_
   }
 }
 
+// LayerNorm backward in ONE pass over dy and x: each warp walks rows with a grid stride, writes dx for its row and keeps
+// the dgamma / dbeta partial sums of the columns its lanes own in registers; warps of a block combine in shared memory,
+// one atomicAdd per (block, column).  Replaces the rows + columns kernel pair (a second read of dy and x) for C <= 768.
+template <bool BF16, int NV>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_fused_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ gamma, uint4* __restrict__ dx,
+                           float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C8) {
+  extern __shared__ float red[];  // [2][C]
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int C = 8 * C8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float pg[NV][8], pb[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pg[v][k] = pb[v][k] = 0.f;
+  const float inv_c = 1.0f / (float)C;
+  for (long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * warps) {
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float g[NV][8], xh[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = lane + 32 * v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[v][k] = xh[v][k] = 0.f;
+      if (i < C8) {
+        const uint4 qd = __ldg(dy + row * C8 + i), qx = __ldg(x + row * C8 + i);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wx[4] = {qx.x, qx.y, qx.z, qx.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 d = H16<BF16>::unpack(wd[k]), xv = H16<BF16>::unpack(wx[k]);
+          xh[v][2 * k] = (xv.x - mu) * rs;
+          xh[v][2 * k + 1] = (xv.y - mu) * rs;
+          pg[v][2 * k] = fmaf(d.x, xh[v][2 * k], pg[v][2 * k]);
+          pg[v][2 * k + 1] = fmaf(d.y, xh[v][2 * k + 1], pg[v][2 * k + 1]);
+          pb[v][2 * k] += d.x;
+          pb[v][2 * k + 1] += d.y;
+          g[v][2 * k] = d.x * gm[2 * k];
+          g[v][2 * k + 1] = d.y * gm[2 * k + 1];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1 += g[v][k];
+          s2 = fmaf(g[v][k], xh[v][k], s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = lane + 32 * v;
+      if (i < C8) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = rs * (g[v][k] - s1 - xh[v][k] * s2);
+        dx[row * C8 + i] = make_uint4(H16<BF16>::pack(o[0], o[1]), H16<BF16>::pack(o[2], o[3]),
+                                      H16<BF16>::pack(o[4], o[5]), H16<BF16>::pack(o[6], o[7]));
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = lane + 32 * v;
+    if (i < C8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&red[i * 8 + k], pg[v][k]);
+        atomicAdd(&red[C + i * 8 + k], pb[v][k]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[C + i]);
+  }
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(512)
 layernorm_bwd_cols_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ mean,
@@ -515,6 +601,7 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 }
 
 // forward coefficients: s[n,c] = 1 + w[c] * Gx[n,c] / (mean_c Gx[n,:] + eps),  Gx = sqrt(sumsq)
+// grid (sample, column chunk of blockDim.x): every block reduces the whole sample row (C values: cheap), writes its chunk
 __global__ void grn_coef_fwd_kernel(const float* __restrict__ sumsq, const float* __restrict__ w,
                                     float* __restrict__ s, int C, float eps) {
   __shared__ float scratch[32];
@@ -522,8 +609,8 @@ __global__ void grn_coef_fwd_kernel(const float* __restrict__ sumsq, const float
   float part = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) part += sqrtf(sumsq[(long long)n * C + c]);
   const float m = block_sum(part, scratch) / C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    s[(long long)n * C + c] = 1.0f + w[c] * sqrtf(sumsq[(long long)n * C + c]) / (m + eps);
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c < C) s[(long long)n * C + c] = 1.0f + w[c] * sqrtf(sumsq[(long long)n * C + c]) / (m + eps);
 }
 
 // backward coefficients from S1[n,c] = sum_r dy * g:
@@ -1010,6 +1097,21 @@ extern "C" int vb200_layernorm_bwd(const void* dy, const void* x, const float* m
   VB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "null pointer");
   VB_SUPPORTED(C % 2 == 0 && C <= 3072, "C (%d) must be even and <= 3072", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if (C % 8 == 0 && C <= 768) {  // up to 3 vectors per lane stay in registers
+    const int C8 = C / 8, nv = (C8 + 31) / 32;
+    long long blocks = (M + 7) / 8;
+    const long long cap = 148LL * 2;  // two resident 256-thread blocks per SM; rows beyond that by grid stride
+    if (blocks > cap) blocks = cap;
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+#define LN_FUSED(NV)                                                                                               \
+  DISPATCH_DT(dtype, (layernorm_bwd_fused_kernel<BF, NV><<<(unsigned)blocks, 256, smem, st>>>(                     \
+                         (const uint4*)dy, (const uint4*)x, mean, rstd, gamma, (uint4*)dx, dgamma, dbeta, M, C8)))
+    if (nv <= 1) LN_FUSED(1);
+    else if (nv <= 2) LN_FUSED(2);
+    else LN_FUSED(3);
+#undef LN_FUSED
+    return check_launch("vb200_layernorm_bwd(fused)");
+  }
   if (C % 8 == 0 && C <= 2048) {
     const int C8 = C / 8, nv = (C8 + 31) / 32;
 #define LN_ROWS(NV) DISPATCH_DT(dtype, (ln_bwd_rows_launch<BF, NV>(dy, x, mean, rstd, gamma, dx, M, C8, st)))
@@ -1057,7 +1159,7 @@ extern "C" int vb200_grn_sumsq(const void* h, float* sumsq, int B, int R, int C,
 extern "C" int vb200_grn_coef_fwd(const float* sumsq, const float* w, float* s, int B, int C, float eps,
                                   vb200_stream_t stream) {
   VB_REQUIRE(sumsq && w && s, "null pointer");
-  grn_coef_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(sumsq, w, s, C, eps);
+  grn_coef_fwd_kernel<<<dim3(B, (C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sumsq, w, s, C, eps);
   return check_launch("vb200_grn_coef_fwd");
 }
 

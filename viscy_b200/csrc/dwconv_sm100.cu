@@ -54,11 +54,11 @@ __device__ __forceinline__ void fill_tile(uint32_t dst, const uint4* __restrict_
   }
 }
 
-template <bool BF16, int WC>
+template <bool BF16, int WC, bool ADD>
 __global__ void __launch_bounds__(NWARP * 32, 2)
 dwconv7_tile_kernel(const uint4* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
-                    const uint32_t* __restrict__ add, uint32_t* __restrict__ y, const Geom g) {
-  constexpr int WR = NWARP / WC, TC = TW * WC + 6;
+                    const uint4* __restrict__ add, uint32_t* __restrict__ y, const Geom g) {
+  constexpr int WR = NWARP / WC, TC = TW * WC + 6, GC = TW * WC;
   extern __shared__ __align__(16) uint32_t tile[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wc = warp % WC, wr = warp / WC;
@@ -68,9 +68,11 @@ dwconv7_tile_kernel(const uint4* __restrict__ x, const float* __restrict__ wt, c
   const int hti = t % g.htiles;
   const int n = t / g.htiles;
   const int chunk = blockIdx.y;
-  const int h0 = hti * (WR * g.rsw), w0 = wti * (TW * WC);
-  const int rows = min(WR * g.rsw, g.H - h0) + 6;
-  fill_tile<TC>(smem_u32(tile), x, n, h0 - 3, w0 - 3, rows, g.H, g.W, g.C2 / 4, chunk);
+  const int h0 = hti * (WR * g.rsw), w0 = wti * GC;
+  const int orows = min(WR * g.rsw, g.H - h0);
+  uint32_t* at = tile + (WR * g.rsw + 6) * TC * 32;  // tile of the addend (data gradient: the shortcut's gradient)
+  fill_tile<TC>(smem_u32(tile), x, n, h0 - 3, w0 - 3, orows + 6, g.H, g.W, g.C2 / 4, chunk);
+  if constexpr (ADD) fill_tile<GC>(smem_u32(at), add, n, h0, w0, orows, g.H, g.W, g.C2 / 4, chunk);
   cp_async_commit();
   // the lane's 49 taps (tap-major fp32 [49][C]: 256 B per warp and tap) while the tile is in flight
   const int cp = chunk * 32 + lane;
@@ -84,11 +86,13 @@ dwconv7_tile_kernel(const uint4* __restrict__ x, const float* __restrict__ wt, c
   if (bias != nullptr && active) b2 = __ldg(reinterpret_cast<const float2*>(bias) + cp);
   cp_async_wait<0>();
   __syncthreads();
-  const int oh0 = h0 + wr * g.rsw;  // first output row of this warp
+  const int r0 = wr * g.rsw;
+  const int oh0 = h0 + r0;  // first output row of this warp
   const int rs = min(g.rsw, g.H - oh0);
   const int ow0 = w0 + TW * wc;
   if (!active || rs <= 0 || ow0 >= g.W) return;
-  const uint32_t* srow = tile + ((wr * g.rsw) * TC + TW * wc) * 32 + lane;
+  const uint32_t* srow = tile + (r0 * TC + TW * wc) * 32 + lane;
+  const uint32_t* arow = at + (r0 * GC + TW * wc) * 32 + lane;
   float2 acc[7][TW];
 #pragma unroll
   for (int s = 0; s < 7; ++s)
@@ -104,15 +108,28 @@ dwconv7_tile_kernel(const uint4* __restrict__ x, const float* __restrict__ wt, c
         float2 in[TW + 6];
 #pragma unroll
         for (int j = 0; j < TW + 6; ++j) in[j] = H16<BF16>::unpack(srow[(ir * TC + j) * 32]);
+        // output row o = ir - kh is fed through filter row kh; its ring slot o % 7 = (p - kh) mod 7 is static
+        if (ir >= 6 && ir < rs) {
+          // interior row: all seven filter rows land on live output rows.  kw outermost: the 28 accumulators of a kw
+          // step are independent, so consecutive FFMA2 never wait on each other
 #pragma unroll
-        for (int kh = 0; kh < 7; ++kh) {
-          const int o = ir - kh;  // output row fed through filter row kh; ring slot o % 7 = (p - kh) mod 7 (static)
-          if (o >= 0 && o < rs) {
+          for (int kw = 0; kw < 7; ++kw)
 #pragma unroll
-            for (int kw = 0; kw < 7; ++kw)
+            for (int kh = 0; kh < 7; ++kh)
 #pragma unroll
               for (int j = 0; j < TW; ++j)
                 acc[(p - kh + 7) % 7][j] = __ffma2_rn(in[j + kw], wreg[kh * 7 + kw], acc[(p - kh + 7) % 7][j]);
+        } else {
+#pragma unroll
+          for (int kh = 0; kh < 7; ++kh) {
+            const int o = ir - kh;
+            if (o >= 0 && o < rs) {
+#pragma unroll
+              for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+                for (int j = 0; j < TW; ++j)
+                  acc[(p - kh + 7) % 7][j] = __ffma2_rn(in[j + kw], wreg[kh * 7 + kw], acc[(p - kh + 7) % 7][j]);
+            }
           }
         }
         const int o = ir - 6;  // this row received its last filter row: store it, recycle the slot
@@ -122,7 +139,7 @@ dwconv7_tile_kernel(const uint4* __restrict__ x, const float* __restrict__ wt, c
           for (int j = 0; j < TW; ++j) {
             if (j < cols_ok) {
               float2 v = acc[(p + 1) % 7][j];
-              if (add != nullptr) v = __fadd2_rn(v, H16<BF16>::unpack(__ldg(add + ob + j * g.C2)));
+              if constexpr (ADD) v = __fadd2_rn(v, H16<BF16>::unpack(arow[(o * GC + j) * 32]));
               y[ob + j * g.C2] = H16<BF16>::pack(v.x, v.y);
             }
             acc[(p + 1) % 7][j] = b2;
@@ -183,15 +200,27 @@ dwconv7_wgrad_tile_kernel(const uint4* __restrict__ x, const uint4* __restrict__
               bsum = __fadd2_rn(bsum, gr[p][j]);
             }
           }
+          // dy row o = ir - kh pairs with this x row through filter row kh.  j outermost: the accumulators touched by
+          // consecutive FFMA2 are all different (49 on interior rows, 7 per filter row on the edge rows)
+          if (ir >= 6 && ir < rs) {
 #pragma unroll
-          for (int kh = 0; kh < 7; ++kh) {
-            const int o = ir - kh;  // dy row paired with this x row through filter row kh
-            if (o >= 0 && o < rs) {
+            for (int j = 0; j < TW; ++j)
 #pragma unroll
-              for (int kw = 0; kw < 7; ++kw)
+              for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 7; ++kw)
+                  acc[kh * 7 + kw] = __ffma2_rn(gr[(p - kh + 7) % 7][j], in[j + kw], acc[kh * 7 + kw]);
+          } else {
+#pragma unroll
+            for (int kh = 0; kh < 7; ++kh) {
+              const int o = ir - kh;
+              if (o >= 0 && o < rs) {
 #pragma unroll
                 for (int j = 0; j < TW; ++j)
-                  acc[kh * 7 + kw] = __ffma2_rn(gr[(p - kh + 7) % 7][j], in[j + kw], acc[kh * 7 + kw]);
+#pragma unroll
+                  for (int kw = 0; kw < 7; ++kw)
+                    acc[kh * 7 + kw] = __ffma2_rn(gr[(p - kh + 7) % 7][j], in[j + kw], acc[kh * 7 + kw]);
+              }
             }
           }
         }
@@ -238,7 +267,7 @@ static Plan make_plan(int B, int H, int W, int C, int max_rsw) {
   p.wtiles = (W + TW * p.wc - 1) / (TW * p.wc);
   int rsw = max_rsw;
   while (rsw > (H + wr - 1) / wr && rsw > 1) rsw = (rsw + 1) / 2;
-  const long long target = 2LL * 2 * sm_count();
+  const long long target = 2LL * sm_count();  // one full wave of 2 CTAs per SM; small maps are latency-bound
   while (rsw > 2 && (long long)B * ((H + wr * rsw - 1) / (wr * rsw)) * p.wtiles * p.chunks < target) rsw = (rsw + 1) / 2;
   p.rsw = rsw;
   p.htiles = (H + wr * rsw - 1) / (wr * rsw);
@@ -261,16 +290,23 @@ static int set_smem(K kern, PerDeviceOnce& once) {
   return VB200_OK;
 }
 
+template <bool BF, int WC, bool ADD>
+static int launch_fwd_k(const void* x, const float* wt, const float* bias, const void* add, void* y, const Geom& g,
+                        const Plan& p, cudaStream_t st) {
+  auto kern = dwconv7_tile_kernel<BF, WC, ADD>;
+  static PerDeviceOnce once;
+  if (int rc = set_smem(kern, once)) return rc;
+  const size_t smem = ADD ? p.smem_wgrad : p.smem_fwd;  // data gradient: the addend's tile rides along
+  if (smem > (size_t)MAX_SMEM) return fail(VB200_ERR_UNSUPPORTED, "dwconv7 tile needs %zu B of shared memory", smem);
+  dim3 grid((unsigned)(g.B * p.htiles * p.wtiles), (unsigned)p.chunks);
+  kern<<<grid, NWARP * 32, smem, st>>>((const uint4*)x, wt, bias, (const uint4*)add, (uint32_t*)y, g);
+  return VB200_OK;
+}
 template <bool BF, int WC>
 static int launch_fwd(const void* x, const float* wt, const float* bias, const void* add, void* y, const Geom& g,
                       const Plan& p, cudaStream_t st) {
-  auto kern = dwconv7_tile_kernel<BF, WC>;
-  static PerDeviceOnce once;
-  if (int rc = set_smem(kern, once)) return rc;
-  if (p.smem_fwd > (size_t)MAX_SMEM) return fail(VB200_ERR_UNSUPPORTED, "dwconv7 tile needs %zu B of shared memory", p.smem_fwd);
-  dim3 grid((unsigned)(g.B * p.htiles * p.wtiles), (unsigned)p.chunks);
-  kern<<<grid, NWARP * 32, p.smem_fwd, st>>>((const uint4*)x, wt, bias, (const uint32_t*)add, (uint32_t*)y, g);
-  return VB200_OK;
+  return add != nullptr ? launch_fwd_k<BF, WC, true>(x, wt, bias, add, y, g, p, st)
+                        : launch_fwd_k<BF, WC, false>(x, wt, bias, add, y, g, p, st);
 }
 
 template <bool BF, int WC>

@@ -91,9 +91,8 @@ def gemm(
         return out, out2
     if epilogue == L.EPI_F32:
         if out is None:
-            out = (torch.zeros if (k_splits > 1 or accumulate) else torch.empty)(
-                (M, N), device=a.device, dtype=torch.float32
-            )
+            out = zeros((M, N), a.device) if (k_splits > 1 or accumulate) else torch.empty(
+                (M, N), device=a.device, dtype=torch.float32)
         d.atomic_out = 1 if (k_splits > 1 or accumulate) else 0
     else:
         if out is None:
@@ -161,6 +160,52 @@ def _act(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+class StepArena:
+    """Every zero-initialised fp32 accumulator of one step (split-K weight gradients, bias / norm-parameter gradient
+    sums, GRN statistics) served from ONE allocation: one memset instead of ~100 fill launches per step.
+
+    `begin()` (called by a model at the start of its forward) allocates a fresh zero buffer sized from the requests of
+    the previous step with the same (device, grad mode) key; slices are handed out once and never recycled, so a slice
+    is zero when handed out and stays valid for as long as any view of it lives (gradients returned to autograd keep the
+    allocation alive; the next step gets a new one).  Requests beyond the buffer fall back to torch.zeros."""
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.need = 0
+        self.key = None
+        self.cap: dict = {}
+
+    def begin(self, device, grad: bool) -> None:
+        if self.key is not None:
+            self.cap[self.key] = max(self.cap.get(self.key, 0), self.need)
+        self.key = (device, grad)
+        self.need = self.off = 0
+        size = self.cap.get(self.key, 0)
+        self.buf = torch.zeros((size,), device=device, dtype=torch.float32) if size else None
+
+    def zeros(self, shape, device) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_al = -(-n // 64) * 64  # 256-byte granules: every slice is aligned for 16-byte vector reductions
+        self.need += n_al
+        b = self.buf
+        if b is not None and b.device == device and self.off + n_al <= b.numel():
+            v = b[self.off:self.off + n].view(*shape)
+            self.off += n_al
+            return v
+        return torch.zeros(tuple(shape), device=device, dtype=torch.float32)
+
+
+STEP = StepArena()
+
+
+def zeros(shape, device) -> torch.Tensor:
+    """Zero-initialised fp32 accumulator (from the step arena when one is active)."""
+    return STEP.zeros(tuple(shape) if not isinstance(shape, int) else (shape,), device)
+
+
 def cast_pack(w: torch.Tensor, dtype: torch.dtype, transpose: bool = False) -> torch.Tensor:
     """fp32 [R, C] parameter -> 16-bit operand copy ([C, R] when transpose)."""
     w2 = _f32(w.detach().reshape(w.shape[0], -1), "w")
@@ -174,7 +219,7 @@ class Arena:
     """One zero-filled fp32 allocation handed out in slices (accumulators that kernels add into)."""
 
     def __init__(self, device, sizes):
-        self.buf = torch.zeros((int(sum(sizes)),), device=device, dtype=torch.float32)
+        self.buf = zeros((int(sum(sizes)),), device)
         self.off = 0
 
     def take(self, *shape):
@@ -210,8 +255,8 @@ def dwconv7_wgrad(x, dy, want_bias=True, arena=None):
     if arena is not None:
         dwt, db = arena.take(49, Cc), (arena.take(Cc) if want_bias else None)
     else:
-        dwt = torch.zeros((49, Cc), device=x.device, dtype=torch.float32)
-        db = torch.zeros((Cc,), device=x.device, dtype=torch.float32) if want_bias else None
+        dwt = zeros((49, Cc), x.device)
+        db = zeros((Cc,), x.device) if want_bias else None
     _call("vb200_dwconv7_wgrad", _p(_act(x, "x")), _p(_act(dy, "dy")), _p(dwt), _p(db), B, H, W, Cc, L.dtype_code(x.dtype))
     return dwt, db
 
@@ -252,8 +297,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, arena=None):
     if arena is not None:
         dgamma, dbeta = arena.take(Cc), arena.take(Cc)
     else:
-        dgamma = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
-        dbeta = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
+        dgamma = zeros((Cc,), x.device)
+        dbeta = zeros((Cc,), x.device)
     _call("vb200_layernorm_bwd", _p(_act(dy, "dy")), _p(_act(x, "x")), _p(mean), _p(rstd), _p(_f32(gamma, "gamma")),
           _p(dx), _p(dgamma), _p(dbeta), C.c_int64(M), Cc, L.dtype_code(x.dtype))
     return dx, dgamma, dbeta
@@ -264,7 +309,7 @@ def gelu_grn_fwd(h, w, b, eps=1e-6):
     _act(h, "h")
     B, R, Cc = h.shape
     dt = L.dtype_code(h.dtype)
-    sumsq = torch.zeros((B, Cc), device=h.device, dtype=torch.float32)
+    sumsq = zeros((B, Cc), h.device)
     _call("vb200_grn_sumsq", _p(h), _p(sumsq), B, R, Cc, dt)
     s = torch.empty_like(sumsq)
     _call("vb200_grn_coef_fwd", _p(sumsq), _p(_f32(w, "grn.weight")), _p(s), B, Cc, C.c_float(eps))
@@ -278,14 +323,14 @@ def gelu_grn_bwd(h, dy, sumsq, s, w, eps=1e-6, want_dbias=True):
     B, R, Cc = h.shape
     dt = L.dtype_code(h.dtype)
     dev = h.device
-    S1 = torch.zeros((B, Cc), device=dev, dtype=torch.float32)
-    sdy = torch.zeros((Cc,), device=dev, dtype=torch.float32)
+    S1 = zeros((B, Cc), dev)
+    sdy = zeros((Cc,), dev)
     _call("vb200_grn_bwd_reduce", _p(_act(h, "h")), _p(_act(dy, "dy")), _p(S1), _p(sdy), B, R, Cc, dt)
     t = torch.empty_like(S1)
-    dw = torch.zeros((Cc,), device=dev, dtype=torch.float32)
+    dw = zeros((Cc,), dev)
     _call("vb200_grn_coef_bwd", _p(sumsq), _p(S1), _p(_f32(w, "grn.weight")), _p(t), _p(dw), B, Cc, C.c_float(eps))
     dh = torch.empty_like(h)
-    dbias = torch.zeros((Cc,), device=dev, dtype=torch.float32) if want_dbias else None
+    dbias = zeros((Cc,), dev) if want_dbias else None
     _call("vb200_grn_apply_bwd", _p(h), _p(dy), _p(s), _p(t), _p(dh), _p(dbias), B, R, Cc, dt)
     return dh, dw, sdy, dbias
 
@@ -293,7 +338,7 @@ def gelu_grn_bwd(h, dy, sumsq, s, w, eps=1e-6, want_dbias=True):
 def colsum(x):
     Cc = x.shape[-1]
     M = x.numel() // Cc
-    out = torch.zeros((Cc,), device=x.device, dtype=torch.float32)
+    out = zeros((Cc,), x.device)
     _call("vb200_colsum", _p(_act(x, "x")), _p(out), C.c_int64(M), Cc, L.dtype_code(x.dtype))
     return out
 
@@ -439,7 +484,7 @@ def conv3d_igemm_wgrad(x, dout, kernel, padding, k_splits=0, stride=(1, 1, 1)):
     if tuple(dout.shape[1:4]) != _conv3d_out((D, H, W), kernel, padding, stride):
         raise ValueError(f"dout extent {tuple(dout.shape[1:4])} does not match the conv geometry")
     d.k_splits = k_splits
-    dw = torch.zeros((Co, kd * kh * kw * Ci), device=x.device, dtype=torch.float32)
+    dw = zeros((Co, kd * kh * kw * Ci), x.device)
     d.x, d.dout, d.dw = x.data_ptr(), dout.data_ptr(), dw.data_ptr()
     L.check(L.lib().vb200_conv3d_igemm_wgrad(C.byref(d), L.stream_ptr()), "vb200_conv3d_igemm_wgrad")
     return dw
@@ -462,7 +507,7 @@ def conv3d_wgrad_kh3(x, dout, kernel, padding, k_splits=0):
     if tuple(dout.shape[1:4]) != _conv3d_out((D, H, W), kernel, padding, (1, 1, 1)):
         raise ValueError(f"dout extent {tuple(dout.shape[1:4])} does not match the conv geometry")
     d.k_splits = k_splits
-    dw = torch.zeros((Co, kd * kh * kw * Ci), device=x.device, dtype=torch.float32)
+    dw = zeros((Co, kd * kh * kw * Ci), x.device)
     d.x, d.dout, d.dw = x.data_ptr(), dout.data_ptr(), dw.data_ptr()
     L.check(L.lib().vb200_conv3d_wgrad_kh3(C.byref(d), L.stream_ptr()), "vb200_conv3d_wgrad_kh3")
     return dw
@@ -559,7 +604,7 @@ def colreduce(x, mode, arena=None, width=None, pivot=None):
     B, R, ld = x.shape
     Cc = ld if width is None else width
     shape = (2, B, Cc) if mode == 2 else (B, Cc)
-    out = arena.take(*shape) if arena is not None else torch.zeros(shape, device=x.device, dtype=torch.float32)
+    out = arena.take(*shape) if arena is not None else zeros(shape, x.device)
     _call("vb200_colreduce_ld", _p(x), _p(out), B, C.c_int64(R), Cc, C.c_int64(ld), mode,
           _p(None if pivot is None else _f32(pivot, "pivot")), L.dtype_code(x.dtype))
     return out
@@ -575,16 +620,17 @@ def grn_pack_w2(w2, s, dtype):
 
 
 def grn_prepare(sumsq, gw, gb, w2, b2, dtype, eps=1e-6):
-    """-> (s [nb,C4] fp32, w2s [nb*C, C4] 16-bit, b2eff [C] fp32): GRN coefficients, per-sample scaled fc2 weights and
-    the effective bias in one launch."""
+    """-> (s [nb,C4] fp32, w2s [nb*C, C4] 16-bit, b2eff [C] fp32): GRN coefficients (one short launch, grid = samples x
+    column chunks), then per-sample scaled fc2 weights + effective bias in one launch.  (The single-launch variant
+    `vb200_grn_prepare2` recomputes the coefficients in every block: measured 2-4x slower, kept for reference.)"""
     nb, C4 = sumsq.shape
     Cc = w2.shape[0]
     s = torch.empty_like(sumsq)
+    _call("vb200_grn_coef_fwd", _p(_f32(sumsq, "sumsq")), _p(_f32(gw, "grn.weight")), _p(s), nb, C4, C.c_float(eps))
     w2s = torch.empty((nb * Cc, C4), device=w2.device, dtype=dtype)
     b2e = torch.empty((Cc,), device=w2.device, dtype=torch.float32)
-    _call("vb200_grn_prepare2", _p(_f32(sumsq, "sumsq")), _p(_f32(gw, "grn.weight")), _p(_f32(gb, "grn.bias")),
-          _p(_f32(w2, "w2")), _p(_f32(b2, "b2")), _p(s), _p(w2s), _p(b2e), nb, Cc, C4, C.c_float(eps),
-          L.dtype_code(dtype))
+    _call("vb200_grn_prepare", _p(s), _p(_f32(gb, "grn.bias")), _p(_f32(w2, "w2")), _p(_f32(b2, "b2")), _p(w2s), _p(b2e),
+          nb, Cc, C4, L.dtype_code(dtype))
     return s, w2s, b2e
 
 
@@ -601,7 +647,7 @@ def grn_wgrad_finish(P, w2, s, bgrn, db2, arena=None):
     nb, Cc, ldp = P.shape
     C4 = w2.shape[1]
     dW2 = torch.empty((Cc, C4), device=P.device, dtype=torch.float32)
-    acc = arena.take(nb + 1, C4) if arena is not None else torch.zeros((nb + 1, C4), device=P.device, dtype=torch.float32)
+    acc = arena.take(nb + 1, C4) if arena is not None else zeros((nb + 1, C4), P.device)
     db2_out = None
     if db2 is None:
         db2_out = torch.empty((Cc,), device=P.device, dtype=torch.float32)
@@ -646,7 +692,7 @@ def conv3d_k3_wgrad(u, dz, padding):
     N, D, H, W, cin = u.shape
     Co = dz.shape[-1]
     pd, ph, pw = padding
-    dw = torch.zeros((Co, 9, 3, 8), device=u.device, dtype=torch.float32)
+    dw = zeros((Co, 9, 3, 8), u.device)
     g = (C.c_int32 * 7)(N, D, H, W, pd, ph, pw)
     _call("vb200_conv3d_k3_wgrad", _p(_act(u, "u")), _p(_act(dz, "dz")), _p(dw), g, cin, Co, L.dtype_code(u.dtype))
     # [co, (kd,kh), kw, ci] -> [co, ci, kd, kh, kw]
@@ -721,7 +767,7 @@ def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training):
     Cc = x.shape[-1]
     M = x.numel() // Cc
     dt = L.dtype_code(x.dtype)
-    s = torch.zeros((2, Cc), device=x.device, dtype=torch.float32)
+    s = zeros((2, Cc), x.device)
     _call("vb200_bn_bwd_reduce", _p(_act(dy, "dy")), _p(x), _p(y), _p(mean), _p(rstd), _p(s[0]), _p(s[1]),
           C.c_int64(M), Cc, int(relu), dt)
     g = (gamma * rstd).contiguous()

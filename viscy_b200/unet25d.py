@@ -240,6 +240,7 @@ class Unet25d(nn.Module):
     def _forward_sm100(self, x: Tensor) -> Tensor:
         dt = resolve_compute_dtype(x, self.compute_dtype)
         F.ops.ACTIVE_PACKS = None  # weight packs are scoped to the model that registered them
+        F.ops.STEP.begin(x.device, torch.is_grad_enabled())  # one zero-filled allocation for the step's accumulators
         with torch.autocast("cuda", enabled=False):
             h = F.to_channels_last_3d(x, dt)
             skips = []

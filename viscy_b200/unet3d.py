@@ -209,6 +209,7 @@ class UNet3DBase(nn.Module):
             raise NotImplementedError(f"sm_100a UNet3DBase: bottleneck {type(self.bottleneck).__name__}")
         dt = resolve_compute_dtype(x, self.compute_dtype)
         F.ops.ACTIVE_PACKS = None  # weight packs are scoped to the model that registered them
+        F.ops.STEP.begin(x.device, torch.is_grad_enabled())  # one zero-filled allocation for the step's accumulators
         with torch.autocast("cuda", enabled=False):
             h = F.conv3d_cl(F.to_channels_last_3d(x, dt), self.inconv)
             if self._cond_inconv is not None and cond is not None:

@@ -129,6 +129,8 @@ class UNeXt2(nn.Module):
     def _forward_sm100(self, x: Tensor) -> Tensor:
         dt = resolve_compute_dtype(x, self.compute_dtype)
         self._weight_packs(dt)
+        from . import ops
+        ops.STEP.begin(x.device, torch.is_grad_enabled())  # one zero-filled allocation for the step's accumulators
         n = self.batch_streams
         with torch.autocast("cuda", enabled=False):
             if n <= 1 or x.shape[0] < n or x.shape[0] % n:

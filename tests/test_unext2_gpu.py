@@ -109,8 +109,11 @@ def test_unext2_full_config_step(cuda):
     torch.cuda.synchronize()
     assert out.shape == (8, 2, 21, 256, 256)
     e = rel(out.float().cpu(), ref.cpu())
-    print(f"\nfull-config forward rel-L2 vs fp32 oracle: {e:.3e}; loss {loss.item():.6f} vs {ref_loss:.6f}")
-    assert e < 8e-3
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):  # the yardstick: stock autocast on the same oracle
+        stock = torch.cat([o(x[i:i + 2]) for i in range(0, 8, 2)]).float()
+    es = rel(stock.cpu(), ref.cpu())
+    print(f"\nfull-config forward rel-L2 vs fp32 oracle: {e:.3e} (stock autocast {es:.3e}); loss {loss.item():.6f} vs {ref_loss:.6f}")
+    assert e <= 1.5 * es + 2e-4 and e < 1.2e-2
     assert abs(loss.item() - ref_loss) < 2e-3 * abs(ref_loss)
     assert torch.equal(outs[0], outs[1])  # deterministic forward
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())

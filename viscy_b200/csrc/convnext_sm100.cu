@@ -750,7 +750,7 @@ colreduce8_kernel(const uint4* __restrict__ x, float* __restrict__ out, float* _
     float pv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) pv[k] = pivot != nullptr ? __ldg(pivot + c8 * 8 + k) : 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = r0 + ry; r < r1; r += RL) {
       const uint4 q = __ldg(xp + (long long)r * ld8);
       const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
@@ -939,9 +939,9 @@ grn_wgrad_finish_kernel(const float* __restrict__ P, const float* __restrict__ W
   const float bg = bgrn[k];
   float dbg = 0.f;
   const long long per = (long long)C * ldp;
-#pragma unroll 2
+#pragma unroll 4
   for (int j = j0; j < j1; ++j) {
-    const float w = W2[(long long)j * C4 + k];
+    const float w = __ldg(W2 + (long long)j * C4 + k);
     float d = 0.f;
     if (db2_in != nullptr) {
       d = db2_in[j];

@@ -42,15 +42,30 @@ struct Geom {
 template <int COLS>
 __device__ __forceinline__ void fill_tile(uint32_t dst, const uint4* __restrict__ src, int n, int h_first, int w_first,
                                           int rows, int H, int W, int C8, int chunk) {
-  const int total = rows * COLS * 8;
-  for (int id = threadIdx.x; id < total; id += NWARP * 32) {
-    const int part = id & 7, pix = id >> 3;
-    const int r = pix / COLS, c = pix - r * COLS;
+  // 128 threads = 16 pixels x 8 parts per step: the thread keeps its part and walks pixels 16 apart with a carry from the
+  // column into the row (no divisions in the loop)
+  constexpr int STEP = NWARP * 32 / 8;
+  const int part = threadIdx.x & 7;
+  const int c8 = chunk * 8 + part;
+  const bool cok = c8 < C8;
+  int pix = threadIdx.x >> 3;
+  int r = pix / COLS, c = pix - r * COLS;
+  const int total = rows * COLS;
+  uint32_t d = dst + threadIdx.x * 16;
+  const uint4* rowp = src + ((long long)(n * H + h_first + r) * W + w_first) * C8 + c8;
+  for (; pix < total; pix += STEP) {
     const int ih = h_first + r, iw = w_first + c;
-    const int c8 = chunk * 8 + part;
-    const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W && c8 < C8;
-    const uint4* p = ok ? src + ((long long)(n * H + ih) * W + iw) * C8 + c8 : src;
-    cp_async_16(dst + id * 16, p, ok ? 16u : 0u);
+    const bool ok = cok && ih >= 0 && ih < H && iw >= 0 && iw < W;
+    cp_async_16(d, ok ? rowp + (long long)c * C8 : src, ok ? 16u : 0u);
+    d += STEP * 8 * 16;
+    c += STEP;
+#pragma unroll
+    for (int k = 0; k < (STEP + COLS - 1) / COLS; ++k)  // carries: one for the wide tiles, up to four for 4-column tiles
+      if (c >= COLS) {
+        c -= COLS;
+        ++r;
+        rowp += (long long)W * C8;
+      }
   }
 }
 
@@ -109,27 +124,15 @@ dwconv7_tile_kernel(const uint4* __restrict__ x, const float* __restrict__ wt, c
 #pragma unroll
         for (int j = 0; j < TW + 6; ++j) in[j] = H16<BF16>::unpack(srow[(ir * TC + j) * 32]);
         // output row o = ir - kh is fed through filter row kh; its ring slot o % 7 = (p - kh) mod 7 is static
-        if (ir >= 6 && ir < rs) {
-          // interior row: all seven filter rows land on live output rows.  kw outermost: the 28 accumulators of a kw
-          // step are independent, so consecutive FFMA2 never wait on each other
 #pragma unroll
-          for (int kw = 0; kw < 7; ++kw)
+        for (int kh = 0; kh < 7; ++kh) {
+          const int o = ir - kh;
+          if (o >= 0 && o < rs) {  // warp-uniform: edge rows skip the filter rows that fall outside the strip
 #pragma unroll
-            for (int kh = 0; kh < 7; ++kh)
+            for (int kw = 0; kw < 7; ++kw)
 #pragma unroll
               for (int j = 0; j < TW; ++j)
                 acc[(p - kh + 7) % 7][j] = __ffma2_rn(in[j + kw], wreg[kh * 7 + kw], acc[(p - kh + 7) % 7][j]);
-        } else {
-#pragma unroll
-          for (int kh = 0; kh < 7; ++kh) {
-            const int o = ir - kh;
-            if (o >= 0 && o < rs) {
-#pragma unroll
-              for (int kw = 0; kw < 7; ++kw)
-#pragma unroll
-                for (int j = 0; j < TW; ++j)
-                  acc[(p - kh + 7) % 7][j] = __ffma2_rn(in[j + kw], wreg[kh * 7 + kw], acc[(p - kh + 7) % 7][j]);
-            }
           }
         }
         const int o = ir - 6;  // this row received its last filter row: store it, recycle the slot
@@ -200,27 +203,17 @@ dwconv7_wgrad_tile_kernel(const uint4* __restrict__ x, const uint4* __restrict__
               bsum = __fadd2_rn(bsum, gr[p][j]);
             }
           }
-          // dy row o = ir - kh pairs with this x row through filter row kh.  j outermost: the accumulators touched by
-          // consecutive FFMA2 are all different (49 on interior rows, 7 per filter row on the edge rows)
-          if (ir >= 6 && ir < rs) {
+          // dy row o = ir - kh pairs with this x row through filter row kh; j outermost: the seven accumulators of a
+          // filter row touched by consecutive FFMA2 are all different
 #pragma unroll
-            for (int j = 0; j < TW; ++j)
+          for (int kh = 0; kh < 7; ++kh) {
+            const int o = ir - kh;
+            if (o >= 0 && o < rs) {
 #pragma unroll
-              for (int kh = 0; kh < 7; ++kh)
+              for (int j = 0; j < TW; ++j)
 #pragma unroll
                 for (int kw = 0; kw < 7; ++kw)
                   acc[kh * 7 + kw] = __ffma2_rn(gr[(p - kh + 7) % 7][j], in[j + kw], acc[kh * 7 + kw]);
-          } else {
-#pragma unroll
-            for (int kh = 0; kh < 7; ++kh) {
-              const int o = ir - kh;
-              if (o >= 0 && o < rs) {
-#pragma unroll
-                for (int j = 0; j < TW; ++j)
-#pragma unroll
-                  for (int kw = 0; kw < 7; ++kw)
-                    acc[kh * 7 + kw] = __ffma2_rn(gr[(p - kh + 7) % 7][j], in[j + kw], acc[kh * 7 + kw]);
-              }
             }
           }
         }

@@ -270,7 +270,7 @@ head_tail_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
 //         dW1 = dt^T act runs on the tensor cores (MN-major tcgen05 GEMM).
 // MODE 1: dz = rstd * (dpre - sdp/R - xhat * sdpx/R), dbz[c] += sum dz
 template <bool BF16, int MODE, int MAXO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ alpha, int alpha_n, const float* __restrict__ W1,
                      const uint16_t* __restrict__ dout, float* __restrict__ sdp, float* __restrict__ sdpx,
@@ -320,6 +320,7 @@ head_tail_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ mean
 #pragma unroll
   for (int o = 0; o < MAXO; ++o) accb[o] = 0.f;
 
+#pragma unroll 2
   for (int row = r0 + rl; row < r1; row += rstep) {
     const int dzi = row / HW;
     const int rem = row - dzi * HW;

@@ -201,6 +201,19 @@ int vb200_grn_prepare2(const float* sumsq, const float* gw, const float* gb, con
                        float* s_out, void* w2s, float* b2e, int nb, int C, int C4, float eps, int dtype,
                        vb200_stream_t stream);
 
+/* ---- GroupNorm (+ timestep scale / shift) + activation on rows [N, R, C] (VM/unet/blocks.py:88-113 with the UNet3DBase
+ * defaults norm="group", activation="silu", VM/unet/unet3d_base.py:58-72).  Statistics come from vb200_colreduce (mode 2,
+ * per sample); the per-(sample, channel) coefficients are formed by the caller:
+ *   y = act(a[n,c] * x + b[n,c]),  act: 0 none, 1 ReLU, 2 SiLU
+ *   backward: dv = dy * act'(a x + b);  s1[n,c] += sum_r dv, s2[n,c] += sum_r dv * x  (pre-zeroed);
+ *             dx = c1 * dv + c2 * x + c3 with coef = five fp32 [N, C] planes (a, b, c1, c2, c3) ---- */
+int vb200_affine_nc_act(const void* x, const float* a, const float* b, void* y, int64_t N, int64_t R, int C, int act,
+                        int dtype, vb200_stream_t stream);
+int vb200_gn_bwd_reduce(const void* dy, const void* x, const float* a, const float* b, float* s1, float* s2, int64_t N,
+                        int64_t R, int C, int act, int dtype, vb200_stream_t stream);
+int vb200_gn_bwd_apply(const void* dy, const void* x, const float* coef, void* dx, int64_t N, int64_t R, int C, int act,
+                       int dtype, vb200_stream_t stream);
+
 /* out[c] += sum_rows x[r][c]  (bias gradients; out pre-zeroed) */
 int vb200_colsum(const void* x, float* out, int64_t M, int C, int dtype, vb200_stream_t stream);
 

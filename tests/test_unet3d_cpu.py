@@ -60,3 +60,20 @@ def test_unet25d_unsupported_configs_raise_on_cuda():
     blk = ConvBlock3D(16, 16, norm="instance").cuda()
     with pytest.raises(NotImplementedError):
         blk.forward_cl(torch.randn(1, 4, 8, 8, 16, device="cuda").half())
+
+
+@pytest.mark.parametrize("name", ["unet3d_base_gn", "unet3d_base_gn_odd"])
+def test_unet3d_base_groupnorm_cpu_matches_reference_golden(name):
+    """UNet3DBase with the class defaults (GroupNorm + SiLU), residual blocks, timestep + conditioning inputs: the host
+    mirror against vectors from the reference's own code (tests/golden/make_golden_unet3d_base.py)."""
+    g = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    cfg = g["cfg"]
+    bott = ConvBottleneck3D(cfg["dims"][-1], time_emb_dim=g["time_embed_dim"], residual=True, groups=cfg["groups"])
+    m = UNet3DBase(bottleneck=bott, time_embed_dim=g["time_embed_dim"], cond_channels=g["cond_channels"], **cfg)
+    assert list(m.state_dict()) == list(g["state_dict"])
+    m.load_state_dict(g["state_dict"])
+    out = m(g["x"], g["cond"], g["t"])
+    torch.testing.assert_close(out, g["out"], rtol=1e-5, atol=1e-6)
+    torch.nn.functional.mse_loss(out, g["target"]).backward()
+    for n, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, g["grads"][n], rtol=1e-4, atol=1e-6, msg=n)

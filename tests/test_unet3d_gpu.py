@@ -125,3 +125,72 @@ def test_boundary_convs_3_to_32_and_32_to_3(cuda):
         y.backward(dyc)
         assert rel(xc.grad.permute(0, 4, 1, 2, 3)[:, :cin], gx) < 2e-3
         assert rel(conv.weight.grad, gw) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,R,C,G,act,cond", [(2, 300, 32, 8, "silu", True), (1, 4096, 64, 8, "silu", False),
+                                               (3, 77, 16, 4, "relu", True), (2, 128, 12, 4, "silu", True)])
+def test_groupnorm_scale_shift_act_vs_torch(cuda, N, R, C, G, act, cond, dtype):
+    """GroupNorm -> * (scale + 1) + shift -> SiLU | ReLU on channels-last rows vs plain torch ops (fp32) on the same
+    16-bit input: forward, input gradient and the gradients of gamma, beta, scale, shift."""
+    from viscy_b200 import functional as VF
+    torch.manual_seed(N + R + C)
+    gn = torch.nn.GroupNorm(G, C).to(cuda)
+    with torch.no_grad():
+        gn.weight.normal_(1.0, 0.3)
+        gn.bias.normal_(0.0, 0.3)
+    Cp = -(-C // 8) * 8
+    x = torch.zeros(N, 1, R, 1, Cp, device=cuda, dtype=dtype)  # [N, D, H, W, Cp], padded channels stay zero
+    x[..., :C] = (torch.randn(N, 1, R, 1, C, device=cuda) * 1.5 + 0.3).to(dtype)
+    scale = (torch.randn(N, C, device=cuda) * 0.3).requires_grad_(True) if cond else None
+    shift = (torch.randn(N, C, device=cuda) * 0.3).requires_grad_(True) if cond else None
+    dy = torch.zeros_like(x)
+    dy[..., :C] = torch.randn(N, 1, R, 1, C, device=cuda).to(dtype)
+    xm = x.clone().requires_grad_(True)
+    y = VF.groupnorm_act_cl(xm, gn, act, scale, shift)
+    y.backward(dy)
+    got = dict(dx=xm.grad[..., :C].float(), dg=gn.weight.grad.clone(), db=gn.bias.grad.clone(),
+               ds=None if scale is None else scale.grad.clone(), dt=None if shift is None else shift.grad.clone())
+    gn.zero_grad()
+    xr = x[..., :C].float().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)  # NCDHW
+    sr = None if scale is None else scale.detach().clone().requires_grad_(True)
+    tr = None if shift is None else shift.detach().clone().requires_grad_(True)
+    h = gn(xr)
+    if cond:
+        h = h * (sr[:, :, None, None, None] + 1) + tr[:, :, None, None, None]
+    ref = F.silu(h) if act == "silu" else F.relu(h)
+    ref.backward(dy[..., :C].float().permute(0, 4, 1, 2, 3))
+    tol = 8e-3 if dtype == torch.bfloat16 else 1.5e-3
+    assert rel(y[..., :C].float().permute(0, 4, 1, 2, 3), ref) < tol
+    assert (y[..., C:] == 0).all()
+    assert rel(got["dx"].permute(0, 4, 1, 2, 3), xr.grad) < tol
+    assert rel(got["dg"], gn.weight.grad) < 2e-3 and rel(got["db"], gn.bias.grad) < 2e-3
+    if cond:
+        assert rel(got["ds"], sr.grad) < 2e-3 and rel(got["dt"], tr.grad) < 2e-3
+
+
+@pytest.mark.parametrize("name", ["unet3d_base_gn", "unet3d_base_gn_odd"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 4e-3), (torch.bfloat16, 3e-2)])
+def test_unet3d_base_groupnorm_silu_timestep_golden(cuda, name, dtype, tol):
+    """UNet3DBase with the reference's class defaults (GroupNorm + SiLU), residual blocks, timestep scale / shift and a
+    conditioning input through the sm_100a kernels vs vectors from the reference's own code."""
+    from viscy_b200 import UNet3DBase
+    from viscy_b200.unet3d import ConvBottleneck3D
+    g = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    cfg = g["cfg"]
+    bott = ConvBottleneck3D(cfg["dims"][-1], time_emb_dim=g["time_embed_dim"], residual=True, groups=cfg["groups"])
+    m = UNet3DBase(bottleneck=bott, time_embed_dim=g["time_embed_dim"], cond_channels=g["cond_channels"], **cfg)
+    m.load_state_dict(g["state_dict"])
+    m = m.to(cuda)
+    dev = lambda v: None if v is None else v.to(cuda)  # noqa: E731
+    with torch.autocast("cuda", dtype=dtype):
+        out = m(dev(g["x"]), dev(g["cond"]), dev(g["t"]))
+        loss = F.mse_loss(out.float(), g["target"].to(cuda))
+    scale = 1024.0 if dtype == torch.float16 else 1.0
+    (loss * scale).backward()
+    e = rel(out.float().cpu(), g["out"])
+    print(f"\n[{name} {dtype}] forward rel-L2 vs reference golden {e:.3e}")
+    assert out.shape == g["out"].shape and e < tol
+    worst = max((rel(p.grad.cpu() / scale, g["grads"][n]), n) for n, p in m.named_parameters() if g["grads"][n].norm() > 1e-6)
+    print("worst gradient:", worst)
+    assert worst[0] < 12 * tol

@@ -913,6 +913,69 @@ def batchnorm_act_cl(x, bn, relu):
     return y
 
 
+class GroupNormActFn(Function):
+    """nn.GroupNorm -> [* (scale + 1) + shift] -> SiLU | ReLU | identity on channels-last rows [N, D, H, W, Cp]
+    (VM/unet/blocks.py:107-113).  Statistics per (sample, group) from one column-reduction pass; the elementwise
+    passes take per-(sample, channel) coefficients (see csrc/groupnorm_sm100.cu).  Channel padding (Cp > C) stays zero."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, eps, scale, shift, act):
+        N, Cp = x.shape[0], x.shape[-1]
+        Cn = weight.numel()
+        R = x.numel() // (N * Cp)
+        cg = Cn // groups
+        st = ops.colreduce(x.view(N, R, Cp), 2)[:, :, :Cn].reshape(2, N, groups, cg).sum(-1) / (R * cg)
+        mean = st[0]
+        rstd = torch.rsqrt((st[1] - mean * mean).clamp_min_(0.0) + eps)  # [N, G]
+        mean_c = mean.repeat_interleave(cg, dim=1)  # [N, C]
+        rstd_c = rstd.repeat_interleave(cg, dim=1)
+        s1p = 1.0 if scale is None else (scale.detach().float() + 1.0)
+        w = weight.detach() * s1p * torch.ones_like(rstd_c)  # gamma (1 + scale)   [N, C]
+        a = rstd_c * w
+        b = (bias.detach() * s1p - mean_c * a) + (0.0 if shift is None else shift.detach().float())
+        if Cp != Cn:
+            a, b = torch.nn.functional.pad(a, (0, Cp - Cn)), torch.nn.functional.pad(b, (0, Cp - Cn))
+        a, b = a.contiguous(), b.contiguous()
+        y = ops.affine_nc_act(x, a, b, act)
+        ctx.save_for_backward(x, a, b, mean_c, rstd_c, w, weight, bias, scale)
+        ctx.meta = (groups, act, Cn, shift is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, a, b, mean_c, rstd_c, w, weight, bias, scale = ctx.saved_tensors
+        groups, act, Cn, has_shift = ctx.meta
+        N, Cp = x.shape[0], x.shape[-1]
+        R = x.numel() // (N * Cp)
+        cg = Cn // groups
+        dy = dy.contiguous()
+        S1, S2 = ops.gn_bwd_reduce(dy, x, a, b, act)
+        S1, S2 = S1[:, :Cn], S2[:, :Cn]
+        S2h = rstd_c * (S2 - mean_c * S1)  # sum_r dv * xhat
+        cnt = float(R * cg)
+        m1 = (w * S1).view(N, groups, cg).sum(-1, keepdim=True).expand(N, groups, cg).reshape(N, Cn) / cnt
+        m2 = (w * S2h).view(N, groups, cg).sum(-1, keepdim=True).expand(N, groups, cg).reshape(N, Cn) / cnt
+        c1 = rstd_c * w
+        c2 = -rstd_c * rstd_c * m2
+        c3 = -rstd_c * m1 - c2 * mean_c
+        coef = torch.stack([a[:, :Cn], b[:, :Cn], c1, c2, c3])
+        if Cp != Cn:
+            coef = torch.nn.functional.pad(coef, (0, Cp - Cn))
+        dx = ops.gn_bwd_apply(dy, x, coef.contiguous(), act)
+        s1p = 1.0 if scale is None else (scale.float() + 1.0)
+        dgamma = (s1p * S2h).sum(0)
+        dbeta = (s1p * S1).sum(0)
+        dscale = (weight * S2h + bias * S1).to(scale.dtype) if scale is not None else None
+        dshift = S1.clone() if has_shift else None
+        return dx, dgamma, dbeta, None, None, dscale, dshift, None
+
+
+def groupnorm_act_cl(x, gn, act: str, scale=None, shift=None):
+    """gn: nn.GroupNorm; scale / shift: [N, C] timestep conditioning or None; act: "silu" | "relu" | "none"."""
+    return GroupNormActFn.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps, scale, shift, act)
+
+
 class Cat2Fn(Function):
     @staticmethod
     def forward(ctx, a, b):

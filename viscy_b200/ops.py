@@ -778,6 +778,40 @@ def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training):
     return dx, s[1], s[0]
 
 
+ACT_CODES = {"none": 0, "relu": 1, "silu": 2}
+
+
+def affine_nc_act(x, a, b, act: str):
+    """y = act(a[n,c] * x + b[n,c]) on rows [N, ..., C] (a, b fp32 [N, C])."""
+    _act(x, "x")
+    N, Cc = x.shape[0], x.shape[-1]
+    R = x.numel() // (N * Cc)
+    y = torch.empty_like(x)
+    _call("vb200_affine_nc_act", _p(x), _p(_f32(a, "a")), _p(_f32(b, "b")), _p(y), C.c_int64(N), C.c_int64(R), Cc,
+          ACT_CODES[act], L.dtype_code(x.dtype))
+    return y
+
+
+def gn_bwd_reduce(dy, x, a, b, act: str):
+    """-> (S1, S2) fp32 [N, C]: sums over rows of dv and dv * x, dv = dy * act'(a x + b)."""
+    N, Cc = x.shape[0], x.shape[-1]
+    R = x.numel() // (N * Cc)
+    s = zeros((2, N, Cc), x.device)
+    _call("vb200_gn_bwd_reduce", _p(_act(dy, "dy")), _p(_act(x, "x")), _p(_f32(a, "a")), _p(_f32(b, "b")), _p(s[0]), _p(s[1]),
+          C.c_int64(N), C.c_int64(R), Cc, ACT_CODES[act], L.dtype_code(x.dtype))
+    return s[0], s[1]
+
+
+def gn_bwd_apply(dy, x, coef, act: str):
+    """dx = c1 * dv + c2 * x + c3; coef fp32 [5, N, C] = (a, b, c1, c2, c3)."""
+    N, Cc = x.shape[0], x.shape[-1]
+    R = x.numel() // (N * Cc)
+    dx = torch.empty_like(x)
+    _call("vb200_gn_bwd_apply", _p(_act(dy, "dy")), _p(_act(x, "x")), _p(_f32(coef, "coef")), _p(dx), C.c_int64(N),
+          C.c_int64(R), Cc, ACT_CODES[act], L.dtype_code(x.dtype))
+    return dx
+
+
 def cat2(a, b):
     _act(a, "a"), _act(b, "b")
     Ca, Cb = a.shape[-1], b.shape[-1]

@@ -2,8 +2,8 @@
 VM/unet/blocks.py:62-292) with the reference constructor / forward / state_dict surface.
 
 CPU tensors: plain torch ops.  CUDA tensors: channels-last 16-bit activations through the sm_100a kernels
-(`functional.conv3d` lowering on the tcgen05 GEMM, fused BatchNorm+ReLU kernels) for the BatchNorm/ReLU family
-(the `Unet3d` preset, BASELINE config 5); GroupNorm/SiLU and timestep conditioning raise NotImplementedError there.
+(`functional.conv3d` lowering on the tcgen05 GEMM; fused BatchNorm+ReLU kernels for the `Unet3d` preset, BASELINE
+config 5; GroupNorm + timestep scale/shift + SiLU kernels for the class defaults, csrc/groupnorm_sm100.cu).
 """
 
 from __future__ import annotations
@@ -51,10 +51,15 @@ class Block(nn.Module):
             x = x * (scale + 1) + shift
         return self.act(x)
 
-    def forward_cl(self, x: Tensor) -> Tensor:
-        if not isinstance(self.norm, nn.BatchNorm3d) or not isinstance(self.act, nn.ReLU):
-            raise NotImplementedError("sm_100a Block: BatchNorm3d + ReLU only (GroupNorm / SiLU are next-round work)")
-        return F.batchnorm_act_cl(F.conv3d_cl(x, self.proj), self.norm, relu=True)
+    def forward_cl(self, x: Tensor, scale_shift: tuple[Tensor, Tensor] | None = None) -> Tensor:
+        h = F.conv3d_cl(x, self.proj)
+        act = "silu" if isinstance(self.act, nn.SiLU) else "relu"
+        if isinstance(self.norm, nn.GroupNorm):
+            scale, shift = scale_shift if scale_shift is not None else (None, None)
+            return F.groupnorm_act_cl(h, self.norm, act, scale, shift)
+        if scale_shift is not None or act != "relu":
+            raise NotImplementedError("sm_100a Block: BatchNorm3d comes with ReLU and without timestep conditioning")
+        return F.batchnorm_act_cl(h, self.norm, relu=True)
 
 
 class ResnetBlock(nn.Module):
@@ -77,9 +82,11 @@ class ResnetBlock(nn.Module):
         return h if self.res_conv is None else h + self.res_conv(x)
 
     def forward_cl(self, x: Tensor, time_emb: Tensor | None = None) -> Tensor:
-        if time_emb is not None and self.mlp is not None:
-            raise NotImplementedError("sm_100a ResnetBlock: timestep conditioning")
-        h = self.block2.forward_cl(self.block1.forward_cl(x))
+        scale_shift = None
+        if self.mlp is not None and time_emb is not None:
+            # [N, 2 C] timestep projection (a few KFLOP): plain fp32 torch ops; only its (scale, shift) enter the kernels
+            scale_shift = self.mlp(time_emb.float()).chunk(2, dim=1)
+        h = self.block2.forward_cl(self.block1.forward_cl(x, scale_shift))
         if self.res_conv is None:
             return h
         r = x if isinstance(self.res_conv, nn.Identity) else F.conv3d_cl(x, self.res_conv)
@@ -203,30 +210,30 @@ class UNet3DBase(nn.Module):
         return self.outconv(h)
 
     def _forward_sm100(self, x: Tensor, cond: Tensor | None, t: Tensor | None) -> Tensor:
-        if t is not None and self._time_embedder is not None:
-            raise NotImplementedError("sm_100a UNet3DBase: timestep conditioning")
         if not hasattr(self.bottleneck, "forward_cl"):
             raise NotImplementedError(f"sm_100a UNet3DBase: bottleneck {type(self.bottleneck).__name__}")
         dt = resolve_compute_dtype(x, self.compute_dtype)
         F.ops.ACTIVE_PACKS = None  # weight packs are scoped to the model that registered them
         F.ops.STEP.begin(x.device, torch.is_grad_enabled())  # one zero-filled allocation for the step's accumulators
         with torch.autocast("cuda", enabled=False):
+            # timestep embedding: sinusoid + 2-layer MLP on [N] scalars (fp32 torch ops; negligible work)
+            te = self._time_embedder(t) if (self._time_embedder is not None and t is not None) else None
             h = F.conv3d_cl(F.to_channels_last_3d(x, dt), self.inconv)
             if self._cond_inconv is not None and cond is not None:
                 h = F.add_cl(h, F.conv3d_cl(F.to_channels_last_3d(cond, dt), self._cond_inconv))
             skips: list[Tensor] = []
             for blocks, down in zip(self._encoder_blocks, self._downsamples):
                 for blk in blocks:
-                    h = blk.forward_cl(h)
+                    h = blk.forward_cl(h, te)
                     skips.append((h, down.in_channels))
                 h = F.conv3d_cl(h, down)
-            h = self.bottleneck.forward_cl(h)
+            h = self.bottleneck.forward_cl(h, te)
             for up, blocks in zip(self._upsamples, self._decoder_blocks):
                 h = F.conv_transpose3d_cl(h, up)
                 ch = up.out_channels
                 for blk in blocks:
                     skip, cs = skips.pop()
-                    h = blk.forward_cl(F.cat_cl(h, skip, ch, cs))  # real channel counts: rows are padded to 8
+                    h = blk.forward_cl(F.cat_cl(h, skip, ch, cs), te)  # real channel counts: rows are padded to 8
             return F.from_channels_last_3d(F.conv3d_cl(h, self.outconv), self.outconv.out_channels)
 
 

@@ -143,60 +143,105 @@ def _event_ms(fn, reps, warm):
     return e0.elapsed_time(e1) / reps
 
 
-def secondary_evidence(dev, tf_sus):
-    """3-D conv blocks of BASELINE config 5 through the implicit-GEMM kernels (forward launch of each level of
-    Unet3d(3,3,4,32) at 128^3, fp16; algorithmic FLOP = 2 * voxels * 27 * Cin * Cout) and one eager training step of
-    configs 5 and 4.  Reported next to the headline, never mixed into it."""
+def _graphed_ms(step_fn, inputs, reps, warm):
+    """ms per step of `step_fn` replayed as one CUDA graph (eager when capture fails; says which)."""
+    from viscy_b200.graphs import GraphedStep
+    try:
+        gs = GraphedStep(step_fn, inputs, warmup=3)
+        return _event_ms(gs.replay, reps, warm), "CUDA graph replay", gs.launches_per_replay
+    except Exception as exc:  # evidence only
+        torch.cuda.synchronize()
+        return _event_ms(lambda: step_fn(*inputs), reps, warm), f"eager ({type(exc).__name__}: {exc})"[:160], None
+
+
+def secondary_evidence(dev, tf_burst):
+    """Evidence next to the headline, never mixed into it:
+      * the 3-D conv blocks of BASELINE config 5 (Unet3d(3,3,4,32) at 128^3, fp16) through the implicit-GEMM kernels:
+        forward, data gradient and weight gradient of each level timed alone (algorithmic FLOP = 2 * voxels * 27 * Cin
+        * Cout per pass) against the BURST tensor peak (isolated launches);
+      * one training step of configs 5 and 4, replayed as CUDA graphs;
+      * the GPU incumbent: the reference math (oracle/models.py) on the same GPU under stock torch.autocast + cuDNN."""
     from viscy_b200 import ContrastiveEncoder, Unet3d, ops
+    from viscy_b200 import functional as VF
     from viscy_b200.loss import NTXentLoss
-    out = {"conv3d_igemm_fwd": {}}
+    out = {"conv3d_igemm": {}}
     g = torch.Generator(device=dev).manual_seed(11)
     for S, ci, co in ((128, 32, 32), (64, 64, 64), (32, 128, 128), (16, 256, 256)):
         x = torch.randn((1, S, S, S, ci), device=dev, generator=g).half()
-        w = (torch.randn((co, 27 * ci), device=dev, generator=g) * 0.02).half()
+        w32 = torch.randn((co, ci, 3, 3, 3), device=dev, generator=g) * 0.02
+        w = w32.permute(0, 2, 3, 4, 1).reshape(co, -1).contiguous().half()
+        wf = ops.cast_pack(VF._conv_weight_rows_flipped(w32, ci, co), torch.float16)
         y = torch.empty((1, S, S, S, co), device=dev, dtype=torch.float16)
-        ms = _event_ms(lambda: ops.conv3d_igemm(x, w, None, (3, 3, 3), (1, 1, 1), out=y), 10, 3)
-        tf = 2.0 * S ** 3 * 27 * ci * co / (ms * 1e-3) / 1e12
-        out["conv3d_igemm_fwd"][f"{ci}->{co}@{S}^3"] = {"ms": ms, "tflops": tf, "frac_of_sustained_tensor_peak": tf / tf_sus}
-        del x, w, y
+        dy = torch.randn((1, S, S, S, co), device=dev, generator=g).half()
+        dx = torch.empty_like(x)
+        flop = 2.0 * S ** 3 * 27 * ci * co
+        row = {}
+        row["fwd"] = _event_ms(lambda: ops.conv3d_igemm(x, w, None, (3, 3, 3), (1, 1, 1), out=y), 10, 3)
+        row["dgrad"] = _event_ms(lambda: ops.conv3d_igemm(dy, wf, None, (3, 3, 3), (1, 1, 1), out=dx), 10, 3)
+        if ops.conv3d_wgrad_kh3_supported((1, S, S, S, ci), co, (3, 3, 3), (1, 1, 1)) and ci <= 128:
+            row["wgrad"] = _event_ms(lambda: ops.conv3d_wgrad_kh3(x, dy, (3, 3, 3), (1, 1, 1)), 10, 3)
+        else:
+            row["wgrad"] = _event_ms(lambda: ops.conv3d_igemm_wgrad(x, dy, (3, 3, 3), (1, 1, 1)), 10, 3)
+        out["conv3d_igemm"][f"{ci}->{co}@{S}^3"] = {
+            k: {"ms": v, "tflops": flop / (v * 1e-3) / 1e12, "frac_of_burst_tensor_peak": flop / (v * 1e-3) / 1e12 / tf_burst}
+            for k, v in row.items()}
+        del x, w, wf, y, dy, dx
     torch.manual_seed(0)
     m = Unet3d(3, 3, 4, 32).to(dev)
-    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True, capturable=True)
+    scaler = torch.amp.GradScaler("cuda")
     x = torch.randn(1, 3, 128, 128, 128, device=dev)
     y = torch.randn(1, 3, 128, 128, 128, device=dev)
 
-    def step5():
+    def step5(xd, yd):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.float16):
-            loss = torch.nn.functional.mse_loss(m(x).float(), y)
-        loss.backward()
-        opt.step()
+            loss = torch.nn.functional.mse_loss(m(xd).float(), yd)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        return loss
 
-    ms = _event_ms(step5, 5, 2)
+    ms, mode, launches = _graphed_ms(step5, (x, y), 10, 3)
     out["config5_unet3d_128_fp16_b1"] = {"ms_per_step": ms, "samples_per_s": 1e3 / ms, "algorithmic_tflops": 3.696 / (ms * 1e-3),
-                                         "mode": "eager (no CUDA graph)"}
+                                         "frac_of_burst_tensor_peak": 3.696 / (ms * 1e-3) / tf_burst, "mode": mode,
+                                         "launches_per_step": launches, "amp": "fp16 autocast + GradScaler"}
     del m, opt, x, y
     torch.cuda.empty_cache()
     m = ContrastiveEncoder("convnext_tiny", in_channels=2, in_stack_depth=15).to(dev)
-    opt = torch.optim.AdamW(m.parameters(), lr=2e-4, fused=True)
+    opt = torch.optim.AdamW(m.parameters(), lr=2e-4, fused=True, capturable=True)
     a = torch.randn(64, 2, 15, 224, 224, device=dev)
     p = torch.randn(64, 2, 15, 224, 224, device=dev)
     labels = torch.cat([torch.arange(64), torch.arange(64)]).to(dev)
     crit = NTXentLoss(temperature=0.07)
 
-    def step4():
+    def step4(ad, pd):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            _, pa = m(a)
-            _, pp = m(p)
+            _, pa = m(ad)
+            _, pp = m(pd)
         loss = crit(torch.cat([pa, pp]).float(), labels)
         loss.backward()
         opt.step()
+        return loss
 
-    ms = _event_ms(step4, 5, 2)
+    ms, mode, launches = _graphed_ms(step4, (a, p), 10, 3)
     out["config4_contrastive_2x64_bf16"] = {"ms_per_step": ms, "samples_per_s": 128e3 / ms,
-                                            "algorithmic_tflops": 3.448 / (ms * 1e-3), "mode": "eager (no CUDA graph)"}
+                                            "algorithmic_tflops": 3.448 / (ms * 1e-3),
+                                            "frac_of_burst_tensor_peak": 3.448 / (ms * 1e-3) / tf_burst, "mode": mode,
+                                            "launches_per_step": launches}
     del m, opt, a, p
+    torch.cuda.empty_cache()
+    # the GPU incumbent (SURVEY.md 8d): the oracle is the thing MEASURED here (a baseline arm), never the product path
+    try:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import incumbent
+        out["incumbent_torch_cudnn"] = {"contiguous": incumbent.time_incumbent(BATCH, 256, 8, 3, False),
+                                        "channels_last": incumbent.time_incumbent(BATCH, 256, 8, 3, True),
+                                        "what": "oracle/models.py (reference composition over restated timm/monai) on this GPU, "
+                                                "torch.autocast(bf16) + cuDNN/cuBLAS, fused AdamW, eager; same config as the headline"}
+    except Exception as exc:
+        out["incumbent_torch_cudnn"] = {"error": f"{type(exc).__name__}: {exc}"}
     torch.cuda.empty_cache()
     return out
 
@@ -227,8 +272,8 @@ def run_gpu(args):
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         static_graph=True)
     elif ddp:
-        from viscy_b200.parallel import FlatGradAllReduce
-        exchange = FlatGradAllReduce(model.parameters())
+        from viscy_b200.parallel import BucketedGradAllReduce
+        exchange = BucketedGradAllReduce(model.parameters())
         exchange.broadcast_parameters(0)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=not args.no_graph)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -242,7 +287,7 @@ def run_gpu(args):
             loss = torch.nn.functional.mse_loss(out.float(), yd)
         loss.backward()
         if exchange is not None:
-            exchange()  # NCCL all-reduce (mean) of the flat fp32 gradient buffer
+            exchange.finish()  # buckets were all-reduced (NCCL, average) as backward produced them; join + hand back
         opt.step()
         return loss
 
@@ -342,12 +387,26 @@ def run_gpu(args):
         b_c4, b_c = rn(C4), rn(C)
         sv, tv = rn(BATCH, C4) * 0.1 + 1.0, rn(BATCH, C4) * 0.1
         o_c4a, o_c4b, o_c = torch.empty_like(a_c4), torch.empty_like(a_c4), torch.empty_like(a_c)
+        gbuf = torch.zeros((M, C4 + 8), device=dev, dtype=torch.bfloat16)  # [g | 1]: bias gradient as the extra column
+        gbuf[:, :C4] = a_c4
+        gbuf[:, C4] = 1
+        lbuf = torch.zeros((M, C + 8), device=dev, dtype=torch.bfloat16)
+        lbuf[:, :C] = a_c
+        lbuf[:, C] = 1
+        dw1, db1x = torch.zeros((C4, C), device=dev), torch.zeros((C4, 8), device=dev)
+        P = torch.empty((BATCH, C, C4 + 8), device=dev)
+        from viscy_b200.functional import _wgrad_splits
         calls = {
             "fc1+gelu": lambda: ops.gemm(a_c, w1, bias=b_c4, epilogue=LL.EPI_GELU_GP, out=o_c4a, out2=o_c4b),
             "fc2+residual": lambda: ops.gemm(a_c4, w2s, bias=b_c, residual=a_c, b_batch_rows=R, out=o_c),
             "dgrad_fc2+grn_gelu_bwd": lambda: ops.gemm(a_c, w2t, epilogue=LL.EPI_DGELU_GRN, aux=a_c4, aux2=o_c4b, tvec=tv,
                                                         svec=sv, rows_per_sample=R, out=o_c4a),
             "dgrad_fc1": lambda: ops.gemm(a_c4, w1t, out=o_c),
+            # the two weight gradients (MN-major, K = pixels): per-sample slabs dout^T [g | 1], and split-K dh^T [l | 1]
+            "wgrad_fc2_per_sample": lambda: ops.gemm(a_c, gbuf, mn_major=True, epilogue=LL.EPI_F32, k_splits=BATCH,
+                                                      split_slabs=True, out=P),
+            "wgrad_fc1": lambda: ops.gemm(a_c4, lbuf, mn_major=True, epilogue=LL.EPI_F32, k_splits=_wgrad_splits(C4, C + 8, M),
+                                           out=dw1, out2=db1x, n_split=C, accumulate=True),
         }
         per = {}
         reps = 10
@@ -365,13 +424,23 @@ def run_gpu(args):
         avg_ms = sum(per.values()) / len(per)
         flops = 2.0 * M * C * C4
         ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
-                # dram__bytes_read+write per launch, mean of the four launches, from the committed `ncu --set full`
-                # capture of these launches (profiles/r1_v7_gemm_dec2_ncu_summary.txt: 385 / 314 / 609 / 228 MB)
-                "traffic": 384.0e6,
-                "kernel": "gemm_kernel<256,K-major,*>: decoder-stage-2 GEMMs M=32768, 736<->2944 (142 GFLOP per launch)",
+        # dram bytes per launch (mean over these launches) from the committed `ncu --set full` capture of the same calls
+        traffic = None
+        tp = ROOT / "profiles" / "r2_gemm_dec2_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("mean_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
+                "traffic": traffic,
+                "kernel": "gemm_kernel<256,*>: the six decoder-stage-2 GEMMs of one ConvNeXt block (M = 32768 pixels, 736 <-> 2944: "
+                          "142 GFLOP algorithmic per launch): fc1+GELU'/GELU, fc2+residual, fc2-dgrad+GRN/GELU-backward, "
+                          "fc1-dgrad and the two weight gradients",
                 "per_launch_ms": per, "avg_ms": avg_ms, "launches_timed": reps * len(per),
-                "peak_source": f"bf16_tflops_sustained ({src})"}
+                "peak_source": f"bf16_tflops burst ({src}): launches timed in isolation, 10 back to back per kind",
+                "frac_of_sustained_peak": ach / tf_sus}
+        del gbuf, lbuf, dw1, db1x, P
         del a_c, a_c4, o_c4a, o_c4b, o_c
 
     # ---- secondary evidence (N=1 only, never part of `value`): the implicit-GEMM 3-D conv launches of BASELINE config 5
@@ -379,7 +448,7 @@ def run_gpu(args):
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         try:
-            secondary = secondary_evidence(dev, tf_sus)
+            secondary = secondary_evidence(dev, tf_burst)
         except Exception as exc:  # evidence only: never fail the headline line
             secondary = {"error": f"{type(exc).__name__}: {exc}"}
 
@@ -399,7 +468,7 @@ def run_gpu(args):
                        "cuda_graph": graphed is not None, "batch_streams": args.batch_streams,
                        "grad_exchange": ("none" if not ddp else
                                          "torch DDP (bucketed NCCL all-reduce)" if args.ddp == "torch" else
-                                         "flat fp32 NCCL all-reduce recorded in the step graph"),
+                                         "bucketed fp32 NCCL all-reduce (average) overlapped with backward, recorded in the step graph"),
                        "l2": "activations per step (>4 GB) exceed the 126 MB L2; no explicit flush",
                        "step_tflop_fraction_of_sustained_peak": value / world * TRAIN_TFLOP_PER_SAMPLE / tf_sus},
             "clocks": clocks,
@@ -412,15 +481,20 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     if ddp:
-        # NCCL communicators captured in CUDA graphs can block a clean teardown: drop the graph, meet at a barrier,
-        # then leave without running destructors (exit code 0 for the launcher).
+        # Clean teardown: drop the graph (it holds the captured NCCL work), meet at a barrier, destroy the process
+        # group.  A watchdog ends the process if a communicator refuses to shut down, so the launcher never hangs.
         graphed = None
+        exchange = None
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def main():

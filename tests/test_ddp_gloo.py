@@ -83,3 +83,60 @@ def test_flat_grad_allreduce_matches_ddp_semantics():
         torch.nn.functional.mse_loss(m(x), y).backward()
         grads.append(torch.cat([p.grad.flatten() for p in m.parameters()]))
     torch.testing.assert_close(res["grad"], (grads[0] + grads[1]) / 2, rtol=1e-5, atol=1e-7)
+
+
+def _bucket_worker(rank, world, init_file, out_file):
+    from viscy_b200 import Unet25d, UNeXt2
+    from viscy_b200.parallel import BucketedGradAllReduce
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    res = {}
+    for name, make, shape in (("unext2", lambda: UNeXt2(in_channels=1, out_channels=1, in_stack_depth=5, backbone="convnextv2_atto"),
+                               (1, 1, 5, 32, 32)),
+                              ("unet25d", lambda: Unet25d(num_filters=(4, 8), num_blocks=1, dropout=0.0), (1, 1, 5, 32, 32))):
+        torch.manual_seed(rank)
+        m = make()
+        ex = BucketedGradAllReduce(m.parameters(), fractions=(0.2, 0.5, 0.9))
+        ex.broadcast_parameters(0)
+        steps = []
+        for step in range(3):  # step 0 records the backward order and builds the buckets; 1 and 2 overlap
+            g = torch.Generator().manual_seed(100 + rank + 10 * step)
+            x = torch.randn(shape, generator=g)
+            m.zero_grad(set_to_none=True)
+            out = m(x)
+            torch.nn.functional.mse_loss(out, torch.randn(out.shape, generator=g)).backward()
+            ex.finish()
+            steps.append(torch.cat([(p.grad if p.grad is not None else torch.full_like(p, float("nan"))).flatten()
+                                    for p in m.parameters()]))
+        res[name] = {"grads": steps, "n_buckets": len(ex.buckets),
+                     "none": [n for n, p in m.named_parameters() if p.grad is None]}
+    if rank == 1:
+        torch.save(res, out_file)
+    dist.destroy_process_group()
+
+
+def test_bucketed_grad_allreduce_overlap_and_unused_parameters():
+    """Bucketed exchange: every step (the recording one and the overlapped ones) yields the mean of the per-rank
+    gradients; parameters without a gradient (Unet25d's unused resid_conv) keep grad=None as under stock DDP."""
+    with tempfile.TemporaryDirectory() as d:
+        init_file, out_file = os.path.join(d, "init"), os.path.join(d, "out.pt")
+        mp.spawn(_bucket_worker, args=(2, init_file, out_file), nprocs=2, join=True)
+        res = torch.load(out_file)
+    from viscy_b200 import Unet25d, UNeXt2
+    for name, make, shape in (("unext2", lambda: UNeXt2(in_channels=1, out_channels=1, in_stack_depth=5, backbone="convnextv2_atto"),
+                               (1, 1, 5, 32, 32)),
+                              ("unet25d", lambda: Unet25d(num_filters=(4, 8), num_blocks=1, dropout=0.0), (1, 1, 5, 32, 32))):
+        assert res[name]["n_buckets"] >= 3
+        for step in range(3):
+            grads = []
+            for rank in range(2):
+                torch.manual_seed(0)
+                m = make()
+                g = torch.Generator().manual_seed(100 + rank + 10 * step)
+                x = torch.randn(shape, generator=g)
+                out = m(x)
+                torch.nn.functional.mse_loss(out, torch.randn(out.shape, generator=g)).backward()
+                grads.append(torch.cat([(p.grad if p.grad is not None else torch.full_like(p, float("nan"))).flatten()
+                                        for p in m.parameters()]))
+            torch.testing.assert_close(res[name]["grads"][step], (grads[0] + grads[1]) / 2, rtol=1e-5, atol=1e-7,
+                                       equal_nan=True)
+    assert any("resid_conv" in n for n in res["unet25d"]["none"]) and not res["unext2"]["none"]

@@ -387,14 +387,15 @@ def run_gpu(args):
         b_c4, b_c = rn(C4), rn(C)
         sv, tv = rn(BATCH, C4) * 0.1 + 1.0, rn(BATCH, C4) * 0.1
         o_c4a, o_c4b, o_c = torch.empty_like(a_c4), torch.empty_like(a_c4), torch.empty_like(a_c)
-        gbuf = torch.zeros((M, C4 + 8), device=dev, dtype=torch.bfloat16)  # [g | 1]: bias gradient as the extra column
+        PAD = ops.ONES_PAD
+        gbuf = torch.zeros((M, C4 + PAD), device=dev, dtype=torch.bfloat16)  # [g | 1]: bias gradient as the extra column
         gbuf[:, :C4] = a_c4
         gbuf[:, C4] = 1
-        lbuf = torch.zeros((M, C + 8), device=dev, dtype=torch.bfloat16)
+        lbuf = torch.zeros((M, C + PAD), device=dev, dtype=torch.bfloat16)
         lbuf[:, :C] = a_c
         lbuf[:, C] = 1
-        dw1, db1x = torch.zeros((C4, C), device=dev), torch.zeros((C4, 8), device=dev)
-        P = torch.empty((BATCH, C, C4 + 8), device=dev)
+        dw1, db1x = torch.zeros((C4, C), device=dev), torch.zeros((C4, PAD), device=dev)
+        P = torch.empty((BATCH, C, C4 + PAD), device=dev)
         from viscy_b200.functional import _wgrad_splits
         calls = {
             "fc1+gelu": lambda: ops.gemm(a_c, w1, bias=b_c4, epilogue=LL.EPI_GELU_GP, out=o_c4a, out2=o_c4b),
@@ -405,7 +406,7 @@ def run_gpu(args):
             # the two weight gradients (MN-major, K = pixels): per-sample slabs dout^T [g | 1], and split-K dh^T [l | 1]
             "wgrad_fc2_per_sample": lambda: ops.gemm(a_c, gbuf, mn_major=True, epilogue=LL.EPI_F32, k_splits=BATCH,
                                                       split_slabs=True, out=P),
-            "wgrad_fc1": lambda: ops.gemm(a_c4, lbuf, mn_major=True, epilogue=LL.EPI_F32, k_splits=_wgrad_splits(C4, C + 8, M),
+            "wgrad_fc1": lambda: ops.gemm(a_c4, lbuf, mn_major=True, epilogue=LL.EPI_F32, k_splits=_wgrad_splits(C4, C + PAD, M),
                                            out=dw1, out2=db1x, n_split=C, accumulate=True),
         }
         per = {}

@@ -143,8 +143,8 @@ int vb200_dwconv7_wgrad(const void* x, const void* dy, float* dwt, float* db, in
 /* LayerNorm over the channel dim of [M, C] rows (timm LayerNorm / LayerNorm2d, eps 1e-6) */
 int vb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                         float* rstd, int64_t M, int C, float eps, int dtype, vb200_stream_t stream);
-/* same with a row pitch ldy (elements) for y.  ones != 0: y[:, C:C+8] = {1,0,..,0} (ldy >= C + 8); ones2 != NULL: the
- * same group at ones2[row * ld2 + col2 ..].  A weight-gradient GEMM against [l | 1] then yields the bias gradient as an
+/* same with a row pitch ldy (elements) for y.  ones = n > 0: y[:, C:C+8n] = {1,0,..,0} (ldy >= C + 8 n); ones2 != NULL:
+ * the same columns at ones2[row * ld2 + col2 ..].  A weight-gradient GEMM against [l | 1] then yields the bias gradient as an
  * extra column, which replaces the column-sum passes over dh / dout (C % 8 == 0, C <= 2048) */
 int vb200_layernorm_fwd_ld(const void* x, const float* gamma, const float* beta, void* y, int64_t ldy, int ones,
                            void* ones2, int64_t ld2, int col2, float* mean, float* rstd, int64_t M, int C, float eps,

@@ -357,9 +357,10 @@ def test_layernorm_fwd_rows_ones_columns(cuda, M, C, dtype):
     assert rel(y, ref) < tol(dtype)
     assert rel(mean, x.float().mean(1)) < 1e-5
     assert rel(rstd, (x.float().var(1, unbiased=False) + 1e-6).rsqrt()) < 1e-4
-    other = torch.full((M, 4 * C + 8), 7.0, device=cuda, dtype=dtype)
+    PAD = ops.ONES_PAD
+    other = torch.full((M, 4 * C + PAD), 7.0, device=cuda, dtype=dtype)
     yb, mean2, rstd2 = ops.layernorm_fwd(x, gm, bt, 1e-6, ones=True, ones2=other, ones2_col=4 * C)
-    assert yb.shape == (M, C + 8)
+    assert yb.shape == (M, C + PAD)
     assert torch.equal(yb[:, :C], y) and torch.equal(mean, mean2) and torch.equal(rstd, rstd2)
     assert (yb[:, C] == 1).all() and (yb[:, C + 1:] == 0).all()
     assert (other[:, 4 * C] == 1).all() and (other[:, 4 * C + 1:] == 0).all() and (other[:, :4 * C] == 7).all()

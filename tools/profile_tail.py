@@ -27,16 +27,16 @@ for (B, H, C) in ((8, 64, 736), (8, 16, 384)):
             ops.dwconv7_wgrad(x, dy)
         if "ln" in which:
             gm, bt = rn(C), rn(C)
-            gbuf = torch.empty((M, C4 + 8), device=dev, dtype=bf)
+            gbuf = torch.empty((M, C4 + 16), device=dev, dtype=bf)
             lb, mean, rstd = ops.layernorm_fwd(x, gm, bt, 1e-6, ones=True, ones2=gbuf, ones2_col=C4)
             ops.layernorm_bwd(dy, x, mean, rstd, gm)
         if "grn" in which or "red" in which:
-            hid = rn(M, C4 + 8).to(bf)
-            sumsq = ops.colreduce(hid.view(B, R, C4 + 8), 1, width=C4)
+            hid = rn(M, C4 + 16).to(bf)
+            sumsq = ops.colreduce(hid.view(B, R, C4 + 16), 1, width=C4)
             if "grn" in which:
                 w2 = rn(C, C4) * 0.02
                 s, w2s, b2e = ops.grn_prepare(sumsq, rn(C4), rn(C4), w2, rn(C), bf)
-                P = rn(B, C, C4 + 8)
+                P = rn(B, C, C4 + 16)
                 dW2, S1, dbg, db2 = ops.grn_wgrad_finish(P, w2, s, rn(C4), None)
                 t = torch.empty_like(S1)
                 dgw = torch.zeros(C4, device=dev)

@@ -297,9 +297,13 @@ layernorm_fwd_rows_kernel(const uint4* __restrict__ x, const float* __restrict__
   if (lane == 0) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
-    const uint4 one = make_uint4(H16<BF16>::pack(1.0f, 0.0f), 0u, 0u, 0u);
-    if (ones) y[row * ldy8 + C8] = one;
-    if (ones2 != nullptr) ones2[row * ld2_8 + c2_8] = one;
+    // `ones` 16-byte groups behind the row: {1, 0 x 7}, then zeros (16 columns keep the row pitch a multiple of 32 B, so
+    // that the 128-byte TMA box rows of the weight-gradient GEMM stay sector-aligned)
+    const uint4 one = make_uint4(H16<BF16>::pack(1.0f, 0.0f), 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = 0; k < ones; ++k) {
+      y[row * ldy8 + C8 + k] = k == 0 ? one : zero;
+      if (ones2 != nullptr) ones2[row * ld2_8 + c2_8 + k] = k == 0 ? one : zero;
+    }
   }
 }
 
@@ -1041,8 +1045,8 @@ static void ln_fwd_rows_launch(const void* x, const float* gamma, const float* b
       (const uint4*)x, gamma, beta, (uint4*)y, ldy8, mean, rstd, M, C8, eps, ones, (uint4*)ones2, ld2_8, c2_8);
 }
 
-/* y row pitch ldy (elements, % 8); ones != 0: y[:, C:C+8] = {1,0,...,0} (needs ldy >= C + 8); ones2 != NULL: the same
- * group written at ones2[row * ld2 + col2 .. +8) */
+/* y row pitch ldy (elements, % 8); ones = n > 0: y[:, C:C+8n] = {1,0,...,0} (needs ldy >= C + 8 n); ones2 != NULL: the
+ * same columns written at ones2[row * ld2 + col2 ..) */
 extern "C" int vb200_layernorm_fwd_ld(const void* x, const float* gamma, const float* beta, void* y, int64_t ldy, int ones,
                                       void* ones2, int64_t ld2, int col2, float* mean, float* rstd, int64_t M, int C,
                                       float eps, int dtype, vb200_stream_t stream) {
@@ -1050,7 +1054,7 @@ extern "C" int vb200_layernorm_fwd_ld(const void* x, const float* gamma, const f
   cudaStream_t st = (cudaStream_t)stream;
   const bool plain = ldy == C && !ones && ones2 == nullptr;
   if (C % 8 == 0 && C <= 2048 && ldy % 8 == 0 && ld2 % 8 == 0 && col2 % 8 == 0) {
-    VB_REQUIRE(ldy >= C + (ones ? 8 : 0), "ldy (%lld) too small", (long long)ldy);
+    VB_REQUIRE(ones >= 0 && ones <= 8 && ldy >= C + 8 * ones, "ldy (%lld) too small", (long long)ldy);
     const int C8 = C / 8, nv = (C8 + 31) / 32;
 #define LN_FWD(NV) DISPATCH_DT(dtype, (ln_fwd_rows_launch<BF, NV>(x, gamma, beta, y, ldy / 8, mean, rstd, M, C8, eps, ones, ones2, ld2 / 8, col2 / 8, st)))
     if (nv <= 1) LN_FWD(1);

@@ -15,6 +15,7 @@ from . import _lib as L
 from . import ops
 
 LN_EPS = 1e-6  # timm LayerNorm / LayerNorm2d
+PAD = ops.ONES_PAD  # columns behind l / g that carry the ones column of the bias-gradient trick
 
 # Backward runs the weight-gradient kernels (wgrad GEMMs, bias column sums, depthwise wgrad) on a side stream so
 # that on small feature maps they overlap the latency-bound dgrad chain; every block joins the side stream before
@@ -73,8 +74,8 @@ class ConvNeXtBlockFn(Function):
     forward:  d = dwconv7(x)+b ; l = LN(d) ; h = l W1^T + b1 ; y = GRN(GELU(h)) | GELU(h) ;
               out = keep[n] * ((y W2^T + b2) [* gamma]) + x        (keep: stochastic-depth scale per sample, or None)
 
-    Bias gradients without column-sum passes (`onescol`, C % 16 == 0): LayerNorm writes l as [M, C + 8] with a ones
-    column and plants the same column behind the GELU output g [M, C4 + 8]; the weight-gradient GEMMs dh^T [l | 1] and
+    Bias gradients without column-sum passes (`onescol`, C % 16 == 0): LayerNorm writes l as [M, C + PAD] with a ones
+    column and plants the same column behind the GELU output g [M, C4 + PAD]; the weight-gradient GEMMs dh^T [l | 1] and
     dout^T [g | 1] then carry d fc1.bias / d fc2.bias as their last column.
     """
 
@@ -91,7 +92,7 @@ class ConvNeXtBlockFn(Function):
         fused = use_grn and R % 128 == 0 and B <= 16
         onescol = (fused or not use_grn) and C % 16 == 0 and C <= 2048 and C4 % 8 == 0
         if onescol:
-            gbuf = torch.empty((M, C4 + 8), device=x.device, dtype=x.dtype)  # [g | 1 0 0 0 0 0 0 0]
+            gbuf = torch.empty((M, C4 + PAD), device=x.device, dtype=x.dtype)  # [g | 1 0 ... 0]
             lbuf, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS, ones=True, ones2=gbuf, ones2_col=C4)
             l2, y2 = lbuf[:, :C], gbuf[:, :C4]
         else:
@@ -102,7 +103,7 @@ class ConvNeXtBlockFn(Function):
             # gp = gelu'(u) and g = gelu(u) from the fc1 epilogue; GRN scale folded into per-sample fc2 weights
             h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP, out2=y2)
             if onescol:
-                sumsq = ops.colreduce(gbuf.view(B, R, C4 + 8), 1, width=C4)
+                sumsq = ops.colreduce(gbuf.view(B, R, C4 + PAD), 1, width=C4)
             else:
                 sumsq = ops.colreduce(y2.view(B, R, C4), 1)
                 gbuf = y2
@@ -144,7 +145,7 @@ class ConvNeXtBlockFn(Function):
         dob = do2 if keep is None else ops.scale_rows(dout, keep).view(M, C)
         l2 = lbuf[:, :C] if onescol else lbuf
         y2 = gbuf[:, :C4] if onescol else gbuf
-        ar = ops.Arena(x.device, [C, (B + 2) * C4, C4, 2 * C, 50 * C] + ([C4 * C, 8 * C4] if onescol else []))
+        ar = ops.Arena(x.device, [C, (B + 2) * C4, C4, 2 * C, 50 * C] + ([C4 * C, PAD * C4] if onescol else []))
         if ctx.fused:
             grn_b = gamma  # the 16th saved tensor is grn.bias on the fused path (V2 blocks carry no layer scale)
             gamma = None
@@ -170,7 +171,7 @@ class ConvNeXtBlockFn(Function):
             else:
                 # ConvNeXt-V1: GELU backward rides in the fc2-dgrad epilogue (h holds gelu'(u))
                 if onescol:
-                    Gx = ops.gemm(dob, gbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(C, C4 + 8, M))
+                    Gx = ops.gemm(dob, gbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(C, C4 + PAD, M))
                     G, db_raw = Gx[:, :C4], Gx[:, C4]  # G = dout^T y (without the layer scale), its ones column
                 else:
                     _, G, db_raw = linear_bwd(dob, y2, w2, need_da=False)
@@ -197,8 +198,8 @@ class ConvNeXtBlockFn(Function):
         with torch.cuda.stream(side):
             if onescol:
                 # dW1 = dh^T [l | 1]: the weight gradient to its own buffer, the ones column (= d fc1.bias) to db1x
-                dw1, db1x = ar.take(C4, C), ar.take(C4, 8)
-                ops.gemm(dh2, lbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(C4, C + 8, M),
+                dw1, db1x = ar.take(C4, C), ar.take(C4, PAD)
+                ops.gemm(dh2, lbuf, mn_major=True, epilogue=L.EPI_F32, k_splits=_wgrad_splits(C4, C + PAD, M),
                          out=dw1, out2=db1x, n_split=C, accumulate=True)
                 db1 = db1x[:, 0].contiguous()
                 dw1 = dw1.view(fc1_w.shape)

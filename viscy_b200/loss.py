@@ -39,30 +39,30 @@ class NTXentLoss(nn.Module):
                                              self.temperature_warmup_epochs)
 
     def forward(self, embeddings: Tensor, labels: Tensor) -> Tensor:
+        """Dense, static-shape form (no index gathering, no host synchronisation: the loss can be recorded into the
+        training step's CUDA graph).  For every ordered positive pair (a, p):
+            loss_ap = -log( exp(s_ap / T) / (exp(s_ap / T) + sum_{n in neg(a)} w_an exp(s_an / T)) ),   mean over pairs
+        with w_an = 1 (PML NTXentLoss) or the hard-negative weights exp(beta s_an) renormalised to the number of
+        negatives (NTXentHCL, VM/contrastive/loss.py:120-185)."""
         emb = torch.nn.functional.normalize(embeddings.float(), dim=1)
         sim = emb @ emb.t()
         same = labels[:, None] == labels[None, :]
         eye = torch.eye(len(labels), dtype=torch.bool, device=sim.device)
-        a1, p = torch.where(same & ~eye)
-        a2, n = torch.where(~same)
-        if a1.numel() == 0 or a2.numel() == 0:
-            return sim.sum() * 0.0
-        dtype = sim.dtype
-        pos = sim[a1, p].unsqueeze(1) / self.temperature
-        neg_raw = sim[a2, n]
-        neg = neg_raw / self.temperature
-        n_per_p = (a2.unsqueeze(0) == a1.unsqueeze(1)).to(dtype)
-        neg_m = neg * n_per_p
-        neg_m[n_per_p == 0] = torch.finfo(dtype).min
-        mx = torch.max(pos, neg_m.max(dim=1, keepdim=True)[0]).detach()
-        num = torch.exp(pos - mx).squeeze(1)
-        w = torch.exp(neg_m - mx)
-        if self.beta != 0.0:  # hard-negative concentration: reweight negatives by exp(beta * sim), renormalised
-            hw = torch.exp(self.beta * neg_raw) * n_per_p
-            hw = hw * n_per_p.sum(dim=1, keepdim=True) / hw.sum(dim=1, keepdim=True).clamp(min=1e-8)
-            w = hw * w
-        den = w.sum(dim=1) + num
-        return (-torch.log(num / den + torch.finfo(dtype).tiny)).mean()
+        pos_m = same & ~eye
+        neg_m = ~same
+        logits = sim / self.temperature
+        ninf = torch.finfo(sim.dtype).min
+        neg_logits = logits
+        if self.beta != 0.0:
+            hw = self.beta * sim  # log of the un-normalised hard-negative weights
+            lse_hw = torch.logsumexp(hw.masked_fill(~neg_m, ninf), dim=1, keepdim=True)
+            cnt = neg_m.sum(dim=1, keepdim=True).clamp_min(1).to(sim.dtype)
+            neg_logits = logits + hw + torch.log(cnt) - lse_hw
+        lneg = torch.logsumexp(neg_logits.masked_fill(~neg_m, ninf), dim=1, keepdim=True)  # [2B, 1]
+        lneg = torch.where(neg_m.any(dim=1, keepdim=True), lneg, torch.full_like(lneg, ninf))
+        per_pair = torch.logaddexp(logits, lneg) - logits  # -log(num / den) for every (a, p)
+        n_pos = pos_m.sum()
+        return (per_pair * pos_m).sum() / n_pos.clamp_min(1).to(sim.dtype)
 
 
 class NTXentHCL(NTXentLoss):

@@ -261,12 +261,15 @@ def dwconv7_wgrad(x, dy, want_bias=True, arena=None):
     return dwt, db
 
 
+ONES_PAD = 16  # columns appended for the ones-column trick: {1, 0 x 15} keeps row pitches multiples of 32 bytes
+
+
 def layernorm_fwd(x, gamma, beta, eps, ones=False, ones2=None, ones2_col=0):
     """x [..., C] 16-bit rows -> (y, mean, rstd).
 
-    ones=True: y is [M, C + 8] with y[:, C] = 1 and y[:, C+1:] = 0 (use y[:, :C] as the normalised rows): a weight
+    ones=True: y is [M, C + ONES_PAD] with y[:, C] = 1 and y[:, C+1:] = 0 (use y[:, :C] as the normalised rows): a weight
     gradient GEMM against it yields the bias gradient as an extra column.  ones2 ([M, ld2] 16-bit, ones2_col % 8 == 0):
-    a second matrix that receives the same {1, 0 x 7} group per row."""
+    a second matrix that receives the same {1, 0, ...} columns per row."""
     _act(x, "x")
     Cc = x.shape[-1]
     M = x.numel() // Cc
@@ -277,16 +280,16 @@ def layernorm_fwd(x, gamma, beta, eps, ones=False, ones2=None, ones2_col=0):
         _call("vb200_layernorm_fwd", _p(x), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(y), _p(mean), _p(rstd),
               C.c_int64(M), Cc, C.c_float(eps), L.dtype_code(x.dtype))
         return y, mean, rstd
-    ldy = Cc + 8 if ones else Cc
+    ldy = Cc + ONES_PAD if ones else Cc
     y = torch.empty((M, ldy), device=x.device, dtype=x.dtype)
     ld2 = 8
     if ones2 is not None:
-        if ones2.dtype != x.dtype or ones2.dim() != 2 or ones2.shape[0] != M or ones2.stride(1) != 1:
-            raise ValueError("ones2 must be a [M, ld] matrix of the activation dtype")
+        if ones2.dtype != x.dtype or ones2.dim() != 2 or ones2.shape[0] != M or ones2.stride(1) != 1 or not ones:
+            raise ValueError("ones2 must be a [M, ld] matrix of the activation dtype (and needs ones=True)")
         ld2 = ones2.stride(0)
     _call("vb200_layernorm_fwd_ld", _p(x), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(y), C.c_int64(ldy),
-          int(ones), _p(ones2), C.c_int64(ld2), int(ones2_col), _p(mean), _p(rstd), C.c_int64(M), Cc, C.c_float(eps),
-          L.dtype_code(x.dtype))
+          ONES_PAD // 8 if ones else 0, _p(ones2), C.c_int64(ld2), int(ones2_col), _p(mean), _p(rstd), C.c_int64(M), Cc,
+          C.c_float(eps), L.dtype_code(x.dtype))
     return y, mean, rstd
 
 

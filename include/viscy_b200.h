@@ -204,7 +204,8 @@ int vb200_grn_prepare2(const float* sumsq, const float* gw, const float* gb, con
 /* ---- GroupNorm (+ timestep scale / shift) + activation on rows [N, R, C] (VM/unet/blocks.py:88-113 with the UNet3DBase
  * defaults norm="group", activation="silu", VM/unet/unet3d_base.py:58-72).  Statistics come from vb200_colreduce (mode 2,
  * per sample); the per-(sample, channel) coefficients are formed by the caller:
- *   y = act(a[n,c] * x + b[n,c]),  act: 0 none, 1 ReLU, 2 SiLU
+ *   y = act(a[n,c] * x + b[n,c]),  act: 0 none, 1 ReLU, 2 SiLU, 3 LeakyReLU(0.01), 4 ELU(1), 5 SELU (the activations of
+ *   ConvBlock3D, VM/components/conv_block_3d.py:213-229; with a = Dropout3d scale, b = 0 this is its dropout + activation)
  *   backward: dv = dy * act'(a x + b);  s1[n,c] += sum_r dv, s2[n,c] += sum_r dv * x  (pre-zeroed);
  *             dx = c1 * dv + c2 * x + c3 with coef = five fp32 [N, C] planes (a, b, c1, c2, c3) ---- */
 int vb200_affine_nc_act(const void* x, const float* a, const float* b, void* y, int64_t N, int64_t R, int C, int act,

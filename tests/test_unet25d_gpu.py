@@ -101,6 +101,39 @@ def test_conv_block_3d_vs_cpu_mirror(cuda, residual, cin, cout):
         assert e < (3e-2 if gref[n].dim() > 1 else 1.5e-1), (n, e)
 
 
+@pytest.mark.parametrize("norm,activation,transpose,order", [
+    ("instance", "relu", False, "can"), ("instance", "leakyrelu", False, "cna"), ("batch", "elu", False, "can"),
+    ("none", "selu", False, "ca"), ("batch", "relu", True, "can"), ("instance", "linear", False, "cn"),
+    ("batch", "relu", False, "cna"), ("instance", "selu", True, "cna"),
+])
+def test_conv_block_3d_variants_vs_cpu_mirror(cuda, norm, activation, transpose, order):
+    """InstanceNorm3d, the non-ReLU activations, other layer orders and transpose=True (conv_block_3d.py:14-28, 213-229)
+    through forward_cl against the block's own torch-op forward (== the reference, tests/test_unet3d_cpu.py)."""
+    from viscy_b200.unet25d import ConvBlock3D
+    torch.manual_seed(11)
+    blk = ConvBlock3D(16, 24, dropout=False, norm=norm, residual=False, activation=activation, transpose=transpose,
+                      kernel_size=(3, 3, 3), num_repeats=2, layer_order=order)
+    x = torch.randn(2, 16, 4, 16, 16)
+    ref = blk(x)
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    gref = {n: p.grad.clone() for n, p in blk.named_parameters() if p.grad is not None}
+    blk.zero_grad()
+    blk = blk.to(cuda)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.reset_running_stats()
+    xc = cl(x.to(cuda)).half().requires_grad_(True)
+    y = blk.forward_cl(xc)
+    assert nc(y).shape == ref.shape
+    assert rel(nc(y).float().cpu(), ref) < 4e-3
+    y.backward(cl(dy.to(cuda)).half())
+    errs = {n: rel(p.grad.cpu(), gref[n]) for n, p in blk.named_parameters() if n in gref and gref[n].norm() > 1e-4}
+    print({k: round(v, 4) for k, v in errs.items()})
+    for n, e in errs.items():
+        assert e < (3e-2 if gref[n].dim() > 1 else 1.5e-1), (n, e)
+
+
 def _autocast_emulation(g, dtype):
     """The CPU mirror (== reference, test_unet3d_cpu.py) in fp32 arithmetic with activations rounded to `dtype` wherever
     CUDA autocast (and the sm_100a path) stores them: after every conv, BatchNorm, pooling and upsampling."""

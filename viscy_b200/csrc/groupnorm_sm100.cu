@@ -12,12 +12,16 @@
 
 namespace vb {
 
-enum { GN_ACT_NONE = 0, GN_ACT_RELU = 1, GN_ACT_SILU = 2 };
+enum { GN_ACT_NONE = 0, GN_ACT_RELU = 1, GN_ACT_SILU = 2, GN_ACT_LEAKY = 3, GN_ACT_ELU = 4, GN_ACT_SELU = 5 };
+constexpr float SELU_ALPHA = 1.6732632423543772f, SELU_SCALE = 1.0507009873554805f;  // torch.nn.SELU
 
 template <int ACT>
 __device__ __forceinline__ float gn_act(float v) {
   if (ACT == GN_ACT_RELU) return fmaxf(v, 0.f);
   if (ACT == GN_ACT_SILU) return v * __frcp_rn(1.0f + __expf(-v));
+  if (ACT == GN_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;  // nn.LeakyReLU() default slope
+  if (ACT == GN_ACT_ELU) return v > 0.f ? v : expm1f(v);     // nn.ELU() alpha = 1
+  if (ACT == GN_ACT_SELU) return SELU_SCALE * (v > 0.f ? v : SELU_ALPHA * expm1f(v));
   return v;
 }
 template <int ACT>
@@ -27,6 +31,9 @@ __device__ __forceinline__ float gn_dact(float v) {
     const float s = __frcp_rn(1.0f + __expf(-v));
     return s * fmaf(v, 1.0f - s, 1.0f);
   }
+  if (ACT == GN_ACT_LEAKY) return v > 0.f ? 1.f : 0.01f;
+  if (ACT == GN_ACT_ELU) return v > 0.f ? 1.f : __expf(v);
+  if (ACT == GN_ACT_SELU) return SELU_SCALE * (v > 0.f ? 1.f : SELU_ALPHA * __expf(v));
   return 1.f;
 }
 
@@ -135,19 +142,24 @@ static unsigned gn_blocks(long long total) { return (unsigned)((total + 255) / 2
 
 using namespace vb;
 
+#define GN_ACTS(...)                                                    \
+  switch (act) {                                                        \
+    case 0: { constexpr int ACT = 0; __VA_ARGS__; } break;              \
+    case 1: { constexpr int ACT = 1; __VA_ARGS__; } break;              \
+    case 2: { constexpr int ACT = 2; __VA_ARGS__; } break;              \
+    case 3: { constexpr int ACT = 3; __VA_ARGS__; } break;              \
+    case 4: { constexpr int ACT = 4; __VA_ARGS__; } break;              \
+    default: { constexpr int ACT = 5; __VA_ARGS__; } break;             \
+  }
 #define GN_DISPATCH(dtype, act, ...)                                                                  \
   do {                                                                                                \
-    if ((act) < 0 || (act) > 2) return vb::fail(VB200_ERR_INVALID, "activation %d", (int)(act));      \
+    if ((act) < 0 || (act) > 5) return vb::fail(VB200_ERR_INVALID, "activation %d", (int)(act));      \
     if ((dtype) == VB200_BF16) {                                                                      \
       constexpr bool BF = true;                                                                       \
-      if ((act) == 0) { constexpr int ACT = 0; __VA_ARGS__; }                                         \
-      else if ((act) == 1) { constexpr int ACT = 1; __VA_ARGS__; }                                    \
-      else { constexpr int ACT = 2; __VA_ARGS__; }                                                    \
+      GN_ACTS(__VA_ARGS__)                                                                            \
     } else if ((dtype) == VB200_FP16) {                                                               \
       constexpr bool BF = false;                                                                      \
-      if ((act) == 0) { constexpr int ACT = 0; __VA_ARGS__; }                                         \
-      else if ((act) == 1) { constexpr int ACT = 1; __VA_ARGS__; }                                    \
-      else { constexpr int ACT = 2; __VA_ARGS__; }                                                    \
+      GN_ACTS(__VA_ARGS__)                                                                            \
     } else {                                                                                          \
       return vb::fail(VB200_ERR_UNSUPPORTED, "dtype %d", (int)(dtype));                               \
     }                                                                                                 \

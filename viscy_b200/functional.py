@@ -977,6 +977,40 @@ def groupnorm_act_cl(x, gn, act: str, scale=None, shift=None):
     return GroupNormActFn.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps, scale, shift, act)
 
 
+def instancenorm_act_cl(x, eps: float, act: str = "none"):
+    """nn.InstanceNorm3d (affine=False, batch statistics) [+ activation] on channels-last rows: GroupNorm with one group
+    per channel and unit affine parameters."""
+    Cn = x.shape[-1]
+    one = torch.ones((Cn,), device=x.device, dtype=torch.float32)
+    return GroupNormActFn.apply(x, one, torch.zeros_like(one), Cn, eps, None, None, act)
+
+
+class ScaleActFn(Function):
+    """act(x * scale[n, c]): nn.Dropout3d (per sample-and-channel scale, or None) fused with any ConvBlock3D activation
+    (relu | leakyrelu | elu | selu | linear) through the per-(sample, channel) affine + activation kernels."""
+
+    @staticmethod
+    def forward(ctx, x, scale, act):
+        N, Cp = x.shape[0], x.shape[-1]
+        a = torch.ones((N, Cp), device=x.device, dtype=torch.float32) if scale is None else scale.contiguous()
+        b = torch.zeros_like(a)
+        ctx.save_for_backward(x, a, b)
+        ctx.act = act
+        return ops.affine_nc_act(x, a, b, act)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, a, b = ctx.saved_tensors
+        zero = torch.zeros_like(a)
+        coef = torch.stack([a, b, a, zero, zero]).contiguous()  # dx = a * dy * act'(a x)
+        return ops.gn_bwd_apply(dy.contiguous(), x, coef, ctx.act), None, None
+
+
+def scale_act_cl(x, scale, act: str):
+    return ScaleActFn.apply(x, scale, act)
+
+
 class Cat2Fn(Function):
     @staticmethod
     def forward(ctx, a, b):

@@ -781,7 +781,7 @@ def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training):
     return dx, s[1], s[0]
 
 
-ACT_CODES = {"none": 0, "relu": 1, "silu": 2}
+ACT_CODES = {"none": 0, "linear": 0, "relu": 1, "silu": 2, "leakyrelu": 3, "elu": 4, "selu": 5}
 
 
 def affine_nc_act(x, a, b, act: str):

@@ -4,8 +4,8 @@ forward, sub-module names and state_dict as the reference.
 CPU tensors (BASELINE config #1, fp32 parity) run in plain torch ops.  CUDA tensors run channels-last 16-bit through the
 sm_100a kernels: every convolution on the tcgen05 GEMM (implicit-GEMM TMA form where the geometry tiles, im2col lowering
 otherwise), Dropout3d + ReLU, BatchNorm3d, (1,2,2) average pooling and trilinear upsampling as HBM-bound kernels.
-Configurations without kernels (InstanceNorm, non-ReLU activations, transposed convs) raise NotImplementedError on CUDA -
-there is no silent cuDNN fallback.
+BatchNorm3d / InstanceNorm3d / no norm, relu | leakyrelu | elu | selu | linear, any layer order and transpose=True all run
+on the kernels; there is no cuDNN fallback.
 """
 
 from __future__ import annotations
@@ -106,38 +106,50 @@ class ConvBlock3D(nn.Module):
 
     register_modules = _register
 
+    def _conv_cl(self, x: Tensor, i: int, pad) -> Tensor:
+        conv = self.conv_list[i]
+        if not self.transpose:
+            return F.Conv3dFn.apply(x, conv.weight, conv.bias, (1, 1, 1), pad)
+        # F.pad(p) then ConvTranspose3d(k, stride 1, padding 0) == the correlation with the flipped, transposed filter
+        # under zero padding k - 1 + p (zero padding composes); autograd carries dW back through flip / transpose
+        w = conv.weight.flip(2, 3, 4).transpose(0, 1)
+        full = tuple(k - 1 + p for k, p in zip(conv.kernel_size, pad))
+        return F.Conv3dFn.apply(x, w, conv.bias, (1, 1, 1), full)
+
+    def _act_cl(self, x: Tensor, scale) -> Tensor:
+        if self.activation == "relu":
+            return F.scale_relu_cl(x, scale, True)
+        return F.scale_act_cl(x, scale, self.activation)
+
     def forward_cl(self, x: Tensor) -> Tensor:
         """sm_100a path on channels-last rows [N,D,H,W,C] (C padded to a multiple of 8)."""
-        if self.transpose:
-            raise NotImplementedError("sm_100a ConvBlock3D: transpose=True")
-        if self.norm == "instance":
-            raise NotImplementedError("sm_100a ConvBlock3D: norm='instance' (BatchNorm3d / none only)")
-        if self.activation not in ("relu", "linear"):
-            raise NotImplementedError(f"sm_100a ConvBlock3D: activation {self.activation!r} (relu / linear only)")
         pw, ph, pd = self.padding[0], self.padding[2], self.padding[4]
-        if (self.padding[1], self.padding[3], self.padding[5]) != (pw, ph, pd):
-            raise NotImplementedError("sm_100a ConvBlock3D: asymmetric padding")
         x0 = x
         for i in range(self.num_repeats):
             order = self.layer_order
             k = 0
             while k < len(order):
                 layer = order[k]
+                act_next = k + 1 < len(order) and order[k + 1] == "a" and self._has_act(i)
                 if layer == "c":
-                    conv = self.conv_list[i]
-                    x = F.Conv3dFn.apply(x, conv.weight, conv.bias, (1, 1, 1), (pd, ph, pw))
+                    x = self._conv_cl(x, i, (pd, ph, pw))
                     scale = F.dropout3d_scale(x, self.dropout, self.training) if self.dropout else None
-                    act_next = k + 1 < len(order) and order[k + 1] == "a" and self._has_act(i)
-                    if act_next:  # conv -> dropout -> ReLU in one pass over the tensor
-                        x = F.scale_relu_cl(x, scale, True)
+                    if act_next:  # conv -> dropout -> activation in one pass over the tensor
+                        x = self._act_cl(x, scale)
                         k += 1
                     elif scale is not None:
                         x = F.scale_relu_cl(x, scale, False)
                 elif layer == "a":
                     if self._has_act(i):
-                        x = F.scale_relu_cl(x, None, True)
+                        x = self._act_cl(x, None)
                 elif layer == "n" and self.norm_list[i] is not None:
-                    x = F.batchnorm_act_cl(x, self.norm_list[i], relu=False)
+                    if self.norm == "instance":  # norm (-> activation) in one pass
+                        x = F.instancenorm_act_cl(x, self.norm_list[i].eps, self.activation if act_next else "none")
+                        k += int(act_next)
+                    else:
+                        fuse = act_next and self.activation == "relu"
+                        x = F.batchnorm_act_cl(x, self.norm_list[i], relu=fuse)
+                        k += int(fuse)
                 k += 1
         if self.residual:
             if self.in_filters > self.out_filters:
@@ -152,7 +164,7 @@ class ConvBlock3D(nn.Module):
         return x
 
     def _has_act(self, i: int) -> bool:
-        return self.activation != "linear" and (i < self.num_repeats - 1 or self.activation != "linear")
+        return self.activation != "linear"
 
     def forward(self, x: Tensor) -> Tensor:
         _reject_cuda(x, "ConvBlock3D")

@@ -307,6 +307,19 @@ int vb200_conv3d_k3(const void* u, const void* wpack, const float* bias, void* o
 int vb200_conv3d_k3_wgrad(const void* u, const void* dz, float* dw, const int32_t* geom, int cin, int cout, int dtype,
                           vb200_stream_t stream);
 
+/* ---- FCMAE (VM/unet/fcmae.py) ---- */
+/* Sparse (masked) path of MaskedConvNeXtV2Block on channels-last rows (masked_patchify / masked_unpatchify / `x *= unmasked`,
+ * fcmae.py:91-141, 215-227): dst[r,:] = (map[r] >= 0 ? src[map[r],:] : 0) + (base ? base[r,:] : 0), r < n_dst, C % 8 == 0.
+ * gather: map = row indices of the unmasked pixels; scatter: map = inverse index (-1 at masked pixels), base = shortcut. */
+int vb200_rows_select(const void* src, const int32_t* map, const void* base, void* dst, int64_t n_dst, int C, int dtype,
+                      vb200_stream_t stream);
+/* PixelToVoxelShuffleHead (VM/components/heads.py:657-695) = monai SubpixelUpsample(scale r, pre_conv=None, pad_pool):
+ * forward (backward == 0): src = decoder rows [B,h,w,Cq*r*r] -> dst [B,Cq,h*r,w*r] (NCHW; == NCDHW after the head's reshape)
+ *   dst = AvgPool2d(r, stride 1)(ConstantPad2d((r-1,0,r-1,0))(pixel_shuffle(src, r)))   (pool == 0: the shuffle alone)
+ * backward (!= 0): src = d dst [B,Cq,h*r,w*r], dst = d decoder rows [B,h,w,Cq*r*r] */
+int vb200_shuffle_pool(const void* src, void* dst, int B, int h, int w, int Cq, int r, int pool, int backward, int dtype,
+                       vb200_stream_t stream);
+
 /* ---- PixelToVoxelHead (VM/components/heads.py:594-641) ---- */
 /* forward (backward == 0): dec [B,h,w,4*Cm] -> u [B,Dz,2h,2w,Cu] = unfold(pool(pixelshuffle2(dec)));
  * backward (!= 0): src = du, dst = ddec */

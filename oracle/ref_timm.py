@@ -63,14 +63,14 @@ class Mlp(nn.Module):
 
 
 class GlobalResponseNormMlp(nn.Module):
-    def __init__(self, in_features, hidden_features, use_conv=False):
+    def __init__(self, in_features, hidden_features, out_features=None, use_conv=False):
         super().__init__()
         lin = (lambda i, o: nn.Conv2d(i, o, 1)) if use_conv else nn.Linear
         self.fc1 = lin(in_features, hidden_features)
         self.act = nn.GELU()
         self.drop1 = nn.Dropout(0.0)
         self.grn = GlobalResponseNorm(hidden_features, channels_last=not use_conv)
-        self.fc2 = lin(hidden_features, in_features)
+        self.fc2 = lin(hidden_features, out_features or in_features)
         self.drop2 = nn.Dropout(0.0)
 
     def forward(self, x):
@@ -253,6 +253,34 @@ def create_model(name, pretrained=False, features_only=False, drop_path_rate=0.0
     return FeatureListNet(m, cfg["dims"]) if features_only else m
 
 
+class Downsample(nn.Module):
+    """timm.models.convnext.Downsample (used by VM/unet/fcmae.py:190-193 only when channels / stride change)."""
+
+    def __init__(self, in_chs, out_chs, stride=1, dilation=1):
+        super().__init__()
+        avg_stride = stride if dilation == 1 else 1
+        if stride > 1 or dilation > 1:
+            self.pool = nn.AvgPool2d(2, avg_stride, ceil_mode=True, count_include_pad=False)
+        else:
+            self.pool = nn.Identity()
+        self.conv = nn.Conv2d(in_chs, out_chs, 1, stride=1) if in_chs != out_chs else nn.Identity()
+
+    def forward(self, x):
+        return self.conv(self.pool(x))
+
+
+def create_conv2d(in_channels, out_channels, kernel_size, **kwargs):
+    """timm.layers.create_conv2d for the one call in VM/unet/fcmae.py:176-182: depthwise, padding '' (= symmetric 'same'
+    padding for stride 1, dilation 1), bias True."""
+    depthwise = kwargs.pop("depthwise", False)
+    stride = kwargs.pop("stride", 1)
+    dilation = kwargs.pop("dilation", 1)
+    groups = in_channels if depthwise else kwargs.pop("groups", 1)
+    padding = ((stride - 1) + dilation * (kernel_size - 1)) // 2
+    return nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                     groups=groups, **kwargs)
+
+
 def as_module() -> types.ModuleType:
     """A module object shaped like `timm` for the symbols the reference touches."""
     timm = types.ModuleType("timm")
@@ -264,5 +292,12 @@ def as_module() -> types.ModuleType:
     timm.models.convnext.ConvNeXtStage = ConvNeXtStage
     timm.models.convnext.ConvNeXtBlock = ConvNeXtBlock
     timm.models.convnext._init_weights = _init_weights
+    # VM/unet/fcmae.py:12-19
+    timm.models.convnext.Downsample = Downsample
+    timm.models.convnext.DropPath = DropPath
+    timm.models.convnext.GlobalResponseNormMlp = GlobalResponseNormMlp
+    timm.models.convnext.LayerNorm2d = LayerNorm2d
+    timm.models.convnext.create_conv2d = create_conv2d
+    timm.models.convnext.trunc_normal_ = nn.init.trunc_normal_
     timm.__oracle_restatement__ = True
     return timm

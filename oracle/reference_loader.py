@@ -24,6 +24,7 @@ _FILES = [
     ("viscy_models.unet.unet3d", "unet/unet3d.py"),
     ("viscy_models.unet.unet25d", "unet/unet25d.py"),
     ("viscy_models.unet.unext2", "unet/unext2.py"),
+    ("viscy_models.unet.fcmae", "unet/fcmae.py"),
     ("viscy_models.contrastive.encoder", "contrastive/encoder.py"),
 ]
 _ns = None
@@ -89,5 +90,8 @@ def load() -> types.SimpleNamespace:
         PixelToVoxelHead=mods["viscy_models.components.heads"].PixelToVoxelHead,
         ContrastiveEncoder=mods["viscy_models.contrastive.encoder"].ContrastiveEncoder,
         ResnetBlock=mods["viscy_models.unet.blocks"].ResnetBlock,
+        FullyConvolutionalMAE=mods["viscy_models.unet.fcmae"].FullyConvolutionalMAE,
+        fcmae=mods["viscy_models.unet.fcmae"],
+        PixelToVoxelShuffleHead=mods["viscy_models.components.heads"].PixelToVoxelShuffleHead,
     )
     return _ns

@@ -420,3 +420,25 @@ class PixelToVoxelHead(nn.Module):
     def forward_cl(self, x: Tensor) -> Tensor:
         c0 = self.conv[0]
         return F.pixel_to_voxel_head(x, c0.conv, c0.adn.A, self.conv[1], self.out_stack_depth, self.pool)
+
+
+class PixelToVoxelShuffleHead(nn.Module):
+    """Pixel-shuffle head that reshapes 2D features into a 3D volume (VM/components/heads.py:657-695); no parameters."""
+
+    def __init__(self, in_channels: int, out_channels: int, out_stack_depth: int = 5, xy_scaling: int = 4,
+                 pool: bool = False):
+        super().__init__()
+        self.out_channels = out_channels
+        self.out_stack_depth = out_stack_depth
+        self.upsample = PixelShuffleUpSample(in_channels, out_stack_depth * out_channels, xy_scaling, None, pool)
+        self.pool = pool
+
+    def forward(self, x: Tensor) -> Tensor:
+        x = self.upsample(x)
+        b, _, h, w = x.shape
+        return x.reshape(b, self.out_channels, self.out_stack_depth, h, w)
+
+    def forward_cl(self, x: Tensor) -> Tensor:
+        y = F.shuffle_pool(x, self.upsample.scale_factor, self.pool)  # [B, out * depth, H, W]
+        b, _, h, w = y.shape
+        return y.view(b, self.out_channels, self.out_stack_depth, h, w)

@@ -1,0 +1,184 @@
+// FCMAE pieces (VM/unet/fcmae.py, VM/components/heads.py:657-695) that the ConvNeXt kernels do not already cover:
+//   * rows_select: the sparse (masked) path's row gather / scatter / masking on channels-last rows
+//     (masked_patchify / masked_unpatchify / `x *= unmasked`, fcmae.py:91-141, 215-227);
+//   * shuffle_pool: PixelToVoxelShuffleHead = pixel shuffle by r + ConstantPad2d((r-1,0,r-1,0)) + AvgPool2d(r, stride 1),
+//     NHWC decoder rows -> NCHW (= NCDHW after the head's reshape) and its adjoint.
+// HBM-bound, 16-byte vectors along the channel dimension, NCHW side coalesced along X.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace vb {
+
+// dst[r, :] = (map[r] >= 0 ? src[map[r], :] : 0) + (base ? base[r, :] : 0);  C8 = channels / 8 (16-byte vectors)
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+rows_select_kernel(const uint4* __restrict__ src, const int* __restrict__ map, const uint4* __restrict__ base,
+                   uint4* __restrict__ dst, long long n_vec, int C8) {
+  using H = H16<BF16>;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n_vec; v += (long long)gridDim.x * blockDim.x) {
+    const long long r = v / C8;
+    const int c8 = (int)(v - r * C8);
+    const int m = __ldg(map + r);
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (m >= 0) q = __ldg(src + (long long)m * C8 + c8);
+    if (base) {
+      const uint4 b = __ldg(base + v);
+      const uint32_t qa[4] = {q.x, q.y, q.z, q.w}, ba[4] = {b.x, b.y, b.z, b.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = H::unpack(qa[k]), y = H::unpack(ba[k]);
+        o[k] = H::pack(x.x + y.x, x.y + y.y);
+      }
+      q = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    dst[v] = q;
+  }
+}
+
+constexpr int SP_W = 16;  // decoder pixels per block along w
+
+// forward: block = (w segment, hh, n).  smem S[2][SP_W + 1][C]: decoder rows hh-1, hh, columns w0-1 .. w0+SP_W-1.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+shuffle_pool_fwd_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int h, int w, int Cq, int r,
+                        int pool) {
+  using H = H16<BF16>;
+  extern __shared__ uint16_t sm[];
+  const int C = Cq * r * r, C8 = C / 8;
+  const int w0 = blockIdx.x * SP_W, hh = blockIdx.y;
+  const long long n = blockIdx.z;
+  uint4* sm4 = reinterpret_cast<uint4*>(sm);
+  for (int idx = threadIdx.x; idx < 2 * (SP_W + 1) * C8; idx += blockDim.x) {
+    const int c8 = idx % C8;
+    int t = idx / C8;
+    const int xl = t % (SP_W + 1), rr = t / (SP_W + 1);
+    const int y = hh - 1 + rr, x = w0 - 1 + xl;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && x >= 0 && x < w) q = __ldg(reinterpret_cast<const uint4*>(src + ((n * h + y) * w + x) * (long long)C) + c8);
+    sm4[idx] = q;
+  }
+  __syncthreads();
+  const int Ws = w * r, Hs = h * r, XW = SP_W * r;
+  const float inv = 1.0f / (float)(r * r);
+  for (int idx = threadIdx.x; idx < Cq * r * XW; idx += blockDim.x) {
+    const int xl = idx % XW;
+    int t = idx / XW;
+    const int i = t % r, cq = t / r;
+    const int X = w0 * r + xl;
+    if (X >= Ws) continue;
+    // S[y, x] (shuffled image, local coords: y in [-r, r), x in [-r, XW)) -> smem row (y>=0), column, channel
+    auto S = [&](int yl, int xx) -> float {
+      const int rr = yl >= 0 ? 1 : 0, ys = yl >= 0 ? yl : yl + r;
+      const int xc = xx >= 0 ? xx / r + 1 : 0, xs = xx >= 0 ? xx % r : xx + r;
+      return H::to_f(*reinterpret_cast<const typename H::T*>(&sm[(rr * (SP_W + 1) + xc) * C + cq * r * r + ys * r + xs]));
+    };
+    float v;
+    if (pool) {
+      v = 0.f;
+      for (int a = 0; a < r; ++a)
+        for (int b = 0; b < r; ++b) v += S(i - a, xl - b);
+      v *= inv;
+    } else {
+      v = S(i, xl);
+    }
+    const typename H::T o = H::from_f(v);
+    dst[((n * Cq + cq) * Hs + hh * r + i) * (long long)Ws + X] = *reinterpret_cast<const uint16_t*>(&o);
+  }
+}
+
+// backward: d_src[n,hh,ww, cq r^2 + i r + j] = pool ? r^-2 sum_{a,b<r} dP[cq, hh r + i + a, ww r + j + b] : dP[cq, hh r + i, ww r + j]
+// smem D[Cq][2r-1][XW + r - 1] (16-bit), loaded coalesced along X.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+shuffle_pool_bwd_kernel(const uint16_t* __restrict__ dP, uint16_t* __restrict__ dsrc, int h, int w, int Cq, int r,
+                        int pool) {
+  using H = H16<BF16>;
+  extern __shared__ uint16_t sm[];
+  const int w0 = blockIdx.x * SP_W, hh = blockIdx.y;
+  const long long n = blockIdx.z;
+  const int Ws = w * r, Hs = h * r, XW = SP_W * r;
+  const int RW = XW + r - 1, RH = 2 * r - 1;
+  for (int idx = threadIdx.x; idx < Cq * RH * RW; idx += blockDim.x) {
+    const int xl = idx % RW;
+    int t = idx / RW;
+    const int yl = t % RH, cq = t / RH;
+    const int Y = hh * r + yl, X = w0 * r + xl;
+    sm[idx] = (Y < Hs && X < Ws) ? __ldg(dP + ((n * Cq + cq) * Hs + Y) * (long long)Ws + X) : (uint16_t)0;
+  }
+  __syncthreads();
+  const int C = Cq * r * r;
+  const float inv = 1.0f / (float)(r * r);
+  for (int idx = threadIdx.x; idx < SP_W * C; idx += blockDim.x) {
+    const int c = idx % C, wl = idx / C;
+    const int ww = w0 + wl;
+    if (ww >= w) continue;
+    const int cq = c / (r * r), ij = c - cq * r * r;
+    const int i = ij / r, j = ij - i * r;
+    const uint16_t* base = sm + (cq * RH + i) * RW + wl * r + j;
+    float v = 0.f;
+    if (pool) {
+      for (int a = 0; a < r; ++a)
+        for (int b = 0; b < r; ++b) v += H::to_f(*reinterpret_cast<const typename H::T*>(base + a * RW + b));
+      v *= inv;
+    } else {
+      v = H::to_f(*reinterpret_cast<const typename H::T*>(base));
+    }
+    const typename H::T o = H::from_f(v);
+    dsrc[((n * h + hh) * w + ww) * (long long)C + c] = *reinterpret_cast<const uint16_t*>(&o);
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vb200_rows_select(const void* src, const int32_t* map, const void* base, void* dst, int64_t n_dst, int C,
+                                 int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(src && map && dst, "null pointer");
+  VB_REQUIRE(C > 0 && C % 8 == 0, "channels (%d) must be a multiple of 8", C);
+  VB_SUPPORTED(dtype == VB200_BF16 || dtype == VB200_FP16, "dtype %d", dtype);
+  if (n_dst <= 0) return VB200_OK;
+  const int C8 = C / 8;
+  const long long n_vec = (long long)n_dst * C8;
+  const unsigned blocks = (unsigned)std::min<long long>((n_vec + 255) / 256, 148LL * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_BF16)
+    rows_select_kernel<true><<<blocks, 256, 0, st>>>((const uint4*)src, map, (const uint4*)base, (uint4*)dst, n_vec, C8);
+  else
+    rows_select_kernel<false><<<blocks, 256, 0, st>>>((const uint4*)src, map, (const uint4*)base, (uint4*)dst, n_vec, C8);
+  return check_launch("rows_select");
+}
+
+extern "C" int vb200_shuffle_pool(const void* src, void* dst, int B, int h, int w, int Cq, int r, int pool, int backward,
+                                  int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(src && dst, "null pointer");
+  VB_REQUIRE(r >= 1 && r <= 8 && Cq > 0, "scale %d / channels %d", r, Cq);
+  VB_SUPPORTED(dtype == VB200_BF16 || dtype == VB200_FP16, "dtype %d", dtype);
+  const int C = Cq * r * r;
+  VB_SUPPORTED(C % 8 == 0, "decoder channels (%d) must be a multiple of 8", C);
+  const size_t smem = backward ? (size_t)Cq * (2 * r - 1) * (SP_W * r + r - 1) * 2 : (size_t)2 * (SP_W + 1) * C * 2;
+  VB_SUPPORTED(smem <= 200 * 1024, "tile of %zu bytes does not fit shared memory", smem);
+  static PerDeviceOnce once[4];
+  const int dev = PerDeviceOnce::device();
+  const int slot = (backward ? 2 : 0) + (dtype == VB200_BF16 ? 1 : 0);
+  if (once[slot].need(dev)) {
+    const void* fn = backward ? (dtype == VB200_BF16 ? (const void*)shuffle_pool_bwd_kernel<true> : (const void*)shuffle_pool_bwd_kernel<false>)
+                              : (dtype == VB200_BF16 ? (const void*)shuffle_pool_fwd_kernel<true> : (const void*)shuffle_pool_fwd_kernel<false>);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    once[slot].done(dev);
+  }
+  dim3 grid((w + SP_W - 1) / SP_W, h, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint16_t* s = (const uint16_t*)src;
+  uint16_t* d = (uint16_t*)dst;
+  if (!backward) {
+    if (dtype == VB200_BF16) shuffle_pool_fwd_kernel<true><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
+    else shuffle_pool_fwd_kernel<false><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
+  } else {
+    if (dtype == VB200_BF16) shuffle_pool_bwd_kernel<true><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
+    else shuffle_pool_bwd_kernel<false><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
+  }
+  return check_launch("shuffle_pool");
+}

@@ -80,12 +80,20 @@ class ConvNeXtBlockFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b, grn_w, grn_b, gamma, keep):
+    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b, grn_w, grn_b, gamma, keep, eps=LN_EPS,
+                dw=True):
         B, H, W, C = x.shape
         M = B * H * W
-        wt, wt_flip = _dw_taps(dw_w)
-        ctx.wt_flip = wt_flip
-        d = ops.dwconv7(x, wt, dw_b)
+        ctx.dw = dw
+        if dw:
+            wt, wt_flip = _dw_taps(dw_w)
+            ctx.wt_flip = wt_flip
+            d = ops.dwconv7(x, wt, dw_b)
+            res = x.view(M, C)
+        else:
+            # rows already behind the depthwise conv (FCMAE sparse path: x = the gathered unmasked rows [B, L, 1, C]);
+            # the shortcut is added by the caller's scatter
+            d, res = x, None
         C4 = fc1_w.shape[0]
         use_grn = grn_w is not None
         R = H * W
@@ -93,10 +101,10 @@ class ConvNeXtBlockFn(Function):
         onescol = (fused or not use_grn) and C % 16 == 0 and C <= 2048 and C4 % 8 == 0
         if onescol:
             gbuf = torch.empty((M, C4 + PAD), device=x.device, dtype=x.dtype)  # [g | 1 0 ... 0]
-            lbuf, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS, ones=True, ones2=gbuf, ones2_col=C4)
+            lbuf, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, eps, ones=True, ones2=gbuf, ones2_col=C4)
             l2, y2 = lbuf[:, :C], gbuf[:, :C4]
         else:
-            l, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, LN_EPS)
+            l, mean, rstd = ops.layernorm_fwd(d, ln_w, ln_b, eps)
             lbuf = l2 = l.view(M, C)
             gbuf = y2 = None
         if fused:
@@ -109,7 +117,7 @@ class ConvNeXtBlockFn(Function):
                 gbuf = y2
             w2 = fc2_w.detach().reshape(C, C4)
             s, w2s, b2e = ops.grn_prepare(sumsq, grn_w.detach(), grn_b.detach(), w2, fc2_b.detach(), x.dtype)
-            out = ops.gemm(y2, w2s, bias=b2e, residual=x.view(M, C), b_batch_rows=R, rvec=keep, rvec_rows=R)
+            out = ops.gemm(y2, w2s, bias=b2e, residual=res, b_batch_rows=R, rvec=keep, rvec_rows=R)
             ctx.save_for_backward(x, d, mean, rstd, lbuf, h, gbuf, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, grn_b, keep)
             ctx.use_grn, ctx.fused, ctx.onescol = True, True, onescol
             return out.view(B, H, W, C)
@@ -124,7 +132,7 @@ class ConvNeXtBlockFn(Function):
             sumsq = s = None
         # ConvNeXt-V1 layer scale: out = gamma * (y W2^T + b2) + x, gamma applied in fp32 in the epilogue
         out = ops.gemm(y2, ops.packed(fc2_w, x.dtype).view(C, C4), bias=fc2_b.detach(),
-                       svec=None if gamma is None else gamma.detach(), residual=x.view(M, C), rvec=keep, rvec_rows=R)
+                       svec=None if gamma is None else gamma.detach(), residual=res, rvec=keep, rvec_rows=R)
         ctx.fused, ctx.onescol = False, onescol
         ctx.save_for_backward(x, d, mean, rstd, lbuf, h, gbuf, sumsq, s, dw_w, ln_w, fc1_w, fc2_w, fc2_b, grn_w, gamma, keep)
         ctx.use_grn = use_grn
@@ -210,6 +218,10 @@ class ConvNeXtBlockFn(Function):
                                k_splits=_wgrad_splits(C4, C, M)).view(fc1_w.shape)
         dl = ops.gemm(dh2, ops.packed(fc1_w, x.dtype, transpose=True))
         dd, dlnw, dlnb = ops.layernorm_bwd(dl.view(B, H, W, C), d, mean, rstd, ln_w, ar)
+        if not ctx.dw:
+            if side is not main:
+                main.wait_stream(side)
+            return dd, None, None, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma, None, None, None
         if side is not main:
             side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -218,7 +230,7 @@ class ConvNeXtBlockFn(Function):
         if side is not main:
             main.wait_stream(side)
         ddw = dwt.t().reshape(dw_w.shape)
-        return dx, ddw, ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma, None
+        return dx, ddw, ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgw, dgb, dgamma, None, None, None
 
 
 def drop_path_scale(x: torch.Tensor, drop_prob: float, training: bool):
@@ -242,6 +254,101 @@ def convnext_block(x, blk, keep=None) -> torch.Tensor:
         blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias,
         None if grn is None else grn.weight, None if grn is None else grn.bias, getattr(blk, "gamma", None), keep,
     )
+
+
+# --------------------------------------------------------------------------------------------------
+# FCMAE (VM/unet/fcmae.py): dense blocks are ConvNeXtBlockFn with nn.LayerNorm's eps; the sparse (masked) path gathers
+# the unmasked rows behind the depthwise conv, runs LN / MLP / GRN on them alone and scatters back onto the shortcut.
+class DwConv7Fn(Function):
+    """Depthwise 7x7 (padding 3) on NHWC rows."""
+
+    @staticmethod
+    def forward(ctx, x, dw_w, dw_b):
+        wt, wt_flip = _dw_taps(dw_w)
+        ctx.save_for_backward(x, dw_w)
+        ctx.wt_flip = wt_flip
+        return ops.dwconv7(x, wt, dw_b)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dd):
+        x, dw_w = ctx.saved_tensors
+        dd = dd.contiguous()
+        dwt, ddb = ops.dwconv7_wgrad(x, dd)
+        dx = ops.dwconv7(dd, ctx.wt_flip, None)
+        return dx, dwt.t().reshape(dw_w.shape), ddb
+
+
+class RowsSelectFn(Function):
+    """dst[r] = (fwd_map[r] >= 0 ? src[fwd_map[r]] : 0) [+ base[r]];  bwd_map is the adjoint's map over the rows of src
+    (gather <-> scatter: row index list <-> inverse index with -1 at the rows that are not selected)."""
+
+    @staticmethod
+    def forward(ctx, src, base, fwd_map, bwd_map):
+        ctx.save_for_backward(bwd_map)
+        ctx.has_base = base is not None
+        return ops.rows_select(src, fwd_map, base=base)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (bwd_map,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        return ops.rows_select(dout, bwd_map), (dout if ctx.has_base else None), None, None
+
+
+class MaskIndex:
+    """Row maps of one boolean foreground mask [B, H, W] (True = kept; the same count L in every sample):
+    idx [B*L] = kept rows in row-major order (masked_patchify's order), inv [B*H*W] = position in idx or -1,
+    keep_self [B*H*W] = own row index or -1 (`x *= unmasked`)."""
+
+    def __init__(self, unmasked: torch.Tensor, rows_per_sample: int):
+        flat = unmasked.reshape(-1)
+        M = flat.numel()
+        n_keep = rows_per_sample * unmasked.shape[0]
+        order = torch.argsort(flat.to(torch.int8), descending=True, stable=True)
+        self.idx = order[:n_keep].to(torch.int32).contiguous()
+        rows = torch.arange(M, device=flat.device, dtype=torch.int32)
+        self.inv = torch.full((M,), -1, device=flat.device, dtype=torch.int32)
+        self.inv[self.idx.long()] = torch.arange(n_keep, device=flat.device, dtype=torch.int32)
+        self.keep_self = torch.where(flat, rows, torch.full_like(rows, -1)).contiguous()
+        self.rows_per_sample = n_keep // unmasked.shape[0]
+
+
+def fcmae_block(x, blk, mi: MaskIndex | None = None, keep=None):
+    """MaskedConvNeXtV2Block (fcmae.py:144-227) on NHWC rows.  mi: row maps of the (upsampled) foreground mask or None."""
+    mlp = blk.mlp
+    args = (blk.layernorm.weight, blk.layernorm.bias, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias,
+            mlp.grn.weight, mlp.grn.bias, None, keep, blk.layernorm.eps)
+    if mi is None:
+        return ConvNeXtBlockFn.apply(x, blk.dwconv.weight, blk.dwconv.bias, *args, True)
+    B, H, W, C = x.shape
+    M = B * H * W
+    xm = RowsSelectFn.apply(x.view(M, C), None, mi.keep_self, mi.keep_self)  # x *= unmasked (the shortcut is masked too)
+    d = DwConv7Fn.apply(xm.view(B, H, W, C), blk.dwconv.weight, blk.dwconv.bias)
+    rows = RowsSelectFn.apply(d.view(M, C), None, mi.idx, mi.inv)            # masked_patchify
+    o = ConvNeXtBlockFn.apply(rows.view(B, mi.rows_per_sample, 1, C), None, None, *args, False)
+    out = RowsSelectFn.apply(o.view(-1, C), xm, mi.inv, mi.idx)              # masked_unpatchify + shortcut
+    return out.view(B, H, W, C)
+
+
+class ShufflePoolFn(Function):
+    """PixelToVoxelShuffleHead (heads.py:657-695): NHWC decoder rows -> (B, Cq, H r, W r)."""
+
+    @staticmethod
+    def forward(ctx, dec, r, pool):
+        ctx.rp = (r, pool)
+        return ops.shuffle_pool_fwd(dec, r, pool)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        r, pool = ctx.rp
+        return ops.shuffle_pool_bwd(dout.contiguous(), r, pool), None, None
+
+
+def shuffle_pool(dec, r, pool):
+    return ShufflePoolFn.apply(dec, r, pool)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -535,6 +535,41 @@ def col2im3d(dcol, geom):
 
 
 # ----------------------------------------------------------------------------------------------
+# FCMAE pieces
+def rows_select(src, rowmap, n_dst=None, base=None):
+    """dst[r] = (rowmap[r] >= 0 ? src[rowmap[r]] : 0) + (base[r] if base is given); src [S, C] / rowmap int32 [n_dst]."""
+    _act(src, "src")
+    Cc = src.shape[-1]
+    n_dst = rowmap.numel() if n_dst is None else n_dst
+    if rowmap.dtype != torch.int32 or not rowmap.is_contiguous():
+        raise ValueError("rowmap must be contiguous int32")
+    if base is not None:
+        _act(base, "base")
+    dst = torch.empty((n_dst, Cc), device=src.device, dtype=src.dtype)
+    _call("vb200_rows_select", _p(src), _p(rowmap), _p(base), _p(dst), C.c_int64(n_dst), Cc, L.dtype_code(src.dtype))
+    return dst
+
+
+def shuffle_pool_fwd(dec, r, pool):
+    """dec [B,h,w,Cq*r*r] -> [B,Cq,h*r,w*r] (pixel shuffle + front pad + r x r average pool, stride 1)"""
+    _act(dec, "dec")
+    B, h, w, Cd = dec.shape
+    Cq = Cd // (r * r)
+    out = torch.empty((B, Cq, h * r, w * r), device=dec.device, dtype=dec.dtype)
+    _call("vb200_shuffle_pool", _p(dec), _p(out), B, h, w, Cq, r, int(pool), 0, L.dtype_code(dec.dtype))
+    return out
+
+
+def shuffle_pool_bwd(dout, r, pool):
+    _act(dout, "dout")
+    B, Cq, Hs, Ws = dout.shape
+    h, w = Hs // r, Ws // r
+    ddec = torch.empty((B, h, w, Cq * r * r), device=dout.device, dtype=dout.dtype)
+    _call("vb200_shuffle_pool", _p(dout), _p(ddec), B, h, w, Cq, r, int(pool), 1, L.dtype_code(dout.dtype))
+    return ddec
+
+
+# ----------------------------------------------------------------------------------------------
 # PixelToVoxelHead pieces
 def head_shuffle_pool_fwd(dec, Dz, pool, Cu):
     _act(dec, "dec")

@@ -26,7 +26,7 @@ extern "C" {
 typedef void* vb200_stream_t; /* cudaStream_t */
 
 enum { VB200_OK = 0, VB200_ERR_INVALID = 1, VB200_ERR_UNSUPPORTED = 2, VB200_ERR_CUDA = 3 };
-enum { VB200_BF16 = 0, VB200_FP16 = 1 };
+enum { VB200_BF16 = 0, VB200_FP16 = 1, VB200_FP32 = 2 /* only where an entry point says so (loss inputs) */ };
 
 /* GEMM epilogues (fused into the tcgen05 kernel's TMEM->register drain) */
 enum {
@@ -319,6 +319,28 @@ int vb200_rows_select(const void* src, const int32_t* map, const void* base, voi
  * backward (!= 0): src = d dst [B,Cq,h*r,w*r], dst = d decoder rows [B,h,w,Cq*r*r] */
 int vb200_shuffle_pool(const void* src, void* dst, int B, int h, int w, int Cq, int r, int pool, int backward, int dtype,
                        vb200_stream_t stream);
+
+/* ---- MixedLoss / ms_ssim_25d (VU/losses/mixed_loss.py:42-69, VU/evaluation/metrics.py:174-349) ----
+ * One pyramid level of ms_ssim_25d in one pass over preds x and target y, both [B,C,D,H,W] contiguous (NCDHW), each of
+ * dtype VB200_BF16 | VB200_FP16 | VB200_FP32.  Rounding points follow _compute_ssim_and_cs_bf16 (metrics.py:174-262): the
+ * five window inputs (x, y, x*x, y*y, x*y; products formed in fp32) and the five window means are rounded to bf16, the window
+ * weight is bf16(1 / (D*kh*kw)), everything else is fp32.  flags: 1 = SSIM (window (D,kh,kw), valid), 2 = L1 / L2 sums,
+ * 4 = avg_pool3d((1,2,2)) of both volumes into x_pool / y_pool [B,C,D,H/2,W/2] (their own dtypes).
+ *   acc [B][4] += per-sample SUMS: ssim map, contrast-sensitivity map, |x-y|, (x-y)^2   (caller zeroes, divides by counts)
+ *   mu  [5][B*C][H-kh+1][W-kw+1] fp32 = the window means (for the backward pass), or NULL
+ *   data_range = device scalar target.max() of this level (metrics.py:296); data_range_next (pre-set to -inf, or NULL)
+ *   receives max(y_pool) */
+int vb200_ssim25d_level_fwd(const void* x, const void* y, int x_dtype, int y_dtype, int B, int C, int D, int H, int W, int kh,
+                            int kw, const float* data_range, float* acc, float* mu, void* x_pool, void* y_pool,
+                            float* data_range_next, int flags, vb200_stream_t stream);
+/* d loss / d x of one level: g_ssim / g_cs [B] = upstream gradients of the per-sample MEANS of the two maps, g_l1 / g_l2 =
+ * device scalars, upstream of mean|x-y| and mean (x-y)^2, g_pool = gradient of x_pool (x's dtype); any of them may be NULL.
+ * dx [B,C,D,H,W] in x's dtype is overwritten. */
+int vb200_ssim25d_level_bwd(const void* x, const void* y, int x_dtype, int y_dtype, int B, int C, int D, int H, int W, int kh,
+                            int kw, const float* data_range, const float* mu, const float* g_ssim, const float* g_cs,
+                            const float* g_l1, const float* g_l2, const void* g_pool, void* dx, vb200_stream_t stream);
+/* max over n elements (target.max(), metrics.py:296) into *out, which the caller pre-sets to -inf */
+int vb200_max_f(const void* x, int dtype, int64_t n, float* out, vb200_stream_t stream);
 
 /* ---- PixelToVoxelHead (VM/components/heads.py:594-641) ---- */
 /* forward (backward == 0): dec [B,h,w,4*Cm] -> u [B,Dz,2h,2w,Cu] = unfold(pool(pixelshuffle2(dec)));

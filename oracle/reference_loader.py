@@ -95,3 +95,53 @@ def load() -> types.SimpleNamespace:
         PixelToVoxelShuffleHead=mods["viscy_models.components.heads"].PixelToVoxelShuffleHead,
     )
     return _ns
+
+
+_loss_ns = None
+
+
+def load_losses() -> types.SimpleNamespace:
+    """The reference's own `MixedLoss` / `ms_ssim_25d` / `ssim_25d` (viscy-utils), executed unmodified.  metrics.py imports
+    scipy (present) and skimage / torchmetrics / torchvision symbols that the SSIM functions never touch: absent packages
+    are replaced by empty shells carrying just those names."""
+    global _loss_ns
+    if _loss_ns is not None:
+        return _loss_ns
+    if not available():
+        raise RuntimeError("/root/reference is not present (GPU box): use tests/golden fixtures instead")
+    src = Path("/root/reference/packages/viscy-utils/src/viscy_utils")
+
+    def shell(name, **attrs):
+        try:
+            return importlib.import_module(name)
+        except Exception:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            return m
+
+    unused = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("not part of the SSIM path"))  # noqa: E731
+    shell("skimage")
+    shell("skimage.measure", label=unused, regionprops=unused)
+    shell("torchmetrics")
+    shell("torchmetrics.detection")
+    shell("torchmetrics.detection.mean_ap", MeanAveragePrecision=unused)
+    shell("torchvision")
+    shell("torchvision.ops", masks_to_boxes=unused)
+    for pkg, sub in (("viscy_utils", ""), ("viscy_utils.evaluation", "evaluation"), ("viscy_utils.losses", "losses")):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = [str(src / sub)]
+            sys.modules[pkg] = m
+    mods = {}
+    for name, rel in (("viscy_utils.evaluation.metrics", "evaluation/metrics.py"),
+                      ("viscy_utils.losses.mixed_loss", "losses/mixed_loss.py")):
+        spec = importlib.util.spec_from_file_location(name, src / rel)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    met = mods["viscy_utils.evaluation.metrics"]
+    _loss_ns = types.SimpleNamespace(MixedLoss=mods["viscy_utils.losses.mixed_loss"].MixedLoss,
+                                     ms_ssim_25d=met.ms_ssim_25d, ssim_25d=met.ssim_25d)
+    return _loss_ns

@@ -342,6 +342,14 @@ int vb200_ssim25d_level_bwd(const void* x, const void* y, int x_dtype, int y_dty
 /* max over n elements (target.max(), metrics.py:296) into *out, which the caller pre-sets to -inf */
 int vb200_max_f(const void* x, int dtype, int64_t n, float* out, vb200_stream_t stream);
 
+/* ---- Prediction path (CY/engine.py:61-71 _center_crop_to_shape, :711-805 predict_sliding_windows;
+ * VU/callbacks/prediction_writer.py:74-111 _blend_in) ----
+ * dst [B*C, Z, H, W] <- window prediction src [B*C, d, Hs, Ws] centre-cropped at (oy, ox), blended into Z range [z0, z0+d):
+ * z0 == 0: dst = src; else samples = min(z0+1, d), f_i = min(d-i, samples), dst = dst*(f-1)/f + src/f.  dtypes: VB200_BF16 |
+ * VB200_FP16 | VB200_FP32, independent for dst and src; arithmetic in fp32. */
+int vb200_blend_window(void* dst, const void* src, int dst_dtype, int src_dtype, int64_t BC, int Z, int H, int W, int d,
+                       int Hs, int Ws, int z0, int oy, int ox, vb200_stream_t stream);
+
 /* ---- PixelToVoxelHead (VM/components/heads.py:594-641) ---- */
 /* forward (backward == 0): dec [B,h,w,4*Cm] -> u [B,Dz,2h,2w,Cu] = unfold(pool(pixelshuffle2(dec)));
  * backward (!= 0): src = du, dst = ddec */

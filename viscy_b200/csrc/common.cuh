@@ -85,6 +85,23 @@ struct H16<false> {
   }
 };
 
+// ---- runtime-typed element access (dt: VB200_BF16 | VB200_FP16 | VB200_FP32) for the loss / prediction kernels ----
+__device__ __forceinline__ float ld_any(const void* p, long long i, int dt) {
+  if (dt == 2) return __ldg(reinterpret_cast<const float*>(p) + i);
+  if (dt == 0) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+  return __half2float(__ldg(reinterpret_cast<const __half*>(p) + i));
+}
+__device__ __forceinline__ float round_any(float v, int dt) {
+  if (dt == 2) return v;
+  if (dt == 0) return __bfloat162float(__float2bfloat16_rn(v));
+  return __half2float(__float2half_rn(v));
+}
+__device__ __forceinline__ void st_any(void* p, long long i, int dt, float v) {
+  if (dt == 2) reinterpret_cast<float*>(p)[i] = v;
+  else if (dt == 0) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+
 // exact-form (erf) GELU, as timm's act_layer='gelu' -> nn.GELU().  erf through
 // Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below 16-bit output rounding) so that GELU and its
 // derivative share one exp:  erf(x) = 1 - (a1 t + ... + a5 t^5) e^{-x^2},  t = 1/(1 + p x),  x >= 0.

@@ -20,21 +20,6 @@ namespace ssim {
 
 constexpr int TH = 32, TW = 64, NT = 256, KMAX = 16;
 
-__device__ __forceinline__ float ld_any(const void* p, long long i, int dt) {
-  if (dt == 2) return __ldg(reinterpret_cast<const float*>(p) + i);
-  if (dt == 0) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p) + i));
-  return __half2float(__ldg(reinterpret_cast<const __half*>(p) + i));
-}
-__device__ __forceinline__ float round_any(float v, int dt) {
-  if (dt == 2) return v;
-  if (dt == 0) return __bfloat162float(__float2bfloat16_rn(v));
-  return __half2float(__float2half_rn(v));
-}
-__device__ __forceinline__ void st_any(void* p, long long i, int dt, float v) {
-  if (dt == 2) reinterpret_cast<float*>(p)[i] = v;
-  else if (dt == 0) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
-  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
-}
 __device__ __forceinline__ float bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {

@@ -16,6 +16,8 @@ REF_SRC = Path("/root/reference/packages/viscy-models/src/viscy_models")
 _FILES = [
     ("viscy_models.schedule", "schedule.py"),
     ("viscy_models.components.conv_block_3d", "components/conv_block_3d.py"),
+    ("viscy_models.components.conv_block_2d", "components/conv_block_2d.py"),
+    ("viscy_models.unet.unet2d", "unet/unet2d.py"),
     ("viscy_models.components.stems", "components/stems.py"),
     ("viscy_models.components.blocks", "components/blocks.py"),
     ("viscy_models.components.heads", "components/heads.py"),
@@ -90,6 +92,8 @@ def load() -> types.SimpleNamespace:
         PixelToVoxelHead=mods["viscy_models.components.heads"].PixelToVoxelHead,
         ContrastiveEncoder=mods["viscy_models.contrastive.encoder"].ContrastiveEncoder,
         ResnetBlock=mods["viscy_models.unet.blocks"].ResnetBlock,
+        Unet2d=mods["viscy_models.unet.unet2d"].Unet2d,
+        ConvBlock2D=mods["viscy_models.components.conv_block_2d"].ConvBlock2D,
         FullyConvolutionalMAE=mods["viscy_models.unet.fcmae"].FullyConvolutionalMAE,
         fcmae=mods["viscy_models.unet.fcmae"],
         PixelToVoxelShuffleHead=mods["viscy_models.components.heads"].PixelToVoxelShuffleHead,

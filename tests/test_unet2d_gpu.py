@@ -1,0 +1,71 @@
+"""Unet2d / ConvBlock2D through the sm_100a kernels (depth-1 volumes on the 3-D conv / norm / pooling kernels) vs the golden
+vectors from the reference's code and, element-wise for the parameter gradients, vs the fp32 CPU mirror (== the reference)."""
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("dtype,ftol", [(torch.float16, 1e-2), (torch.bfloat16, 8e-2)])
+@pytest.mark.parametrize("name", ["unet2d", "unet2d_res"])
+def test_unet2d_against_reference_golden(cuda, name, dtype, ftol):
+    from viscy_b200 import Unet2d
+    g = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    torch.manual_seed(g["seed"])
+    ref = Unet2d(**g["cfg"])
+    m = Unet2d(**g["cfg"])
+    m.load_state_dict(ref.state_dict())
+    m = m.to(cuda)
+    torch.nn.functional.mse_loss(ref(g["x"]), g["target"]).backward()
+    with torch.autocast("cuda", dtype=dtype):
+        out = m(g["x"].to(cuda))
+        loss = torch.nn.functional.mse_loss(out.float(), g["target"].to(cuda))
+    scale = 256.0 if dtype == torch.float16 else 1.0
+    (loss * scale).backward()
+    assert out.shape == g["out"].shape and out.dtype == dtype
+    e = rel(out.float().cpu(), g["out"])
+    print(f"\n[{name} {dtype}] forward rel-L2 vs reference golden {e:.3e}; loss {loss.item():.5f} vs {g['loss']:.5f}")
+    assert e < ftol  # BatchNorm-after-ReLU stacks amplify 16-bit storage rounding (see tests/test_unet25d_gpu.py)
+    assert abs(loss.item() - g["loss"]) < 2 * ftol * abs(g["loss"])
+    refg = dict(ref.named_parameters())
+    worst = []
+    for n, p in m.named_parameters():
+        gr = refg[n].grad
+        if gr is None:
+            assert p.grad is None, n
+            continue
+        if gr.dim() > 1 and gr.norm() > 1e-6:
+            worst.append((rel(p.grad.cpu() / scale, gr), n))
+    worst.sort(reverse=True)
+    print("worst weight grads:", [(f"{w:.2e}", n) for w, n in worst[:4]])
+    assert worst[0][0] < (8e-2 if dtype == torch.float16 else 4e-1)
+    # running statistics were updated once, like the reference's
+    bn = m.down_conv_block_0.batch_norm_0
+    torch.testing.assert_close(bn.running_mean.cpu(), ref.down_conv_block_0.batch_norm_0.running_mean, rtol=2e-2, atol=2e-3)
+    assert int(bn.num_batches_tracked) == 1
+
+
+def test_conv_block_2d_variants(cuda):
+    from viscy_b200 import ConvBlock2D
+    for kw in (dict(norm="instance", activation="leakyrelu", layer_order="cna"), dict(norm="batch", activation="selu"),
+               dict(norm="none", activation="linear", num_repeats=1, residual=False), dict(filter_steps="last", kernel_size=(3, 5))):
+        torch.manual_seed(7)
+        blk = ConvBlock2D(16, 32, **kw)
+        x = torch.randn(2, 16, 24, 40)
+        ref = blk(x)
+        blk = blk.to(cuda)
+        for mod in blk.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.reset_running_stats()
+        xc = x.to(cuda).permute(0, 2, 3, 1).unsqueeze(1).contiguous().half()  # [N, 1, H, W, C]
+        y = blk.forward_cl(xc)
+        e = rel(y[:, 0].permute(0, 3, 1, 2).float().cpu(), ref)
+        print(kw, f"{e:.3e}")
+        assert e < 4e-3, (kw, e)

@@ -1184,6 +1184,8 @@ def dropout3d_scale(x, p: float, training: bool):
     """Per-(sample, channel) scale of nn.Dropout3d on channels-last rows, or None when it is the identity."""
     if not training or p <= 0.0:
         return None
+    if p >= 1.0:
+        return torch.zeros((x.shape[0], x.shape[-1]), device=x.device, dtype=torch.float32)
     keep = torch.full((x.shape[0], x.shape[-1]), 1.0 - p, device=x.device, dtype=torch.float32)
     return torch.bernoulli(keep) / (1.0 - p)
 

@@ -29,6 +29,51 @@ def _reject_cuda(x: Tensor, what: str) -> None:
         )
 
 
+def conv_block_forward_cl(blk, x: Tensor, pad, drop_p: float) -> Tensor:
+    """The layer loop shared by ConvBlock3D and ConvBlock2D (conv_block_3d.py:261-298, conv_block_2d.py forward) on
+    channels-last rows: `blk` provides _conv_cl(x, i, pad), _act_cl, _has_act, norm_list, norm, activation, layer_order,
+    residual, resid_conv, in_filters / out_filters; drop_p is the channel-dropout probability."""
+    x0 = x
+    for i in range(blk.num_repeats):
+        order = blk.layer_order
+        k = 0
+        while k < len(order):
+            layer = order[k]
+            act_next = k + 1 < len(order) and order[k + 1] == "a" and blk._has_act(i)
+            if layer == "c":
+                x = blk._conv_cl(x, i, pad)
+                scale = F.dropout3d_scale(x, drop_p, blk.training) if drop_p else None
+                if act_next:  # conv -> dropout -> activation in one pass over the tensor
+                    x = blk._act_cl(x, scale)
+                    k += 1
+                elif scale is not None:
+                    x = F.scale_relu_cl(x, scale, False)
+            elif layer == "a":
+                if blk._has_act(i):
+                    x = blk._act_cl(x, None)
+            elif layer == "n" and blk.norm_list[i] is not None:
+                if blk.norm == "instance":  # norm (-> activation) in one pass
+                    x = F.instancenorm_act_cl(x, blk.norm_list[i].eps, blk.activation if act_next else "none")
+                    k += int(act_next)
+                else:
+                    fuse = act_next and blk.activation == "relu"
+                    x = F.batchnorm_act_cl(x, blk.norm_list[i], relu=fuse)
+                    k += int(fuse)
+            k += 1
+    if blk.residual:
+        if blk.in_filters > blk.out_filters:
+            x0 = F.Conv3dFn.apply(x0, blk.resid_conv.weight.reshape(blk.out_filters, blk.in_filters, 1, 1, 1),
+                                  blk.resid_conv.bias, (1, 1, 1), (0, 0, 0))
+        elif blk.in_filters < blk.out_filters:
+            cin_rows, cout_rows = x0.shape[-1], x.shape[-1]
+            if cin_rows != blk.in_filters or cout_rows != blk.out_filters:
+                raise NotImplementedError("sm_100a conv block: residual channel growth needs channel counts % 8 == 0")
+            zeros = torch.zeros((*x0.shape[:-1], cout_rows - cin_rows), device=x0.device, dtype=x0.dtype)
+            x0 = F.cat_cl(zeros, x0)  # identity lands on the LAST in_filters channels (conv_block_3d.py:281-287)
+        x = F.add_cl(x, x0)
+    return x
+
+
 class ConvBlock3D(nn.Module):
     """`num_repeats` x [pad -> conv -> (dropout) -> act -> norm] in the order given by `layer_order`, plus an optional
     residual path (1x1x1 conv when channels shrink, zero channels prepended when they grow)."""
@@ -124,44 +169,7 @@ class ConvBlock3D(nn.Module):
     def forward_cl(self, x: Tensor) -> Tensor:
         """sm_100a path on channels-last rows [N,D,H,W,C] (C padded to a multiple of 8)."""
         pw, ph, pd = self.padding[0], self.padding[2], self.padding[4]
-        x0 = x
-        for i in range(self.num_repeats):
-            order = self.layer_order
-            k = 0
-            while k < len(order):
-                layer = order[k]
-                act_next = k + 1 < len(order) and order[k + 1] == "a" and self._has_act(i)
-                if layer == "c":
-                    x = self._conv_cl(x, i, (pd, ph, pw))
-                    scale = F.dropout3d_scale(x, self.dropout, self.training) if self.dropout else None
-                    if act_next:  # conv -> dropout -> activation in one pass over the tensor
-                        x = self._act_cl(x, scale)
-                        k += 1
-                    elif scale is not None:
-                        x = F.scale_relu_cl(x, scale, False)
-                elif layer == "a":
-                    if self._has_act(i):
-                        x = self._act_cl(x, None)
-                elif layer == "n" and self.norm_list[i] is not None:
-                    if self.norm == "instance":  # norm (-> activation) in one pass
-                        x = F.instancenorm_act_cl(x, self.norm_list[i].eps, self.activation if act_next else "none")
-                        k += int(act_next)
-                    else:
-                        fuse = act_next and self.activation == "relu"
-                        x = F.batchnorm_act_cl(x, self.norm_list[i], relu=fuse)
-                        k += int(fuse)
-                k += 1
-        if self.residual:
-            if self.in_filters > self.out_filters:
-                x0 = F.conv3d_cl(x0, self.resid_conv)
-            elif self.in_filters < self.out_filters:
-                cin_rows, cout_rows = x0.shape[-1], x.shape[-1]
-                if cin_rows != self.in_filters or cout_rows != self.out_filters:
-                    raise NotImplementedError("sm_100a ConvBlock3D: residual channel growth needs channel counts % 8 == 0")
-                zeros = torch.zeros((*x0.shape[:-1], cout_rows - cin_rows), device=x0.device, dtype=x0.dtype)
-                x0 = F.cat_cl(zeros, x0)  # identity lands on the LAST in_filters channels (conv_block_3d.py:281-287)
-            x = F.add_cl(x, x0)
-        return x
+        return conv_block_forward_cl(self, x, (pd, ph, pw), self.dropout if self.dropout else 0.0)
 
     def _has_act(self, i: int) -> bool:
         return self.activation != "linear"

@@ -65,11 +65,11 @@ def conv_block_forward_cl(blk, x: Tensor, pad, drop_p: float) -> Tensor:
             x0 = F.Conv3dFn.apply(x0, blk.resid_conv.weight.reshape(blk.out_filters, blk.in_filters, 1, 1, 1),
                                   blk.resid_conv.bias, (1, 1, 1), (0, 0, 0))
         elif blk.in_filters < blk.out_filters:
-            cin_rows, cout_rows = x0.shape[-1], x.shape[-1]
-            if cin_rows != blk.in_filters or cout_rows != blk.out_filters:
-                raise NotImplementedError("sm_100a conv block: residual channel growth needs channel counts % 8 == 0")
-            zeros = torch.zeros((*x0.shape[:-1], cout_rows - cin_rows), device=x0.device, dtype=x0.dtype)
-            x0 = F.cat_cl(zeros, x0)  # identity lands on the LAST in_filters channels (conv_block_3d.py:281-287)
+            grow = blk.out_filters - blk.in_filters
+            zeros = torch.zeros((*x0.shape[:-1], -(-grow // 8) * 8), device=x0.device, dtype=x0.dtype)
+            # identity lands on the LAST in_filters channels (conv_block_3d.py:281-287); real channel counts so that
+            # padded rows are compacted to [zeros | x0 | pad]
+            x0 = F.cat_cl(zeros, x0, grow, blk.in_filters)
         x = F.add_cl(x, x0)
     return x
 

@@ -34,7 +34,25 @@ def test_unet2d_against_reference_golden(cuda, name, dtype, ftol):
     print(f"\n[{name} {dtype}] forward rel-L2 vs reference golden {e:.3e}; loss {loss.item():.5f} vs {g['loss']:.5f}")
     assert e < ftol  # BatchNorm-after-ReLU stacks amplify 16-bit storage rounding (see tests/test_unet25d_gpu.py)
     assert abs(loss.item() - g["loss"]) < 2 * ftol * abs(g["loss"])
-    refg = dict(ref.named_parameters())
+    # gradient yardstick: the fp32 mirror with activations rounded to `dtype` at autocast's storage points (conv, norm,
+    # activation, pooling outputs).  This BatchNorm-after-ReLU stack turns a 6e-3 forward perturbation into a ~1.4e-1
+    # weight-gradient deviation all by itself (fp16); the sm_100a path must stay within 1.5 x that, per tensor.
+    class Round16(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, v):
+            return v.to(dtype).float()
+
+        @staticmethod
+        def backward(ctx, gr):
+            return gr
+
+    torch.manual_seed(g["seed"])
+    emu = Unet2d(**g["cfg"])
+    for mod in emu.modules():
+        if isinstance(mod, (torch.nn.Conv2d, torch.nn.BatchNorm2d, torch.nn.ReLU, torch.nn.AvgPool2d)):
+            mod.register_forward_hook(lambda _m, _i, o: Round16.apply(o))
+    torch.nn.functional.mse_loss(emu(g["x"].to(dtype).float()), g["target"]).backward()
+    refg, emug = dict(ref.named_parameters()), dict(emu.named_parameters())
     worst = []
     for n, p in m.named_parameters():
         gr = refg[n].grad
@@ -42,10 +60,11 @@ def test_unet2d_against_reference_golden(cuda, name, dtype, ftol):
             assert p.grad is None, n
             continue
         if gr.dim() > 1 and gr.norm() > 1e-6:
-            worst.append((rel(p.grad.cpu() / scale, gr), n))
+            e_ours, e_emu = rel(p.grad.cpu() / scale, gr), rel(emug[n].grad, gr)
+            worst.append((e_ours / max(e_emu, 1e-2), e_ours, e_emu, n))
     worst.sort(reverse=True)
-    print("worst weight grads:", [(f"{w:.2e}", n) for w, n in worst[:4]])
-    assert worst[0][0] < (8e-2 if dtype == torch.float16 else 4e-1)
+    print("worst weight grads (ratio, ours, yardstick):", [(f"{r:.2f}", f"{a:.2e}", f"{b:.2e}", n) for r, a, b, n in worst[:4]])
+    assert worst[0][0] < 1.5, worst[:3]
     # running statistics were updated once, like the reference's
     bn = m.down_conv_block_0.batch_norm_0
     torch.testing.assert_close(bn.running_mean.cpu(), ref.down_conv_block_0.batch_norm_0.running_mean, rtol=2e-2, atol=2e-3)

@@ -368,6 +368,14 @@ int vb200_head_tail_bwd(int phase, const void* z, const float* mean, const float
                         int alpha_n, const float* W1, const void* dout, float* sdp, float* sdpx, float* db1,
                         float* dalpha, void* act_out, void* dt_out, void* dz, float* dbz, int B, int Dz, int H, int W,
                         int Cmid, int Co4, int dtype, vb200_stream_t stream);
+/* Streaming form of vb200_head_tail_bwd for the BASELINE head geometry (Cmid == 32, Co4 == 8, 256 % W == 0,
+ * Dz*H*W % 256 == 0; anything else returns VB200_ERR_UNSUPPORTED): z tiles and the pixel-shuffled dout lines stream through
+ * a bulk-copy / mbarrier ring, nothing is materialised.  phase 0 accumulates sdp, sdpx [B,32], db1 [8], dalpha, dW1 [8,32]
+ * (all pre-zeroed, fp32); phase 1 writes dz [B,R,32] and accumulates dbz [32] (pre-zeroed) from the finished sums. */
+int vb200_head_tail_bwd_stream(int phase, const void* z, const float* mean, const float* rstd, const float* alpha,
+                               int alpha_n, const float* W1, const void* dout, float* sdp, float* sdpx, float* db1,
+                               float* dalpha, float* dW1, void* dz, float* dbz, int B, int Dz, int H, int W, int Cmid, int Co4,
+                               int dtype, vb200_stream_t stream);
 
 /* copies the last error message of the calling thread into buf (NUL terminated) */
 int vb200_last_error(char* buf, size_t n);

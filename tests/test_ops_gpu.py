@@ -213,10 +213,13 @@ def test_head_shuffle_pool(cuda, dtype, pool):
     assert rel(ddec, df.grad.permute(0, 2, 3, 1)) < tol(dtype)
 
 
+# (5,12,16): generic two-phase kernels; the others (256 % W == 0, Dz*H*W % 256 == 0) take the streaming kernels
+@pytest.mark.parametrize("geom", [(2, 5, 12, 16), (2, 5, 16, 32), (3, 4, 8, 128), (1, 3, 256, 256), (2, 7, 64, 64)])
 @pytest.mark.parametrize("dtype", DT)
-def test_head_tail(cuda, dtype):
+def test_head_tail(cuda, dtype, geom):
     from viscy_b200 import ops
-    B, Dz, H, W, Cmid, Co = 2, 5, 12, 16, 32, 2
+    B, Dz, H, W = geom
+    Cmid, Co = 32, 2
     z = rnd((B, Dz * H * W, Cmid), cuda, 1, dtype)
     alpha = torch.tensor([0.25], device=cuda)
     w1 = rnd((Co * 4, Cmid), cuda, 2) * 0.2

@@ -608,12 +608,27 @@ def head_tail_fwd(z, mean, rstd, alpha, W1, b1, Dz, H, W):
     return out
 
 
+HEAD_BWD_STREAM = True  # False: the generic two-phase kernels for every geometry (A/B timing, tests)
+
+
 def head_tail_bwd(z, mean, rstd, alpha, W1, dout, Dz, H, W):
     """-> dz, dW1, db1, dalpha, dbz (bias gradient of the conv that produced z)"""
     B, R, Cmid = z.shape
     Co4 = W1.shape[0]
     ldt = -(-Co4 // 8) * 8
     dev = z.device
+    dout = _act(dout, "dout")
+    if HEAD_BWD_STREAM and Cmid == 32 and Co4 == 8 and W >= 4 and 256 % W == 0 and R % 256 == 0:
+        # streaming form: nothing materialised, dW1 / db1 / dalpha / per-sample sums formed in registers
+        ar = Arena(dev, [2 * B * Cmid, Co4, alpha.numel(), Cmid, Co4 * Cmid])
+        sdp, sdpx = ar.take(B, Cmid), ar.take(B, Cmid)
+        db1, dalpha, dbz, dW1 = ar.take(Co4), ar.take(alpha.numel()), ar.take(Cmid), ar.take(Co4, Cmid)
+        dz = torch.empty_like(z)
+        for phase in (0, 1):
+            _call("vb200_head_tail_bwd_stream", phase, _p(z), _p(mean), _p(rstd), _p(alpha), alpha.numel(), _p(W1), _p(dout),
+                  _p(sdp), _p(sdpx), _p(db1), _p(dalpha), _p(dW1), _p(dz), _p(dbz), B, Dz, H, W, Cmid, Co4,
+                  L.dtype_code(z.dtype))
+        return dz, dW1, db1, dalpha, dbz
     ar = Arena(dev, [2 * B * Cmid, Co4, alpha.numel(), Cmid])
     sdp, sdpx = ar.take(B, Cmid), ar.take(B, Cmid)
     db1, dalpha, dbz = ar.take(Co4), ar.take(alpha.numel()), ar.take(Cmid)
@@ -621,7 +636,6 @@ def head_tail_bwd(z, mean, rstd, alpha, W1, dout, Dz, H, W):
     dt_rows = torch.empty((B, R, ldt), device=dev, dtype=z.dtype)
     dz = torch.empty_like(z)
     dt = L.dtype_code(z.dtype)
-    dout = _act(dout, "dout")
     for phase in (0, 1):
         _call("vb200_head_tail_bwd", phase, _p(z), _p(mean), _p(rstd), _p(alpha), alpha.numel(), _p(W1), _p(dout),
               _p(sdp), _p(sdpx), _p(db1), _p(dalpha), _p(act), _p(dt_rows), _p(dz), _p(dbz), B, Dz, H, W, Cmid, Co4, dt)

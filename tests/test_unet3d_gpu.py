@@ -39,6 +39,47 @@ def test_unet3d_against_reference_golden(cuda, dtype, tol):
     assert int(m.bottleneck.block.block1.norm.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 4e-3), (torch.bfloat16, 3e-2)])
+def test_unet3d_depth4_against_reference_golden(cuda, dtype, tol):
+    """The config-5 architecture Unet3d(3, 3, depth 4, mult_chan 32) on a 64^3 volume (fixture from the reference's own
+    code): 32-channel 64^3 levels run the patch-form / resident-filter kernels, 64 ... 512 channels the implicit-GEMM forms,
+    transposed convs the parity-class form.  Output vs the golden, every weight gradient element-wise vs the fp32 mirror,
+    bounded by 1.5 x the 16-bit-storage yardstick (tests/yardstick.py)."""
+    from viscy_b200 import Unet3d
+    from yardstick import add_storage_rounding, gradient_ratios
+    g = torch.load(GOLD / "unet3d_d4.pt", weights_only=False)
+    gen = torch.Generator().manual_seed(g["seed"] + 1000)
+    x = torch.randn(g["xshape"], generator=gen)
+    tgt = torch.randn(g["out"].shape, generator=gen)
+    torch.manual_seed(g["seed"])
+    ref = Unet3d(**g["cfg"])
+    m = Unet3d(**g["cfg"])
+    m.load_state_dict(ref.state_dict())
+    m = m.to(cuda)
+    F.mse_loss(ref(x), tgt).backward()
+    torch.manual_seed(g["seed"])
+    emu = add_storage_rounding(Unet3d(**g["cfg"]), dtype, (torch.nn.Conv3d, torch.nn.ConvTranspose3d, torch.nn.BatchNorm3d, torch.nn.ReLU))
+    F.mse_loss(emu(x.to(dtype).float()), tgt).backward()
+    with torch.autocast("cuda", dtype=dtype):
+        out = m(x.to(cuda))
+        loss = F.mse_loss(out.float(), tgt.to(cuda))
+    scale = 1024.0 if dtype == torch.float16 else 1.0
+    (loss * scale).backward()
+    e = rel(out.float().cpu(), g["out"].float())
+    print(f"\n[{dtype}] Unet3d depth-4 64^3 forward rel-L2 vs reference golden {e:.3e}; loss {loss.item():.5f} vs {g['loss']:.5f}")
+    assert out.shape == g["out"].shape and e < tol
+    assert abs(loss.item() - g["loss"]) < 3 * tol * abs(g["loss"])
+    worst = gradient_ratios(m, ref, emu, scale)
+    print("worst weight grads (ratio, ours, yardstick):", [(f"{r:.2f}", f"{a:.2e}", f"{b:.2e}", n) for r, a, b, n in worst[:4]])
+    assert worst[0][0] < 1.5, worst[:3]
+    for n, p in m.named_parameters():
+        gn = g["grad_norms"][n]
+        if gn < 1e-5:
+            continue
+        got = p.grad.float().norm().item() / scale
+        assert abs(got - gn) <= (0.05 if dtype == torch.float16 else 0.25) * gn, (n, got, gn)
+
+
 @pytest.mark.parametrize("stride,pad,k", [((1, 1, 1), (1, 1, 1), 3), ((2, 2, 2), (1, 1, 1), 3), ((1, 1, 1), (0, 0, 0), 1)])
 def test_conv3d_cl_vs_torch(cuda, stride, pad, k):
     from viscy_b200 import functional as VF

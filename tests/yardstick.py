@@ -1,0 +1,42 @@
+"""Test helper: the 16-bit-storage yardstick.  The fp32 mirror (== the reference on CPU) is run with every activation rounded
+to the autocast dtype at the points where CUDA autocast (and the sm_100a path) stores it; its deviation from the plain fp32
+run is what ANY 16-bit implementation of the network shows.  The sm_100a path is then held, tensor by tensor, to a small
+multiple of that deviation instead of to a hand-picked absolute tolerance."""
+import torch
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def add_storage_rounding(model, dtype, module_types):
+    class Round16(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, v):
+            return v.to(dtype).float()
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    for mod in model.modules():
+        if isinstance(mod, module_types):
+            mod.register_forward_hook(lambda _m, _i, o: Round16.apply(o))
+    return model
+
+
+def gradient_ratios(gpu_model, ref_model, emu_model, scale=1.0, floor=1e-2, min_norm=1e-6):
+    """[(ratio, err_ours, err_yardstick, name)] sorted worst first, over the weight tensors (dim > 1) that carry gradient."""
+    refg, emug = dict(ref_model.named_parameters()), dict(emu_model.named_parameters())
+    out = []
+    for n, p in gpu_model.named_parameters():
+        gr = refg[n].grad
+        if gr is None:
+            assert p.grad is None, n
+            continue
+        assert p.grad is not None, n
+        if gr.dim() > 1 and gr.norm() > min_norm:
+            e_ours, e_emu = rel(p.grad.float().cpu() / scale, gr), rel(emug[n].grad, gr)
+            out.append((e_ours / max(e_emu, floor), e_ours, e_emu, n))
+    out.sort(reverse=True)
+    return out

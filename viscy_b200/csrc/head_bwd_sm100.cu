@@ -2,9 +2,9 @@
 // VM/components/heads.py:607-641) for the BASELINE head geometry (Cmid = 32, 4*Cout = 8).
 //
 // The generic two-phase kernels in head_sm100.cu materialise act = prelu(xhat) (176 MB at config 2) and the un-shuffled
-// output gradient so that dW1 = dt^T act can run as a GEMM, and they fetch dout with scattered 4-byte loads.  Here a
-// producer warp streams 256-row tiles of z (one contiguous 16 KB bulk copy) and the matching pixel-shuffled dout lines
-// (4 planes x lines, 4W bytes each) through a 3-stage mbarrier ring; 256 consumer threads (thread = row x 8-channel
+// output gradient so that dW1 = dt^T act can run as a GEMM, and they fetch dout with scattered 4-byte loads.  Here one
+// elected thread streams 256-row tiles of z (one contiguous 16 KB bulk copy) and the matching pixel-shuffled dout lines
+// (4 planes x lines, 4W bytes each) through a 3-stage mbarrier ring; the 256 threads (thread = row x 8-channel
 // chunk, W1 slice in registers) form everything in registers:
 //   phase 0: sdp[n,c] = sum dpre, sdpx[n,c] = sum dpre*xhat, dalpha, db1[o] = sum dt[o], dW1[o][c] = sum dt[o]*act[c]
 //   phase 1: dz = rstd * (dpre - sdp/R - xhat * sdpx/R) (coalesced 16-byte stores), dbz[c] = sum dz
@@ -38,7 +38,7 @@ struct Params {
 __device__ __forceinline__ void named_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <bool BF16, int MODE>
-__global__ void __launch_bounds__(NCOMP + 32, 1) head_bwd_stream_kernel(const Params p) {
+__global__ void __launch_bounds__(NCOMP, 1) head_bwd_stream_kernel(const Params p) {
   using H = H16<BF16>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* zs = smem;                          // [STAGES][ZB]
@@ -60,49 +60,51 @@ __global__ void __launch_bounds__(NCOMP + 32, 1) head_bwd_stream_kernel(const Pa
   for (int i = threadIdx.x; i < NRED; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 
-  if (threadIdx.x >= NCOMP) {
-    // ---------------------------------------------------------------- producer warp
-    if (threadIdx.x == NCOMP) {
-      const int L = TR / p.W;  // lines per tile
-      for (int t = t0, it = 0; t < t1; ++t, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&full[s], ZB + DB);
-        const int n = t / p.tiles_per_sample, tt = t - n * p.tiles_per_sample;
-        const long long row0 = (long long)tt * TR;
-        bulk_load_1d(zs + s * ZB, p.z + ((long long)n * p.R + row0) * (CM * 2), ZB, &full[s]);
-        const int line0 = (int)(row0 / p.W);
-        const uint32_t seg = (uint32_t)p.W * 4;  // 2W elements of 2 bytes
-        for (int l = 0; l < L; ++l) {
-          const int ln = line0 + l, dzi = ln / p.H, y = ln - dzi * p.H;
+  // thread 0 doubles as the producer: it issues the bulk copies of tile it + STAGES - 1 before working on tile it
+  // (256 threads = 8 warps: a ninth warp would cost a fourth of the register file to the 4-warp allocation granule)
+  auto produce = [&](int it) {
+    const int t = t0 + it;
+    if (t >= t1) return;
+    const int s = it % STAGES;
+    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+    mbar_expect_tx(&full[s], ZB + DB);
+    const int n = t / p.tiles_per_sample, tt = t - n * p.tiles_per_sample;
+    const long long row0 = (long long)tt * TR;
+    bulk_load_1d(zs + s * ZB, p.z + ((long long)n * p.R + row0) * (CM * 2), ZB, &full[s]);
+    const int L = TR / p.W, line0 = (int)(row0 / p.W);
+    const uint32_t seg = (uint32_t)p.W * 4;  // 2W elements of 2 bytes
+    for (int l = 0; l < L; ++l) {
+      const int ln = line0 + l, dzi = ln / p.H, y = ln - dzi * p.H;
 #pragma unroll
-          for (int pl = 0; pl < 4; ++pl) {
-            const int co = pl >> 1, i = pl & 1;
-            const long long off = ((((long long)n * 2 + co) * p.Dz + dzi) * (2 * p.H) + 2 * y + i) * (2LL * p.W);
-            bulk_load_1d(ds + s * DB + (l * 4 + pl) * seg, p.dout + off * 2, seg, &full[s]);
-          }
-        }
+      for (int pl = 0; pl < 4; ++pl) {
+        const int co = pl >> 1, i = pl & 1;
+        const long long off = ((((long long)n * 2 + co) * p.Dz + dzi) * (2 * p.H) + 2 * y + i) * (2LL * p.W);
+        bulk_load_1d(ds + s * DB + (l * 4 + pl) * seg, p.dout + off * 2, seg, &full[s]);
       }
     }
-    return;
+  };
+  if (threadIdx.x == 0) {
+    for (int it = 0; it < STAGES - 1; ++it) produce(it);
   }
   // ------------------------------------------------------------------ consumers
   const int v = threadIdx.x & 3, rl = threadIdx.x >> 2;  // channel chunk, row within a 64-row pass
-  float w[8][8];  // w[k][o] = W1[o][v*8 + k]
+  float2 w2[4][8];  // w2[kp][o] = (W1[o][v*8 + 2kp], W1[o][v*8 + 2kp + 1]): channel pairs ride the packed fp32x2 pipe
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
+  for (int kp = 0; kp < 4; ++kp)
 #pragma unroll
-    for (int o = 0; o < 8; ++o) w[k][o] = __ldg(p.W1 + o * CM + v * 8 + k);
+    for (int o = 0; o < 8; ++o)
+      w2[kp][o] = make_float2(__ldg(p.W1 + o * CM + v * 8 + 2 * kp), __ldg(p.W1 + o * CM + v * 8 + 2 * kp + 1));
   float al[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) al[k] = __ldg(p.alpha + (p.alpha_n == 1 ? 0 : v * 8 + k));
   float mu[8], rs[8], m1[8], m2[8];
-  float a_dp[8], a_dpx[8], a_al[8], a_db[8], a_dw[8][8];
+  float a_dp[8], a_dpx[8], a_al[8], a_db[8];
+  float2 a_dw2[8][4];  // [o][channel pair]
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     a_dp[k] = a_dpx[k] = a_al[k] = a_db[k] = 0.f;
 #pragma unroll
-    for (int o = 0; o < 8; ++o) a_dw[o][k] = 0.f;
+    for (int o = 0; o < 8; ++o) a_dw2[o][k >> 1] = make_float2(0.f, 0.f);
   }
   int cur_n = -1;
   const int lane = threadIdx.x & 31;
@@ -119,7 +121,10 @@ __global__ void __launch_bounds__(NCOMP + 32, 1) head_bwd_stream_kernel(const Pa
           a_al[k] += __shfl_xor_sync(0xffffffffu, a_al[k], off);
           a_db[k] += __shfl_xor_sync(0xffffffffu, a_db[k], off);
 #pragma unroll
-          for (int o = 0; o < 8; ++o) a_dw[o][k] += __shfl_xor_sync(0xffffffffu, a_dw[o][k], off);
+          for (int o = 0; o < 8; ++o) {
+            float& e = (k & 1) ? a_dw2[o][k >> 1].y : a_dw2[o][k >> 1].x;
+            e += __shfl_xor_sync(0xffffffffu, e, off);
+          }
         }
       }
     }
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(NCOMP + 32, 1) head_bwd_stream_kernel(const Pa
           atomicAdd(&red[CM + c], a_dpx[k]);
           atomicAdd(&red[2 * CM + c], a_al[k]);
 #pragma unroll
-          for (int o = 0; o < 8; ++o) atomicAdd(&red[3 * CM + o * CM + c], a_dw[o][k]);
+          for (int o = 0; o < 8; ++o) atomicAdd(&red[3 * CM + o * CM + c], (k & 1) ? a_dw2[o][k >> 1].y : a_dw2[o][k >> 1].x);
         }
       }
       if (MODE == 0 && v == 0) {
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(NCOMP + 32, 1) head_bwd_stream_kernel(const Pa
     for (int k = 0; k < 8; ++k) {
       a_dp[k] = a_dpx[k] = a_al[k] = a_db[k] = 0.f;
 #pragma unroll
-      for (int o = 0; o < 8; ++o) a_dw[o][k] = 0.f;
+      for (int o = 0; o < 8; ++o) a_dw2[o][k >> 1] = make_float2(0.f, 0.f);
     }
   };
 
@@ -179,6 +184,8 @@ __global__ void __launch_bounds__(NCOMP + 32, 1) head_bwd_stream_kernel(const Pa
         m2[k] = MODE == 1 ? p.sdpx[(long long)n * CM + c] * invR : 0.f;
       }
     }
+    if (threadIdx.x == 0) produce(it + STAGES - 1);
+    __syncwarp();
     mbar_wait(&full[s], (it / STAGES) & 1);
     const uint4* zt = reinterpret_cast<const uint4*>(zs + s * ZB);
     const uint32_t* dt32 = reinterpret_cast<const uint32_t*>(ds + s * DB);
@@ -203,21 +210,29 @@ __global__ void __launch_bounds__(NCOMP + 32, 1) head_bwd_stream_kernel(const Pa
         xh[2 * k + 1] = (f.y - mu[2 * k + 1]) * rs[2 * k + 1];
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float da = 0.f;
+      for (int kp = 0; kp < 4; ++kp) {
+        float2 da2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int o = 0; o < 8; ++o) da = fmaf(w[k][o], dt[o], da);
-        const bool pos = xh[k] > 0.f;
-        const float dpre = pos ? da : da * al[k];
+        for (int o = 0; o < 8; ++o) da2 = __ffma2_rn(w2[kp][o], make_float2(dt[o], dt[o]), da2);
+        float2 act2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = 2 * kp + h;
+          const float da = h ? da2.y : da2.x;
+          const bool pos = xh[k] > 0.f;
+          const float dpre = pos ? da : da * al[k];
+          if (MODE == 0) {
+            (h ? act2.y : act2.x) = pos ? xh[k] : xh[k] * al[k];
+            a_dp[k] += dpre;
+            a_dpx[k] = fmaf(dpre, xh[k], a_dpx[k]);
+            a_al[k] += pos ? 0.f : da * xh[k];
+          } else {
+            o8[k] = rs[k] * (dpre - m1[k] - xh[k] * m2[k]);
+          }
+        }
         if (MODE == 0) {
-          const float act = pos ? xh[k] : xh[k] * al[k];
-          a_dp[k] += dpre;
-          a_dpx[k] = fmaf(dpre, xh[k], a_dpx[k]);
-          a_al[k] += pos ? 0.f : da * xh[k];
 #pragma unroll
-          for (int o = 0; o < 8; ++o) a_dw[o][k] = fmaf(dt[o], act, a_dw[o][k]);
-        } else {
-          o8[k] = rs[k] * (dpre - m1[k] - xh[k] * m2[k]);
+          for (int o = 0; o < 8; ++o) a_dw2[o][kp] = __ffma2_rn(make_float2(dt[o], dt[o]), act2, a_dw2[o][kp]);
         }
       }
       if (MODE == 0) {
@@ -279,9 +294,9 @@ extern "C" int vb200_head_tail_bwd_stream(int phase, const void* z, const float*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   cudaStream_t st = (cudaStream_t)stream;
-  if (slot == 0) hb::head_bwd_stream_kernel<true, 0><<<grid, hb::NCOMP + 32, smem, st>>>(p);
-  else if (slot == 1) hb::head_bwd_stream_kernel<true, 1><<<grid, hb::NCOMP + 32, smem, st>>>(p);
-  else if (slot == 2) hb::head_bwd_stream_kernel<false, 0><<<grid, hb::NCOMP + 32, smem, st>>>(p);
-  else hb::head_bwd_stream_kernel<false, 1><<<grid, hb::NCOMP + 32, smem, st>>>(p);
+  if (slot == 0) hb::head_bwd_stream_kernel<true, 0><<<grid, hb::NCOMP, smem, st>>>(p);
+  else if (slot == 1) hb::head_bwd_stream_kernel<true, 1><<<grid, hb::NCOMP, smem, st>>>(p);
+  else if (slot == 2) hb::head_bwd_stream_kernel<false, 0><<<grid, hb::NCOMP, smem, st>>>(p);
+  else hb::head_bwd_stream_kernel<false, 1><<<grid, hb::NCOMP, smem, st>>>(p);
   return check_launch("vb200_head_tail_bwd_stream");
 }

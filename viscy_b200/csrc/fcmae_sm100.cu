@@ -39,17 +39,19 @@ rows_select_kernel(const uint4* __restrict__ src, const int* __restrict__ map, c
 
 constexpr int SP_W = 16;  // decoder pixels per block along w
 
-// forward: block = (w segment, hh, n).  smem S[2][SP_W + 1][C]: decoder rows hh-1, hh, columns w0-1 .. w0+SP_W-1.
-template <bool BF16>
+// forward: block = (w segment, hh, n).  Shared memory holds the SHUFFLED image region the block's outputs look at,
+// P[Cq][2R-1][SP_W*R + R-1] (rows hh*R-(R-1) .. hh*R+R-1, columns w0*R-(R-1) .. (w0+SP_W)*R-1; zeros outside the image = the
+// front padding), filled from 16-byte channel vectors of decoder rows hh-1, hh; every output is then an R x R window sum
+// at compile-time strides.
+template <bool BF16, int R>
 __global__ void __launch_bounds__(256)
-shuffle_pool_fwd_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int h, int w, int Cq, int r,
-                        int pool) {
+shuffle_pool_fwd_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int h, int w, int Cq, int pool) {
   using H = H16<BF16>;
   extern __shared__ uint16_t sm[];
-  const int C = Cq * r * r, C8 = C / 8;
+  constexpr int PR = 2 * R - 1, PW = SP_W * R + R - 1, XW = SP_W * R, RR = R * R;
+  const int C = Cq * RR, C8 = C / 8;
   const int w0 = blockIdx.x * SP_W, hh = blockIdx.y;
   const long long n = blockIdx.z;
-  uint4* sm4 = reinterpret_cast<uint4*>(sm);
   for (int idx = threadIdx.x; idx < 2 * (SP_W + 1) * C8; idx += blockDim.x) {
     const int c8 = idx % C8;
     int t = idx / C8;
@@ -57,70 +59,74 @@ shuffle_pool_fwd_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__
     const int y = hh - 1 + rr, x = w0 - 1 + xl;
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
     if (y >= 0 && x >= 0 && x < w) q = __ldg(reinterpret_cast<const uint4*>(src + ((n * h + y) * w + x) * (long long)C) + c8);
-    sm4[idx] = q;
+    const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 * 8 + k;
+      const int cq = c / RR, ij = c % RR, i = ij / R, j = ij % R;
+      const int pr = rr * R + i - 1, pc = xl * R + j - 1;
+      if (pr >= 0 && pc >= 0) sm[(cq * PR + pr) * PW + pc] = static_cast<uint16_t>(k & 1 ? qw[k >> 1] >> 16 : qw[k >> 1] & 0xffffu);
+    }
   }
   __syncthreads();
-  const int Ws = w * r, Hs = h * r, XW = SP_W * r;
-  const float inv = 1.0f / (float)(r * r);
-  for (int idx = threadIdx.x; idx < Cq * r * XW; idx += blockDim.x) {
+  const int Ws = w * R, Hs = h * R;
+  constexpr float inv = 1.0f / (float)RR;
+  for (int idx = threadIdx.x; idx < Cq * R * XW; idx += blockDim.x) {
     const int xl = idx % XW;
-    int t = idx / XW;
-    const int i = t % r, cq = t / r;
-    const int X = w0 * r + xl;
+    const int t = idx / XW;
+    const int i = t % R, cq = t / R;
+    const int X = w0 * R + xl;
     if (X >= Ws) continue;
-    // S[y, x] (shuffled image, local coords: y in [-r, r), x in [-r, XW)) -> smem row (y>=0), column, channel
-    auto S = [&](int yl, int xx) -> float {
-      const int rr = yl >= 0 ? 1 : 0, ys = yl >= 0 ? yl : yl + r;
-      const int xc = xx >= 0 ? xx / r + 1 : 0, xs = xx >= 0 ? xx % r : xx + r;
-      return H::to_f(*reinterpret_cast<const typename H::T*>(&sm[(rr * (SP_W + 1) + xc) * C + cq * r * r + ys * r + xs]));
-    };
-    float v;
+    const uint16_t* base = sm + (cq * PR + i) * PW + xl;
+    float v = 0.f;
     if (pool) {
-      v = 0.f;
-      for (int a = 0; a < r; ++a)
-        for (int b = 0; b < r; ++b) v += S(i - a, xl - b);
+#pragma unroll
+      for (int a = 0; a < R; ++a)
+#pragma unroll
+        for (int b = 0; b < R; ++b) v += H::to_f(*reinterpret_cast<const typename H::T*>(base + a * PW + b));
       v *= inv;
     } else {
-      v = S(i, xl);
+      v = H::to_f(*reinterpret_cast<const typename H::T*>(base + (R - 1) * PW + R - 1));
     }
     const typename H::T o = H::from_f(v);
-    dst[((n * Cq + cq) * Hs + hh * r + i) * (long long)Ws + X] = *reinterpret_cast<const uint16_t*>(&o);
+    dst[((n * Cq + cq) * Hs + hh * R + i) * (long long)Ws + X] = *reinterpret_cast<const uint16_t*>(&o);
   }
 }
 
-// backward: d_src[n,hh,ww, cq r^2 + i r + j] = pool ? r^-2 sum_{a,b<r} dP[cq, hh r + i + a, ww r + j + b] : dP[cq, hh r + i, ww r + j]
-// smem D[Cq][2r-1][XW + r - 1] (16-bit), loaded coalesced along X.
-template <bool BF16>
+// backward: d_src[n,hh,ww, cq R^2 + i R + j] = pool ? R^-2 sum_{a,b<R} dP[cq, hh R + i + a, ww R + j + b] : dP[cq, hh R + i, ww R + j]
+// smem D[Cq][2R-1][XW + R - 1] (16-bit), loaded coalesced along X.
+template <bool BF16, int R>
 __global__ void __launch_bounds__(256)
-shuffle_pool_bwd_kernel(const uint16_t* __restrict__ dP, uint16_t* __restrict__ dsrc, int h, int w, int Cq, int r,
-                        int pool) {
+shuffle_pool_bwd_kernel(const uint16_t* __restrict__ dP, uint16_t* __restrict__ dsrc, int h, int w, int Cq, int pool) {
   using H = H16<BF16>;
   extern __shared__ uint16_t sm[];
+  constexpr int XW = SP_W * R, RW = XW + R - 1, RH = 2 * R - 1, RR = R * R;
   const int w0 = blockIdx.x * SP_W, hh = blockIdx.y;
   const long long n = blockIdx.z;
-  const int Ws = w * r, Hs = h * r, XW = SP_W * r;
-  const int RW = XW + r - 1, RH = 2 * r - 1;
+  const int Ws = w * R, Hs = h * R;
   for (int idx = threadIdx.x; idx < Cq * RH * RW; idx += blockDim.x) {
     const int xl = idx % RW;
-    int t = idx / RW;
+    const int t = idx / RW;
     const int yl = t % RH, cq = t / RH;
-    const int Y = hh * r + yl, X = w0 * r + xl;
+    const int Y = hh * R + yl, X = w0 * R + xl;
     sm[idx] = (Y < Hs && X < Ws) ? __ldg(dP + ((n * Cq + cq) * Hs + Y) * (long long)Ws + X) : (uint16_t)0;
   }
   __syncthreads();
-  const int C = Cq * r * r;
-  const float inv = 1.0f / (float)(r * r);
+  const int C = Cq * RR;
+  constexpr float inv = 1.0f / (float)RR;
   for (int idx = threadIdx.x; idx < SP_W * C; idx += blockDim.x) {
     const int c = idx % C, wl = idx / C;
     const int ww = w0 + wl;
     if (ww >= w) continue;
-    const int cq = c / (r * r), ij = c - cq * r * r;
-    const int i = ij / r, j = ij - i * r;
-    const uint16_t* base = sm + (cq * RH + i) * RW + wl * r + j;
+    const int cq = c / RR, ij = c % RR;
+    const int i = ij / R, j = ij % R;
+    const uint16_t* base = sm + (cq * RH + i) * RW + wl * R + j;
     float v = 0.f;
     if (pool) {
-      for (int a = 0; a < r; ++a)
-        for (int b = 0; b < r; ++b) v += H::to_f(*reinterpret_cast<const typename H::T*>(base + a * RW + b));
+#pragma unroll
+      for (int a = 0; a < R; ++a)
+#pragma unroll
+        for (int b = 0; b < R; ++b) v += H::to_f(*reinterpret_cast<const typename H::T*>(base + a * RW + b));
       v *= inv;
     } else {
       v = H::to_f(*reinterpret_cast<const typename H::T*>(base));
@@ -128,6 +134,24 @@ shuffle_pool_bwd_kernel(const uint16_t* __restrict__ dP, uint16_t* __restrict__ 
     const typename H::T o = H::from_f(v);
     dsrc[((n * h + hh) * w + ww) * (long long)C + c] = *reinterpret_cast<const uint16_t*>(&o);
   }
+}
+
+template <bool BF16, int R>
+static int shuffle_pool_launch(const uint16_t* s, uint16_t* d, int B, int h, int w, int Cq, int pool, int backward,
+                               cudaStream_t st) {
+  const size_t smem = (size_t)Cq * (2 * R - 1) * (SP_W * R + R - 1) * 2;  // same extent both ways
+  if (smem > 200 * 1024) return fail(VB200_ERR_UNSUPPORTED, "tile of %zu bytes does not fit shared memory", smem);
+  static PerDeviceOnce once[2];
+  const int dev = PerDeviceOnce::device();
+  if (once[backward ? 1 : 0].need(dev)) {
+    const void* fn = backward ? (const void*)shuffle_pool_bwd_kernel<BF16, R> : (const void*)shuffle_pool_fwd_kernel<BF16, R>;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    once[backward ? 1 : 0].done(dev);
+  }
+  dim3 grid((w + SP_W - 1) / SP_W, h, B);
+  if (!backward) shuffle_pool_fwd_kernel<BF16, R><<<grid, 256, smem, st>>>(s, d, h, w, Cq, pool);
+  else shuffle_pool_bwd_kernel<BF16, R><<<grid, 256, smem, st>>>(s, d, h, w, Cq, pool);
+  return check_launch("shuffle_pool");
 }
 
 }  // namespace vb
@@ -154,31 +178,20 @@ extern "C" int vb200_rows_select(const void* src, const int32_t* map, const void
 extern "C" int vb200_shuffle_pool(const void* src, void* dst, int B, int h, int w, int Cq, int r, int pool, int backward,
                                   int dtype, vb200_stream_t stream) {
   VB_REQUIRE(src && dst, "null pointer");
-  VB_REQUIRE(r >= 1 && r <= 8 && Cq > 0, "scale %d / channels %d", r, Cq);
+  VB_REQUIRE(r >= 1 && Cq > 0, "scale %d / channels %d", r, Cq);
+  VB_SUPPORTED(r == 1 || r == 2 || r == 4 || r == 8, "pixel-shuffle scale %d (1, 2, 4, 8 are built)", r);
   VB_SUPPORTED(dtype == VB200_BF16 || dtype == VB200_FP16, "dtype %d", dtype);
-  const int C = Cq * r * r;
-  VB_SUPPORTED(C % 8 == 0, "decoder channels (%d) must be a multiple of 8", C);
-  const size_t smem = backward ? (size_t)Cq * (2 * r - 1) * (SP_W * r + r - 1) * 2 : (size_t)2 * (SP_W + 1) * C * 2;
-  VB_SUPPORTED(smem <= 200 * 1024, "tile of %zu bytes does not fit shared memory", smem);
-  static PerDeviceOnce once[4];
-  const int dev = PerDeviceOnce::device();
-  const int slot = (backward ? 2 : 0) + (dtype == VB200_BF16 ? 1 : 0);
-  if (once[slot].need(dev)) {
-    const void* fn = backward ? (dtype == VB200_BF16 ? (const void*)shuffle_pool_bwd_kernel<true> : (const void*)shuffle_pool_bwd_kernel<false>)
-                              : (dtype == VB200_BF16 ? (const void*)shuffle_pool_fwd_kernel<true> : (const void*)shuffle_pool_fwd_kernel<false>);
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    once[slot].done(dev);
-  }
-  dim3 grid((w + SP_W - 1) / SP_W, h, B);
+  VB_SUPPORTED((Cq * r * r) % 8 == 0, "decoder channels (%d) must be a multiple of 8", Cq * r * r);
   cudaStream_t st = (cudaStream_t)stream;
   const uint16_t* s = (const uint16_t*)src;
   uint16_t* d = (uint16_t*)dst;
-  if (!backward) {
-    if (dtype == VB200_BF16) shuffle_pool_fwd_kernel<true><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
-    else shuffle_pool_fwd_kernel<false><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
-  } else {
-    if (dtype == VB200_BF16) shuffle_pool_bwd_kernel<true><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
-    else shuffle_pool_bwd_kernel<false><<<grid, 256, smem, st>>>(s, d, h, w, Cq, r, pool);
+#define SP_CASE(RV)                                                                                            \
+  case RV:                                                                                                     \
+    return dtype == VB200_BF16 ? shuffle_pool_launch<true, RV>(s, d, B, h, w, Cq, pool, backward, st)           \
+                               : shuffle_pool_launch<false, RV>(s, d, B, h, w, Cq, pool, backward, st);
+  switch (r) {
+    SP_CASE(1) SP_CASE(2) SP_CASE(4) SP_CASE(8)
   }
-  return check_launch("shuffle_pool");
+#undef SP_CASE
+  return fail(VB200_ERR_UNSUPPORTED, "scale %d", r);
 }

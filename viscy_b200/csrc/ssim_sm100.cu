@@ -22,6 +22,28 @@ constexpr int TH = 32, TW = 64, NT = 256, KMAX = 16;
 
 __device__ __forceinline__ float bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// compile-time typed element access (DT: VB200_BF16 | VB200_FP16 | VB200_FP32) so that the unrolled depth loops carry no
+// dtype branches
+template <int DT>
+__device__ __forceinline__ float ldt(const void* p, long long i) {
+  if constexpr (DT == 2) return __ldg(reinterpret_cast<const float*>(p) + i);
+  else if constexpr (DT == 0) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+  else return __half2float(__ldg(reinterpret_cast<const __half*>(p) + i));
+}
+template <int DT>
+__device__ __forceinline__ float rnd(float v) {
+  if constexpr (DT == 2) return v;
+  else if constexpr (DT == 0) return __bfloat162float(__float2bfloat16_rn(v));
+  else return __half2float(__float2half_rn(v));
+}
+template <int DT>
+__device__ __forceinline__ void stt(void* p, long long i, float v) {
+  if constexpr (DT == 2) reinterpret_cast<float*>(p)[i] = v;
+  else if constexpr (DT == 0) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+constexpr int DU = 8;  // depth slices in flight per thread: independent loads issued together (the loops are latency-bound)
+
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
@@ -52,7 +74,8 @@ struct Params {
   float wbf, k1, k2;
 };
 
-__global__ void __launch_bounds__(NT) level_fwd_kernel(const Params p) {
+template <int XDT, int YDT>
+__global__ void __launch_bounds__(NT, 2) level_fwd_kernel(const Params p) {
   extern __shared__ float sm[];  // [5][RH][RW]
   __shared__ float red[4][NT / 32];
   const int RH = TH + p.kh - 1, RW = TW + p.kw - 1, RP = RH * RW;
@@ -69,13 +92,22 @@ __global__ void __launch_bounds__(NT) level_fwd_kernel(const Params p) {
       float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
       if (h < p.H && w < p.W) {
         const long long o = base + (long long)h * p.W + w;
-        for (int d = 0; d < p.D; ++d) {
-          const float xv = ld_any(p.x, o + d * plane, p.xdt), yv = ld_any(p.y, o + d * plane, p.ydt);
-          sx += bf(xv);
-          sy += bf(yv);
-          sxx += bf(xv * xv);
-          syy += bf(yv * yv);
-          sxy += bf(xv * yv);
+        for (int d0 = 0; d0 < p.D; d0 += DU) {
+          float xv[DU], yv[DU];
+#pragma unroll
+          for (int u = 0; u < DU; ++u) {
+            const bool on = d0 + u < p.D;
+            xv[u] = on ? ldt<XDT>(p.x, o + (d0 + u) * plane) : 0.f;
+            yv[u] = on ? ldt<YDT>(p.y, o + (d0 + u) * plane) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < DU; ++u) {  // zeros past the last slice add nothing
+            sx += bf(xv[u]);
+            sy += bf(yv[u]);
+            sxx += bf(xv[u] * xv[u]);
+            syy += bf(yv[u] * yv[u]);
+            sxy += bf(xv[u] * yv[u]);
+          }
         }
       }
       sm[idx] = sx;
@@ -119,10 +151,16 @@ __global__ void __launch_bounds__(NT) level_fwd_kernel(const Params p) {
       const int h = h0 + r, w = w0 + c;
       if (h >= p.H || w >= p.W) continue;
       const long long o = base + (long long)h * p.W + w;
-      for (int d = 0; d < p.D; ++d) {
-        const float df = ld_any(p.x, o + d * plane, p.xdt) - ld_any(p.y, o + d * plane, p.ydt);
-        l1 += fabsf(df);
-        l2 += df * df;
+      for (int d0 = 0; d0 < p.D; d0 += DU) {
+        float df[DU];
+#pragma unroll
+        for (int u = 0; u < DU; ++u)
+          df[u] = d0 + u < p.D ? ldt<XDT>(p.x, o + (d0 + u) * plane) - ldt<YDT>(p.y, o + (d0 + u) * plane) : 0.f;
+#pragma unroll
+        for (int u = 0; u < DU; ++u) {
+          l1 += fabsf(df[u]);
+          l2 += df[u] * df[u];
+        }
       }
     }
   }
@@ -135,16 +173,25 @@ __global__ void __launch_bounds__(NT) level_fwd_kernel(const Params p) {
       const int h2 = h0 / 2 + r, w2 = w0 / 2 + c;
       if (h2 >= H2 || w2 >= W2) continue;
       const long long o = base + (long long)(2 * h2) * p.W + 2 * w2;
-      for (int d = 0; d < p.D; ++d) {
-        const long long od = o + d * plane;
-        const float xs = ld_any(p.x, od, p.xdt) + ld_any(p.x, od + 1, p.xdt) + ld_any(p.x, od + p.W, p.xdt) +
-                         ld_any(p.x, od + p.W + 1, p.xdt);
-        const float ys = ld_any(p.y, od, p.ydt) + ld_any(p.y, od + 1, p.ydt) + ld_any(p.y, od + p.W, p.ydt) +
-                         ld_any(p.y, od + p.W + 1, p.ydt);
-        const long long o2 = base2 + d * plane2 + (long long)h2 * W2 + w2;
-        st_any(p.xp, o2, p.xdt, 0.25f * xs);
-        st_any(p.yp, o2, p.ydt, 0.25f * ys);
-        ymax = fmaxf(ymax, round_any(0.25f * ys, p.ydt));
+      constexpr int PU = 4;
+      for (int d0 = 0; d0 < p.D; d0 += PU) {
+        float xs[PU], ys[PU];
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+          const long long od = o + (d0 + u) * plane;
+          const bool on = d0 + u < p.D;
+          xs[u] = on ? ldt<XDT>(p.x, od) + ldt<XDT>(p.x, od + 1) + ldt<XDT>(p.x, od + p.W) + ldt<XDT>(p.x, od + p.W + 1) : 0.f;
+          ys[u] = on ? ldt<YDT>(p.y, od) + ldt<YDT>(p.y, od + 1) + ldt<YDT>(p.y, od + p.W) + ldt<YDT>(p.y, od + p.W + 1) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+          if (d0 + u < p.D) {
+            const long long o2 = base2 + (d0 + u) * plane2 + (long long)h2 * W2 + w2;
+            stt<XDT>(p.xp, o2, 0.25f * xs[u]);
+            stt<YDT>(p.yp, o2, 0.25f * ys[u]);
+            ymax = fmaxf(ymax, rnd<YDT>(0.25f * ys[u]));
+          }
+        }
       }
     }
   }
@@ -184,7 +231,8 @@ struct BwdParams {
   float wbf, k1, k2;
 };
 
-__global__ void __launch_bounds__(NT) level_bwd_kernel(const BwdParams p) {
+template <int XDT, int YDT>
+__global__ void __launch_bounds__(NT, 3) level_bwd_kernel(const BwdParams p) {
   extern __shared__ float sm[];  // [3][RH][RW]: G_mux, G_muxx, G_muxy at output pixels (h0 - kh + 1 + r, w0 - kw + 1 + c)
   const int RH = TH + p.kh - 1, RW = TW + p.kw - 1, RP = RH * RW;
   const int h0 = blockIdx.y * TH, w0 = blockIdx.x * TW;
@@ -243,18 +291,27 @@ __global__ void __launch_bounds__(NT) level_bwd_kernel(const BwdParams p) {
     const bool pooled = p.g_pool != nullptr && (h >> 1) < H2 && (w >> 1) < W2;
     const long long o = base + (long long)h * p.W + w;
     const long long o2 = base2 + (long long)(h >> 1) * W2 + (w >> 1);
-    for (int d = 0; d < p.D; ++d) {
-      float g = 0.f;
-      if (do_ssim || l12) {
-        const float xv = ld_any(p.x, o + d * plane, p.xdt), yv = ld_any(p.y, o + d * plane, p.ydt);
-        g = A + xv * Bq + yv * Cq;
-        if (l12) {
-          const float df = xv - yv;
-          g += gl1 * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) + gl2 * df;
+    for (int d0 = 0; d0 < p.D; d0 += DU) {
+      float xv[DU], yv[DU], gp[DU];
+#pragma unroll
+      for (int u = 0; u < DU; ++u) {
+        const bool on = d0 + u < p.D;
+        xv[u] = (on && (do_ssim || l12)) ? ldt<XDT>(p.x, o + (d0 + u) * plane) : 0.f;
+        yv[u] = (on && (do_ssim || l12)) ? ldt<YDT>(p.y, o + (d0 + u) * plane) : 0.f;
+        gp[u] = (on && pooled) ? ldt<XDT>(p.g_pool, o2 + (d0 + u) * plane2) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < DU; ++u) {
+        if (d0 + u < p.D) {
+          float g = A + xv[u] * Bq + yv[u] * Cq;
+          if (l12) {
+            const float df = xv[u] - yv[u];
+            g += gl1 * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) + gl2 * df;
+          }
+          g += 0.25f * gp[u];
+          stt<XDT>(p.dx, o + (d0 + u) * plane, g);
         }
       }
-      if (pooled) g += 0.25f * ld_any(p.g_pool, o2 + d * plane2, p.xdt);
-      st_any(p.dx, o + d * plane, p.xdt, g);
     }
   }
 }
@@ -319,11 +376,17 @@ extern "C" int vb200_ssim25d_level_fwd(const void* x, const void* y, int x_dtype
   p.Ho = H - kh + 1; p.Wo = W - kw + 1; p.flags = flags;
   p.wbf = bf16_round_host(1.0f / (float)(D * kh * kw));
   p.k1 = 0.01f; p.k2 = 0.03f;
-  static PerDeviceOnce once;
-  ssim_smem_opt_in((const void*)level_fwd_kernel, once);
   const size_t smem = (flags & 1) ? (size_t)5 * (TH + kh - 1) * (TW + kw - 1) * sizeof(float) : 0;
   dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
-  level_fwd_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(p);
+  static PerDeviceOnce once[9];
+#define SSIM_FWD(XD, YD)                                                                     \
+  if (x_dtype == XD && y_dtype == YD) {                                                      \
+    ssim_smem_opt_in((const void*)level_fwd_kernel<XD, YD>, once[XD * 3 + YD]);              \
+    level_fwd_kernel<XD, YD><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+  }
+  SSIM_FWD(0, 0) SSIM_FWD(0, 1) SSIM_FWD(0, 2) SSIM_FWD(1, 0) SSIM_FWD(1, 1) SSIM_FWD(1, 2) SSIM_FWD(2, 0) SSIM_FWD(2, 1)
+  SSIM_FWD(2, 2)
+#undef SSIM_FWD
   return check_launch("ssim25d_level_fwd");
 }
 
@@ -342,10 +405,16 @@ extern "C" int vb200_ssim25d_level_bwd(const void* x, const void* y, int x_dtype
   p.Ho = H - kh + 1; p.Wo = W - kw + 1;
   p.wbf = bf16_round_host(1.0f / (float)(D * kh * kw));
   p.k1 = 0.01f; p.k2 = 0.03f;
-  static PerDeviceOnce once;
-  ssim_smem_opt_in((const void*)level_bwd_kernel, once);
   const size_t smem = do_ssim ? (size_t)3 * (TH + kh - 1) * (TW + kw - 1) * sizeof(float) : 0;
   dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
-  level_bwd_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(p);
+  static PerDeviceOnce once[9];
+#define SSIM_BWD(XD, YD)                                                                     \
+  if (x_dtype == XD && y_dtype == YD) {                                                      \
+    ssim_smem_opt_in((const void*)level_bwd_kernel<XD, YD>, once[XD * 3 + YD]);              \
+    level_bwd_kernel<XD, YD><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+  }
+  SSIM_BWD(0, 0) SSIM_BWD(0, 1) SSIM_BWD(0, 2) SSIM_BWD(1, 0) SSIM_BWD(1, 1) SSIM_BWD(1, 2) SSIM_BWD(2, 0) SSIM_BWD(2, 1)
+  SSIM_BWD(2, 2)
+#undef SSIM_BWD
   return check_launch("ssim25d_level_bwd");
 }

@@ -39,6 +39,41 @@ rows_select_kernel(const uint4* __restrict__ src, const int* __restrict__ map, c
 
 constexpr int SP_W = 16;  // decoder pixels per block along w
 
+// out[j] = sum_{a<R, b<R} P[a][j + b] (pool) or P[off][j + off] (no pool), j < R, from a window whose first element is 4-byte
+// aligned and whose row pitch is even: R rows x 2R columns read as 32-bit pairs
+template <typename H, int R>
+__device__ __forceinline__ void window_outputs(const uint16_t* base, int pitch, int pool, int off, float (&o)[R]) {
+  if (!pool) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) o[j] = H::to_f(*reinterpret_cast<const typename H::T*>(base + off * pitch + j + off));
+    return;
+  }
+  if constexpr (R == 1) {
+    o[0] = H::to_f(*reinterpret_cast<const typename H::T*>(base));
+  } else {
+    float col[2 * R];
+#pragma unroll
+    for (int b = 0; b < 2 * R; ++b) col[b] = 0.f;
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(base + a * pitch);
+#pragma unroll
+      for (int b2 = 0; b2 < R; ++b2) {
+        const float2 f = H::unpack(row[b2]);
+        col[2 * b2] += f.x;
+        col[2 * b2 + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      float v = 0.f;
+#pragma unroll
+      for (int b = 0; b < R; ++b) v += col[j + b];
+      o[j] = v;
+    }
+  }
+}
+
 // forward: block = (w segment, hh, n).  Shared memory holds the SHUFFLED image region the block's outputs look at,
 // P[Cq][2R-1][SP_W*R + R-1] (rows hh*R-(R-1) .. hh*R+R-1, columns w0*R-(R-1) .. (w0+SP_W)*R-1; zeros outside the image = the
 // front padding), filled from 16-byte channel vectors of decoder rows hh-1, hh; every output is then an R x R window sum
@@ -48,10 +83,12 @@ __global__ void __launch_bounds__(256)
 shuffle_pool_fwd_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int h, int w, int Cq, int pool) {
   using H = H16<BF16>;
   extern __shared__ uint16_t sm[];
-  constexpr int PR = 2 * R - 1, PW = SP_W * R + R - 1, XW = SP_W * R, RR = R * R;
+  constexpr int PR = 2 * R - 1, PW = SP_W * R + R + (R & 1), XW = SP_W * R, RR = R * R;  // PW even: rows stay 4-byte aligned
   const int C = Cq * RR, C8 = C / 8;
   const int w0 = blockIdx.x * SP_W, hh = blockIdx.y;
   const long long n = blockIdx.z;
+  for (int idx = threadIdx.x; idx < Cq * PR; idx += blockDim.x)  // pad columns behind the XW + R - 1 real ones
+    for (int c = XW + R - 1; c < PW; ++c) sm[idx * PW + c] = 0;
   for (int idx = threadIdx.x; idx < 2 * (SP_W + 1) * C8; idx += blockDim.x) {
     const int c8 = idx % C8;
     int t = idx / C8;
@@ -71,25 +108,21 @@ shuffle_pool_fwd_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__
   __syncthreads();
   const int Ws = w * R, Hs = h * R;
   constexpr float inv = 1.0f / (float)RR;
-  for (int idx = threadIdx.x; idx < Cq * R * XW; idx += blockDim.x) {
-    const int xl = idx % XW;
-    const int t = idx / XW;
+  // thread = (cq, i, group of R consecutive x): column sums of the R x 2R window, then R sliding outputs
+  for (int idx = threadIdx.x; idx < Cq * R * SP_W; idx += blockDim.x) {
+    const int g = idx % SP_W;
+    const int t = idx / SP_W;
     const int i = t % R, cq = t / R;
-    const int X = w0 * R + xl;
-    if (X >= Ws) continue;
-    const uint16_t* base = sm + (cq * PR + i) * PW + xl;
-    float v = 0.f;
-    if (pool) {
+    const int X = (w0 + g) * R;
+    if (w0 + g >= w) continue;
+    float o[R];
+    window_outputs<H, R>(sm + (cq * PR + i) * PW + g * R, PW, pool, R - 1, o);
+    uint16_t* dp = dst + ((n * Cq + cq) * Hs + hh * R + i) * (long long)Ws + X;
 #pragma unroll
-      for (int a = 0; a < R; ++a)
-#pragma unroll
-        for (int b = 0; b < R; ++b) v += H::to_f(*reinterpret_cast<const typename H::T*>(base + a * PW + b));
-      v *= inv;
-    } else {
-      v = H::to_f(*reinterpret_cast<const typename H::T*>(base + (R - 1) * PW + R - 1));
+    for (int j = 0; j < R; ++j) {
+      const typename H::T v = H::from_f(pool ? o[j] * inv : o[j]);
+      dp[j] = *reinterpret_cast<const uint16_t*>(&v);
     }
-    const typename H::T o = H::from_f(v);
-    dst[((n * Cq + cq) * Hs + hh * R + i) * (long long)Ws + X] = *reinterpret_cast<const uint16_t*>(&o);
   }
 }
 
@@ -100,7 +133,7 @@ __global__ void __launch_bounds__(256)
 shuffle_pool_bwd_kernel(const uint16_t* __restrict__ dP, uint16_t* __restrict__ dsrc, int h, int w, int Cq, int pool) {
   using H = H16<BF16>;
   extern __shared__ uint16_t sm[];
-  constexpr int XW = SP_W * R, RW = XW + R - 1, RH = 2 * R - 1, RR = R * R;
+  constexpr int XW = SP_W * R, RW = XW + R + (R & 1), RH = 2 * R - 1, RR = R * R;  // RW even (zero pad columns)
   const int w0 = blockIdx.x * SP_W, hh = blockIdx.y;
   const long long n = blockIdx.z;
   const int Ws = w * R, Hs = h * R;
@@ -114,32 +147,27 @@ shuffle_pool_bwd_kernel(const uint16_t* __restrict__ dP, uint16_t* __restrict__ 
   __syncthreads();
   const int C = Cq * RR;
   constexpr float inv = 1.0f / (float)RR;
-  for (int idx = threadIdx.x; idx < SP_W * C; idx += blockDim.x) {
-    const int c = idx % C, wl = idx / C;
+  // thread = (decoder pixel wl, cq, i): the R channels j = 0..R-1 are R sliding sums over the same R x (2R-1) window
+  for (int idx = threadIdx.x; idx < SP_W * Cq * R; idx += blockDim.x) {
+    const int ci = idx % (Cq * R), wl = idx / (Cq * R);
     const int ww = w0 + wl;
     if (ww >= w) continue;
-    const int cq = c / RR, ij = c % RR;
-    const int i = ij / R, j = ij % R;
-    const uint16_t* base = sm + (cq * RH + i) * RW + wl * R + j;
-    float v = 0.f;
-    if (pool) {
+    const int cq = ci / R, i = ci % R;
+    float o[R];
+    window_outputs<H, R>(sm + (cq * RH + i) * RW + wl * R, RW, pool, 0, o);
+    uint16_t* dp = dsrc + ((n * h + hh) * w + ww) * (long long)C + cq * RR + i * R;
 #pragma unroll
-      for (int a = 0; a < R; ++a)
-#pragma unroll
-        for (int b = 0; b < R; ++b) v += H::to_f(*reinterpret_cast<const typename H::T*>(base + a * RW + b));
-      v *= inv;
-    } else {
-      v = H::to_f(*reinterpret_cast<const typename H::T*>(base));
+    for (int j = 0; j < R; ++j) {
+      const typename H::T v = H::from_f(pool ? o[j] * inv : o[j]);
+      dp[j] = *reinterpret_cast<const uint16_t*>(&v);
     }
-    const typename H::T o = H::from_f(v);
-    dsrc[((n * h + hh) * w + ww) * (long long)C + c] = *reinterpret_cast<const uint16_t*>(&o);
   }
 }
 
 template <bool BF16, int R>
 static int shuffle_pool_launch(const uint16_t* s, uint16_t* d, int B, int h, int w, int Cq, int pool, int backward,
                                cudaStream_t st) {
-  const size_t smem = (size_t)Cq * (2 * R - 1) * (SP_W * R + R - 1) * 2;  // same extent both ways
+  const size_t smem = (size_t)Cq * (2 * R - 1) * (SP_W * R + R + (R & 1)) * 2;  // same extent both ways
   if (smem > 200 * 1024) return fail(VB200_ERR_UNSUPPORTED, "tile of %zu bytes does not fit shared memory", smem);
   static PerDeviceOnce once[2];
   const int dev = PerDeviceOnce::device();

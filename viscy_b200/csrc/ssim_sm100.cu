@@ -18,7 +18,8 @@
 namespace vb {
 namespace ssim {
 
-constexpr int TH = 32, TW = 64, NT = 256, KMAX = 16;
+constexpr int NT = 256, KMAX = 16;
+// tile of owned pixels per block: 32 x 64 on large planes (halo overhead 1.5x), 16 x 32 when that would leave SMs idle
 
 __device__ __forceinline__ float bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
@@ -74,7 +75,7 @@ struct Params {
   float wbf, k1, k2;
 };
 
-template <int XDT, int YDT>
+template <int XDT, int YDT, int TH, int TW>
 __global__ void __launch_bounds__(NT, 2) level_fwd_kernel(const Params p) {
   extern __shared__ float sm[];  // [5][RH][RW]
   __shared__ float red[4][NT / 32];
@@ -231,7 +232,7 @@ struct BwdParams {
   float wbf, k1, k2;
 };
 
-template <int XDT, int YDT>
+template <int XDT, int YDT, int TH, int TW>
 __global__ void __launch_bounds__(NT, 3) level_bwd_kernel(const BwdParams p) {
   extern __shared__ float sm[];  // [3][RH][RW]: G_mux, G_muxx, G_muxy at output pixels (h0 - kh + 1 + r, w0 - kw + 1 + c)
   const int RH = TH + p.kh - 1, RW = TW + p.kw - 1, RP = RH * RW;
@@ -376,13 +377,20 @@ extern "C" int vb200_ssim25d_level_fwd(const void* x, const void* y, int x_dtype
   p.Ho = H - kh + 1; p.Wo = W - kw + 1; p.flags = flags;
   p.wbf = bf16_round_host(1.0f / (float)(D * kh * kw));
   p.k1 = 0.01f; p.k2 = 0.03f;
+  const bool big = (long long)((W + 63) / 64) * ((H + 31) / 32) * B * C >= 2 * 148;
+  const int TH = big ? 32 : 16, TW = big ? 64 : 32;
   const size_t smem = (flags & 1) ? (size_t)5 * (TH + kh - 1) * (TW + kw - 1) * sizeof(float) : 0;
   dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
-  static PerDeviceOnce once[9];
-#define SSIM_FWD(XD, YD)                                                                     \
-  if (x_dtype == XD && y_dtype == YD) {                                                      \
-    ssim_smem_opt_in((const void*)level_fwd_kernel<XD, YD>, once[XD * 3 + YD]);              \
-    level_fwd_kernel<XD, YD><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+  static PerDeviceOnce once[18];
+#define SSIM_FWD(XD, YD)                                                                               \
+  if (x_dtype == XD && y_dtype == YD) {                                                                \
+    if (big) {                                                                                         \
+      ssim_smem_opt_in((const void*)level_fwd_kernel<XD, YD, 32, 64>, once[XD * 3 + YD]);              \
+      level_fwd_kernel<XD, YD, 32, 64><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+    } else {                                                                                           \
+      ssim_smem_opt_in((const void*)level_fwd_kernel<XD, YD, 16, 32>, once[9 + XD * 3 + YD]);          \
+      level_fwd_kernel<XD, YD, 16, 32><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+    }                                                                                                  \
   }
   SSIM_FWD(0, 0) SSIM_FWD(0, 1) SSIM_FWD(0, 2) SSIM_FWD(1, 0) SSIM_FWD(1, 1) SSIM_FWD(1, 2) SSIM_FWD(2, 0) SSIM_FWD(2, 1)
   SSIM_FWD(2, 2)
@@ -405,13 +413,20 @@ extern "C" int vb200_ssim25d_level_bwd(const void* x, const void* y, int x_dtype
   p.Ho = H - kh + 1; p.Wo = W - kw + 1;
   p.wbf = bf16_round_host(1.0f / (float)(D * kh * kw));
   p.k1 = 0.01f; p.k2 = 0.03f;
+  const bool big = (long long)((W + 63) / 64) * ((H + 31) / 32) * B * C >= 2 * 148;
+  const int TH = big ? 32 : 16, TW = big ? 64 : 32;
   const size_t smem = do_ssim ? (size_t)3 * (TH + kh - 1) * (TW + kw - 1) * sizeof(float) : 0;
   dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
-  static PerDeviceOnce once[9];
-#define SSIM_BWD(XD, YD)                                                                     \
-  if (x_dtype == XD && y_dtype == YD) {                                                      \
-    ssim_smem_opt_in((const void*)level_bwd_kernel<XD, YD>, once[XD * 3 + YD]);              \
-    level_bwd_kernel<XD, YD><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+  static PerDeviceOnce once[18];
+#define SSIM_BWD(XD, YD)                                                                               \
+  if (x_dtype == XD && y_dtype == YD) {                                                                \
+    if (big) {                                                                                         \
+      ssim_smem_opt_in((const void*)level_bwd_kernel<XD, YD, 32, 64>, once[XD * 3 + YD]);              \
+      level_bwd_kernel<XD, YD, 32, 64><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+    } else {                                                                                           \
+      ssim_smem_opt_in((const void*)level_bwd_kernel<XD, YD, 16, 32>, once[9 + XD * 3 + YD]);          \
+      level_bwd_kernel<XD, YD, 16, 32><<<grid, NT, smem, (cudaStream_t)stream>>>(p);                   \
+    }                                                                                                  \
   }
   SSIM_BWD(0, 0) SSIM_BWD(0, 1) SSIM_BWD(0, 2) SSIM_BWD(1, 0) SSIM_BWD(1, 1) SSIM_BWD(1, 2) SSIM_BWD(2, 0) SSIM_BWD(2, 1)
   SSIM_BWD(2, 2)

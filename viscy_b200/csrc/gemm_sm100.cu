@@ -9,6 +9,8 @@
 // reference hot path (VM/components/blocks.py:60-74, VM/components/stems.py:26-50).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -41,19 +43,22 @@ struct EpiWarps {
 // MODE_CONVKPW: CONVKP with the whole filter resident in shared memory (fetched once per CTA, <= 110 KB: Cin x Cout up to
 // 64 x 32 / 32 x 64 at 27 taps), so that a K block is the 160 A rows only -- the weight sub-tiles were over half of the
 // box rows the TMA unit had to deliver per K block.
-enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4, MODE_CONVKPW = 5 };
+// MODE_KMAJOR2: the K-major form on a CTA pair (cluster of two CTAs, tcgen05 cta_group::2): one MMA covers a 256 x BN tile,
+// 128 rows per CTA, each CTA stages only its half of the B rows - half the B traffic into and out of shared memory per SM.
+enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4, MODE_CONVKPW = 5, MODE_KMAJOR2 = 6 };
 
 // BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
-template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false, bool WRES = false>
+template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false, bool WRES = false, bool PAIR = false>
 struct Cfg {
   static constexpr int A_BYTES = (PATCH ? 160 : BM) * BKE * 2;
-  static constexpr int B_TAP_BYTES = BN * BKE * 2;
+  static constexpr int B_TAP_BYTES = (PAIR ? BN / 2 : BN) * BKE * 2;
   static constexpr int B_BYTES = WRES ? 0 : (PATCH ? 3 : 1) * B_TAP_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // (the 16-warp epilogues need 32 KB of staging tiles: one operand stage less on the 256-wide tile)
   static constexpr int STAGES =
       WRES  ? (BKE == 64 ? 4 : 8)
       : PATCH ? (BKE == 64 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 8 : 5))
+      : PAIR ? (EW == 16 ? 4 : 6)
             : (BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12)));
   static_assert(!PATCH || BN <= 128, "patch conv form: tiles up to 128 output channels");
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
@@ -393,7 +398,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int NUM_EPI_WARPS = EpiWarps<BN, EPI>::value;
   constexpr bool WRES = MODE == MODE_CONVKPW;
   constexpr bool PATCH = MODE == MODE_CONVKP || WRES;
-  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH, WRES>;
+  constexpr bool PAIR = MODE == MODE_KMAJOR2;
+  static_assert(!PAIR || BN == 256, "CTA-pair form: 256-wide tiles");
+  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH, WRES, PAIR>;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int COL_GROUPS = NUM_EPI_WARPS / 4;  // warps sharing a TMEM lane quarter split the tile's columns
   constexpr bool MN_MAJOR = MODE == MODE_MNMAJOR || MODE == MODE_CONVMN;
   static_assert(BKE == 64 || (BKE == 32 && (MODE == MODE_CONVK || PATCH)), "BKE = 32 is the 32-channel conv form only");
@@ -421,14 +429,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair: both CTAs' epilogues release the leader
     }
     if constexpr (WRES) mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc2(tmem_ptr, C::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   // MN-major forms with M <= 64 (weight gradients of <= 64-channel layers): rows 64..127 of the A tile are all padding.
   // They are zeroed once here and their TMA box is never issued, which saves a third of the boxes per K block.
@@ -442,6 +455,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -461,8 +475,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const int split = unit / tiles;
         const int t = unit - split * tiles;
-        const int m0 = (t / p.tiles_n) * BM;
-        const int n0 = (t % p.tiles_n) * BN;
+        // pair form: CTAs 2c, 2c+1 (one cluster) walk units 2q, 2q+1 in lockstep = the two 128-row halves of pair tile q
+        const int m0 = PAIR ? (((t >> 1) / p.tiles_n) * 2 + (int)rank) * BM : (t / p.tiles_n) * BM;
+        const int n0 = PAIR ? ((t >> 1) % p.tiles_n) * BN : (t % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         // conv forms: CONVK walks (tap, channel chunk) along K for a fixed 128-voxel box; CONVMN walks 64-voxel boxes
@@ -504,6 +519,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
+          if constexpr (PAIR) {
+            // both CTAs' boxes are counted on the LEADER's full barrier (it issues the MMA that reads both halves)
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(sa, &tmA, lead_bar, kb * BK, m0);
+            const int brow = (p.b_batch_rows > 0 ? (m0 / p.b_batch_rows) * p.N + n0 : n0) + (int)rank * (BN / 2);
+            tma_load_2d_pair(sb, &tmB, lead_bar, kb * BK, brow);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], a_half ? C::STAGE_BYTES - 64 * BK * 2 : C::STAGE_BYTES);
           if constexpr (PATCH) {
             tma_load_5d(sa, &tmA, &full_bar[stage], chunk * BKE, cx + kw, cy, cz + kd, cn);
@@ -575,7 +600,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are built once per stage and advanced by
     // adding byte offsets >> 4 to their address field: with 16-32-cycle MMAs (N = 32 / 64 tiles) the issue loop of this
     // single thread, not the tensor pipe, was the measured limit.
-    const uint32_t idesc = make_idesc(BM, WRES ? p.cwrows : BN, p.bf16 != 0, MN_MAJOR, MN_MAJOR);
+    const uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, WRES ? p.cwrows : BN, p.bf16 != 0, MN_MAJOR, MN_MAJOR);
     const uint64_t desc_a0 = BKE == 32 ? make_smem_desc_sw64(0, 0, 512)
                              : (MN_MAJOR ? make_smem_desc(0, 64 * BK * 2, 1024) : make_smem_desc(0, 0, 1024));
     const uint64_t desc_b0 = desc_a0;
@@ -591,6 +616,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
     }
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      if (PAIR && rank != 0) break;  // the leader CTA issues for the pair
       const int split = unit / tiles;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -625,10 +651,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // K-major: step 16 elements (32 B) inside the swizzled row; MN-major: step 16 k rows = 2048 B
             constexpr int KSTEP = MN_MAJOR ? 2048 : 32;
 #pragma unroll
-            for (int k = 0; k < BKE / 16; ++k)
-              tc_mma_f16(d_tmem, da_s + ((k * KSTEP) >> 4), db_s + ((k * KSTEP) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BKE / 16; ++k) {
+              if constexpr (PAIR)
+                tc_mma_f16_2(d_tmem, da_s + ((k * KSTEP) >> 4), db_s + ((k * KSTEP) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else
+                tc_mma_f16(d_tmem, da_s + ((k * KSTEP) >> 4), db_s + ((k * KSTEP) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if constexpr (PAIR) tc_commit2(&empty_bar[stage]);  // frees the slot in both CTAs
+          else tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         }
         __syncwarp();
         if constexpr (WRES) {
@@ -640,7 +671,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-      if (leader) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      if (leader) {  // accumulator complete -> epilogue (of both CTAs in the pair form)
+        if constexpr (PAIR) tc_commit2(&tmem_full[acc]);
+        else tc_commit(&tmem_full[acc]);
+      }
       __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -660,8 +694,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
       const int split = unit / tiles;
       const int t = unit - split * tiles;
-      const int m0 = (t / p.tiles_n) * BM;
-      int n0 = (t % p.tiles_n) * BN;
+      const int m0 = PAIR ? (((t >> 1) / p.tiles_n) * 2 + (int)rank) * BM : (t / p.tiles_n) * BM;
+      int n0 = PAIR ? ((t >> 1) % p.tiles_n) * BN : (t % p.tiles_n) * BN;
       int n_lim = p.N;
       if constexpr (MODE == MODE_CONVMN) {  // N tile = (tap, channel tile): columns [tap*cin + ci0, (tap+1)*cin)
         const int tn = t % p.tiles_n;
@@ -754,7 +788,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else if (!more) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+              else mbar_arrive(&tmem_empty[acc]);
+            }
             released = true;
           }
           // this warp's 32 rows x 32 columns: math per row, then row-contiguous stores through the staging tile
@@ -822,7 +859,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (!released) {  // this warp's column range lies past the tile's valid columns
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+          else mbar_arrive(&tmem_empty[acc]);
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -834,10 +874,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -942,7 +984,7 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   const int dev = PerDeviceOnce::device();
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
   using LC = Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store,
-                 MODE == MODE_CONVKP || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW>;
+                 MODE == MODE_CONVKP || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW, MODE == MODE_KMAJOR2>;
   const int smem_bytes = MODE == MODE_CONVKPW ? LC::W_OFFSET + 1024 + p.cwbytes : LC::SMEM_BYTES;
   if (once.need(dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -957,6 +999,23 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
       if (int rc = make_tmap_2d(&om.o2, p.out2, p.M, p.N, p.ldo2, 32, 32, BF16, true)) return rc;
   }
   if (smem_bytes > 232448) return fail(VB200_ERR_UNSUPPORTED, "resident filter does not fit shared memory (%d B)", smem_bytes);
+  if constexpr (MODE == MODE_KMAJOR2) {  // clusters of two CTAs: the pair shares one tcgen05 cta_group::2 MMA
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(64 + 32 * EpiWarps<BN, EPI>::value);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, om, p);
+    if (e != cudaSuccess) return fail(VB200_ERR_CUDA, "vb200_gemm (CTA pair): %s", cudaGetErrorString(e));
+    return check_launch("vb200_gemm");
+  }
   kern<<<grid, 64 + 32 * EpiWarps<BN, EPI>::value, smem_bytes, st>>>(ta, tb, om, p);
   return check_launch("vb200_gemm");
 }
@@ -970,6 +1029,17 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     return p.bf16 ? launch_dt<BN, MODE, EPI, BKE, true>(ta, tb, p, grid, st)
                   : launch_dt<BN, MODE, EPI, BKE, false>(ta, tb, p, grid, st);
   }
+}
+
+// K-major GEMM on CTA pairs (256-wide tiles): the epilogues of the decoder-stage GEMMs
+static int launch_epi_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                           cudaStream_t st) {
+  switch (epi) {
+    case VB200_EPI_STORE: return launch<256, MODE_KMAJOR2, VB200_EPI_STORE>(ta, tb, p, grid, st);
+    case VB200_EPI_DGELU_GRN: return launch<256, MODE_KMAJOR2, VB200_EPI_DGELU_GRN>(ta, tb, p, grid, st);
+    case VB200_EPI_GELU_GP: return launch<256, MODE_KMAJOR2, VB200_EPI_GELU_GP>(ta, tb, p, grid, st);
+  }
+  return fail(VB200_ERR_INVALID, "no CTA-pair form of epilogue %d", epi);
 }
 
 template <int BN, bool MN_MAJOR>
@@ -1041,11 +1111,17 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
   int kb_per = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per - 1) / kb_per;  // no empty split
 
+  // CTA-pair form: K-major, 256-wide tiles, an even number of 128-row tiles, enough pair tiles for every SM pair
+  static const int pair_mode = [] { const char* e = getenv("VB200_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  const bool pair = pair_mode && !d->mn_major && bn == 256 && splits == 1 && tiles_m % 2 == 0 && sms % 2 == 0 &&
+                    (epi == VB200_EPI_STORE || epi == VB200_EPI_DGELU_GRN || epi == VB200_EPI_GELU_GP) &&
+                    (long long)tiles_m * tiles_n >= sms && (d->b_batch_rows == 0 || d->b_batch_rows % (2 * BM) == 0) &&
+                    (d->rows_per_sample == 0 || d->rows_per_sample % (2 * BM) == 0) && (d->rvec_rows == 0 || d->rvec_rows % (2 * BM) == 0);
   CUtensorMap ta, tb;
   int rc;
   if (!d->mn_major) {
     if ((rc = make_tmap_2d(&ta, d->A, d->M, d->K, d->lda, BK, BM, bf16))) return rc;
-    if ((rc = make_tmap_2d(&tb, d->B, (long long)d->N * nb, d->K, d->ldb, BK, bn, bf16))) return rc;
+    if ((rc = make_tmap_2d(&tb, d->B, (long long)d->N * nb, d->K, d->ldb, BK, pair ? bn / 2 : bn, bf16))) return rc;
   } else {
     if ((rc = make_tmap_2d(&ta, d->A, d->K, d->M, d->lda, 64, BK, bf16))) return rc;
     if ((rc = make_tmap_2d(&tb, d->B, d->K, d->N, d->ldb, 64, BK, bf16))) return rc;
@@ -1076,6 +1152,7 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
   const long long units = (long long)tiles_m * tiles_n * splits;
   const int grid = (int)(units < sms ? units : sms);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pair) return launch_epi_pair(epi, ta, tb, p, grid & ~1, st);
   if (!d->mn_major) {
     if (bn == 256) return launch_epi<256, false>(epi, ta, tb, p, grid, st);
     if (bn == 128) return launch_epi<128, false>(epi, ta, tb, p, grid, st);

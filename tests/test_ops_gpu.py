@@ -238,7 +238,8 @@ def test_head_tail(cuda, dtype, geom):
     dz, dW1, db1, dalpha, dbz = ops.head_tail_bwd(z, mean, rstd, alpha, w1, dout, Dz, H, W)
     assert rel(dz.view(B, Dz, H, W, Cmid).permute(0, 4, 1, 2, 3), zf.grad) < tol(dtype) * 2
     assert rel(dW1, wf.grad) < 2e-3 and rel(db1, bf.grad) < 2e-3 and rel(dalpha, af.grad) < 2e-3
-    assert rel(dbz, dz.float().sum((0, 1))) < 1e-3
+    # sum_rows dz is analytically zero per (sample, channel) (InstanceNorm backward): compare against the size of the terms
+    assert (dbz - dz.float().sum((0, 1))).abs().max() <= 1e-4 * dz.float().abs().sum((0, 1)).max()
 
 
 @pytest.mark.parametrize("dtype", DT)

@@ -152,29 +152,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// u -> d = gelu'(u), g = gelu(u) for two elements with ONE MUFU op (ex2) per element; everything else rides the packed
-// fp32x2 pipe.  q = erfc(|u|/sqrt2)/2 = e * S(|u|), e = exp(-u^2/2), where S (a scaled Mills ratio, smooth and slowly
-// decaying) is a degree-8 polynomial in z = 2|u|/7 - 1 on |u| <= 7, fitted to minimise the absolute error of q
-// (1.6e-6 in fp32; beyond 7, e < 3e-11).  The epilogues that call this were bound by the MUFU pipe with the rational
-// (Abramowitz-Stegun) form, which needs a reciprocal per element on top of the exp.  With h = 1/2 - q:
+// u -> d = gelu'(u), g = gelu(u) for two elements, one exp and one reciprocal each, everything else on the packed
+// fp32x2 pipe.  With q = erfc(|u|/sqrt2)/2 (Abramowitz-Stegun 7.1.26, coefficients pre-scaled by -1/2) and h = 1/2 - q:
 //   cdf = 1/2 + sgn(u) h,   gelu = u/2 + |u| h,   gelu' = cdf + u pdf = 1/2 + sgn(u) (h + |u| pdf)
 __device__ __forceinline__ void gelu_gp2(float2 u, float2& d, float2& g) {
   const float2 uu = __fmul2_rn(u, u);
   const float2 ea = __fmul2_rn(uu, make_float2(-0.72134752044448170f, -0.72134752044448170f));
   const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));  // exp(-u^2/2)
   const float2 x = make_float2(fabsf(u.x), fabsf(u.y));
-  const float2 xc = make_float2(fminf(x.x, 7.0f), fminf(x.y, 7.0f));
-  const float2 z = __ffma2_rn(xc, make_float2(0.2857142857f, 0.2857142857f), make_float2(-1.f, -1.f));
-#define VB_C2(v) make_float2(v, v)
-  float2 poly = __ffma2_rn(z, VB_C2(-0.853352963924408f), VB_C2(-2.868135929107666f));  // -S(|u|), Horner in z
-  poly = __ffma2_rn(poly, z, VB_C2(-4.270120620727539f));
-  poly = __ffma2_rn(poly, z, VB_C2(-3.291111946105957f));
-  poly = __ffma2_rn(poly, z, VB_C2(-1.4793893098831177f));
-  poly = __ffma2_rn(poly, z, VB_C2(-0.2393750250339508f));
-  poly = __ffma2_rn(poly, z, VB_C2(-0.091727614402771f));
-  poly = __ffma2_rn(poly, z, VB_C2(0.09813942015171051f));
-  poly = __ffma2_rn(poly, z, VB_C2(-0.105891652405262f));
-#undef VB_C2
+  const float2 den = __ffma2_rn(x, make_float2(0.23164190541f, 0.23164190541f), make_float2(1.f, 1.f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 poly = __ffma2_rn(t, make_float2(-0.5307027145f, -0.5307027145f), make_float2(0.7265760135f, 0.7265760135f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.7107068705f, -0.7107068705f));
+  poly = __ffma2_rn(poly, t, make_float2(0.142248368f, 0.142248368f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.127414796f, -0.127414796f));
+  poly = __fmul2_rn(poly, t);                                       // -q / e
   const float2 h = __ffma2_rn(poly, e, make_float2(0.5f, 0.5f));    // 1/2 - q
   const float2 pdf = __fmul2_rn(e, make_float2(0.3989422804014327f, 0.3989422804014327f));
   const float2 s = __ffma2_rn(x, pdf, h);

@@ -232,6 +232,40 @@ def secondary_evidence(dev, tf_burst):
                                             "launches_per_step": launches}
     del m, opt, a, p
     torch.cuda.empty_cache()
+    # the same UNeXt2 step with the recipes' MixedLoss (0.5 L1 + 0.5 MS-DSSIM, VU/losses/mixed_loss.py) instead of MSE, and
+    # one FCMAE (VSCyto3D-style: dense encoder, conv head) fine-tuning step at the same input shape
+    try:
+        import warnings
+        from viscy_b200 import FullyConvolutionalMAE, UNeXt2
+        from viscy_b200.losses import MixedLoss
+        warnings.filterwarnings("ignore", message="Input depth")
+        x = torch.randn((BATCH, *SHAPE_IN), device=dev)
+        y = torch.rand((BATCH, *SHAPE_OUT), device=dev)
+        for tag, make in (("unext2_mixed_loss_b8", lambda: UNeXt2(**CFG)),
+                          ("fcmae_finetune_mixed_loss_b8", lambda: FullyConvolutionalMAE(
+                              1, 2, in_stack_depth=21, stem_kernel_size=(7, 4, 4), pretraining=False, head_conv=True))):
+            torch.manual_seed(0)
+            m = make().to(dev)
+            opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True, capturable=True)
+            crit = MixedLoss(l1_alpha=0.5, l2_alpha=0.0, ms_dssim_alpha=0.5)
+
+            def step_ml(xd, yd, m=m, opt=opt, crit=crit):
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = crit(m(xd), yd)
+                loss.backward()
+                opt.step()
+                return loss
+
+            ms, mode, launches = _graphed_ms(step_ml, (x, y), 10, 3)
+            out[tag] = {"ms_per_step": ms, "samples_per_s": BATCH * 1e3 / ms, "mode": mode, "launches_per_step": launches,
+                        "loss": "MixedLoss(0.5 L1 + 0.5 MS-DSSIM) on the sm_100a SSIM kernels"}
+            del m, opt
+            torch.cuda.empty_cache()
+        del x, y
+    except Exception as exc:  # evidence only
+        out["mixed_loss_steps"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    torch.cuda.empty_cache()
     # the GPU incumbent: the oracle is the thing MEASURED here (a baseline arm), never the product path
     try:
         sys.path.insert(0, str(ROOT / "tools"))

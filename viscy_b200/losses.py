@@ -126,14 +126,34 @@ def ssim_25d(preds: torch.Tensor, target: torch.Tensor, in_plane_window_size: tu
     return (ssim, cs) if return_contrast_sensitivity else ssim
 
 
+_BETAS: dict = {}
+
+
+def _betas(betas, device) -> torch.Tensor:
+    """The level exponents as a [levels, 1] device tensor, uploaded once per (values, device): no host-to-device copy in the
+    step, so the loss can be captured into a CUDA graph."""
+    key = (tuple(float(b) for b in betas), str(device))
+    t = _BETAS.get(key)
+    if t is None:
+        t = _BETAS[key] = torch.tensor(key[0], device=device).view(-1, 1)
+    return t
+
+
 def _combine(ssim_last, cs_list, clamp, betas, base_min=1e-4):
     """metrics.py:337-349: clamp, replace the last level's cs by its ssim, weight by the betas, product, batch mean."""
     if clamp:
         cs_list = [c.clamp(min=base_min) for c in cs_list]
         ssim_last = ssim_last.clamp(min=base_min)
     stack = torch.stack(cs_list[:-1] + [ssim_last])
-    b = torch.tensor(betas, device=stack.device).view(-1, 1)
-    return torch.prod(stack**b, axis=0).mean()
+    if not stack.is_cuda:
+        return torch.prod(stack ** torch.tensor(betas, device=stack.device).view(-1, 1), axis=0).mean()
+    # CUDA: an explicit product chain - torch.prod's backward inspects the input for zeros on the host (a sync that a CUDA
+    # graph capture of the training step cannot contain)
+    w = stack ** _betas(betas, stack.device)
+    r = w[0]
+    for i in range(1, w.shape[0]):
+        r = r * w[i]
+    return r.mean()
 
 
 def _ms_ssim_cuda(preds, target, window, clamp, betas, l1l2: bool):

@@ -62,7 +62,9 @@ struct Cfg {
             : (BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12)));
   static_assert(!PATCH || BN <= 128, "patch conv form: tiles up to 128 output channels");
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
-  static constexpr int COLV_BYTES = 2 * 3 * BN * 4;  // [2 tiles in flight][bias, s, t][BN] fp32
+  // per epilogue warp: [bias, s, t][its BN / (EW / 4) columns] fp32 (private: no CTA-wide barrier per tile)
+  // (the patch conv forms carry a bias only and sit at the shared-memory limit: one vector)
+  static constexpr int COLV_BYTES = EW * (PATCH ? 1 : 3) * (BN / (EW / 4)) * 4;
   // per-warp 32 rows x 64 B staging tile(s): one, or two for the 16-warp epilogues whose outputs leave through TMA stores
   static constexpr int STG_PER_WARP = TWO_TILES ? 4096 : 2048;
   static constexpr int STG_BYTES = EW * STG_PER_WARP;
@@ -327,7 +329,7 @@ __device__ __forceinline__ void stage_store(uint32_t stg, int lane, const uint4*
 
 // Epilogue math for 8 consecutive columns of one row.  cv = shared-space address of the staged [bias | s | t] of the
 // tile (fp32).  v: accumulators in, primary result out; w: secondary result (dual-output epilogues).
-template <int EPI, int BN, bool BF16>
+template <int EPI, int BN, bool BF16, int CVP>
 __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, float* w, int cl, uint32_t cv,
                                                const uint4& xa, const uint4& xb, float rs) {
   {
@@ -339,7 +341,7 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
   if constexpr (EPI == VB200_EPI_STORE) {
     if (p.svec != nullptr) {  // per-column fp32 scale (ConvNeXt-V1 layer scale gamma): (acc + bias) * s
       float s8[8];
-      lds_f8(cv + (BN + cl) * 4, s8);
+      lds_f8(cv + (CVP + cl) * 4, s8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= s8[j];
     }
@@ -382,8 +384,8 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
     float g[8], gp[8], s8[8], t8[8];
     unpack8<BF16>(xa, g);
     unpack8<BF16>(xb, gp);
-    lds_f8(cv + (BN + cl) * 4, s8);
-    lds_f8(cv + (2 * BN + cl) * 4, t8);
+    lds_f8(cv + (CVP + cl) * 4, s8);
+    lds_f8(cv + (2 * CVP + cl) * 4, t8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaf(g[j], t8[j], v[j] * s8[j]) * gp[j];
   }
@@ -684,7 +686,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int e = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int half = e >> 2;       // which group of BN / COL_GROUPS columns
-    const int et = threadIdx.x - 64;
     float* colv = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
     const uint32_t stg = smem_u32(smem + C::STG_OFFSET + e * C::STG_PER_WARP);
     constexpr bool TMA_STORE = EpiWarps<BN, EPI>::tma_store;
@@ -703,19 +704,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         n0 = tap * p.ccin + (tn - tap * p.cchunks) * BN;
         n_lim = (tap + 1) * p.ccin;
       }
-      // stage this tile's per-column vectors (bias and, for the fused GRN backward, s and t of the tile's sample)
-      float* cvp = colv + acc * 3 * BN;
-      const uint32_t cv = smem_u32(cvp);
-      if (et < BN) {
-        const int col = n0 + et;
+      // this warp's per-column vectors (bias and, for the fused GRN backward, s and t of the tile's sample) for its own
+      // BN / COL_GROUPS columns, in its private slice of shared memory: a __syncwarp instead of a barrier across all epilogue
+      // warps per tile (the barrier cost 12 % of the epilogue warps' time in the source-level profile)
+      constexpr int CW = BN / COL_GROUPS;
+      float* cvp = colv + e * (PATCH ? 1 : 3) * CW;
+      const uint32_t cv = smem_u32(cvp) - static_cast<uint32_t>(half * CW) * 4u;  // indexed by the column within the tile
+      __syncwarp();  // the previous tile's reads of this slice are done
+#pragma unroll
+      for (int i = lane; i < CW; i += 32) {
+        const int col = n0 + half * CW + i;
         const bool ok = col < p.N;
-        cvp[et] = (p.bias != nullptr && split == 0 && ok) ? __ldg(p.bias + col) : 0.0f;
-        if constexpr (EPI == VB200_EPI_DGELU_GRN || EPI == VB200_EPI_STORE) {
+        cvp[i] = (p.bias != nullptr && split == 0 && ok) ? __ldg(p.bias + col) : 0.0f;
+        if constexpr ((EPI == VB200_EPI_DGELU_GRN || EPI == VB200_EPI_STORE) && !PATCH) {
           const long long ns = p.rows_per_sample > 0 ? m0 / p.rows_per_sample : 0;
-          cvp[BN + et] = (p.svec != nullptr && ok) ? __ldg(p.svec + ns * p.N + col) : 1.0f;
-          cvp[2 * BN + et] = (p.tvec != nullptr && ok) ? __ldg(p.tvec + ns * p.N + col) : 0.0f;
+          cvp[CW + i] = (p.svec != nullptr && ok) ? __ldg(p.svec + ns * p.N + col) : 1.0f;
+          cvp[2 * CW + i] = (p.tvec != nullptr && ok) ? __ldg(p.tvec + ns * p.N + col) : 0.0f;
         }
       }
+      __syncwarp();
       const long long row0 = m0 + quarter * 32;
       long long rowoff[4];
       bool scatter = false;
@@ -750,7 +757,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       AuxRegs aux[APRE ? 2 : 1];
       const int cc0 = half * (BN / COL_GROUPS);
       load_aux<EPI>(p, row0, n0 + cc0, lane, aux[0]);
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // cv visible to all epilogue warps
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr =
@@ -789,8 +795,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
-              else mbar_arrive(&tmem_empty[acc]);
+              // relaxed: the barrier guards TMEM only (tcgen05.fence above); a release would wait for every store in flight
+              if constexpr (PAIR) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+              else mbar_arrive_relaxed(&tmem_empty[acc]);
             }
             released = true;
           }
@@ -804,7 +811,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float v[8], w[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[TPRE ? (c & 1) : 0][g * 8 + j]);
-              epilogue_math8<EPI, BN, BF16>(p, v, w, cc + g * 8, cv, aux[AB].a[g], aux[AB].b[g], rscale);
+              epilogue_math8<EPI, BN, BF16, CW>(p, v, w, cc + g * 8, cv, aux[AB].a[g], aux[AB].b[g], rscale);
               if constexpr (EPI == VB200_EPI_F32) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f32buf[g * 8 + j] = v[j];
@@ -860,8 +867,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
-          else mbar_arrive(&tmem_empty[acc]);
+          if constexpr (PAIR) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+          else mbar_arrive_relaxed(&tmem_empty[acc]);
         }
       }
       acc ^= 1;

@@ -146,4 +146,4 @@ def test_mixed_loss_step_is_cuda_graph_capturable(cuda):
     out = gs(x, y)
     torch.cuda.synchronize()
     assert abs(out.item() - eager.item()) < 1e-4 * abs(eager.item())  # fp32 atomic sums: order differs run to run
-    torch.testing.assert_close(grads[-1].float(), g_eager.float(), rtol=1e-2, atol=1e-9)
+    assert rel(grads[-1].float(), g_eager.float()) < 2e-3  # bf16 gradient: last-bit differences from the atomic sum order

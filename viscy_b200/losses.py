@@ -238,3 +238,13 @@ class MixedLoss(nn.Module):
             if ms is not None:
                 loss = loss + (1 - ms) * self.ms_dssim_alpha
             return loss
+
+
+class MaskedMSELoss(nn.Module):
+    """Masked MSE loss for FCMAE pre-training (CY/engine.py:104-125): a handful of elementwise / reduction ops on the
+    reconstruction, kept as torch ops (FcmaeUNet itself insists on its own class, engine.py:877-878; this one is for callers
+    outside that engine)."""
+
+    def forward(self, preds, original, mask):
+        loss = TF.mse_loss(preds, original, reduction="none")
+        return (loss.mean(2) * mask).sum() / mask.sum()

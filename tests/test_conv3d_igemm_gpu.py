@@ -34,6 +34,10 @@ CASES = [
     (1, 8, 64, 128, 32, 32, (3, 3, 3), (1, 1, 1)),    # 32-row weight sub-tiles, MMA N = 32; dgrad the same form
     (1, 5, 64, 128, 64, 32, (3, 3, 3), (1, 1, 1)),    # 64 -> 32; its dgrad is the 32 -> 64 form (64-row sub-tiles)
     (2, 3, 64, 64, 32, 16, (1, 3, 3), (0, 1, 1)),     # 9 taps, two samples
+    # >= 148 patches, 64-channel K blocks, filter too large to stay resident: the patch form on CTA pairs (cta_group::2)
+    (1, 16, 32, 64, 64, 64, (3, 3, 3), (1, 1, 1)),    # 256 patches, 64-wide tile (each CTA stages 32 filter rows per tap)
+    (2, 8, 64, 32, 128, 128, (3, 3, 3), (1, 1, 1)),   # 256 patches, 128-wide tile, two channel chunks, two samples
+    (1, 20, 24, 32, 64, 128, (3, 3, 3), (1, 1, 1)),   # 180 patches: ragged last wave of pairs
 ]
 
 

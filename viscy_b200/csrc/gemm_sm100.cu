@@ -45,7 +45,7 @@ struct EpiWarps {
 // box rows the TMA unit had to deliver per K block.
 // MODE_KMAJOR2: the K-major form on a CTA pair (cluster of two CTAs, tcgen05 cta_group::2): one MMA covers a 256 x BN tile,
 // 128 rows per CTA, each CTA stages only its half of the B rows - half the B traffic into and out of shared memory per SM.
-enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4, MODE_CONVKPW = 5, MODE_KMAJOR2 = 6 };
+enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4, MODE_CONVKPW = 5, MODE_KMAJOR2 = 6, MODE_CONVKP2 = 7 };  // CONVKP2: the patch conv form on CTA pairs
 
 // BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
 template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false, bool WRES = false, bool PAIR = false>
@@ -57,7 +57,7 @@ struct Cfg {
   // (the 16-warp epilogues need 32 KB of staging tiles: one operand stage less on the 256-wide tile)
   static constexpr int STAGES =
       WRES  ? (BKE == 64 ? 4 : 8)
-      : PATCH ? (BKE == 64 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 8 : 5))
+      : PATCH ? (PAIR ? (BN == 64 ? 5 : 4) : (BKE == 64 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 8 : 5)))
       : PAIR ? (EW == 16 ? 4 : 6)
             : (BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12)));
   static_assert(!PATCH || BN <= 128, "patch conv form: tiles up to 128 output channels");
@@ -399,9 +399,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ OutMaps tmOut, const GemmParams p) {
   constexpr int NUM_EPI_WARPS = EpiWarps<BN, EPI>::value;
   constexpr bool WRES = MODE == MODE_CONVKPW;
-  constexpr bool PATCH = MODE == MODE_CONVKP || WRES;
-  constexpr bool PAIR = MODE == MODE_KMAJOR2;
-  static_assert(!PAIR || BN == 256, "CTA-pair form: 256-wide tiles");
+  constexpr bool PATCH = MODE == MODE_CONVKP || MODE == MODE_CONVKP2 || WRES;
+  constexpr bool PAIR = MODE == MODE_KMAJOR2 || MODE == MODE_CONVKP2;
+  static_assert(MODE != MODE_KMAJOR2 || BN == 256, "CTA-pair GEMM: 256-wide tiles");
+  static_assert(MODE != MODE_CONVKP2 || BKE == 64, "CTA-pair patch conv: 64-channel K blocks");
   using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH, WRES, PAIR>;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int COL_GROUPS = NUM_EPI_WARPS / 4;  // warps sharing a TMEM lane quarter split the tile's columns
@@ -488,7 +489,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         //  coordinates are decomposed once per unit and then advanced with carries)
         int cx = 0, cy = 0, cz = 0, cn = 0, chunk = 0, ci0 = 0, kw = 0, kh = 0, kd = 0, tapi = 0;
         if constexpr (PATCH) {  // M tile -> (n, z, patch row, patch column); K blocks walk (kd, kw, chunk)
-          int mt = t / p.tiles_n;
+          int mt = PAIR ? ((t >> 1) / p.tiles_n) * 2 + (int)rank : t / p.tiles_n;  // pair: two x-adjacent patches
           cx = (mt % p.cpxn) * 16 - p.cpw;
           mt /= p.cpxn;
           cy = (mt % p.cpyn) * 8 - p.cph;
@@ -521,7 +522,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          if constexpr (PAIR) {
+          if constexpr (PAIR && PATCH) {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_5d_pair(sa, &tmA, lead_bar, chunk * BKE, cx + kw, cy, cz + kd, cn);
+#pragma unroll
+            for (int h = 0; h < 3; ++h)  // this CTA's half of the output channels of each kh sub-tile
+              tma_load_2d_pair(sb + h * C::B_TAP_BYTES, &tmB, lead_bar, ((kd * 3 + h) * p.cKW + kw) * p.ccin + chunk * BKE,
+                               n0 + (int)rank * (BN / 2));
+            if (++chunk == p.cchunks) {
+              chunk = 0;
+              if (++kw == p.cKW) {
+                kw = 0;
+                ++kd;
+              }
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          } else if constexpr (PAIR) {
             // both CTAs' boxes are counted on the LEADER's full barrier (it issues the MMA that reads both halves)
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
             const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -645,9 +663,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const uint64_t db_h = WRES ? desc_b0 + ((wres0 + static_cast<uint32_t>(widx + h * wplane) * wsub) >> 4)
                                          : db_s + ((h * C::B_TAP_BYTES) >> 4);
 #pragma unroll
-              for (int k = 0; k < BKE / 16; ++k)
-                tc_mma_f16(d_tmem, da_s + ((h * 16 * (BKE * 2) + k * 32) >> 4), db_h + ((k * 32) >> 4), idesc,
-                           (kb > kb0 || h > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BKE / 16; ++k) {
+                if constexpr (PAIR)
+                  tc_mma_f16_2(d_tmem, da_s + ((h * 16 * (BKE * 2) + k * 32) >> 4), db_h + ((k * 32) >> 4), idesc,
+                               (kb > kb0 || h > 0 || k > 0) ? 1u : 0u);
+                else
+                  tc_mma_f16(d_tmem, da_s + ((h * 16 * (BKE * 2) + k * 32) >> 4), db_h + ((k * 32) >> 4), idesc,
+                             (kb > kb0 || h > 0 || k > 0) ? 1u : 0u);
+              }
             }
           } else {
             // K-major: step 16 elements (32 B) inside the swizzled row; MN-major: step 16 k rows = 2048 B
@@ -728,7 +751,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       bool scatter = false;
       if constexpr (PATCH) {  // rows of the tile = voxels of a 16 x 8 patch: each goes to its own output row
         scatter = true;
-        int mt = t / p.tiles_n;
+        int mt = PAIR ? ((t >> 1) / p.tiles_n) * 2 + (int)rank : t / p.tiles_n;
         const int px = mt % p.cpxn;
         mt /= p.cpxn;
         const int py = mt % p.cpyn;
@@ -991,7 +1014,8 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   const int dev = PerDeviceOnce::device();
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
   using LC = Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store,
-                 MODE == MODE_CONVKP || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW, MODE == MODE_KMAJOR2>;
+                 MODE == MODE_CONVKP || MODE == MODE_CONVKP2 || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW,
+                 MODE == MODE_KMAJOR2 || MODE == MODE_CONVKP2>;
   const int smem_bytes = MODE == MODE_CONVKPW ? LC::W_OFFSET + 1024 + p.cwbytes : LC::SMEM_BYTES;
   if (once.need(dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1006,7 +1030,7 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
       if (int rc = make_tmap_2d(&om.o2, p.out2, p.M, p.N, p.ldo2, 32, 32, BF16, true)) return rc;
   }
   if (smem_bytes > 232448) return fail(VB200_ERR_UNSUPPORTED, "resident filter does not fit shared memory (%d B)", smem_bytes);
-  if constexpr (MODE == MODE_KMAJOR2) {  // clusters of two CTAs: the pair shares one tcgen05 cta_group::2 MMA
+  if constexpr (MODE == MODE_KMAJOR2 || MODE == MODE_CONVKP2) {  // clusters of two CTAs: the pair shares one cta_group::2 MMA
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(64 + 32 * EpiWarps<BN, EPI>::value);
@@ -1295,6 +1319,16 @@ extern "C" int vb200_conv3d_igemm(const vb200_conv3d_desc* d, vb200_stream_t str
                        : launch<64, MODE_CONVKPW, VB200_EPI_STORE, 32>(ta, tb, p, pgrid, st);
     }
     if (bke == 64) {
+      // CTA pairs (two x-adjacent patches per MMA, each CTA stages half of the filter rows): shared-memory operand reads per
+      // MMA drop from A + B to A + B / 2 - these <= 128-channel tiles are bound by exactly that
+      static const int conv_pair = [] { const char* e = getenv("VB200_CONV_PAIR"); return e ? atoi(e) : 1; }();
+      if (conv_pair && p.tiles_n == 1 && p.cpxn % 2 == 0 && p.tiles_m % 2 == 0 && sms % 2 == 0 && punits >= sms && N % 16 == 0 &&
+          N == bn) {
+        if (int rc = make_tmap_2d(&tb, d->w, N, (long long)wtaps * d->cin, (long long)wtaps * d->cin, bke, bn / 2, bf16, false))
+          return rc;
+        if (bn == 128) return launch<128, MODE_CONVKP2, VB200_EPI_STORE, 64>(ta, tb, p, pgrid & ~1, st);
+        return launch<64, MODE_CONVKP2, VB200_EPI_STORE, 64>(ta, tb, p, pgrid & ~1, st);
+      }
       if (bn == 128) return launch<128, MODE_CONVKP, VB200_EPI_STORE, 64>(ta, tb, p, pgrid, st);
       return launch<64, MODE_CONVKP, VB200_EPI_STORE, 64>(ta, tb, p, pgrid, st);
     }

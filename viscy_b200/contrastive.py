@@ -104,6 +104,18 @@ class ContrastiveEncoder(nn.Module):
         self.encoder = encoder
         self.projection = projection
         self.compute_dtype: torch.dtype | None = None
+        self._packs = None
+
+    def _weight_packs(self, dt: torch.dtype) -> None:
+        """One-launch refresh of the 16-bit operand copies of every ConvNeXt block's fc1 / fc2 / conv_dw weights (instead
+        of one cast launch per use: 166 launches, 0.9 ms per two-view step)."""
+        from .components import ConvNeXtBlock
+        if self._packs is None or self._packs.dtype != dt or self._packs.stale():
+            blocks = [m for m in self.modules() if isinstance(m, ConvNeXtBlock)]
+            lin = [w for b in blocks for w in (b.mlp.fc1.weight, b.mlp.fc2.weight)]
+            self._packs = F.ops.WeightPacks(lin, [b.conv_dw.weight for b in blocks], dt)
+        self._packs.refresh()
+        F.ops.ACTIVE_PACKS = self._packs
 
     def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:
         """Return (embedding, projection)."""
@@ -116,7 +128,7 @@ class ContrastiveEncoder(nn.Module):
 
     def _forward_sm100(self, x: Tensor) -> tuple[Tensor, Tensor]:
         dt = resolve_compute_dtype(x, self.compute_dtype)
-        F.ops.ACTIVE_PACKS = None  # weight packs are scoped to the model that registered them
+        self._weight_packs(dt)
         F.ops.STEP.begin(x.device, torch.is_grad_enabled())  # one zero-filled allocation for the step's accumulators
         with torch.autocast("cuda", enabled=False):
             f = self.stem.forward_cl(x, dt)

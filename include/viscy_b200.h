@@ -196,6 +196,14 @@ int vb200_grn_wgrad_finish(const float* P, const float* W2, const float* s, cons
 int vb200_grn_wgrad_finish_ld(const float* P, int64_t ldp, const float* W2, const float* s, const float* bgrn,
                               const float* db2_in, float* dW2, float* S1, float* dbgrn, float* db2_out, int nb, int C,
                               int C4, vb200_stream_t stream);
+/* ConvNeXt-V1 layer scale, backward side (timm ConvNeXtBlock `x = x * gamma`, VM/contrastive/encoder.py:93-124 via
+ * convnext_tiny) in one launch: G [C, ldg] fp32 = dout^T y, W2 [C, C4], gamma / b2 / db_raw [C] ->
+ * dW2 = G * gamma[:, None]; db2 = db_raw * gamma; dgamma (pre-zeroed) += sum_j G * W2 + db_raw * b2;
+ * w2t [C4, C] 16-bit = (W2 * gamma / max|gamma|)^T (operand of the fc2 data gradient); sv [C4] = max|gamma|.
+ * db_raw / db2 may be NULL (no bias). */
+int vb200_layerscale_bwd(const float* G, int64_t ldg, const float* W2, const float* gamma, const float* b2,
+                         const float* db_raw, void* w2t, float* dgamma, float* dW2, float* db2, float* sv, int C, int C4,
+                         int dtype, vb200_stream_t stream);
 /* vb200_grn_coef_fwd + vb200_grn_prepare in one launch: s (fp32 [nb,C4], written), w2s, b2e from sumsq */
 int vb200_grn_prepare2(const float* sumsq, const float* gw, const float* gb, const float* W2, const float* b2,
                        float* s_out, void* w2s, float* b2e, int nb, int C, int C4, float eps, int dtype,

@@ -1318,3 +1318,100 @@ extern "C" int vb200_grn_prepare(const float* s, const float* gb, const float* W
   DISPATCH_DT(dtype, grn_prepare_kernel<BF><<<grid, 256, 0, st>>>(s, gb, W2, b2, (uint4*)w2s, b2e, nb, C, C4));
   return check_launch("vb200_grn_prepare");
 }
+
+// ---- ConvNeXt-V1 layer scale, backward side (timm ConvNeXtBlock: out = gamma * (y W2^T + b2) + x) in ONE launch:
+//   G [C, ldg] fp32 = dout^T [y | 1] (the weight-gradient GEMM without the layer scale; its ones column, when present, is
+//   passed separately as db_raw), W2 [C, C4], gamma, b2 [C]  ->
+//     dW2 = G * gamma[:, None],  db2 = db_raw * gamma,  dgamma = sum_j G * W2 + db_raw * b2   (dgamma pre-zeroed),
+//     w2t16 [C4, C] = 16-bit (W2 * gamma / max|gamma|)^T  (the fc2 data-gradient operand; the epilogue multiplies by sv),
+//     sv [C4] = max|gamma|.
+// Tile = 32 output channels x 64 hidden columns, transposed through shared memory so that both W2 reads and w2t16 writes
+// are row-contiguous.  Replaces ~12 torch elementwise / reduction launches per block.
+namespace vb {
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+layerscale_bwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ W2, const float* __restrict__ gamma,
+                      const float* __restrict__ b2, const float* __restrict__ db_raw, uint16_t* __restrict__ w2t,
+                      float* __restrict__ dgamma, float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ sv,
+                      int C, int C4) {
+  __shared__ float gmax_s;
+  __shared__ float tile[32][65];
+  __shared__ float part[32][9];
+  // max |gamma| (C <= a few thousand fp32 values out of L2: every block recomputes it)
+  float m = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(gamma + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) part[0][threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t = fmaxf(t, part[0][w]);
+    gmax_s = fmaxf(t, 1e-30f);
+  }
+  __syncthreads();
+  const float gmax = gmax_s;
+  const int c0 = blockIdx.y * 32, j0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 columns x 4 row lanes
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 4 * i, j = j0 + tx;
+    float g = 0.f, w = 0.f, gam = 0.f;
+    if (c < C && j < C4) {
+      g = __ldg(G + (long long)c * ldg + j);
+      w = __ldg(W2 + (long long)c * C4 + j);
+      gam = __ldg(gamma + c);
+      dW2[(long long)c * C4 + j] = g * gam;
+    }
+    acc[i] = g * w;
+    tile[ty + 4 * i][tx] = w * (gam / gmax);
+  }
+  // dgamma: sum over the tile's 64 columns (two warps per row lane)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if ((threadIdx.x & 31) == 0) {
+      const int c = c0 + ty + 4 * i;
+      if (c < C) atomicAdd(dgamma + c, acc[i]);
+    }
+  }
+  __syncthreads();
+  // transposed 16-bit store: w2t[j, c0 .. c0 + 31]
+  for (int e = threadIdx.x; e < 64 * 32; e += blockDim.x) {
+    const int jj = e >> 5, cc = e & 31;
+    const int j = j0 + jj, c = c0 + cc;
+    if (j < C4 && c < C) {
+      const typename H16<BF16>::T v = H16<BF16>::from_f(tile[cc][jj]);
+      w2t[(long long)j * C + c] = *reinterpret_cast<const uint16_t*>(&v);
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+      const int c = c0 + i;
+      if (c < C) {
+        const float dr = db_raw ? __ldg(db_raw + c) : 0.f, gam = __ldg(gamma + c);
+        if (db2) db2[c] = dr * gam;
+        if (db_raw) atomicAdd(dgamma + c, dr * __ldg(b2 + c));
+      }
+    }
+  }
+  if (blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x)
+      if (j0 + i < C4) sv[j0 + i] = gmax;
+  }
+}
+}  // namespace vb
+
+extern "C" int vb200_layerscale_bwd(const float* G, int64_t ldg, const float* W2, const float* gamma, const float* b2,
+                                    const float* db_raw, void* w2t, float* dgamma, float* dW2, float* db2, float* sv, int C,
+                                    int C4, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(G && W2 && gamma && b2 && w2t && dgamma && dW2 && sv, "null pointer");
+  VB_REQUIRE(C > 0 && C4 > 0 && ldg >= C4, "shape %d x %d (ld %lld)", C, C4, (long long)ldg);
+  dim3 grid((C4 + 63) / 64, (C + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, layerscale_bwd_kernel<BF><<<grid, 256, 0, st>>>(G, ldg, W2, gamma, b2, db_raw, (uint16_t*)w2t, dgamma,
+                                                                     dW2, db2, sv, C, C4));
+  return check_launch("vb200_layerscale_bwd");
+}

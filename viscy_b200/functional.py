@@ -153,7 +153,7 @@ class ConvNeXtBlockFn(Function):
         dob = do2 if keep is None else ops.scale_rows(dout, keep).view(M, C)
         l2 = lbuf[:, :C] if onescol else lbuf
         y2 = gbuf[:, :C4] if onescol else gbuf
-        ar = ops.Arena(x.device, [C, (B + 2) * C4, C4, 2 * C, 50 * C] + ([C4 * C, PAD * C4] if onescol else []))
+        ar = ops.Arena(x.device, [2 * C, (B + 2) * C4, C4, 2 * C, 50 * C] + ([C4 * C, PAD * C4] if onescol else []))
         if ctx.fused:
             grn_b = gamma  # the 16th saved tensor is grn.bias on the fused path (V2 blocks carry no layer scale)
             gamma = None
@@ -184,15 +184,14 @@ class ConvNeXtBlockFn(Function):
                 else:
                     _, G, db_raw = linear_bwd(dob, y2, w2, need_da=False)
                 if gamma is not None:
-                    # out = gamma * (y W2^T + b2): weights carry gamma / max|gamma| (16-bit safe), the epilogue the rest
-                    gmax = gamma.abs().max().clamp_min(1e-30)
-                    w2n = w2 * (gamma / gmax)[:, None]
-                    sv = gmax.expand(C4).contiguous()
-                    dgamma = (G * w2).sum(1) + db_raw * fc2_b
-                    dw2, db2 = (G * gamma[:, None]).view(fc2_w.shape), db_raw * gamma
+                    # out = gamma * (y W2^T + b2): weights carry gamma / max|gamma| (16-bit safe), the epilogue the rest;
+                    # dW2, db2, dgamma, the scaled transposed 16-bit operand and sv from one kernel
+                    w2t, sv, dgamma, dw2, db2 = ops.layerscale_bwd(G, w2.contiguous(), gamma, fc2_b, db_raw.contiguous(),
+                                                                   x.dtype, ar)
+                    dw2 = dw2.view(fc2_w.shape)
                 else:
-                    w2n, sv, dgamma, dw2, db2 = w2, None, None, G.reshape(fc2_w.shape), db_raw.contiguous()
-                w2t = ops.cast_pack(w2n, x.dtype, transpose=True)
+                    sv, dgamma, dw2, db2 = None, None, G.reshape(fc2_w.shape), db_raw.contiguous()
+                    w2t = ops.packed(fc2_w, x.dtype, transpose=True)
                 dh = ops.gemm(dob, w2t, epilogue=L.EPI_DGELU_GRN, aux2=h, svec=sv,
                               rows_per_sample=128 * (-(-M // 128)) if sv is not None else 0)
                 if not onescol:

@@ -686,6 +686,23 @@ def grn_prepare(sumsq, gw, gb, w2, b2, dtype, eps=1e-6):
     return s, w2s, b2e
 
 
+def layerscale_bwd(G, w2, gamma, b2, db_raw, dtype, arena=None):
+    """ConvNeXt-V1 layer-scale backward pieces in one launch.  G fp32 [C, >= C4] (row pitch = its stride) ->
+    (w2t16 [C4, C], sv [C4], dgamma [C], dW2 [C, C4], db2 [C])."""
+    Cc, C4 = w2.shape
+    dev = w2.device
+    w2t = torch.empty((C4, Cc), device=dev, dtype=dtype)
+    dgamma = arena.take(Cc) if arena is not None else zeros((Cc,), dev)
+    dW2 = torch.empty((Cc, C4), device=dev, dtype=torch.float32)
+    db2 = torch.empty((Cc,), device=dev, dtype=torch.float32)
+    sv = torch.empty((C4,), device=dev, dtype=torch.float32)
+    if G.dtype != torch.float32 or G.stride(1) != 1:
+        raise ValueError("G must be fp32 with unit inner stride")
+    _call("vb200_layerscale_bwd", _p(G), C.c_int64(G.stride(0)), _p(_f32(w2, "w2")), _p(_f32(gamma, "gamma")), _p(_f32(b2, "b2")),
+          _p(_f32(db_raw, "db_raw")), _p(w2t), _p(dgamma), _p(dW2), _p(db2), _p(sv), Cc, C4, L.dtype_code(dtype))
+    return w2t, sv, dgamma, dW2, db2
+
+
 def grn_bias_eff(w2, bgrn, b2):
     Cc, C4 = w2.shape
     out = torch.empty((Cc,), device=w2.device, dtype=torch.float32)

@@ -235,3 +235,37 @@ def test_unet3d_base_groupnorm_silu_timestep_golden(cuda, name, dtype, tol):
     worst = max((rel(p.grad.cpu() / scale, g["grads"][n]), n) for n, p in m.named_parameters() if g["grads"][n].norm() > 1e-6)
     print("worst gradient:", worst)
     assert worst[0] < 12 * tol
+
+
+@pytest.mark.parametrize("make,xshape", [
+    (lambda: __import__("viscy_b200").Unet3d(1, 1, depth=2, mult_chan=4), (1, 1, 16, 32, 32)),
+    (lambda: __import__("viscy_b200").Unet3d(2, 3, depth=2, mult_chan=12), (1, 2, 16, 32, 32)),
+    (lambda: __import__("viscy_b200").Unet25d(num_filters=(4, 8, 12), num_blocks=2, dropout=0.0, task="reg", residual=True),
+     (2, 1, 5, 32, 32)),
+])
+def test_channel_counts_not_multiple_of_8(cuda, make, xshape):
+    """Skip concatenation / residual growth with channel counts that are not multiples of 8: rows are padded per tensor, the
+    concatenated rows must be [a | b | pad] (what the next conv's weight rows assume), not [a | pad | b | pad]."""
+    torch.manual_seed(3)
+    ref = make()
+    m = make()
+    m.load_state_dict(ref.state_dict())
+    m = m.to(cuda)
+    x = torch.randn(xshape)
+    out_ref = ref(x)
+    tgt = torch.randn_like(out_ref)
+    F.mse_loss(out_ref, tgt).backward()
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = m(x.to(cuda))
+        loss = F.mse_loss(out.float(), tgt.to(cuda))
+    (loss * 256.0).backward()
+    e = rel(out.float().cpu(), out_ref)
+    print(f"\nforward rel-L2 vs the fp32 mirror {e:.3e}")
+    assert out.shape == out_ref.shape and e < 1e-2
+    refg = dict(ref.named_parameters())
+    for n, p in m.named_parameters():
+        gr = refg[n].grad
+        if gr is None:
+            assert p.grad is None, n
+        elif gr.dim() > 1 and gr.norm() > 1e-6:
+            assert rel(p.grad.cpu() / 256.0, gr) < 0.25, n  # a mis-laid concat shows up as O(1) errors

@@ -1231,8 +1231,11 @@ extern "C" int vb200_colreduce_ld(const void* x, float* out, int B, int64_t R, i
   const int C8 = C / 8;
   const long long ld8 = ld / 8;
   const ColRedShape sh = ColRedShape::make(C8);
-  // ~2 blocks of 512 threads per SM, at least 4 rows per row lane
-  long long rpb = (R * sh.colb * B + 148 * 2 - 1) / (148 * 2);
+  // ONE wave of 2 blocks of 512 threads per SM: the row split is rounded DOWN so that colb * row blocks * B never exceeds the
+  // resident slots (13 row blocks x 24 gave 312 blocks on 296 slots = a second, almost empty wave); at least 4 rows per lane
+  long long ny = (148 * 2) / ((long long)sh.colb * B);
+  if (ny < 1) ny = 1;
+  long long rpb = (R + ny - 1) / ny;
   const long long min_rows = 4LL * (512 >> sh.cw_log2);
   if (rpb < min_rows) rpb = min_rows;
   if (rpb > R) rpb = R;

@@ -9,6 +9,8 @@
 //   phase 0: sdp[n,c] = sum dpre, sdpx[n,c] = sum dpre*xhat, dalpha, db1[o] = sum dt[o], dW1[o][c] = sum dt[o]*act[c]
 //   phase 1: dz = rstd * (dpre - sdp/R - xhat * sdpx/R) (coalesced 16-byte stores), dbz[c] = sum dz
 // Algorithmic traffic: phase 0 reads z + dout (220 MB at config 2), phase 1 reads the same and writes dz (176 MB).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -255,6 +257,291 @@ __global__ void __launch_bounds__(NCOMP, 1) head_bwd_stream_kernel(const Params 
   if (cur_n >= 0) flush(cur_n);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core form of the same two phases (legacy warp-level mma.sync: these 32 x 8 contractions are far too small for a
+// tcgen05 tile).  A warp owns 32 rows of the staged tile; everything is kept TRANSPOSED ([channel][row]) so that one fragment
+// layout serves all three roles (the flash-attention C-fragment -> A-fragment trick):
+//   z^T      : ldmatrix.x4.trans of the row-major z tile            -> [ch g / g+8][rows 2q, 2q+1 (+8)] bf16 pairs
+//   da^T     = W1^T [16 ch x 8 o] . dt^T [8 o x 8 rows]   (m16n8k8)  -> C fragment in the same [ch][row pair] layout
+//   dW1^T   += act^T [16 ch x 16 rows] . dt [16 rows x 8 o] (m16n8k16), act^T packed straight from the element-wise results
+// ~6 MMAs + 16 element-wise channel-row values per thread and 16 rows, instead of 128 FFMA2 per row chunk.
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void stsm_x4_trans(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void mma_k8_zero(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  if constexpr (BF16)
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0), "f"(0.f));
+  else
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0), "f"(0.f));
+}
+template <bool BF16>
+__device__ __forceinline__ void mma_k8_acc(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  if constexpr (BF16)
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+  else
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+template <bool BF16>
+__device__ __forceinline__ void mma_k16_acc(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool BF16, int MODE>
+__global__ void __launch_bounds__(NCOMP, 2) head_bwd_mma_kernel(const Params p) {
+  using H = H16<BF16>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* zs = smem;                          // [STAGES][ZB]
+  uint8_t* ds = smem + STAGES * ZB;            // [STAGES][DB]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (ZB + DB));
+  uint64_t* empty = full + STAGES;
+  float* red = reinterpret_cast<float*>(empty + STAGES);
+  constexpr int NRED = MODE == 0 ? 3 * CM + CO4 * CM + CO4 : CM;
+
+  const int t0 = (int)((long long)blockIdx.x * p.n_tiles / gridDim.x);
+  const int t1 = (int)((long long)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCOMP);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < NRED; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  auto produce = [&](int it) {
+    const int t = t0 + it;
+    if (t >= t1) return;
+    const int s = it % STAGES;
+    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+    mbar_expect_tx(&full[s], ZB + DB);
+    const int n = t / p.tiles_per_sample, tt = t - n * p.tiles_per_sample;
+    const long long row0 = (long long)tt * TR;
+    bulk_load_1d(zs + s * ZB, p.z + ((long long)n * p.R + row0) * (CM * 2), ZB, &full[s]);
+    const int L = TR / p.W, line0 = (int)(row0 / p.W);
+    const uint32_t seg = (uint32_t)p.W * 4;
+    for (int l = 0; l < L; ++l) {
+      const int ln = line0 + l, dzi = ln / p.H, y = ln - dzi * p.H;
+#pragma unroll
+      for (int pl = 0; pl < 4; ++pl) {
+        const int co = pl >> 1, i = pl & 1;
+        const long long off = ((((long long)n * 2 + co) * p.Dz + dzi) * (2 * p.H) + 2 * y + i) * (2LL * p.W);
+        bulk_load_1d(ds + s * DB + (l * 4 + pl) * seg, p.dout + off * 2, seg, &full[s]);
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    for (int it = 0; it < STAGES - 1; ++it) produce(it);
+  }
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  // this thread's four channels: ch(mt, hi) = 16 mt + g + 8 hi
+  // W1^T A fragments of the da MMA (rows = channels, k = output o = 2q, 2q + 1), split into a 16-bit head and a 16-bit
+  // remainder so that the fp32 weights enter the tensor-core product at ~16 mantissa bits (two MMAs per fragment)
+  uint32_t wa[2][2], wb[2][2];
+  float al[4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int ch = 16 * mt + g + 8 * hi;
+      const float w0 = __ldg(p.W1 + (2 * q) * CM + ch), w1 = __ldg(p.W1 + (2 * q + 1) * CM + ch);
+      wa[mt][hi] = H::pack(w0, w1);
+      const float2 back = H::unpack(wa[mt][hi]);
+      wb[mt][hi] = H::pack(w0 - back.x, w1 - back.y);
+      al[mt * 2 + hi] = __ldg(p.alpha + (p.alpha_n == 1 ? 0 : ch));
+    }
+  float mu[4], rs[4], m1[4], m2[4];
+  float a_dp[4], a_dpx[4], a_al[4], a_db[2], a_dw[2][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a_dp[k] = a_dpx[k] = a_al[k] = a_dw[0][k] = a_dw[1][k] = 0.f;
+  a_db[0] = a_db[1] = 0.f;
+  int cur_n = -1;
+
+  auto flush = [&](int n) {
+    // per-channel sums: the four lanes of a quad (q = 0..3) hold different rows of the same channels
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int off = 1; off <= 2; off <<= 1) {
+        a_dp[k] += __shfl_xor_sync(0xffffffffu, a_dp[k], off);
+        if (MODE == 0) {
+          a_dpx[k] += __shfl_xor_sync(0xffffffffu, a_dpx[k], off);
+          a_al[k] += __shfl_xor_sync(0xffffffffu, a_al[k], off);
+        }
+      }
+    }
+    if (MODE == 0) {  // db1[o = 2q, 2q + 1]: the eight lanes with the same q hold different rows
+#pragma unroll
+      for (int off = 4; off <= 16; off <<= 1) {
+        a_db[0] += __shfl_xor_sync(0xffffffffu, a_db[0], off);
+        a_db[1] += __shfl_xor_sync(0xffffffffu, a_db[1], off);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const int ch = 16 * mt + g + 8 * hi, k = mt * 2 + hi;
+        if (q == 0) {
+          atomicAdd(&red[ch], a_dp[k]);
+          if (MODE == 0) {
+            atomicAdd(&red[CM + ch], a_dpx[k]);
+            atomicAdd(&red[2 * CM + ch], a_al[k]);
+          }
+        }
+        if (MODE == 0) {  // dW1[o][ch]: every lane owns its own (ch, o) entries
+          atomicAdd(&red[3 * CM + (2 * q) * CM + ch], a_dw[mt][hi * 2]);
+          atomicAdd(&red[3 * CM + (2 * q + 1) * CM + ch], a_dw[mt][hi * 2 + 1]);
+        }
+      }
+    if (MODE == 0 && g == 0) {
+      atomicAdd(&red[3 * CM + CO4 * CM + 2 * q], a_db[0]);
+      atomicAdd(&red[3 * CM + CO4 * CM + 2 * q + 1], a_db[1]);
+    }
+    named_sync();
+    for (int i = threadIdx.x; i < NRED; i += NCOMP) {
+      const float val = red[i];
+      if (MODE == 0) {
+        if (i < CM) atomicAdd(p.sdp + (long long)n * CM + i, val);
+        else if (i < 2 * CM) atomicAdd(p.sdpx + (long long)n * CM + i - CM, val);
+        else if (i < 3 * CM) atomicAdd(p.dalpha + (p.alpha_n == 1 ? 0 : i - 2 * CM), val);
+        else if (i < 3 * CM + CO4 * CM) atomicAdd(p.dW1 + i - 3 * CM, val);
+        else atomicAdd(p.db1 + i - 3 * CM - CO4 * CM, val);
+      } else {
+        atomicAdd(p.dbz + i, val);
+      }
+      red[i] = 0.f;
+    }
+    named_sync();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a_dp[k] = a_dpx[k] = a_al[k] = a_dw[0][k] = a_dw[1][k] = 0.f;
+    a_db[0] = a_db[1] = 0.f;
+  };
+
+  for (int t = t0, it = 0; t < t1; ++t, ++it) {
+    const int s = it % STAGES;
+    const int n = t / p.tiles_per_sample, tt = t - n * p.tiles_per_sample;
+    if (n != cur_n) {
+      if (cur_n >= 0) flush(cur_n);
+      cur_n = n;
+      const float invR = 1.0f / (float)p.R;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          const int ch = 16 * mt + g + 8 * hi, k = mt * 2 + hi;
+          mu[k] = __ldg(p.mean + (long long)n * CM + ch);
+          rs[k] = __ldg(p.rstd + (long long)n * CM + ch);
+          m1[k] = MODE == 1 ? p.sdp[(long long)n * CM + ch] * invR : 0.f;
+          m2[k] = MODE == 1 ? p.sdpx[(long long)n * CM + ch] * invR : 0.f;
+        }
+    }
+    if (threadIdx.x == 0) produce(it + STAGES - 1);
+    __syncwarp();
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const uint32_t zt = smem_u32(zs + s * ZB);
+    const uint32_t* dt32 = reinterpret_cast<const uint32_t*>(ds + s * DB);
+#pragma unroll 1
+    for (int gi = 0; gi < 2; ++gi) {
+      const int rb = warp * 32 + gi * 16;  // first of this group's 16 rows
+      // dt fragments: B of the da MMA (row g of each half, outputs 2q, 2q+1) and B of the dW MMA (rows 2q, 2q+1, output g)
+      uint32_t bda[2], bdw[2];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int r1 = rb + hf * 8 + g;
+        const int l1 = r1 / p.W, x1 = r1 - l1 * p.W;
+        bda[hf] = dt32[(l1 * 4 + q) * p.W + x1];
+        const int r2 = rb + hf * 8 + 2 * q;
+        const int l2 = r2 / p.W, x2 = r2 - l2 * p.W;
+        const uint2 w2 = *reinterpret_cast<const uint2*>(dt32 + (l2 * 4 + (g >> 1)) * p.W + x2);
+        bdw[hf] = __byte_perm(w2.x, w2.y, (g & 1) ? 0x7632 : 0x5410);
+        if (MODE == 0) {
+          const float2 f = H::unpack(bda[hf]);
+          a_db[0] += f.x;
+          a_db[1] += f.y;
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        uint32_t zf[4];  // z^T: [hf * 2 + hi] = (ch 16 mt + g + 8 hi, rows rb + 8 hf + 2q, +1)
+        const uint32_t addr = zt + static_cast<uint32_t>(((rb + ((lane >> 4) << 3) + (lane & 7)) * CM + 16 * mt + ((lane >> 3) & 1) * 8) * 2);
+        ldsm_x4_trans(zf, addr);
+        // ldmatrix order: matrix 0 = (rows 0-7, ch 0-7), 1 = (rows 0-7, ch 8-15), 2 = (rows 8-15, ch 0-7), 3 = (rows 8-15, ch 8-15)
+        uint32_t af[4];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float da[4];
+          mma_k8_zero<BF16>(da, wa[mt][0], wa[mt][1], bda[hf]);
+          mma_k8_acc<BF16>(da, wb[mt][0], wb[mt][1], bda[hf]);
+#pragma unroll
+          for (int hi = 0; hi < 2; ++hi) {
+            const int k = mt * 2 + hi;
+            const float2 zz = H::unpack(zf[hf * 2 + hi]);
+            float o2[2];
+#pragma unroll
+            for (int rp = 0; rp < 2; ++rp) {
+              const float xh = ((rp ? zz.y : zz.x) - mu[k]) * rs[k];
+              const float d = da[hi * 2 + rp];
+              const bool pos = xh > 0.f;
+              const float dpre = pos ? d : d * al[k];
+              if (MODE == 0) {
+                o2[rp] = pos ? xh : xh * al[k];  // act
+                a_dp[k] += dpre;
+                a_dpx[k] = fmaf(dpre, xh, a_dpx[k]);
+                a_al[k] += pos ? 0.f : d * xh;
+              } else {
+                o2[rp] = rs[k] * (dpre - m1[k] - xh * m2[k]);
+              }
+            }
+            af[hf * 2 + hi] = H::pack(o2[0], o2[1]);
+            if (MODE == 1) {
+              const float2 rr = H::unpack(af[hf * 2 + hi]);
+              a_dp[k] += rr.x + rr.y;
+            }
+          }
+        }
+        if (MODE == 0) mma_k16_acc<BF16>(a_dw[mt], af, bdw[0], bdw[1]);
+        else stsm_x4_trans(addr, af);  // dz back over the z tile (row-major [row][32 ch])
+      }
+      if (MODE == 1) {
+        __syncwarp();
+        // the group's 16 rows x 64 B are contiguous in the tile and in dz: 64 16-byte vectors, two per lane
+        const uint4* src = reinterpret_cast<const uint4*>(zs + s * ZB + rb * CM * 2);
+        uint4* dst = p.dz + ((long long)n * p.R + (long long)tt * TR + rb) * 4;
+        dst[lane] = src[lane];
+        dst[lane + 32] = src[lane + 32];
+      }
+    }
+    mbar_arrive(&empty[s]);
+  }
+  if (cur_n >= 0) flush(cur_n);
+}
+
 }  // namespace hb
 }  // namespace vb
 
@@ -292,8 +579,24 @@ extern "C" int vb200_head_tail_bwd_stream(int phase, const void* z, const float*
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   cudaStream_t st = (cudaStream_t)stream;
+  static const int use_mma = [] { const char* e = getenv("VB200_HEAD_BWD_MMA"); return e ? atoi(e) : 1; }();
+  if (use_mma) {
+    const void* mf[4] = {(const void*)hb::head_bwd_mma_kernel<true, 0>, (const void*)hb::head_bwd_mma_kernel<true, 1>,
+                         (const void*)hb::head_bwd_mma_kernel<false, 0>, (const void*)hb::head_bwd_mma_kernel<false, 1>};
+    static PerDeviceOnce monce[4];
+    if (monce[slot].need(dev)) {
+      cudaFuncSetAttribute(mf[slot], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      monce[slot].done(dev);
+    }
+    const int mgrid = p.n_tiles < 2 * sms ? p.n_tiles : 2 * sms;  // two CTAs per SM
+    if (slot == 0) hb::head_bwd_mma_kernel<true, 0><<<mgrid, hb::NCOMP, smem, st>>>(p);
+    else if (slot == 1) hb::head_bwd_mma_kernel<true, 1><<<mgrid, hb::NCOMP, smem, st>>>(p);
+    else if (slot == 2) hb::head_bwd_mma_kernel<false, 0><<<mgrid, hb::NCOMP, smem, st>>>(p);
+    else hb::head_bwd_mma_kernel<false, 1><<<mgrid, hb::NCOMP, smem, st>>>(p);
+    return check_launch("vb200_head_tail_bwd_stream");
+  }
+  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   if (slot == 0) hb::head_bwd_stream_kernel<true, 0><<<grid, hb::NCOMP, smem, st>>>(p);
   else if (slot == 1) hb::head_bwd_stream_kernel<true, 1><<<grid, hb::NCOMP, smem, st>>>(p);
   else if (slot == 2) hb::head_bwd_stream_kernel<false, 0><<<grid, hb::NCOMP, smem, st>>>(p);

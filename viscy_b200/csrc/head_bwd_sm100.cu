@@ -17,7 +17,7 @@
 namespace vb {
 namespace hb {
 
-constexpr int TR = 256, STAGES = 3, CM = 32, CO4 = 8, NCOMP = 256;
+constexpr int TR = 256, STAGES = 3, MSTAGES = 5, CM = 32, CO4 = 8, NCOMP = 256;  // MSTAGES: ring depth of the MMA form (2 CTAs / SM)
 constexpr int ZB = TR * CM * 2, DB = TR * CO4 * 2;  // bytes per stage: z tile, dout tile
 
 struct Params {
@@ -35,6 +35,7 @@ struct Params {
   uint4* dz;             // [B, R, 32] 16-bit
   float* dbz;            // [32]
   int alpha_n, Dz, H, W, R, tiles_per_sample, n_tiles;
+  int wshift;  // log2(W): 256 % W == 0 makes W a power of two
 };
 
 __device__ __forceinline__ void named_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -313,17 +314,17 @@ template <bool BF16, int MODE>
 __global__ void __launch_bounds__(NCOMP, 2) head_bwd_mma_kernel(const Params p) {
   using H = H16<BF16>;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* zs = smem;                          // [STAGES][ZB]
-  uint8_t* ds = smem + STAGES * ZB;            // [STAGES][DB]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (ZB + DB));
-  uint64_t* empty = full + STAGES;
-  float* red = reinterpret_cast<float*>(empty + STAGES);
+  uint8_t* zs = smem;                          // [MSTAGES][ZB]
+  uint8_t* ds = smem + MSTAGES * ZB;            // [MSTAGES][DB]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + MSTAGES * (ZB + DB));
+  uint64_t* empty = full + MSTAGES;
+  float* red = reinterpret_cast<float*>(empty + MSTAGES);
   constexpr int NRED = MODE == 0 ? 3 * CM + CO4 * CM + CO4 : CM;
 
   const int t0 = (int)((long long)blockIdx.x * p.n_tiles / gridDim.x);
   const int t1 = (int)((long long)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MSTAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NCOMP);
     }
@@ -335,8 +336,8 @@ __global__ void __launch_bounds__(NCOMP, 2) head_bwd_mma_kernel(const Params p) 
   auto produce = [&](int it) {
     const int t = t0 + it;
     if (t >= t1) return;
-    const int s = it % STAGES;
-    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+    const int s = it % MSTAGES;
+    mbar_wait(&empty[s], ((it / MSTAGES) & 1) ^ 1);
     mbar_expect_tx(&full[s], ZB + DB);
     const int n = t / p.tiles_per_sample, tt = t - n * p.tiles_per_sample;
     const long long row0 = (long long)tt * TR;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(NCOMP, 2) head_bwd_mma_kernel(const Params p) 
     }
   };
   if (threadIdx.x == 0) {
-    for (int it = 0; it < STAGES - 1; ++it) produce(it);
+    for (int it = 0; it < MSTAGES - 1; ++it) produce(it);
   }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(NCOMP, 2) head_bwd_mma_kernel(const Params p) 
   };
 
   for (int t = t0, it = 0; t < t1; ++t, ++it) {
-    const int s = it % STAGES;
+    const int s = it % MSTAGES;
     const int n = t / p.tiles_per_sample, tt = t - n * p.tiles_per_sample;
     if (n != cur_n) {
       if (cur_n >= 0) flush(cur_n);
@@ -461,9 +462,9 @@ __global__ void __launch_bounds__(NCOMP, 2) head_bwd_mma_kernel(const Params p) 
           m2[k] = MODE == 1 ? p.sdpx[(long long)n * CM + ch] * invR : 0.f;
         }
     }
-    if (threadIdx.x == 0) produce(it + STAGES - 1);
+    if (threadIdx.x == 0) produce(it + MSTAGES - 1);
     __syncwarp();
-    mbar_wait(&full[s], (it / STAGES) & 1);
+    mbar_wait(&full[s], (it / MSTAGES) & 1);
     const uint32_t zt = smem_u32(zs + s * ZB);
     const uint32_t* dt32 = reinterpret_cast<const uint32_t*>(ds + s * DB);
 #pragma unroll 1
@@ -474,10 +475,10 @@ __global__ void __launch_bounds__(NCOMP, 2) head_bwd_mma_kernel(const Params p) 
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int r1 = rb + hf * 8 + g;
-        const int l1 = r1 / p.W, x1 = r1 - l1 * p.W;
+        const int l1 = r1 >> p.wshift, x1 = r1 & (p.W - 1);
         bda[hf] = dt32[(l1 * 4 + q) * p.W + x1];
         const int r2 = rb + hf * 8 + 2 * q;
-        const int l2 = r2 / p.W, x2 = r2 - l2 * p.W;
+        const int l2 = r2 >> p.wshift, x2 = r2 & (p.W - 1);
         const uint2 w2 = *reinterpret_cast<const uint2*>(dt32 + (l2 * 4 + (g >> 1)) * p.W + x2);
         bdw[hf] = __byte_perm(w2.x, w2.y, (g & 1) ? 0x7632 : 0x5410);
         if (MODE == 0) {
@@ -567,6 +568,8 @@ extern "C" int vb200_head_tail_bwd_stream(int phase, const void* z, const float*
   p.sdp = sdp; p.sdpx = sdpx; p.db1 = db1; p.dalpha = dalpha; p.dW1 = dW1; p.dz = (uint4*)dz; p.dbz = dbz;
   p.alpha_n = alpha_n; p.Dz = Dz; p.H = H; p.W = W; p.R = (int)R; p.tiles_per_sample = (int)(R / hb::TR);
   p.n_tiles = p.tiles_per_sample * B;
+  p.wshift = 0;
+  while ((1 << p.wshift) < W) ++p.wshift;
   const size_t smem = hb::STAGES * (hb::ZB + hb::DB) + 2 * hb::STAGES * sizeof(uint64_t) + 368 * sizeof(float);
   const void* fns[4] = {(const void*)hb::head_bwd_stream_kernel<true, 0>, (const void*)hb::head_bwd_stream_kernel<true, 1>,
                         (const void*)hb::head_bwd_stream_kernel<false, 0>, (const void*)hb::head_bwd_stream_kernel<false, 1>};
@@ -585,15 +588,16 @@ extern "C" int vb200_head_tail_bwd_stream(int phase, const void* z, const float*
     const void* mf[4] = {(const void*)hb::head_bwd_mma_kernel<true, 0>, (const void*)hb::head_bwd_mma_kernel<true, 1>,
                          (const void*)hb::head_bwd_mma_kernel<false, 0>, (const void*)hb::head_bwd_mma_kernel<false, 1>};
     static PerDeviceOnce monce[4];
+    const size_t msmem = hb::MSTAGES * (hb::ZB + hb::DB) + 2 * hb::MSTAGES * sizeof(uint64_t) + 368 * sizeof(float);
     if (monce[slot].need(dev)) {
-      cudaFuncSetAttribute(mf[slot], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(mf[slot], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
       monce[slot].done(dev);
     }
     const int mgrid = p.n_tiles < 2 * sms ? p.n_tiles : 2 * sms;  // two CTAs per SM
-    if (slot == 0) hb::head_bwd_mma_kernel<true, 0><<<mgrid, hb::NCOMP, smem, st>>>(p);
-    else if (slot == 1) hb::head_bwd_mma_kernel<true, 1><<<mgrid, hb::NCOMP, smem, st>>>(p);
-    else if (slot == 2) hb::head_bwd_mma_kernel<false, 0><<<mgrid, hb::NCOMP, smem, st>>>(p);
-    else hb::head_bwd_mma_kernel<false, 1><<<mgrid, hb::NCOMP, smem, st>>>(p);
+    if (slot == 0) hb::head_bwd_mma_kernel<true, 0><<<mgrid, hb::NCOMP, msmem, st>>>(p);
+    else if (slot == 1) hb::head_bwd_mma_kernel<true, 1><<<mgrid, hb::NCOMP, msmem, st>>>(p);
+    else if (slot == 2) hb::head_bwd_mma_kernel<false, 0><<<mgrid, hb::NCOMP, msmem, st>>>(p);
+    else hb::head_bwd_mma_kernel<false, 1><<<mgrid, hb::NCOMP, msmem, st>>>(p);
     return check_launch("vb200_head_tail_bwd_stream");
   }
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;

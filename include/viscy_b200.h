@@ -75,6 +75,10 @@ typedef struct vb200_gemm_desc {
   int32_t rvec_rows;     /* rows per sample for rvec */
   const float* rvec;     /* EPI_STORE, optional: per-sample fp32 scale applied to (acc + bias) * s before the residual is
                             added, row r uses rvec[r / rvec_rows] (timm DropPath / stochastic depth on the residual branch) */
+  float* colsq;          /* EPI_GELU_GP, optional: fp32 [M / rows_per_sample, N] (pre-zeroed), accumulates sum over each sample's
+                            rows of out2^2 (the 16-bit-rounded GELU output) = the GRN statistic, so that no separate pass over the
+                            hidden tensor is needed.  Only on the 256-wide TMA-store tiles (else VB200_ERR_UNSUPPORTED); needs
+                            rows_per_sample % 128 == 0 */
 } vb200_gemm_desc;
 
 int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);

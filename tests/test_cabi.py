@@ -32,7 +32,7 @@ def test_gemm_desc_layout_matches_header():
     body = header[header.index("typedef struct vb200_gemm_desc {"):header.index("} vb200_gemm_desc;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
-    for decl in re.findall(r"(?:int32_t|int64_t|const void\*|void\*|const float\*)\s+([^;]+);", body):
+    for decl in re.findall(r"(?:int32_t|int64_t|const void\*|void\*|const float\*|float\*)\s+([^;]+);", body):
         fields += [f.strip() for f in decl.split(",")]
     assert fields == [f[0] for f in _lib.GemmDesc._fields_]
 

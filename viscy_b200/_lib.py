@@ -34,7 +34,7 @@ class GemmDesc(C.Structure):
         ("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p),
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("aux", C.c_void_p), ("aux2", C.c_void_p),
         ("tvec", C.c_void_p), ("svec", C.c_void_p),
-        ("n_split", C.c_int32), ("rvec_rows", C.c_int32), ("rvec", C.c_void_p),
+        ("n_split", C.c_int32), ("rvec_rows", C.c_int32), ("rvec", C.c_void_p), ("colsq", C.c_void_p),
     ]
 
 

@@ -98,6 +98,7 @@ struct GemmParams {
   const float* svec;
   const float* rvec;  // EPI_STORE: per-sample scale of (acc + bias) * s before the residual: rvec[row / rvec_rows]
   int rvec_rows;
+  float* colsq;       // EPI_GELU_GP (TMA-store tiles): [M / rows_per_sample, N] += column sums of out2^2 per sample
   // implicit-GEMM conv forms: output extent, filter extent, padding, channel chunks per tap (CONVK) / channel tiles per
   // tap (CONVMN), channels of the activation operand
   int cOW, cOH, cOD, cKW, cKH, cpw, cph, cpd, cchunks, ccin;
@@ -876,6 +877,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 // two tiles, two stores in flight: each waits only for the store that last read its own tile
                 tma_stage_store<1>(stg, lane, o1, &tmOut.o, col0, row0);
                 tma_stage_store<1>(stg + 2048, lane, o2, &tmOut.o2, col0, row0);
+                if constexpr (EPI == VB200_EPI_GELU_GP) {
+                  if (p.colsq != nullptr) {
+                    // GRN statistic: column sums of g^2 over this warp's 32 rows, read back (as stored, 16-bit rounded)
+                    // from the staged tile - lane = column; row r, 16-byte group q sits at r * 64 + ((q ^ (r >> 1 & 3)) << 4)
+                    const uint32_t gt = stg + 2048 + static_cast<uint32_t>((lane & 7) * 2);
+                    const int q8 = lane >> 3;
+                    float sq = 0.f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                      uint16_t hv;
+                      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(gt + rr * 64 + ((q8 ^ ((rr >> 1) & 3)) << 4)));
+                      const float f = H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&hv));
+                      if (rr < rows_valid) sq = fmaf(f, f, sq);
+                    }
+                    const int col = col0 + lane;
+                    if (col < n_lim) atomicAdd(p.colsq + (row0 / p.rows_per_sample) * p.N + col, sq);
+                  }
+                }
               }
             } else {
               stage_store<false>(stg, lane, o1, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid,
@@ -1170,6 +1189,12 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
     VB_REQUIRE(epi == VB200_EPI_STORE && !d->mn_major && d->rvec_rows > 0, "rvec: K-major EPI_STORE with rvec_rows > 0");
     p.rvec = d->rvec;
     p.rvec_rows = d->rvec_rows;
+  }
+  if (d->colsq != nullptr) {
+    VB_REQUIRE(epi == VB200_EPI_GELU_GP && !d->mn_major && d->rows_per_sample > 0 && d->rows_per_sample % BM == 0,
+               "colsq: EPI_GELU_GP with rows_per_sample %% %d == 0", BM);
+    VB_SUPPORTED(bn == 256, "colsq needs the 256-wide TMA-store tiles (M x N = %d x %d picks %d-wide tiles)", d->M, d->N, bn);
+    p.colsq = d->colsq;
   }
   if (d->n_split > 0) {
     VB_REQUIRE(epi == VB200_EPI_F32 && d->out2 != nullptr && d->n_split % 16 == 0 && d->n_split < d->N &&

@@ -22,6 +22,7 @@ PAD = ops.ONES_PAD  # columns behind l / g that carry the ones column of the bia
 # it returns.  Inside a CUDA graph this becomes a fork/join of parallel branches.
 _SIDE: dict[int, torch.cuda.Stream] = {}
 OVERLAP_WGRAD = True
+FUSE_GRN_SUMSQ = True  # GRN sum of squares in the fc1 + GELU'/GELU epilogue where the 256-wide tiles run (False: column pass)
 
 
 def _side_stream(device: torch.device) -> torch.cuda.Stream:
@@ -42,10 +43,12 @@ def _wgrad_splits(n_out: int, k_in: int, pixels: int) -> int:
     return max(1, min(want, kb // 4 if kb >= 4 else 1, 64))
 
 
-def linear_fwd(a2d, w, bias, *, residual=None, act=L.ACT_NONE, epilogue=L.EPI_STORE, out2=None):
+def linear_fwd(a2d, w, bias, *, residual=None, act=L.ACT_NONE, epilogue=L.EPI_STORE, out2=None, colsq=None,
+               rows_per_sample=0):
     """a2d [M,K] 16-bit, w fp32 [N,K,...] -> [M,N] 16-bit."""
     wp = ops.packed(w, a2d.dtype)
-    return ops.gemm(a2d, wp, bias=bias, residual=residual, act=act, epilogue=epilogue, out2=out2)
+    return ops.gemm(a2d, wp, bias=bias, residual=residual, act=act, epilogue=epilogue, out2=out2, colsq=colsq,
+                    rows_per_sample=rows_per_sample)
 
 
 def linear_bwd(dout2d, a2d, w, *, need_da=True, need_db=True):
@@ -109,12 +112,19 @@ class ConvNeXtBlockFn(Function):
             gbuf = y2 = None
         if fused:
             # gp = gelu'(u) and g = gelu(u) from the fc1 epilogue; GRN scale folded into per-sample fc2 weights
-            h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP, out2=y2)
-            if onescol:
-                sumsq = ops.colreduce(gbuf.view(B, R, C4 + PAD), 1, width=C4)
+            if FUSE_GRN_SUMSQ and ops.gemm_uses_wide_tiles(M, C4):
+                # the GRN statistic sum_rows g^2 accumulates in the fc1 epilogue (no pass over the hidden tensor)
+                sumsq = ops.zeros((B, C4), x.device)
+                h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP, out2=y2, colsq=sumsq, rows_per_sample=R)
+                if not onescol:
+                    gbuf = y2
             else:
-                sumsq = ops.colreduce(y2.view(B, R, C4), 1)
-                gbuf = y2
+                h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP, out2=y2)
+                if onescol:
+                    sumsq = ops.colreduce(gbuf.view(B, R, C4 + PAD), 1, width=C4)
+                else:
+                    sumsq = ops.colreduce(y2.view(B, R, C4), 1)
+                    gbuf = y2
             w2 = fc2_w.detach().reshape(C, C4)
             s, w2s, b2e = ops.grn_prepare(sumsq, grn_w.detach(), grn_b.detach(), w2, fc2_b.detach(), x.dtype)
             out = ops.gemm(y2, w2s, bias=b2e, residual=res, b_batch_rows=R, rvec=keep, rvec_rows=R)

@@ -42,6 +42,7 @@ def gemm(
     n_split: int = 0,
     rvec: torch.Tensor | None = None,
     rvec_rows: int = 0,
+    colsq: torch.Tensor | None = None,
 ) -> torch.Tensor | tuple[torch.Tensor, torch.Tensor]:
     """tcgen05 GEMM.  K-major form: a [M,K], b [N,K] -> [M,N].  MN-major (wgrad) form: a [P,M], b [P,N]."""
     lda = _rowmajor2d(a, "a")
@@ -126,6 +127,10 @@ def gemm(
         if svec.dtype != torch.float32 or not svec.is_contiguous():
             raise ValueError("svec must be contiguous fp32")
         d.svec = svec.data_ptr()
+    if colsq is not None:
+        if colsq.dtype != torch.float32 or not colsq.is_contiguous() or rows_per_sample <= 0:
+            raise ValueError("colsq must be contiguous fp32 [M / rows_per_sample, N] with rows_per_sample set")
+        d.colsq = colsq.data_ptr()
     if rvec is not None:
         if rvec.dtype != torch.float32 or not rvec.is_contiguous() or rvec_rows <= 0 or rvec.numel() * rvec_rows < M:
             raise ValueError("rvec must be contiguous fp32 with one entry per rvec_rows rows")
@@ -135,6 +140,15 @@ def gemm(
     if epilogue in (L.EPI_GELU_DUAL, L.EPI_GELU_GP):
         return out, out2
     return out
+
+
+def gemm_uses_wide_tiles(M: int, N: int) -> bool:
+    """True when vb200_gemm picks the 256-wide (TMA-store) tiles for a K-major [M, N] product: the same rule as the host
+    code (N > 128 and at least one tile per SM)."""
+    return N > 128 and (-(-M // 128)) * (-(-N // 256)) >= SM_COUNT
+
+
+SM_COUNT = 148
 
 
 # ----------------------------------------------------------------------------------------------

@@ -31,6 +31,8 @@ struct EpiWarps {
   static constexpr int value = (BN == 256 && (EPI == VB200_EPI_GELU_GP || EPI == VB200_EPI_DGELU_GRN)) ? 16 : 8;
   // dual-output epilogue: results leave through TMA stores (two staging tiles, two bulk groups in flight per warp)
   static constexpr bool tma_store = value == 16 && EPI == VB200_EPI_GELU_GP;
+  // fused GRN+GELU backward on CTA pairs: g and gp chunks land in per-warp tiles by TMA, one chunk ahead of the math
+  static constexpr bool aux_tma(bool pair) { return pair && value == 16 && EPI == VB200_EPI_DGELU_GRN; }
 };
 
 // Operand forms.  The two CONV forms are the implicit-GEMM 3-D convolution: one operand is the channels-last activation
@@ -48,7 +50,9 @@ struct EpiWarps {
 enum { MODE_KMAJOR = 0, MODE_MNMAJOR = 1, MODE_CONVK = 2, MODE_CONVMN = 3, MODE_CONVKP = 4, MODE_CONVKPW = 5, MODE_KMAJOR2 = 6, MODE_CONVKP2 = 7 };  // CONVKP2: the patch conv form on CTA pairs
 
 // BKE = K elements per stage: 64 (SWIZZLE_128B rows) or, for 32-channel conv operands, 32 (SWIZZLE_64B rows)
-template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false, bool WRES = false, bool PAIR = false>
+// AUXT: the 16-bit epilogue operands (g, gp of the fused GRN+GELU backward) arrive through TMA into two more per-warp tiles
+template <int BN, int BKE = BK, int EW = 8, bool TWO_TILES = false, bool PATCH = false, bool WRES = false, bool PAIR = false,
+          bool AUXT = false>
 struct Cfg {
   static constexpr int A_BYTES = (PATCH ? 160 : BM) * BKE * 2;
   static constexpr int B_TAP_BYTES = (PAIR ? BN / 2 : BN) * BKE * 2;
@@ -58,7 +62,7 @@ struct Cfg {
   static constexpr int STAGES =
       WRES  ? (BKE == 64 ? 4 : 8)
       : PATCH ? (PAIR ? (BN == 64 ? 5 : 4) : (BKE == 64 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 8 : 5)))
-      : PAIR ? (EW == 16 ? 4 : 6)
+      : PAIR ? (EW == 16 ? (AUXT ? 3 : 4) : 6)
             : (BKE == 64 ? ((BN == 256) ? (EW == 16 ? 3 : 4) : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 8 : (BN == 128 ? 10 : 12)));
   static_assert(!PATCH || BN <= 128, "patch conv form: tiles up to 128 output channels");
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
@@ -66,7 +70,8 @@ struct Cfg {
   // (the patch conv forms carry a bias only and sit at the shared-memory limit: one vector)
   static constexpr int COLV_BYTES = EW * (PATCH ? 1 : 3) * (BN / (EW / 4)) * 4;
   // per-warp 32 rows x 64 B staging tile(s): one, or two for the 16-warp epilogues whose outputs leave through TMA stores
-  static constexpr int STG_PER_WARP = TWO_TILES ? 4096 : 2048;
+  static constexpr int STG_PER_WARP = AUXT ? 6144 : (TWO_TILES ? 4096 : 2048);
+  static_assert(!AUXT || (EW == 16 && PAIR && STAGES <= 6), "TMA-fed epilogue operands: the 16-warp CTA-pair form");
   static constexpr int STG_BYTES = EW * STG_PER_WARP;
   static_assert(!TWO_TILES || EW == 16, "TMA-store epilogues run 16 warps");
   // The staging tiles that TMA stores read (SWIZZLE_64B output maps) must sit on the swizzle period: the hardware
@@ -279,10 +284,12 @@ template <bool ATOMIC>
 __device__ __forceinline__ void stage_store(uint32_t stg, int lane, const uint4* vals, void* gbase, long long ld_bytes,
                                             long long row0, int rows_valid, long long col_byte0, int cols16_valid,
                                             const long long* rowoff = nullptr) {
-  __syncwarp();
-  const int sw = (lane >> 1) & 3;
+  if (vals != nullptr) {  // (nullptr: the caller has written the tile already, behind a __syncwarp of its own)
+    __syncwarp();
+    const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) sts128(stg + lane * 64 + ((g ^ sw) << 4), vals[g]);
+    for (int g = 0; g < 4; ++g) sts128(stg + lane * 64 + ((g ^ sw) << 4), vals[g]);
+  }
   __syncwarp();
   const int ch = lane & 3;
   if (rowoff != nullptr) {
@@ -333,7 +340,7 @@ __device__ __forceinline__ void stage_store(uint32_t stg, int lane, const uint4*
 template <int EPI, int BN, bool BF16, int CVP>
 __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, float* w, int cl, uint32_t cv,
                                                const uint4& xa, const uint4& xb, float rs) {
-  {
+  if constexpr (EPI != VB200_EPI_DGELU_GRN) {  // (a data gradient carries no bias)
     float b8[8];
     lds_f8(cv + cl * 4, b8);
 #pragma unroll
@@ -392,6 +399,53 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, float* v, fl
   }
 }
 
+__device__ __forceinline__ void lds_f2x4(uint32_t addr, float2* f) {  // 8 consecutive fp32 as 4 pairs
+  const uint4 a = lds128(addr), b = lds128(addr + 16);
+  f[0] = make_float2(__uint_as_float(a.x), __uint_as_float(a.y));
+  f[1] = make_float2(__uint_as_float(a.z), __uint_as_float(a.w));
+  f[2] = make_float2(__uint_as_float(b.x), __uint_as_float(b.y));
+  f[3] = make_float2(__uint_as_float(b.z), __uint_as_float(b.w));
+}
+
+// Fused GRN + GELU backward of one row's 32-column chunk: dh = (acc * s + g * t) * gp on the packed fp32x2 pipe (three
+// instructions per column pair); the s / t vectors of the next 4 columns are requested before the current 4 are used, so
+// their shared-memory latency runs under the math instead of in front of every group; results go straight into the
+// warp's staging tile (stg_row = this lane's 64-byte row, sw = its swizzle phase).
+// cv_s / cv_t: shared-space addresses of s and t at this chunk's first column.
+// Steps [H0, H1) of 4 columns each (8 steps = the chunk); xa / xb = g / gp of the 8-column groups H0/2 ... as uint4.
+template <bool BF16, int H0, int H1>
+__device__ __forceinline__ void dgelu_grn_steps(const uint32_t* acc, const uint4* xa, const uint4* xb, uint32_t cv_s,
+                                                uint32_t cv_t, uint32_t stg_row, int sw) {
+  uint4 sv[2], tv[2];  // s / t of 4 columns, fetched one step ahead (16 registers in flight)
+  sv[H0 & 1] = lds128(cv_s + H0 * 16);
+  tv[H0 & 1] = lds128(cv_t + H0 * 16);
+#pragma unroll
+  for (int h = H0; h < H1; ++h) {
+    if (h + 1 < H1) {
+      sv[(h + 1) & 1] = lds128(cv_s + (h + 1) * 16);
+      tv[(h + 1) & 1] = lds128(cv_t + (h + 1) * 16);
+    }
+    const int g = h >> 1, gl = g - (H0 >> 1), w = (h & 1) * 2;
+    const uint32_t ga[4] = {xa[gl].x, xa[gl].y, xa[gl].z, xa[gl].w};
+    const uint32_t gb[4] = {xb[gl].x, xb[gl].y, xb[gl].z, xb[gl].w};
+    const uint4 s4 = sv[h & 1], t4 = tv[h & 1];
+    const float2 s2[2] = {make_float2(__uint_as_float(s4.x), __uint_as_float(s4.y)),
+                          make_float2(__uint_as_float(s4.z), __uint_as_float(s4.w))};
+    const float2 t2[2] = {make_float2(__uint_as_float(t4.x), __uint_as_float(t4.y)),
+                          make_float2(__uint_as_float(t4.z), __uint_as_float(t4.w))};
+    uint32_t q[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 a2 = make_float2(__uint_as_float(acc[h * 4 + 2 * j]), __uint_as_float(acc[h * 4 + 2 * j + 1]));
+      const float2 v2 = __fmul2_rn(__ffma2_rn(H16<BF16>::unpack(ga[w + j]), t2[j], __fmul2_rn(a2, s2[j])),
+                                   H16<BF16>::unpack(gb[w + j]));
+      q[j] = H16<BF16>::pack(v2.x, v2.y);
+    }
+    // this lane's row of the staging tile (swizzled 16-byte groups), 8 bytes per step
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(stg_row + ((g ^ sw) << 4) + (h & 1) * 8), "r"(q[0]), "r"(q[1]) : "memory");
+  }
+}
+
 // BF16: element type of the 16-bit epilogue operands / outputs (compile-time so that the unrolled epilogue of a chunk is
 // one basic block; the MMA element type comes from the instruction descriptor, p.bf16)
 template <int BN, int MODE, int EPI, int BKE = BK, bool BF16 = true>
@@ -404,7 +458,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr bool PAIR = MODE == MODE_KMAJOR2 || MODE == MODE_CONVKP2;
   static_assert(MODE != MODE_KMAJOR2 || BN == 256, "CTA-pair GEMM: 256-wide tiles");
   static_assert(MODE != MODE_CONVKP2 || BKE == 64, "CTA-pair patch conv: 64-channel K blocks");
-  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH, WRES, PAIR>;
+  constexpr bool AUXT = EpiWarps<BN, EPI>::aux_tma(PAIR);
+  using C = Cfg<BN, BKE, NUM_EPI_WARPS, EpiWarps<BN, EPI>::tma_store, PATCH, WRES, PAIR, AUXT>;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int COL_GROUPS = NUM_EPI_WARPS / 4;  // warps sharing a TMEM lane quarter split the tile's columns
   constexpr bool MN_MAJOR = MODE == MODE_MNMAJOR || MODE == MODE_CONVMN;
@@ -419,6 +474,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* w_bar = tmem_empty + 3;             // CONVKPW: resident filter landed
+  uint64_t* aux_bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + 128);  // AUXT: one per epilogue warp
   uint8_t* wres = smem + C::W_OFFSET;           // CONVKPW: [tap][chunk][BN x BKE] sub-tiles
 
   const int warp = threadIdx.x >> 5;
@@ -436,6 +492,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tmem_empty[i], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair: both CTAs' epilogues release the leader
     }
     if constexpr (WRES) mbar_init(w_bar, 1);
+    if constexpr (AUXT) {
+      for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&aux_bars[i], 1);
+      tma_prefetch_desc(&tmOut.o);
+      tma_prefetch_desc(&tmOut.o2);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -520,7 +581,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           voxel_coords(p, kb0 * BK, cx, cy, cz, cn);
         }
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (AUXT) mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
+          else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           if constexpr (PAIR && PATCH) {
@@ -641,7 +703,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int split = unit / tiles;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      if constexpr (AUXT) mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 32);
+      else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
       // CONVKPW: resident sub-tile index of tap (kd, h = 0, kw), chunk: +1 per K block, +2 filter rows when kw wraps
@@ -714,9 +777,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t stg = smem_u32(smem + C::STG_OFFSET + e * C::STG_PER_WARP);
     constexpr bool TMA_STORE = EpiWarps<BN, EPI>::tma_store;
     constexpr int NCH = BN / (32 * COL_GROUPS);  // 32-column chunks per warp
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t tile_it = 0;  // accumulator buffer = bit 0, its barrier phase = bit 1
+    // AUXT: this warp's g / gp chunk (32 rows x 64 B each) is fetched by TMA into its second and third tile (SWIZZLE_64B,
+    // the layout `unstage` reads) and the chunk after it is requested as soon as this one sits in registers, so the
+    // operand latency runs under the math and stores of the previous chunk instead of in front of every chunk.
+    // The request cursor (unit, pair-tile row / column, chunk) runs one chunk ahead of the consumer and advances without
+    // divisions: a step of gridDim.x units is a fixed (rows, columns) step through the pair-tile grid.
+    const uint32_t aux_bar = smem_u32(aux_bars + e);
+    uint32_t aux_phase = 0;
+    int pf_u = blockIdx.x, pf_c = -1, pf_mi = 0, pf_ni = 0, pf_dq = 0, pf_dr = 0;
+    if constexpr (AUXT) {
+      const int q0 = blockIdx.x >> 1, qs = gridDim.x >> 1;
+      pf_mi = q0 / p.tiles_n;
+      pf_ni = q0 - pf_mi * p.tiles_n;
+      pf_dq = qs / p.tiles_n;
+      pf_dr = qs - pf_dq * p.tiles_n;
+    }
+    auto aux_prefetch = [&]() {  // warp-uniform: advance to the next chunk this warp owns and request it
+      if constexpr (AUXT) {
+        ++pf_c;
+        while (pf_u < units) {
+          const int ac0 = pf_ni * BN + half * (BN / COL_GROUPS) + pf_c * 32;
+          if (pf_c < NCH && ac0 < p.N) {
+            if (lane == 0) {
+              const int ar0 = (pf_mi * 2 + (int)rank) * BM + quarter * 32;
+              const bool with_g = p.tvec != nullptr;
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(aux_bar), "r"(with_g ? 4096u : 2048u)
+                           : "memory");
+              if (with_g)
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                                 "r"(stg + 2048u), "l"(reinterpret_cast<uint64_t>(&tmOut.o)), "r"(aux_bar), "r"(ac0), "r"(ar0)
+                             : "memory");
+              asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                               "r"(stg + 4096u), "l"(reinterpret_cast<uint64_t>(&tmOut.o2)), "r"(aux_bar), "r"(ac0), "r"(ar0)
+                           : "memory");
+            }
+            return;
+          }
+          pf_u += gridDim.x;
+          pf_c = 0;
+          pf_mi += pf_dq;
+          pf_ni += pf_dr;
+          if (pf_ni >= p.tiles_n) {
+            pf_ni -= p.tiles_n;
+            ++pf_mi;
+          }
+        }
+      }
+    };
+    aux_prefetch();
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int acc = tile_it & 1;
+      const uint32_t acc_phase = (tile_it >> 1) & 1;
       const int split = unit / tiles;
       const int t = unit - split * tiles;
       const int m0 = PAIR ? (((t >> 1) / p.tiles_n) * 2 + (int)rank) * BM : (t / p.tiles_n) * BM;
@@ -780,7 +892,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr bool APRE = NUM_EPI_WARPS == 8;  // aux operands fetched one chunk ahead (second register buffer)
       AuxRegs aux[APRE ? 2 : 1];
       const int cc0 = half * (BN / COL_GROUPS);
-      load_aux<EPI>(p, row0, n0 + cc0, lane, aux[0]);
+      if constexpr (!AUXT) load_aux<EPI>(p, row0, n0 + cc0, lane, aux[0]);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr =
@@ -795,7 +907,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if constexpr (EPI == VB200_EPI_STORE) {
         if (p.rvec != nullptr) rscale = __ldg(p.rvec + min(row0 + lane, (long long)p.M - 1) / p.rvec_rows);
       }
-      bool released = false;
       if (TPRE && n0 + cc0 < n_lim) tmem_ld32(t_addr + cc0, r[0]);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -805,13 +916,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const bool more = c + 1 < NCH && col0 + 32 < n_lim;
           if constexpr (!TPRE) tmem_ld32(t_addr + cc, r[0]);
           const int AB = APRE ? (c & 1) : 0;
-          if constexpr (APRE) {
-            if (more) load_aux<EPI>(p, row0, col0 + 32, lane, aux[(c + 1) & 1]);
+          if constexpr (AUXT) {
+            asm volatile(
+                "{\n\t.reg .pred P1;\n\t"
+                "AUX_WAIT:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                "@P1 bra AUX_DONE;\n\t"
+                "bra AUX_WAIT;\n\t"
+                "AUX_DONE:\n\t}\n" ::"r"(aux_bar),
+                "r"(aux_phase)
+                : "memory");
+            aux_phase ^= 1;
           } else {
-            if (c > 0) load_aux<EPI>(p, row0, col0, lane, aux[0]);
+            if constexpr (APRE) {
+              if (more) load_aux<EPI>(p, row0, col0 + 32, lane, aux[(c + 1) & 1]);
+            } else {
+              if (c > 0) load_aux<EPI>(p, row0, col0, lane, aux[0]);
+            }
+            if (has_a) unstage(stg, lane, aux[AB].a);
+            if constexpr (EPI == VB200_EPI_DGELU_GRN) unstage(stg, lane, aux[AB].b);
           }
-          if (has_a) unstage(stg, lane, aux[AB].a);
-          if constexpr (EPI == VB200_EPI_DGELU_GRN) unstage(stg, lane, aux[AB].b);
           tmem_ld_wait();
           if (TPRE && more) {
             tmem_ld32(t_addr + cc + 32, r[(c + 1) & 1]);
@@ -823,15 +947,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if constexpr (PAIR) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
               else mbar_arrive_relaxed(&tmem_empty[acc]);
             }
-            released = true;
           }
           // this warp's 32 rows x 32 columns: math per row, then row-contiguous stores through the staging tile
           const int cols8_valid = min(4, (n_lim - col0) >> 3);
           if (rows_valid > 0) {
             uint4 o1[4], o2[4];
             float f32buf[32];
+            if constexpr (EPI == VB200_EPI_DGELU_GRN) {
+              const uint32_t cv_s = cv + static_cast<uint32_t>(CW + cc) * 4u, cv_t = cv + static_cast<uint32_t>(2 * CW + cc) * 4u;
+              const int sw = (lane >> 1) & 3;
+              if constexpr (AUXT) {
+                // g / gp leave their tiles 16 columns at a time (16 registers instead of 32); once the second half is in
+                // registers the tiles are free and the next chunk is requested, under the second half's math and the stores
+                uint4 xa[2], xb[2];
+                __syncwarp();  // the previous chunk's row-contiguous reads of the staging tile are done
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 2; ++g) {
+                  xa[g] = has_a ? lds128(stg + 2048 + lane * 64 + ((g ^ sw) << 4)) : make_uint4(0, 0, 0, 0);
+                  xb[g] = lds128(stg + 4096 + lane * 64 + ((g ^ sw) << 4));
+                }
+                dgelu_grn_steps<BF16, 0, 4>(r[0], xa, xb, cv_s, cv_t, stg + lane * 64, sw);
+#pragma unroll
+                for (int g = 2; g < 4; ++g) {
+                  xa[g - 2] = has_a ? lds128(stg + 2048 + lane * 64 + ((g ^ sw) << 4)) : make_uint4(0, 0, 0, 0);
+                  xb[g - 2] = lds128(stg + 4096 + lane * 64 + ((g ^ sw) << 4));
+                }
+                __syncwarp();
+                if (lane == 0) fence_proxy_async_smem();  // the warp's generic-proxy reads precede the async-proxy refill
+                aux_prefetch();
+                dgelu_grn_steps<BF16, 4, 8>(r[0], xa, xb, cv_s, cv_t, stg + lane * 64, sw);
+              } else {
+                dgelu_grn_steps<BF16, 0, 8>(r[0], aux[AB].a, aux[AB].b, cv_s, cv_t, stg + lane * 64, sw);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < (EPI == VB200_EPI_DGELU_GRN ? 0 : 4); ++g) {
               float v[8], w[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[TPRE ? (c & 1) : 0][g * 8 + j]);
@@ -897,15 +1047,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               }
             } else {
-              stage_store<false>(stg, lane, o1, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid,
-                                 scatter ? rowoff : nullptr);
+              if constexpr (EPI == VB200_EPI_DGELU_GRN)
+                stage_store<false>(stg, lane, nullptr, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
+              else
+                stage_store<false>(stg, lane, o1, p.out, p.ldo * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid,
+                                   scatter ? rowoff : nullptr);
               if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP)
                 stage_store<false>(stg, lane, o2, p.out2, p.ldo2 * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
             }
+          } else if constexpr (AUXT) {  // rows past M: the (zero-filled) chunk still has to be retired
+            __syncwarp();
+            aux_prefetch();
           }
         }
       }
-      if (!released) {  // this warp's column range lies past the tile's valid columns
+      if (n0 + cc0 >= n_lim) {  // this warp's column range lies past the tile's valid columns: nothing drained above
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -913,8 +1069,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else mbar_arrive_relaxed(&tmem_empty[acc]);
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      ++tile_it;
     }
     if constexpr (TMA_STORE) {  // the staging tiles must outlive the bulk stores that read them
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1032,9 +1187,10 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   static PerDeviceOnce once;  // per instantiation and device
   const int dev = PerDeviceOnce::device();
   auto kern = gemm_kernel<BN, MODE, EPI, BKE, BF16>;
+  constexpr bool LPAIR = MODE == MODE_KMAJOR2 || MODE == MODE_CONVKP2;
   using LC = Cfg<BN, BKE, EpiWarps<BN, EPI>::value, EpiWarps<BN, EPI>::tma_store,
-                 MODE == MODE_CONVKP || MODE == MODE_CONVKP2 || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW,
-                 MODE == MODE_KMAJOR2 || MODE == MODE_CONVKP2>;
+                 MODE == MODE_CONVKP || MODE == MODE_CONVKP2 || MODE == MODE_CONVKPW, MODE == MODE_CONVKPW, LPAIR,
+                 EpiWarps<BN, EPI>::aux_tma(LPAIR)>;
   const int smem_bytes = MODE == MODE_CONVKPW ? LC::W_OFFSET + 1024 + p.cwbytes : LC::SMEM_BYTES;
   if (once.need(dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1047,6 +1203,11 @@ static int launch_dt(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     if (int rc = make_tmap_2d(&om.o, p.out, p.M, p.N, p.ldo, 32, 32, BF16, true)) return rc;
     if (p.out2 != nullptr)
       if (int rc = make_tmap_2d(&om.o2, p.out2, p.M, p.N, p.ldo2, 32, 32, BF16, true)) return rc;
+  }
+  if constexpr (EpiWarps<BN, EPI>::aux_tma(LPAIR)) {  // the maps carry the epilogue's input operands instead
+    if (p.tvec != nullptr)
+      if (int rc = make_tmap_2d(&om.o, p.aux, p.M, p.N, p.ldaux, 32, 32, BF16, true)) return rc;
+    if (int rc = make_tmap_2d(&om.o2, p.aux2, p.M, p.N, p.ldaux2, 32, 32, BF16, true)) return rc;
   }
   if (smem_bytes > 232448) return fail(VB200_ERR_UNSUPPORTED, "resident filter does not fit shared memory (%d B)", smem_bytes);
   if constexpr (MODE == MODE_KMAJOR2 || MODE == MODE_CONVKP2) {  // clusters of two CTAs: the pair shares one cta_group::2 MMA
@@ -1131,6 +1292,7 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
   if (d->residual) VB_REQUIRE(d->ldr % 8 == 0, "ldr %% 8");
   if (epi == VB200_EPI_DGELU_GRN && (d->svec || d->tvec))
     VB_REQUIRE(d->rows_per_sample % BM == 0, "rows_per_sample (%d) must be a multiple of %d", d->rows_per_sample, BM);
+  if (epi == VB200_EPI_DGELU_GRN) VB_REQUIRE(d->bias == nullptr && d->k_splits <= 1, "DGELU_GRN: no bias, no K split");
   if (epi == VB200_EPI_DGELU_GRN)
     VB_REQUIRE(d->aux2 && d->ldaux2 % 8 == 0 && (!d->tvec || (d->aux && d->ldaux % 8 == 0)) &&
                    ((!d->tvec && !d->svec) || d->rows_per_sample > 0),

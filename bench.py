@@ -130,6 +130,17 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ secondary evidence
+OPTIMIZER = os.environ.get("VB200_BENCH_OPTIMIZER", "native")  # "native": viscy_b200.optim.AdamW, "torch": torch fused AdamW
+
+
+def _adamw(params, lr, capturable=True):
+    """The step's optimizer: the one-launch sm_100a AdamW (same semantics as torch.optim.AdamW) unless --optimizer torch."""
+    if OPTIMIZER == "native":
+        from viscy_b200.optim import AdamW
+        return AdamW(params, lr=lr)
+    return torch.optim.AdamW(params, lr=lr, fused=True, capturable=capturable)
+
+
 def _event_ms(fn, reps, warm):
     for _ in range(warm):
         fn()
@@ -188,7 +199,7 @@ def secondary_evidence(dev, tf_burst):
         del x, w, wf, y, dy, dx
     torch.manual_seed(0)
     m = Unet3d(3, 3, 4, 32).to(dev)
-    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True, capturable=True)
+    opt = _adamw(m.parameters(), 1e-3)
     scaler = torch.amp.GradScaler("cuda")
     x = torch.randn(1, 3, 128, 128, 128, device=dev)
     y = torch.randn(1, 3, 128, 128, 128, device=dev)
@@ -209,7 +220,7 @@ def secondary_evidence(dev, tf_burst):
     del m, opt, x, y
     torch.cuda.empty_cache()
     m = ContrastiveEncoder("convnext_tiny", in_channels=2, in_stack_depth=15).to(dev)
-    opt = torch.optim.AdamW(m.parameters(), lr=2e-4, fused=True, capturable=True)
+    opt = _adamw(m.parameters(), 2e-4)
     a = torch.randn(64, 2, 15, 224, 224, device=dev)
     p = torch.randn(64, 2, 15, 224, 224, device=dev)
     labels = torch.cat([torch.arange(64), torch.arange(64)]).to(dev)
@@ -246,7 +257,7 @@ def secondary_evidence(dev, tf_burst):
                               1, 2, in_stack_depth=21, stem_kernel_size=(7, 4, 4), pretraining=False, head_conv=True))):
             torch.manual_seed(0)
             m = make().to(dev)
-            opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True, capturable=True)
+            opt = _adamw(m.parameters(), 1e-3)
             crit = MixedLoss(l1_alpha=0.5, l2_alpha=0.0, ms_dssim_alpha=0.5)
 
             def step_ml(xd, yd, m=m, opt=opt, crit=crit):
@@ -309,7 +320,7 @@ def run_gpu(args):
         from viscy_b200.parallel import BucketedGradAllReduce
         exchange = BucketedGradAllReduce(model.parameters())
         exchange.broadcast_parameters(0)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=not args.no_graph)
+    opt = _adamw(model.parameters(), 1e-3, capturable=not args.no_graph)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn((BATCH, *SHAPE_IN), device=dev, generator=g)
     y = torch.randn((BATCH, *SHAPE_OUT), device=dev, generator=g)
@@ -501,6 +512,8 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"dp{world}",
                        "cuda_graph": graphed is not None, "batch_streams": args.batch_streams,
+                       "optimizer": ("viscy_b200.optim.AdamW (one sm_100a launch per step)" if OPTIMIZER == "native"
+                                     else "torch.optim.AdamW(fused=True)"),
                        "grad_exchange": ("none" if not ddp else
                                          "torch DDP (bucketed NCCL all-reduce)" if args.ddp == "torch" else
                                          "bucketed fp32 NCCL all-reduce (average) overlapped with backward, recorded in the step graph"),
@@ -533,6 +546,7 @@ def run_gpu(args):
 
 
 def main():
+    global OPTIMIZER
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -544,8 +558,11 @@ def main():
                     help="N>1 gradient exchange: flat all-reduce inside the CUDA graph (default) or stock torch DDP (eager)")
     ap.add_argument("--batch-streams", type=int, default=1,
                     help="split the per-GPU batch into this many chunks on concurrent CUDA streams (exact: per-sample norms)")
+    ap.add_argument("--optimizer", default=OPTIMIZER, choices=["native", "torch"],
+                    help="native: viscy_b200.optim.AdamW (one launch per step); torch: torch.optim.AdamW(fused=True)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    OPTIMIZER = args.optimizer
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

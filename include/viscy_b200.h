@@ -362,6 +362,21 @@ int vb200_max_f(const void* x, int dtype, int64_t n, float* out, vb200_stream_t 
 int vb200_blend_window(void* dst, const void* src, int dst_dtype, int src_dtype, int64_t BC, int Z, int H, int W, int d,
                        int Hs, int Ws, int z0, int oy, int ox, vb200_stream_t stream);
 
+/* ---- Optimizer step of the training path (VU/optimizers.py:10-61 configure_adamw_scheduler; CY/engine.py:547-554 and
+ * the contrastive engine's configure_optimizers: torch.optim.AdamW over model.parameters()) ----
+ * One AdamW step (decoupled weight decay, bias-corrected moments, fp32) over n_tensors parameter tensors:
+ *   p -= lr*wd*p;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps),  t = *step + 1
+ * table: DEVICE [n_tensors][4] pointers {p, m, v, step}: step = fp32 count of this tensor's completed steps, advanced by the
+ * call; grads: HOST array of n_tensors device pointers (fp32, dense);
+ * chunk_start: HOST [n_tensors+1] prefix sums of chunks per tensor; chunks: DEVICE [chunk_start[n_tensors]][4] int32
+ * {tensor index within its window of 448 tensors, element offset, count <= 2048, 0}.  done: DEVICE uint32 scratch (zero).
+ * lr_ptr / grad_scale / found_inf: optional DEVICE fp32
+ * scalars (scheduler-driven lr; GradScaler: gradients are divided by *grad_scale and written back, *found_inf == 1 skips the
+ * step). */
+int vb200_adamw_step(const void* table, void* const* grads, const int32_t* chunk_start, int n_tensors, const void* chunks,
+                     uint32_t* done, float lr, const float* lr_ptr, float beta1, float beta2, float eps,
+                     float weight_decay, int maximize, const float* grad_scale, const float* found_inf, vb200_stream_t stream);
+
 /* ---- PixelToVoxelHead (VM/components/heads.py:594-641) ---- */
 /* forward (backward == 0): dec [B,h,w,4*Cm] -> u [B,Dz,2h,2w,Cu] = unfold(pool(pixelshuffle2(dec)));
  * backward (!= 0): src = du, dst = ddec */

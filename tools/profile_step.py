@@ -11,7 +11,9 @@ from viscy_b200 import UNeXt2  # noqa: E402
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = UNeXt2(**bench.CFG).to(dev)
-opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+from viscy_b200.optim import AdamW  # noqa: E402
+
+opt = AdamW(model.parameters(), lr=1e-3)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else bench.BATCH
 x = torch.randn((B, *bench.SHAPE_IN), device=dev)
 y = torch.randn((B, *bench.SHAPE_OUT), device=dev)

@@ -25,6 +25,12 @@ import torch
 import torch.distributed as dist
 
 
+def _slot(p: torch.Tensor) -> int:
+    """Elements a gradient occupies in the flat buffer: padded to 16 bytes so that every view is float4-aligned (the
+    one-launch AdamW reads gradients 16 bytes at a time; the pads stay zero and ride along in the all-reduce)."""
+    return (p.numel() + 3) // 4 * 4
+
+
 class _Bucket:
     def __init__(self, params: list[torch.nn.Parameter], flat: torch.Tensor):
         self.params = params
@@ -33,7 +39,7 @@ class _Bucket:
         off = 0
         for p in params:
             self.views.append(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            off += _slot(p)
         self.pending = len(params)
         self.launched = False
 
@@ -46,7 +52,7 @@ class BucketedGradAllReduce:
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.numel = sum(p.numel() for p in self.params)
+        self.numel = sum(_slot(p) for p in self.params)
         self.fractions = tuple(fractions)
         self.order: list[torch.nn.Parameter] = []
         self._seen: set[int] = set()
@@ -80,7 +86,7 @@ class BucketedGradAllReduce:
         groups, cur, acc, ci = [], [], 0, 0
         for p in ordered:
             cur.append(p)
-            acc += p.numel()
+            acc += _slot(p)
             if acc >= cuts[ci]:
                 groups.append(cur)
                 cur = []
@@ -90,7 +96,7 @@ class BucketedGradAllReduce:
             groups.append(cur)
         self.buckets, off = [], 0
         for g in groups:
-            n = sum(p.numel() for p in g)
+            n = sum(_slot(p) for p in g)
             b = _Bucket(g, self.flat[off:off + n])
             off += n
             self.buckets.append(b)

@@ -77,8 +77,7 @@ typedef struct vb200_gemm_desc {
                             added, row r uses rvec[r / rvec_rows] (timm DropPath / stochastic depth on the residual branch) */
   float* colsq;          /* EPI_GELU_GP, optional: fp32 [M / rows_per_sample, N] (pre-zeroed), accumulates sum over each sample's
                             rows of out2^2 (the 16-bit-rounded GELU output) = the GRN statistic, so that no separate pass over the
-                            hidden tensor is needed.  Only on the 256-wide TMA-store tiles (else VB200_ERR_UNSUPPORTED); needs
-                            rows_per_sample % 128 == 0 */
+                            hidden tensor is needed.  Needs rows_per_sample % 32 == 0 (an epilogue warp's rows lie in one sample) */
 } vb200_gemm_desc;
 
 int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream);

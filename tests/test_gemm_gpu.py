@@ -160,21 +160,22 @@ def test_gemm_row_scale_per_sample(cuda, M, N, K, R, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("M,N,K,R", [(8192, 2944, 736, 4096), (32768, 384, 96, 4096), (20 * 1024, 1536, 384, 1024)])
+@pytest.mark.parametrize("M,N,K,R", [(8192, 2944, 736, 4096), (32768, 384, 96, 4096), (20 * 1024, 1536, 384, 1024),
+                                     (2048, 1536, 384, 256), (512, 3072, 768, 64), (480, 200, 96, 96), (256, 64, 96, 32)])
 def test_gemm_gelu_gp_column_sumsq(cuda, M, N, K, R, dtype):
     """EPI_GELU_GP with the fused GRN statistic: colsq[n, c] = sum over sample n's rows of gelu(u)^2 (of the stored, rounded
-    values), next to the two outputs, on the 256-wide TMA-store tiles (single CTA and CTA pair)."""
+    values), next to the two outputs: 256-wide TMA-store tiles (single CTA and CTA pair) and the narrower tiles of the small
+    feature maps (M = 2048 / 512 rows), ragged N and M included."""
     from viscy_b200 import _lib as L, ops
     g = torch.Generator(device=cuda).manual_seed(5)
     a = (torch.randn((M, K), device=cuda, generator=g) * 0.5).to(dtype)
     w = (torch.randn((N, K), device=cuda, generator=g) * 0.05).to(dtype)
     bias = torch.randn((N,), device=cuda, generator=g) * 0.1
-    assert ops.gemm_uses_wide_tiles(M, N)
     sq = torch.zeros((M // R, N), device=cuda)
     gp, gl = ops.gemm(a, w, bias=bias, epilogue=L.EPI_GELU_GP, colsq=sq, rows_per_sample=R)
     ref = (gl.float() ** 2).view(M // R, R, N).sum(1)
     assert ((sq - ref).norm() / ref.norm()).item() < 1e-5
     u = a.float() @ w.float().t() + bias
     assert ((gl.float() - torch.nn.functional.gelu(u)).norm() / torch.nn.functional.gelu(u).norm()).item() < (2e-3 if dtype == torch.float16 else 8e-3)
-    with pytest.raises(NotImplementedError):  # narrow tiles have no fused statistic: the caller keeps the column pass
-        ops.gemm(a[:256], w[:64], epilogue=L.EPI_GELU_GP, colsq=torch.zeros((1, 64), device=cuda), rows_per_sample=256)
+    with pytest.raises(RuntimeError):  # a warp's 32 rows must lie in one sample
+        ops.gemm(a[:240], w[:64], epilogue=L.EPI_GELU_GP, colsq=torch.zeros((5, 64), device=cuda), rows_per_sample=48)

@@ -103,7 +103,7 @@ struct GemmParams {
   const float* svec;
   const float* rvec;  // EPI_STORE: per-sample scale of (acc + bias) * s before the residual: rvec[row / rvec_rows]
   int rvec_rows;
-  float* colsq;       // EPI_GELU_GP (TMA-store tiles): [M / rows_per_sample, N] += column sums of out2^2 per sample
+  float* colsq;       // EPI_GELU_GP: [M / rows_per_sample, N] += column sums of out2^2 per sample
   // implicit-GEMM conv forms: output extent, filter extent, padding, channel chunks per tap (CONVK) / channel tiles per
   // tap (CONVMN), channels of the activation operand
   int cOW, cOH, cOD, cKW, cKH, cpw, cph, cpd, cchunks, ccin;
@@ -444,6 +444,25 @@ __device__ __forceinline__ void dgelu_grn_steps(const uint32_t* acc, const uint4
     // this lane's row of the staging tile (swizzled 16-byte groups), 8 bytes per step
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(stg_row + ((g ^ sw) << 4) + (h & 1) * 8), "r"(q[0]), "r"(q[1]) : "memory");
   }
+}
+
+// GRN statistic: column sums of g^2 over a warp's 32 rows, read back (as stored, 16-bit rounded) from the staged tile -
+// lane = column; row r, 16-byte group q sits at r * 64 + ((q ^ (r >> 1 & 3)) << 4).  One atomicAdd per column.
+template <bool BF16>
+__device__ __forceinline__ void colsq_from_tile(uint32_t tile, int lane, int rows_valid, float* colsq, int N, long long sample,
+                                                int col0, int n_lim) {
+  const uint32_t gt = tile + static_cast<uint32_t>((lane & 7) * 2);
+  const int q8 = lane >> 3;
+  float sq = 0.f;
+#pragma unroll 8
+  for (int rr = 0; rr < 32; ++rr) {
+    uint16_t hv;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(gt + rr * 64 + ((q8 ^ ((rr >> 1) & 3)) << 4)));
+    const float f = H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&hv));
+    if (rr < rows_valid) sq = fmaf(f, f, sq);
+  }
+  const int col = col0 + lane;
+  if (col < n_lim) atomicAdd(colsq + sample * N + col, sq);
 }
 
 // BF16: element type of the 16-bit epilogue operands / outputs (compile-time so that the unrolled epilogue of a chunk is
@@ -1028,22 +1047,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tma_stage_store<1>(stg, lane, o1, &tmOut.o, col0, row0);
                 tma_stage_store<1>(stg + 2048, lane, o2, &tmOut.o2, col0, row0);
                 if constexpr (EPI == VB200_EPI_GELU_GP) {
-                  if (p.colsq != nullptr) {
-                    // GRN statistic: column sums of g^2 over this warp's 32 rows, read back (as stored, 16-bit rounded)
-                    // from the staged tile - lane = column; row r, 16-byte group q sits at r * 64 + ((q ^ (r >> 1 & 3)) << 4)
-                    const uint32_t gt = stg + 2048 + static_cast<uint32_t>((lane & 7) * 2);
-                    const int q8 = lane >> 3;
-                    float sq = 0.f;
-#pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) {
-                      uint16_t hv;
-                      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(gt + rr * 64 + ((q8 ^ ((rr >> 1) & 3)) << 4)));
-                      const float f = H16<BF16>::to_f(*reinterpret_cast<const typename H16<BF16>::T*>(&hv));
-                      if (rr < rows_valid) sq = fmaf(f, f, sq);
-                    }
-                    const int col = col0 + lane;
-                    if (col < n_lim) atomicAdd(p.colsq + (row0 / p.rows_per_sample) * p.N + col, sq);
-                  }
+                  if (p.colsq != nullptr) colsq_from_tile<BF16>(stg + 2048, lane, rows_valid, p.colsq, p.N, row0 / p.rows_per_sample, col0, n_lim);
                 }
               }
             } else {
@@ -1054,6 +1058,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                    scatter ? rowoff : nullptr);
               if constexpr (EPI == VB200_EPI_GELU_DUAL || EPI == VB200_EPI_GELU_GP)
                 stage_store<false>(stg, lane, o2, p.out2, p.ldo2 * 2, row0, rows_valid, (long long)col0 * 2, cols8_valid);
+              if constexpr (EPI == VB200_EPI_GELU_GP) {  // the staging tile still holds g
+                if (p.colsq != nullptr) colsq_from_tile<BF16>(stg, lane, rows_valid, p.colsq, p.N, row0 / p.rows_per_sample, col0, n_lim);
+              }
             }
           } else if constexpr (AUXT) {  // rows past M: the (zero-filled) chunk still has to be retired
             __syncwarp();
@@ -1353,9 +1360,8 @@ extern "C" int vb200_gemm(const vb200_gemm_desc* d, vb200_stream_t stream) {
     p.rvec_rows = d->rvec_rows;
   }
   if (d->colsq != nullptr) {
-    VB_REQUIRE(epi == VB200_EPI_GELU_GP && !d->mn_major && d->rows_per_sample > 0 && d->rows_per_sample % BM == 0,
-               "colsq: EPI_GELU_GP with rows_per_sample %% %d == 0", BM);
-    VB_SUPPORTED(bn == 256, "colsq needs the 256-wide TMA-store tiles (M x N = %d x %d picks %d-wide tiles)", d->M, d->N, bn);
+    VB_REQUIRE(epi == VB200_EPI_GELU_GP && !d->mn_major && d->rows_per_sample > 0 && d->rows_per_sample % 32 == 0,
+               "colsq: EPI_GELU_GP with rows_per_sample %% 32 == 0 (an epilogue warp's 32 rows belong to one sample)");
     p.colsq = d->colsq;
   }
   if (d->n_split > 0) {

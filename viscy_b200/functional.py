@@ -22,7 +22,7 @@ PAD = ops.ONES_PAD  # columns behind l / g that carry the ones column of the bia
 # it returns.  Inside a CUDA graph this becomes a fork/join of parallel branches.
 _SIDE: dict[int, torch.cuda.Stream] = {}
 OVERLAP_WGRAD = True
-FUSE_GRN_SUMSQ = True  # GRN sum of squares in the fc1 + GELU'/GELU epilogue where the 256-wide tiles run (False: column pass)
+FUSE_GRN_SUMSQ = True  # GRN sum of squares in the fc1 + GELU'/GELU epilogue (False, or feature maps under 32 pixels: column pass)
 
 
 def _side_stream(device: torch.device) -> torch.cuda.Stream:
@@ -112,7 +112,7 @@ class ConvNeXtBlockFn(Function):
             gbuf = y2 = None
         if fused:
             # gp = gelu'(u) and g = gelu(u) from the fc1 epilogue; GRN scale folded into per-sample fc2 weights
-            if FUSE_GRN_SUMSQ and ops.gemm_uses_wide_tiles(M, C4):
+            if FUSE_GRN_SUMSQ and R % 32 == 0:
                 # the GRN statistic sum_rows g^2 accumulates in the fc1 epilogue (no pass over the hidden tensor)
                 sumsq = ops.zeros((B, C4), x.device)
                 h, y2 = linear_fwd(l2, fc1_w, fc1_b, epilogue=L.EPI_GELU_GP, out2=y2, colsq=sumsq, rows_per_sample=R)

@@ -972,59 +972,83 @@ grn_wgrad_finish_kernel(const float* __restrict__ P, const float* __restrict__ W
   atomicAdd(dbgrn + k, dbg);
 }
 
-// four columns per thread (16-byte loads of P, W2, s; 16-byte stores of dW2): C4 % 4 == 0, ldp % 4 == 0, nb <= 8
+// four columns per thread (16-byte loads of P, W2, s; 16-byte stores of dW2): C4 % 4 == 0, ldp % 4 == 0, nb <= 8.
+// Block = 32 column quads x 4 row groups: the four row groups of a block combine their S1 / dbgrn partial sums through
+// shared memory, so a block issues 36 x 32 atomics instead of 36 x 128 (the atomics, not the 16-byte loads, were the cost).
 __global__ void __launch_bounds__(128)
 grn_wgrad_finish4_kernel(const float* __restrict__ P, const float* __restrict__ W2, const float* __restrict__ s,
                          const float* __restrict__ bgrn, const float* __restrict__ db2_in, float* __restrict__ dW2,
                          float* __restrict__ S1, float* __restrict__ dbgrn, float* __restrict__ db2_out, int nb, int C, int C4,
                          long long ldp, int jchunk) {
   constexpr int NB = 8;
-  const int k = (blockIdx.x * 128 + threadIdx.x) * 4;
-  if (k >= C4) return;
+  __shared__ float4 red[3][9][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = (blockIdx.x * 32 + tx) * 4;
+  const bool active = k < C4;
   const int j0 = blockIdx.y * jchunk, j1 = min(C, j0 + jchunk);
   float4 sv[NB], s1[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
-    sv[n] = n < nb ? __ldg(reinterpret_cast<const float4*>(s + (long long)n * C4 + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sv[n] = (active && n < nb) ? __ldg(reinterpret_cast<const float4*>(s + (long long)n * C4 + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
     s1[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const float4 bg = __ldg(reinterpret_cast<const float4*>(bgrn + k));
+  const float4 bg = active ? __ldg(reinterpret_cast<const float4*>(bgrn + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 dbg = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long per = (long long)C * ldp;
+  if (active) {
 #pragma unroll 2
-  for (int j = j0; j < j1; ++j) {
-    const float4 w = __ldg(reinterpret_cast<const float4*>(W2 + (long long)j * C4 + k));
-    float4 pv[NB];
-#pragma unroll
-    for (int n = 0; n < NB; ++n)
-      pv[n] = n < nb ? __ldg(reinterpret_cast<const float4*>(P + n * per + (long long)j * ldp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float d = 0.f;
-    if (db2_in != nullptr) {
-      d = db2_in[j];
-    } else {
+    for (int j = j0 + ty; j < j1; j += 4) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W2 + (long long)j * C4 + k));
+      float4 pv[NB];
 #pragma unroll
       for (int n = 0; n < NB; ++n)
-        if (n < nb) d += __ldg(P + n * per + (long long)j * ldp + C4);
-      if (k == 0) db2_out[j] = d;
-    }
-    float4 acc = make_float4(bg.x * d, bg.y * d, bg.z * d, bg.w * d);
-    dbg.x = fmaf(w.x, d, dbg.x); dbg.y = fmaf(w.y, d, dbg.y); dbg.z = fmaf(w.z, d, dbg.z); dbg.w = fmaf(w.w, d, dbg.w);
+        pv[n] = n < nb ? __ldg(reinterpret_cast<const float4*>(P + n * per + (long long)j * ldp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float d = 0.f;
+      if (db2_in != nullptr) {
+        d = db2_in[j];
+      } else {
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-      acc.x = fmaf(sv[n].x, pv[n].x, acc.x); acc.y = fmaf(sv[n].y, pv[n].y, acc.y);
-      acc.z = fmaf(sv[n].z, pv[n].z, acc.z); acc.w = fmaf(sv[n].w, pv[n].w, acc.w);
-      s1[n].x = fmaf(w.x, pv[n].x, s1[n].x); s1[n].y = fmaf(w.y, pv[n].y, s1[n].y);
-      s1[n].z = fmaf(w.z, pv[n].z, s1[n].z); s1[n].w = fmaf(w.w, pv[n].w, s1[n].w);
+        for (int n = 0; n < NB; ++n)
+          if (n < nb) d += __ldg(P + n * per + (long long)j * ldp + C4);
+        if (k == 0) db2_out[j] = d;
+      }
+      float4 acc = make_float4(bg.x * d, bg.y * d, bg.z * d, bg.w * d);
+      dbg.x = fmaf(w.x, d, dbg.x); dbg.y = fmaf(w.y, d, dbg.y); dbg.z = fmaf(w.z, d, dbg.z); dbg.w = fmaf(w.w, d, dbg.w);
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        acc.x = fmaf(sv[n].x, pv[n].x, acc.x); acc.y = fmaf(sv[n].y, pv[n].y, acc.y);
+        acc.z = fmaf(sv[n].z, pv[n].z, acc.z); acc.w = fmaf(sv[n].w, pv[n].w, acc.w);
+        s1[n].x = fmaf(w.x, pv[n].x, s1[n].x); s1[n].y = fmaf(w.y, pv[n].y, s1[n].y);
+        s1[n].z = fmaf(w.z, pv[n].z, s1[n].z); s1[n].w = fmaf(w.w, pv[n].w, s1[n].w);
+      }
+      *reinterpret_cast<float4*>(dW2 + (long long)j * C4 + k) = acc;
     }
-    *reinterpret_cast<float4*>(dW2 + (long long)j * C4 + k) = acc;
   }
+  if (ty > 0) {
 #pragma unroll
-  for (int n = 0; n < NB; ++n)
-    if (n < nb) {
-      float* o = S1 + (long long)n * C4 + k;
-      atomicAdd(o, s1[n].x); atomicAdd(o + 1, s1[n].y); atomicAdd(o + 2, s1[n].z); atomicAdd(o + 3, s1[n].w);
+    for (int n = 0; n < NB; ++n) red[ty - 1][n][tx] = s1[n];
+    red[ty - 1][8][tx] = dbg;
+  }
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        const float4 v = red[g][n][tx];
+        s1[n].x += v.x; s1[n].y += v.y; s1[n].z += v.z; s1[n].w += v.w;
+      }
+      const float4 v = red[g][8][tx];
+      dbg.x += v.x; dbg.y += v.y; dbg.z += v.z; dbg.w += v.w;
     }
-  atomicAdd(dbgrn + k, dbg.x); atomicAdd(dbgrn + k + 1, dbg.y); atomicAdd(dbgrn + k + 2, dbg.z); atomicAdd(dbgrn + k + 3, dbg.w);
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+      if (n < nb) {
+        float* o = S1 + (long long)n * C4 + k;
+        atomicAdd(o, s1[n].x); atomicAdd(o + 1, s1[n].y); atomicAdd(o + 2, s1[n].z); atomicAdd(o + 3, s1[n].w);
+      }
+    atomicAdd(dbgrn + k, dbg.x); atomicAdd(dbgrn + k + 1, dbg.y); atomicAdd(dbgrn + k + 2, dbg.z); atomicAdd(dbgrn + k + 3, dbg.w);
+  }
 }
 
 static int rows_per_block_for(long long rows, int col_blocks, int samples) {
@@ -1339,9 +1363,10 @@ extern "C" int vb200_grn_wgrad_finish_ld(const float* P, int64_t ldp, const floa
   if (nb <= 8 && C4 % 4 == 0 && ldp % 4 == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(W2) & 15) == 0 && (reinterpret_cast<uintptr_t>(dW2) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(s) & 15) == 0 && (reinterpret_cast<uintptr_t>(bgrn) & 15) == 0) {
-    const int colb4 = (C4 / 4 + 127) / 128;
+    const int colb4 = (C4 / 4 + 31) / 32;  // 32 column quads per block, its four warps take rows j0 + {0..3} + 4 i
     int jc = (C * colb4 + 148 * 4 - 1) / (148 * 4);
-    if (jc < 4) jc = 4;
+    jc = (jc + 3) / 4 * 4;
+    if (jc < 16) jc = 16;
     dim3 grid4(colb4, (C + jc - 1) / jc);
     grn_wgrad_finish4_kernel<<<grid4, 128, 0, st>>>(P, W2, s, bgrn, db2_in, dW2, S1, dbgrn, db2_out, nb, C, C4, ldp, jc);
     return check_launch("vb200_grn_wgrad_finish");

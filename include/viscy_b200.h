@@ -256,6 +256,12 @@ int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t s
 int vb200_pack_multi(const void* table, int n_items, int64_t total_blocks, int dtype, vb200_stream_t stream);
 /* fp32 [R,Cc] -> 16-bit (weight packing); transpose != 0 writes [Cc,R] */
 int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t Cc, int transpose, int dtype, vb200_stream_t stream);
+/* nn.Conv3d weight [Co, Ci, KD, KH, KW] fp32 -> 16-bit GEMM rows (VM/unet/unet3d.py, unet25d.py, conv_block_3d.py convs):
+ * flipped == 0: out [cout_pad][(kd, kh, kw, cin_pad)] (forward / weight-gradient order);
+ * flipped != 0: out [cin_pad][(kd, kh, kw, cout_pad)] of the spatially flipped filter (the data gradient's filter).
+ * Padding rows / channels are zero-filled.  Up to 27 taps. */
+int vb200_conv_weight_rows(const float* w, void* out, int Co, int Ci, int KD, int KH, int KW, int cin_pad, int cout_pad,
+                           int flipped, int dtype, vb200_stream_t stream);
 
 /* ---- 3-D U-Net family: UNet3DBase / Unet3d (VM/unet/unet3d_base.py:145-198, VM/unet/blocks.py:88-113) ---- */
 /* model boundary: x (N,C,S) [x_dtype 0 bf16 | 1 fp16 | 2 fp32] -> y (N,S,Cpad) 16-bit channels-last, zero channel padding */

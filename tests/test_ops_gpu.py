@@ -465,3 +465,20 @@ def test_weight_packs_one_launch(cuda, dtype):
         C = w.shape[0]
         assert torch.equal(packs.get(w, "dw"), w.reshape(C, 49).t().contiguous())
         assert torch.equal(packs.get(w, "dwf"), w.flip(2, 3).reshape(C, 49).t().contiguous())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("Co,Ci,ks", [(32, 3, (3, 3, 3)), (64, 32, (3, 3, 3)), (20, 36, (1, 3, 3)), (8, 8, (1, 1, 1)),
+                                       (40, 72, (2, 2, 2)), (256, 128, (3, 3, 3))])
+def test_conv_weight_rows_matches_torch_layout(cuda, Co, Ci, ks, dtype):
+    """One-launch Conv3d weight packing == permute / pad / (flip) / cast of the torch formulation, padding zero-filled."""
+    from viscy_b200 import functional as F, ops
+    g = torch.Generator(device=cuda).manual_seed(3)
+    w = torch.randn((Co, Ci, *ks), device=cuda, generator=g)
+    cp, cop = -(-Ci // 8) * 8, -(-Co // 8) * 8
+    got = ops.conv_weight_rows(w, cp, cop, dtype)
+    ref = F._conv_weight_rows(w, cp, cop).to(dtype)
+    assert got.shape == ref.shape and torch.equal(got, ref)
+    gotf = ops.conv_weight_rows(w, cp, cop, dtype, flipped=True)
+    reff = F._conv_weight_rows_flipped(w, cp, cop).to(dtype)
+    assert gotf.shape == reff.shape and torch.equal(gotf, reff)

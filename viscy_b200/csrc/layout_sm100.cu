@@ -402,6 +402,61 @@ extern "C" int vb200_cast_pack(const float* src, void* dst, int64_t R, int64_t C
   return check_launch("vb200_cast_pack");
 }
 
+// nn.Conv3d weight [Co, Ci, KD, KH, KW] fp32 -> 16-bit GEMM rows in one launch (was permute + pad + contiguous + cast,
+// plus a flip for the data gradient: 3-4 ATen launches per convolution and step).
+//   flipped == 0: out [cout_pad][(kd, kh, kw, cin_pad)]            = W[co][ci][kd][kh][kw]       (forward / wgrad order)
+//   flipped != 0: out [cin_pad][(kd, kh, kw, cout_pad)]            = W[co][ci][KD-1-kd][KH-1-kh][KW-1-kw]  (data gradient)
+// One block per (output row, chunk of 32 inner channels): the 32 x T source floats are read in runs of T (contiguous per
+// channel pair), transposed through shared memory, and written as 64-byte runs per tap; padding rows / channels are zeros.
+namespace vb {
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+conv_weight_rows_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Co, int Ci, int KD, int KH, int KW,
+                        int cin_pad, int cout_pad, int flipped) {
+  __shared__ float tile[32][28];
+  const int T = KD * KH * KW;
+  const int n_outer = flipped ? Ci : Co, n_inner = flipped ? Co : Ci, inner_pad = flipped ? cout_pad : cin_pad;
+  const int o = blockIdx.x, i0 = blockIdx.y * 32;
+  const long long so = flipped ? (long long)T : (long long)Ci * T, si = flipped ? (long long)Ci * T : (long long)T;
+  for (int idx = threadIdx.x; idx < 32 * T; idx += 128) {
+    const int i = idx / T, t = idx - i * T;
+    float v = 0.f;
+    if (o < n_outer && i0 + i < n_inner) v = __ldg(w + o * so + (i0 + i) * si + t);
+    tile[i][t] = v;
+  }
+  __syncthreads();
+  using H = typename H16<BF16>::T;
+  H* orow = reinterpret_cast<H*>(out) + (long long)o * T * inner_pad;
+  for (int idx = threadIdx.x; idx < 32 * T; idx += 128) {
+    const int t = idx >> 5, i = idx & 31;
+    if (i0 + i >= inner_pad) continue;
+    int ts = t;
+    if (flipped) {
+      const int kw = t % KW, kh = (t / KW) % KH, kd = t / (KW * KH);
+      ts = ((KD - 1 - kd) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw);
+    }
+    orow[(long long)t * inner_pad + i0 + i] = H16<BF16>::from_f(tile[i][ts]);
+  }
+}
+}  // namespace vb
+
+extern "C" int vb200_conv_weight_rows(const float* w, void* out, int Co, int Ci, int KD, int KH, int KW, int cin_pad,
+                                      int cout_pad, int flipped, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(w && out, "null pointer");
+  VB_REQUIRE(Co > 0 && Ci > 0 && cin_pad >= Ci && cout_pad >= Co, "padded channel counts (%d, %d) below (%d, %d)", cin_pad, cout_pad, Ci, Co);
+  VB_SUPPORTED(KD * KH * KW <= 27 && KD > 0 && KH > 0 && KW > 0, "up to 27 taps (%d x %d x %d)", KD, KH, KW);
+  const int rows = flipped ? cin_pad : cout_pad, inner_pad = flipped ? cout_pad : cin_pad;
+  dim3 grid(rows, (inner_pad + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_BF16)
+    vb::conv_weight_rows_kernel<true><<<grid, 128, 0, st>>>(w, (uint16_t*)out, Co, Ci, KD, KH, KW, cin_pad, cout_pad, flipped);
+  else if (dtype == VB200_FP16)
+    vb::conv_weight_rows_kernel<false><<<grid, 128, 0, st>>>(w, (uint16_t*)out, Co, Ci, KD, KH, KW, cin_pad, cout_pad, flipped);
+  else
+    return fail(VB200_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return check_launch("vb200_conv_weight_rows");
+}
+
 extern "C" int vb200_dw_pack(const float* w, float* wt, float* wtf, int C, vb200_stream_t stream) {
   VB_REQUIRE(w && wt && wtf, "null pointer");
   dw_pack_kernel<<<blocks_for(49LL * C), 256, 0, (cudaStream_t)stream>>>(w, wt, wtf, C);

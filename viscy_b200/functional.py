@@ -571,7 +571,7 @@ class HeadFn(Function):
                 dconv_w = ops.conv3d_k3_wgrad(u, dz5, (0, 1, 1))[:, :Cc]
             if Cmid % 32 == 0 and ops.conv3d_igemm_supported(tuple(dz5.shape), 8, (3, 3, 3), (2, 1, 1)):
                 # data gradient on the patch-form implicit GEMM (filter resident in shared memory)
-                du = ops.conv3d_igemm(dz5, ops.cast_pack(_conv_weight_rows_flipped(conv_w, 8, Cmid), dz.dtype), None,
+                du = ops.conv3d_igemm(dz5, ops.conv_weight_rows(conv_w, 8, Cmid, dz.dtype, flipped=True), None,
                                       (3, 3, 3), (2, 1, 1))
             else:
                 wpt = ops.conv3d_pack_weights(conv_w, dz.dtype, Cmid, 16, transpose_flip=True)
@@ -759,19 +759,20 @@ class Conv3dFn(Function):
         geom = ops.conv3d_geom((N, D, H, W, Cp), ks, stride, padding)
         pointwise = ks == (1, 1, 1) and stride == (1, 1, 1) and padding == (0, 0, 0)
         igemm = not pointwise and ops.conv3d_igemm_supported((N, D, H, W, Cp), Cop, ks, padding, stride=stride)
-        wk = _conv_weight_rows(w.detach(), Cp, Cop)
+        w16 = ops.conv_weight_rows(w, Cp, Cop, x.dtype) if w.numel() // (Co * w.shape[1]) <= 27 else \
+            ops.cast_pack(_conv_weight_rows(w.detach(), Cp, Cop), x.dtype)
         bias = None
         if b is not None:
             bias = b.detach() if Cop == Co else torch.nn.functional.pad(b.detach(), (0, Cop - Co))
         if igemm:
-            out = ops.conv3d_igemm(x, ops.cast_pack(wk, x.dtype), bias, ks, padding, stride=stride)
+            out = ops.conv3d_igemm(x, w16, bias, ks, padding, stride=stride)
         elif _small_k3(ks, stride, Cp, Cop):
             # model-boundary convs (3 -> 32 channels): the 130-voxel-line kernel, taps as views of resident lines
             cpad = 16 if Cop <= 16 else 32
             out = ops.conv3d_k3(x, ops.conv3d_pack_weights(w, x.dtype, Cp, cpad), bias, padding, cpad, Cop)
         else:
             col = x.view(-1, Cp) if pointwise else ops.im2col3d(x, geom)
-            out = ops.gemm(col, ops.cast_pack(wk, x.dtype), bias=bias)
+            out = ops.gemm(col, w16, bias=bias)
         ctx.save_for_backward(x, w)
         ctx.meta = (geom, pointwise, stride, Cop, b is not None, padding)
         return out.view(N, geom[14], geom[15], geom[16], Cop)
@@ -792,8 +793,7 @@ class Conv3dFn(Function):
         # data gradient at stride 1: the conv of dout with the flipped, transposed filter and padding k-1-p
         bpad = tuple(k - 1 - p for k, p in zip(ks, padding))
         if need_dx and unit and ops.conv3d_igemm_supported(tuple(dout.shape), Cp, ks, bpad):
-            wf = _conv_weight_rows_flipped(w, Cp, Cop)
-            dx = ops.conv3d_igemm(dout, ops.cast_pack(wf, x.dtype), None, ks, bpad)
+            dx = ops.conv3d_igemm(dout, ops.conv_weight_rows(w, Cp, Cop, x.dtype, flipped=True), None, ks, bpad)
             need_dx = False
         if unit and Cp <= 128 and ops.conv3d_wgrad_kh3_supported((N, D, H, W, Cp), Cop, ks, padding):
             dwk = ops.conv3d_wgrad_kh3(x, dout, ks, padding)  # few channels: patch form, kh taps share one haloed box

@@ -229,6 +229,19 @@ def cast_pack(w: torch.Tensor, dtype: torch.dtype, transpose: bool = False) -> t
     return out
 
 
+def conv_weight_rows(w: torch.Tensor, cin_pad: int, cout_pad: int, dtype: torch.dtype, flipped: bool = False) -> torch.Tensor:
+    """nn.Conv3d weight [Co,Ci,kd,kh,kw] fp32 -> 16-bit [cout_pad, (kd,kh,kw,cin_pad)], or with flipped=True the data
+    gradient's filter [cin_pad, (kd,kh,kw flipped, cout_pad)]; zero padded; one launch."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():  # e.g. the flipped / transposed view a transposed conv passes
+        w = w.float().contiguous()
+    Co, Ci, KD, KH, KW = w.shape
+    rows, inner = (cin_pad, cout_pad) if flipped else (cout_pad, cin_pad)
+    out = torch.empty((rows, KD * KH * KW * inner), device=w.device, dtype=dtype)
+    _call("vb200_conv_weight_rows", _p(w), _p(out), Co, Ci, KD, KH, KW, cin_pad, cout_pad, int(flipped), L.dtype_code(dtype))
+    return out
+
+
 class Arena:
     """One zero-filled fp32 allocation handed out in slices (accumulators that kernels add into)."""
 

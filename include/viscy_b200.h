@@ -278,6 +278,18 @@ int vb200_bn_bwd_reduce(const void* dy, const void* x, const void* y, const floa
 int vb200_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* mean, const float* rstd, const float* g,
                        const float* m1, const float* m2, void* dx, int64_t M, int C, int relu, int dtype,
                        vb200_stream_t stream);
+/* the same with the raw operands: g = gamma * rstd, m1 = s1 * inv_m, m2 = s2 * inv_m formed in the kernel (s1 / s2 = the
+ * column sums of vb200_bn_bwd_reduce, inv_m = 1 / rows in training mode, 0 in eval mode) */
+int vb200_bn_bwd_apply_raw(const void* dy, const void* x, const void* y, const float* mean, const float* rstd, const float* gamma,
+                           const float* s1, const float* s2, float inv_m, void* dx, int64_t M, int C, int relu, int dtype,
+                           vb200_stream_t stream);
+/* BatchNorm3d statistics -> apply-pass operands (nn.BatchNorm3d of VM/unet/unet3d.py / conv_block_3d.py, training and eval):
+ * sums [2][Cc] = column sums of (x - pivot) and (x - pivot)^2 over M rows (null: eval mode, running statistics);
+ * scale = weight * rstd, shift = bias - mean * scale, mean, rstd (fp32 [Cc]; channels >= Cn are padding: scale = shift = 0);
+ * momentum >= 0 updates run_mean / run_var in place (unbiased variance), as torch does in training mode */
+int vb200_bn_finalize(const float* sums, const float* pivot, const float* weight, const float* bias, float* run_mean,
+                      float* run_var, int Cn, int Cc, double M, float eps, float momentum, float* scale, float* shift,
+                      float* mean, float* rstd, vb200_stream_t stream);
 /* torch.cat([a, b], 1) on channels-last rows (inverse != 0: split out back into a and b) */
 int vb200_cat2(void* a, void* b, void* out, int64_t M, int Ca, int Cb, int inverse, vb200_stream_t stream);
 /* y = x (+ other) (+ bias[c]) on rows [M,C] */

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ g,
                     const float* __restrict__ m1, const float* __restrict__ m2, uint4* __restrict__ dx, int C8,
-                    int relu, long long total8) {
+                    int relu, long long total8, int raw, float inv_m) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int c0 = (int)(i % C8) * 8;
@@ -130,8 +130,12 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, c
     }
     const int c = c0 + 2 * k;
     const float xa = (xv.x - __ldg(mean + c)) * __ldg(rstd + c), xb = (xv.y - __ldg(mean + c + 1)) * __ldg(rstd + c + 1);
-    o[k] = H16<BF16>::pack(__ldg(g + c) * (d.x - __ldg(m1 + c) - xa * __ldg(m2 + c)),
-                           __ldg(g + c + 1) * (d.y - __ldg(m1 + c + 1) - xb * __ldg(m2 + c + 1)));
+    // raw: g = gamma, m1 / m2 = the column sums of the reduce pass (scaled here instead of by three tiny torch launches)
+    const float ga = raw ? __ldg(g + c) * __ldg(rstd + c) : __ldg(g + c);
+    const float gb = raw ? __ldg(g + c + 1) * __ldg(rstd + c + 1) : __ldg(g + c + 1);
+    const float sc = raw ? inv_m : 1.f;
+    o[k] = H16<BF16>::pack(ga * (d.x - __ldg(m1 + c) * sc - xa * (__ldg(m2 + c) * sc)),
+                           gb * (d.y - __ldg(m1 + c + 1) * sc - xb * (__ldg(m2 + c + 1) * sc)));
   }
   dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -255,8 +259,67 @@ extern "C" int vb200_bn_bwd_apply(const void* dy, const void* x, const void* y, 
   VB_SUPPORTED(C % 8 == 0, "C (%d) %% 8", C);
   const long long total8 = M * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  DT_SWITCH(dtype, bn_bwd_apply_kernel<BF><<<nblocks(total8), 256, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y, mean, rstd, g, m1, m2, (uint4*)dx, C / 8, relu, total8));
+  DT_SWITCH(dtype, bn_bwd_apply_kernel<BF><<<nblocks(total8), 256, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y, mean, rstd, g, m1, m2, (uint4*)dx, C / 8, relu, total8, 0, 1.f));
   return check_launch("vb200_bn_bwd_apply");
+}
+
+extern "C" int vb200_bn_bwd_apply_raw(const void* dy, const void* x, const void* y, const float* mean, const float* rstd,
+                                      const float* gamma, const float* s1, const float* s2, float inv_m, void* dx, int64_t M,
+                                      int C, int relu, int dtype, vb200_stream_t stream) {
+  VB_REQUIRE(dy && x && mean && rstd && gamma && s1 && s2 && dx && (y || !relu), "null pointer");
+  VB_SUPPORTED(C % 8 == 0, "C (%d) %% 8", C);
+  const long long total8 = M * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  DT_SWITCH(dtype, bn_bwd_apply_kernel<BF><<<nblocks(total8), 256, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y, mean, rstd, gamma, s1, s2, (uint4*)dx, C / 8, relu, total8, 1, inv_m));
+  return check_launch("vb200_bn_bwd_apply_raw");
+}
+
+// BatchNorm statistics -> everything the apply pass and the backward need, plus the running-statistics update, in one
+// launch (was ~14 torch launches on [C]-sized vectors per layer and step).  sums = [2][Cc] column sums of (x - pivot) and
+// (x - pivot)^2 (training) or null (eval: running statistics).  weight / bias / run_* have Cn entries, outputs Cc
+// (channel-padded rows: padded channels get scale = shift = 0).  momentum < 0: no running-statistics update.
+namespace vb {
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ pivot,
+                                   const float* __restrict__ weight, const float* __restrict__ bias, float* run_mean,
+                                   float* run_var, int Cn, int Cc, float inv_m, float unbias, float eps, float momentum,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cc) return;
+  const bool real = c < Cn;
+  float mean, var;
+  if (sums != nullptr) {
+    const float a = sums[c] * inv_m, q = sums[Cc + c] * inv_m;
+    var = fmaxf(q - a * a, 0.f);
+    mean = pivot != nullptr ? a + pivot[c] : a;
+    if (real && momentum >= 0.f && run_mean != nullptr) {
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (var * unbias);
+    }
+  } else {
+    mean = real ? run_mean[c] : 0.f;
+    var = real ? run_var[c] : 1.f;
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float sc = real ? weight[c] * rstd : 0.f;
+  scale[c] = sc;
+  shift[c] = real ? bias[c] - mean * sc : 0.f;
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
+}
+}  // namespace vb
+
+extern "C" int vb200_bn_finalize(const float* sums, const float* pivot, const float* weight, const float* bias,
+                                 float* run_mean, float* run_var, int Cn, int Cc, double M, float eps, float momentum,
+                                 float* scale, float* shift, float* mean, float* rstd, vb200_stream_t stream) {
+  VB_REQUIRE(weight && bias && scale && shift && mean && rstd, "null pointer");
+  VB_REQUIRE(sums != nullptr || (run_mean != nullptr && run_var != nullptr), "eval mode needs running statistics");
+  VB_REQUIRE(Cn > 0 && Cc >= Cn && M >= 1.0, "Cn %d Cc %d M %g", Cn, Cc, M);
+  const float unbias = (float)(M / (M > 1.0 ? M - 1.0 : 1.0));
+  vb::bn_finalize_kernel<<<(Cc + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, pivot, weight, bias, run_mean, run_var, Cn, Cc,
+                                                                         (float)(1.0 / M), unbias, eps, momentum, scale, shift,
+                                                                         mean, rstd);
+  return check_launch("vb200_bn_finalize");
 }
 
 extern "C" int vb200_cat2(void* a, void* b, void* out, int64_t M, int Ca, int Cb, int inverse, vb200_stream_t stream) {

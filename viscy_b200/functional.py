@@ -977,57 +977,51 @@ def conv_transpose3d_cl(x, conv):
 
 
 class BatchNormActFn(Function):
-    """nn.BatchNorm3d (+ ReLU) on channels-last rows; batch statistics from the vectorised column reductions."""
+    """nn.BatchNorm3d (+ ReLU) on channels-last rows: y = act(x * scale + shift) with the operands `batchnorm_act_cl`
+    prepared (statistics, running-statistics update and the affine coefficients come from one column-reduction pass and
+    one finalize launch); backward = the full batch-norm backward (through the batch statistics in training mode)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, run_mean, run_var, eps, training, relu):
-        Cc = x.shape[-1]
-        M = x.numel() // Cc
-        if training:
-            # sums and sums of squares in one pass, taken about the running mean (a per-channel pivot close to the batch
-            # mean): E[(x-p)^2] - E[x-p]^2 does not cancel catastrophically when |mean| >> std
-            pivot = run_mean.detach().contiguous() if run_mean is not None else None
-            st = ops.colreduce(x.view(1, M, Cc), 2, pivot=pivot).view(2, Cc) / M
-            var = (st[1] - st[0] * st[0]).clamp_min_(0.0)
-            mean = st[0] if pivot is None else st[0] + pivot
-        else:
-            mean, var = run_mean, run_var
-        rstd = torch.rsqrt(var + eps)
-        scale = (weight.detach() * rstd).contiguous()
-        shift = (bias.detach() - mean * scale).contiguous()
+    def forward(ctx, x, weight, bias, scale, shift, mean, rstd, training, relu):
         y = ops.affine_act(x, scale, shift, relu)
-        ctx.save_for_backward(x, y, weight, mean.contiguous(), rstd.contiguous())
+        ctx.save_for_backward(x, y, weight, mean, rstd)
         ctx.flags = (training, relu)
-        var_unb = var * (M / max(M - 1, 1))
-        ctx.mark_non_differentiable(mean, var_unb)
-        return y, mean, var_unb
+        return y
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy, _m, _v):
+    def backward(ctx, dy):
         x, y, weight, mean, rstd = ctx.saved_tensors
         training, relu = ctx.flags
-        dx, dg, db = ops.bn_bwd(dy.contiguous(), x, y, mean, rstd, weight, relu, training)
-        return dx, dg, db, None, None, None, None, None
+        Cc = x.shape[-1]
+        gamma = weight.detach()
+        if gamma.numel() != Cc:  # channel-padded rows
+            gamma = torch.nn.functional.pad(gamma, (0, Cc - gamma.numel()))
+        dx, dg, db = ops.bn_bwd(dy.contiguous(), x, y, mean, rstd, gamma, relu, training)
+        n = weight.numel()
+        return dx, dg[:n], db[:n], None, None, None, None, None, None
 
 
 def batchnorm_act_cl(x, bn, relu):
     training = bn.training or bn.running_mean is None
     Cc, Cn = x.shape[-1], bn.num_features
-    weight, bias, rm, rv = bn.weight, bn.bias, bn.running_mean, bn.running_var
-    if Cn != Cc:  # channel-padded rows (e.g. a 1-channel terminal block): padded channels are all-zero and stay zero
-        pad = (0, Cc - Cn)
-        weight, bias = torch.nn.functional.pad(weight, pad), torch.nn.functional.pad(bias, pad)
-        if rm is not None:
-            rm, rv = torch.nn.functional.pad(rm, pad), torch.nn.functional.pad(rv, pad, value=1.0)
-    y, mean, var_unb = BatchNormActFn.apply(x, weight, bias, rm, rv, bn.eps, training, relu)
-    if bn.training and bn.track_running_stats and bn.running_mean is not None:
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
-            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-            bn.running_mean.mul_(1 - mom).add_(mean[:Cn], alpha=mom)
-            bn.running_var.mul_(1 - mom).add_(var_unb[:Cn], alpha=mom)
-    return y
+    M = x.numel() // Cc
+    rm, rv = bn.running_mean, bn.running_var
+    with torch.no_grad():
+        sums = pivot = None
+        momentum = -1.0
+        if training:
+            # sums and sums of squares in one pass, taken about the running mean (a per-channel pivot close to the batch
+            # mean): E[(x-p)^2] - E[x-p]^2 does not cancel catastrophically when |mean| >> std
+            if rm is not None:
+                pivot = rm if Cn == Cc else torch.nn.functional.pad(rm, (0, Cc - Cn))
+                pivot = pivot.contiguous()
+            sums = ops.colreduce(x.view(1, M, Cc), 2, pivot=pivot)
+            if bn.training and bn.track_running_stats and rm is not None:
+                bn.num_batches_tracked += 1
+                momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        scale, shift, mean, rstd = ops.bn_finalize(sums, pivot, bn.weight, bn.bias, rm, rv, Cc, M, bn.eps, momentum)
+    return BatchNormActFn.apply(x, bn.weight, bn.bias, scale, shift, mean, rstd, training, relu)
 
 
 class GroupNormActFn(Function):

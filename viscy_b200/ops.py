@@ -866,12 +866,22 @@ def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training):
     s = zeros((2, Cc), x.device)
     _call("vb200_bn_bwd_reduce", _p(_act(dy, "dy")), _p(x), _p(y), _p(mean), _p(rstd), _p(s[0]), _p(s[1]),
           C.c_int64(M), Cc, int(relu), dt)
-    g = (gamma * rstd).contiguous()
-    m = (s / M) if training else torch.zeros_like(s)
     dx = torch.empty_like(x)
-    _call("vb200_bn_bwd_apply", _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(m[0]), _p(m[1]), _p(dx),
-          C.c_int64(M), Cc, int(relu), dt)
+    _call("vb200_bn_bwd_apply_raw", _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(_f32(gamma.detach(), "gamma")), _p(s[0]), _p(s[1]),
+          C.c_float(1.0 / M if training else 0.0), _p(dx), C.c_int64(M), Cc, int(relu), dt)
     return dx, s[1], s[0]
+
+
+def bn_finalize(sums, pivot, weight, bias, run_mean, run_var, Cc, M, eps, momentum):
+    """BatchNorm statistics -> (scale, shift, mean, rstd) fp32 [Cc] in one launch; updates run_mean / run_var in place when
+    momentum >= 0 (training).  sums=None: eval mode (running statistics).  weight / bias / run_* may be shorter than Cc
+    (channel-padded rows)."""
+    dev = weight.device
+    out = torch.empty((4, Cc), device=dev, dtype=torch.float32)
+    _call("vb200_bn_finalize", _p(sums), _p(pivot), _p(_f32(weight.detach(), "weight")), _p(_f32(bias.detach(), "bias")),
+          _p(run_mean), _p(run_var), weight.numel(), Cc, C.c_double(float(M)), C.c_float(eps), C.c_float(momentum),
+          _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]))
+    return out[0], out[1], out[2], out[3]
 
 
 ACT_CODES = {"none": 0, "linear": 0, "relu": 1, "silu": 2, "leakyrelu": 3, "elu": 4, "selu": 5}

@@ -11,7 +11,9 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 m = Unet3d(3, 3, 4, 32).to(dev)
-opt = torch.optim.AdamW(m.parameters(), lr=1e-3, fused=True)
+from viscy_b200.optim import AdamW  # noqa: E402
+
+opt = AdamW(m.parameters(), lr=1e-3)
 x = torch.randn(1, 3, S, S, S, device=dev)
 y = torch.randn(1, 3, S, S, S, device=dev)
 

@@ -243,6 +243,31 @@ def secondary_evidence(dev, tf_burst):
                                             "launches_per_step": launches}
     del m, opt, a, p
     torch.cuda.empty_cache()
+    # BASELINE configs[0] (the reference's CPU-runnable case: Unet25d 1->1 channel, 5 x 128 x 128 patches) on the GPU path:
+    # at the reference batch of 2 the step is launch-latency bound, so a training-sized batch of 32 is timed beside it
+    try:
+        from viscy_b200 import Unet25d
+        for tag, bs in (("config1_unet25d_5x128x128_bf16_b2", 2), ("config1_unet25d_5x128x128_bf16_b32", 32)):
+            torch.manual_seed(0)
+            m = Unet25d(in_channels=1, out_channels=1, in_stack_depth=5).to(dev)
+            opt = _adamw(m.parameters(), 1e-3)
+            x = torch.randn((bs, 1, 5, 128, 128), device=dev)
+            y = torch.randn((bs, 1, 1, 128, 128), device=dev)
+
+            def step1(xd, yd, m=m, opt=opt):
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = torch.nn.functional.mse_loss(m(xd).float(), yd)
+                loss.backward()
+                opt.step()
+                return loss
+
+            ms, mode, launches = _graphed_ms(step1, (x, y), 10, 3)
+            out[tag] = {"ms_per_step": ms, "samples_per_s": bs * 1e3 / ms, "mode": mode, "launches_per_step": launches}
+            del m, opt, x, y
+            torch.cuda.empty_cache()
+    except Exception as e:  # evidence block only: never take the headline down with it
+        out["config1_unet25d"] = {"error": repr(e)[:200]}
     # the same UNeXt2 step with the recipes' MixedLoss (0.5 L1 + 0.5 MS-DSSIM, VU/losses/mixed_loss.py) instead of MSE, and
     # one FCMAE (VSCyto3D-style: dense encoder, conv head) fine-tuning step at the same input shape
     try:

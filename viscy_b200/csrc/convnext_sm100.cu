@@ -383,8 +383,52 @@ layernorm_bwd_fused_kernel(const uint4* __restrict__ dy, const uint4* __restrict
 #pragma unroll
     for (int k = 0; k < 8; ++k) pg[v][k] = pb[v][k] = 0.f;
   const float inv_c = 1.0f / (float)C;
-  for (long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * warps) {
-    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+  // Rows of one warp are a serial chain (load -> two warp reductions -> store): with <= 2 vectors per lane the next row's
+  // operands are requested before the current row is reduced, so its HBM latency runs under the math (PRE); with 3 vectors
+  // the register file has no room for a second row.
+  constexpr bool PRE = NV <= 2;
+  const long long rstride = (long long)gridDim.x * warps;
+  long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  uint4 nd[PRE ? NV : 1], nx[PRE ? NV : 1];
+  float nmu = 0.f, nrs = 0.f;
+  if constexpr (PRE) {
+    if (row < M) {
+      nmu = __ldg(mean + row);
+      nrs = __ldg(rstd + row);
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (lane + 32 * v < C8) {
+          nd[v] = __ldg(dy + row * C8 + lane + 32 * v);
+          nx[v] = __ldg(x + row * C8 + lane + 32 * v);
+        }
+    }
+  }
+  for (; row < M; row += rstride) {
+    float mu, rs;
+    uint4 cd[NV], cx[NV];
+    if constexpr (PRE) {
+      mu = nmu;
+      rs = nrs;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        cd[v] = nd[v];
+        cx[v] = nx[v];
+      }
+      const long long rn = row + rstride;
+      if (rn < M) {
+        nmu = __ldg(mean + rn);
+        nrs = __ldg(rstd + rn);
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (lane + 32 * v < C8) {
+            nd[v] = __ldg(dy + rn * C8 + lane + 32 * v);
+            nx[v] = __ldg(x + rn * C8 + lane + 32 * v);
+          }
+      }
+    } else {
+      mu = __ldg(mean + row);
+      rs = __ldg(rstd + row);
+    }
     float g[NV][8], xh[NV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -393,7 +437,7 @@ layernorm_bwd_fused_kernel(const uint4* __restrict__ dy, const uint4* __restrict
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[v][k] = xh[v][k] = 0.f;
       if (i < C8) {
-        const uint4 qd = __ldg(dy + row * C8 + i), qx = __ldg(x + row * C8 + i);
+        const uint4 qd = PRE ? cd[v] : __ldg(dy + row * C8 + i), qx = PRE ? cx[v] : __ldg(x + row * C8 + i);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i);
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i + 1);
         const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};

@@ -38,3 +38,18 @@ def test_chunk_table_covers_every_element_once():
         cs = plan_chunks[start[i]:start[i + 1]]
         assert [c[1] for c in cs] == list(range(0, n, optim.CHUNK)) and sum(c[2] for c in cs) == n
         assert all(c[0] == i and 0 < c[2] <= optim.CHUNK for c in cs)
+
+
+def test_flat_gradient_slots_are_16_byte_aligned():
+    """parallel._Bucket pads every gradient's slot in the flat buffer to 4 elements, so the views handed back as `.grad`
+    keep the one-launch AdamW on its float4 path even behind tensors with odd element counts (a 2-element bias)."""
+    from viscy_b200.parallel import _Bucket, _slot
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((2,), (3, 5), (8,), (1,), (7, 7))]
+    flat = torch.zeros(sum(_slot(p) for p in params))
+    b = _Bucket(params, flat)
+    assert [_slot(p) for p in params] == [4, 16, 8, 4, 52]
+    for p, v in zip(params, b.views):
+        assert v.shape == p.shape and (v.data_ptr() - flat.data_ptr()) % 16 == 0
+    for v in b.views:
+        v.fill_(1.0)
+    assert float(flat.sum()) == sum(p.numel() for p in params)  # the pads stay zero

@@ -129,3 +129,24 @@ def test_loud_failures():
     q.grad = torch.ones_like(q)
     with pytest.raises(NotImplementedError):
         AdamW([q]).step()
+
+
+def test_param_groups_tensor_lr_and_maximize():
+    """Two parameter groups with their own hyper-parameters, a device-tensor learning rate (what a capturable scheduler
+    writes into) and maximize=True, against torch.optim.AdamW."""
+    from viscy_b200.optim import AdamW
+    ma, mb = _models()
+    pa, pb = list(ma.parameters()), list(mb.parameters())
+    lr_t = torch.tensor(3e-3, device="cuda")
+    oa = AdamW([{"params": pa[:20], "lr": lr_t, "weight_decay": 0.0}, {"params": pa[20:], "betas": (0.8, 0.95)}], lr=1e-3, maximize=True)
+    ob = torch.optim.AdamW([{"params": pb[:20], "lr": 3e-3, "weight_decay": 0.0}, {"params": pb[20:], "betas": (0.8, 0.95)}], lr=1e-3,
+                           maximize=True)
+    for step in range(3):
+        _fill_grads(ma, mb, 60 + step)
+        if step == 2:  # the scheduler's move
+            lr_t.fill_(1e-3)
+            ob.param_groups[0]["lr"] = 1e-3
+        oa.step()
+        ob.step()
+    for a, b in zip(pa, pb):
+        torch.testing.assert_close(a, b, rtol=2e-6, atol=1e-7)

@@ -150,3 +150,17 @@ def test_param_groups_tensor_lr_and_maximize():
         ob.step()
     for a, b in zip(pa, pb):
         torch.testing.assert_close(a, b, rtol=2e-6, atol=1e-7)
+
+
+def test_capture_before_first_step_is_refused():
+    """State and launch tables are created by an eager step; creating them under capture would replay the zero-fills."""
+    from viscy_b200.optim import AdamW
+    ma, mb = _models()
+    oa = AdamW(ma.parameters(), lr=1e-3)
+    _fill_grads(ma, mb, 70)
+    graph = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="eager step"):
+        with torch.cuda.graph(graph):
+            oa.step()
+    torch.cuda.synchronize()
+    oa.step()  # and the optimizer is still usable eagerly

@@ -2,7 +2,9 @@
 
 The hot path is ~800 short kernels per step; launched eagerly from Python the host becomes the bottleneck, so the
 step is recorded once on a side stream and replayed.  Everything the step touches must be static: inputs are
-copied into fixed buffers, the optimizer must be `capturable=True`, no host synchronisation inside the step.
+copied into fixed buffers, the optimizer must be capturable (torch optimizers: `capturable=True`;
+`viscy_b200.optim.AdamW` always is, its state being created by the eager warm-up steps below), no host synchronisation
+inside the step.
 """
 
 from __future__ import annotations

@@ -79,6 +79,7 @@ class AdamW(torch.optim.Optimizer):
                 loss = closure()
         grad_scale = getattr(self, "grad_scale", None)
         found_inf = getattr(self, "found_inf", None)
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
@@ -92,6 +93,9 @@ class AdamW(torch.optim.Optimizer):
                     raise NotImplementedError("viscy_b200.optim.AdamW takes dense contiguous fp32 parameters and gradients")
                 st = self.state[p]
                 if "exp_avg" not in st:
+                    if capturing:  # the zero-initialisation would be replayed with the graph
+                        raise RuntimeError("viscy_b200.optim.AdamW: run one eager step before CUDA-graph capture "
+                                           "(state is created on the first step)")
                     st["step"] = torch.zeros((), dtype=torch.float32, device=dev)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
@@ -99,6 +103,9 @@ class AdamW(torch.optim.Optimizer):
             plan = self._plans.get(gi)
             key = tuple((p.data_ptr(), m.data_ptr()) for p, (m, _, _) in zip(params, moments))
             if plan is None or plan.key != key:
+                if capturing:  # building the launch tables copies from pageable host memory
+                    raise RuntimeError("viscy_b200.optim.AdamW: the set of parameters with gradients changed under CUDA-graph "
+                                       "capture; run one eager step with the same set first")
                 plan = self._plans[gi] = _Plan(params, moments)
             for i, p in enumerate(params):
                 g = p.grad

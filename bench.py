@@ -350,11 +350,15 @@ def run_gpu(args):
     x = torch.randn((BATCH, *SHAPE_IN), device=dev, generator=g)
     y = torch.randn((BATCH, *SHAPE_OUT), device=dev, generator=g)
 
+    from viscy_b200.losses import MSELoss
+    # nn.MSELoss semantics (the reference's default loss_function): two passes over the 22 M-voxel output; --loss torch times
+    # torch.nn.functional.mse_loss on the fp32 copy of the prediction instead
+    mse = MSELoss() if args.loss == "native" else (lambda o, t: torch.nn.functional.mse_loss(o.float(), t))
+
     def step(xd, yd):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = net(xd)
-            loss = torch.nn.functional.mse_loss(out.float(), yd)
+            loss = mse(net(xd), yd)
         loss.backward()
         if exchange is not None:
             exchange.finish()  # buckets were all-reduced (NCCL, average) as backward produced them; join + hand back
@@ -537,6 +541,7 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"dp{world}",
                        "cuda_graph": graphed is not None, "batch_streams": args.batch_streams,
+                       "loss": "viscy_b200.losses.MSELoss" if args.loss == "native" else "torch mse_loss on out.float()",
                        "optimizer": ("viscy_b200.optim.AdamW (one sm_100a launch per step)" if OPTIMIZER == "native"
                                      else "torch.optim.AdamW(fused=True)"),
                        "grad_exchange": ("none" if not ddp else
@@ -585,6 +590,8 @@ def main():
                     help="split the per-GPU batch into this many chunks on concurrent CUDA streams (exact: per-sample norms)")
     ap.add_argument("--optimizer", default=OPTIMIZER, choices=["native", "torch"],
                     help="native: viscy_b200.optim.AdamW (one launch per step); torch: torch.optim.AdamW(fused=True)")
+    ap.add_argument("--loss", default="native", choices=["native", "torch"],
+                    help="native: viscy_b200.losses.MSELoss (fused passes); torch: F.mse_loss(out.float(), y)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     OPTIMIZER = args.optimizer

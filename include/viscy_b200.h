@@ -394,6 +394,15 @@ int vb200_adamw_step(const void* table, void* const* grads, const int32_t* chunk
                      uint32_t* done, float lr, const float* lr_ptr, float beta1, float beta2, float eps,
                      float weight_decay, int maximize, const float* grad_scale, const float* found_inf, vb200_stream_t stream);
 
+/* ---- The step's default loss (CY/engine.py:197 nn.MSELoss on the autocast prediction and the fp32 target) ----
+ * dtypes: VB200_BF16 | VB200_FP16 | VB200_FP32, independent for pred and target; arithmetic in fp32; n elements, bases 32-byte
+ * aligned.  vb200_mse_sum: *sum += scale * sum_i (pred_i - target_i)^2 (sum pre-zeroed; scale = 1/n for the mean).
+ * vb200_mse_bwd: dpred_i = (pred_i - target_i) * (*gout) * scale in pred's dtype (scale = 2/n for the mean). */
+int vb200_mse_sum(const void* pred, const void* target, int pred_dtype, int target_dtype, int64_t n, float scale, float* sum,
+                  vb200_stream_t stream);
+int vb200_mse_bwd(const void* pred, const void* target, int pred_dtype, int target_dtype, int64_t n, const float* gout,
+                  float scale, void* dpred, vb200_stream_t stream);
+
 /* ---- PixelToVoxelHead (VM/components/heads.py:594-641) ---- */
 /* forward (backward == 0): dec [B,h,w,4*Cm] -> u [B,Dz,2h,2w,Cu] = unfold(pool(pixelshuffle2(dec)));
  * backward (!= 0): src = du, dst = ddec */

@@ -147,3 +147,27 @@ def test_mixed_loss_step_is_cuda_graph_capturable(cuda):
     torch.cuda.synchronize()
     assert abs(out.item() - eager.item()) < 1e-4 * abs(eager.item())  # fp32 atomic sums: order differs run to run
     assert rel(grads[-1].float(), g_eager.float()) < 2e-3  # bf16 gradient: last-bit differences from the atomic sum order
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+@pytest.mark.parametrize("pdt,tdt,shape", [(torch.bfloat16, torch.float32, (2, 2, 5, 64, 64)), (torch.float16, torch.float16, (3, 1, 7, 33)),
+                                           (torch.float32, torch.float32, (1, 1003)), (torch.bfloat16, torch.bfloat16, (5,)),
+                                           (torch.float16, torch.float32, (8, 2, 21, 64, 64))])
+def test_mse_loss_matches_torch(pdt, tdt, shape, reduction):
+    """viscy_b200.losses.MSELoss == torch mse_loss on the fp32 copies (what autocast computes): scalar and gradient, ragged
+    sizes (tails of the 8-element vectors), every dtype pair, under a scaled upstream gradient."""
+    from viscy_b200.losses import MSELoss
+    g = torch.Generator(device="cuda").manual_seed(11)
+    p = torch.randn(shape, device="cuda", generator=g).to(pdt).requires_grad_(True)
+    t = torch.randn(shape, device="cuda", generator=g).to(tdt)
+    loss = MSELoss(reduction)(p, t)
+    (loss * 3.0).backward()
+    pr = p.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(pr.float(), t.float(), reduction=reduction)
+    (ref * 3.0).backward()
+    assert loss.dtype == torch.float32 and loss.shape == ()
+    torch.testing.assert_close(loss, ref, rtol=2e-5, atol=1e-7)
+    assert p.grad.dtype == pdt
+    # (fp16 gradients of a mean over ~1e6 elements are subnormal: allow two quanta of 2^-24)
+    torch.testing.assert_close(p.grad.float(), pr.grad.float(), rtol=1e-2 if pdt != torch.float32 else 1e-6,
+                               atol=1.2e-7 if pdt == torch.float16 else 1e-9)

@@ -240,6 +240,57 @@ class MixedLoss(nn.Module):
             return loss
 
 
+class _MSEFn(Function):
+    """sum or mean of (pred - target)^2 in one pass over the two tensors, gradient w.r.t. pred in a second one."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mean):
+        n = pred.numel()
+        out = torch.zeros((), device=pred.device, dtype=torch.float32)
+        _call("vb200_mse_sum", L.ptr(pred), L.ptr(target), _dt(pred), _dt(target), C.c_int64(n),
+              C.c_float(1.0 / n if mean else 1.0), L.ptr(out))
+        ctx.save_for_backward(pred, target)
+        ctx.scale = 2.0 / n if mean else 2.0
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("MSELoss on the sm_100a path: gradient with respect to the prediction only")
+        dpred = torch.empty_like(pred)
+        g = g.to(torch.float32).contiguous()
+        _call("vb200_mse_bwd", L.ptr(pred), L.ptr(target), _dt(pred), _dt(target), C.c_int64(pred.numel()), L.ptr(g),
+              C.c_float(ctx.scale), L.ptr(dpred))
+        return dpred, None, None
+
+
+class MSELoss(nn.Module):
+    """``torch.nn.MSELoss`` (the reference's default ``loss_function``, CY/engine.py:197) for the training step: on CUDA the
+    16-bit prediction and the fp32 target are read once per pass (no fp32 copy of the prediction, no separate reduction),
+    the result is the fp32 scalar autocast's ``mse_loss`` returns.  reduction: "mean" (default) | "sum".  CPU tensors run
+    ``torch.nn.functional.mse_loss``."""
+
+    def __init__(self, reduction: str = "mean"):
+        super().__init__()
+        if reduction not in ("mean", "sum"):
+            raise ValueError(f"reduction {reduction!r}: 'mean' or 'sum' (use torch.nn.MSELoss for 'none')")
+        self.reduction = reduction
+
+    def forward(self, preds: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        if not preds.is_cuda:
+            return TF.mse_loss(preds, target, reduction=self.reduction)
+        if preds.shape != target.shape:
+            raise ValueError(f"preds {tuple(preds.shape)} and target {tuple(target.shape)} must have the same shape")
+        preds, target = preds.contiguous(), target.contiguous()
+        if preds.data_ptr() % 32:  # views at odd offsets: the kernels read 32-byte vectors
+            preds = preds.clone()
+        if target.data_ptr() % 32:
+            target = target.clone()
+        return _MSEFn.apply(preds, target, self.reduction == "mean")
+
+
 class MaskedMSELoss(nn.Module):
     """Masked MSE loss for FCMAE pre-training (CY/engine.py:104-125): a handful of elementwise / reduction ops on the
     reconstruction, kept as torch ops (FcmaeUNet itself insists on its own class, engine.py:877-878; this one is for callers
